@@ -1,0 +1,182 @@
+/*
+ * mri_b200.h -- C ABI of libmri_b200.so: the B200 (sm_100a) kernels behind the diffusion hot
+ * path of NickB42/mri-image-generation (denoising UNet forward + DDPM q_sample / reverse step).
+ *
+ * The reference has no FFI layer of its own: every FLOP of this path runs inside
+ * torch.nn modules.  Each entry point below therefore cites the reference *call site* whose
+ * arithmetic it replaces (paths relative to the reference's model_scripts/ directory).
+ *
+ * Conventions
+ *   - plain C types only; device pointers are passed as void* / typed pointers to DEVICE memory
+ *     unless the parameter name ends in _host;
+ *   - no allocation or free inside any compute call: the caller owns every buffer;
+ *   - every compute call takes the CUDA stream (cudaStream_t as void*) it must be enqueued on;
+ *   - return value 0 = success, negative = error; mri_last_error() returns a message for the
+ *     calling thread's last failure;
+ *   - activations are channels-last bf16 (N[D]HWC) inside the path; public tensors of the
+ *     reference API (NC[D]HW fp32) are converted at the edges by mri_im2col_* / mri_nhwc_to_nchw.
+ */
+#ifndef MRI_B200_H
+#define MRI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRI_B200_ABI_VERSION 1
+
+int mri_abi_version(void);
+const char* mri_last_error(void);
+/* 1 if the current device is compute capability 10.x, 0 otherwise, <0 on CUDA error. */
+int mri_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------
+ * TMA descriptors.  Encodes a CUtensorMap (128 bytes, written to out_map_host) for a tiled
+ * view of up to rank 5.  dtype: 0 = bf16, 1 = fp32.  swizzle: 0 none, 1 = 32B, 2 = 64B, 3 = 128B.
+ * strides_bytes has rank-1 entries (stride of dims 1..rank-1; dim 0 is contiguous).
+ * ------------------------------------------------------------------------------------------ */
+int mri_tmap_encode(void* out_map_host, uint64_t global_addr, int dtype, int rank,
+                    const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                    int swizzle);
+
+/* ------------------------------------------------------------------------------------------
+ * Implicit-GEMM on tcgen05 tensor cores:  D[m, n] = sum_k A[m, k] * B[n, k]  (+ epilogue)
+ *
+ * Replaces every nn.Conv2d / nn.Conv3d / nn.ConvTranspose2d / nn.ConvTranspose3d call of
+ *   slice_cond_2d_ddpm/unet.py:31-32,40,70,89,142,167, ddpm_25d_all_modalities/unet.py (same),
+ *   ddpm_3d_ldm/unet_attention.py:34-35,65,72,75,114,123,142,155 (and ddpm_3d_ldm/unet.py),
+ * and the two einsums of AttentionBlock3D (unet_attention.py:49-51).
+ *
+ * One CTA computes a 128 x block_n tile.  Its 128 rows are a box (box[0..3]) of output
+ * positions along the four outer dims x1..x4 of the A maps (dim 0 = channels); the K loop
+ * walks `n_kb` entries of `ktable`, each naming one 64-channel slab: which A map to read, the
+ * channel offset, the (o1..o4) shift of the box (= the filter tap; out-of-bounds rows are
+ * zero-filled by TMA, which is the convolution's zero padding) and the K coordinate of the
+ * matching 64-wide slab of B (the packed weights).  Stride-2 convolutions and transposed
+ * convolutions use parity-view A / output maps, `n_class` > 1 selects per-output-parity tables.
+ *
+ * ktable entry (8 x int32): { a_map_index, c0, o1, o2, o3, o4, b_k, 0 }.
+ * Epilogue: + bias[n] + rowbias[sample, n] + bias_m[x1] + residual tile, optional GroupNorm
+ * partial sums (sum, sum of squares per (sample, stats group)) and a TMA store through o_maps.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MriGemmArgs {
+  const void* a_maps;     /* device: CUtensorMap[], rank-5 bf16, box {64, box[0..3]}, swizzle 128B */
+  const void* b_map;      /* device: CUtensorMap, rank-4 bf16 {K, rows, z1, z2}, box {64, block_n,1,1} */
+  const void* o_maps;     /* device: CUtensorMap[n_class], rank-5 output, box {chunk, box[0..3]} */
+  const void* r_maps;     /* device: CUtensorMap[n_class] residual (bf16, same boxes) or NULL */
+  const int32_t* ktable;  /* device: [n_class][n_kb][8] */
+  int32_t n_kb;
+  int32_t n_class;
+  int32_t tiles[4];       /* number of boxes along x1..x4 */
+  int32_t box[4];         /* box extent along x1..x4; product <= 128 */
+  int32_t ext[4];         /* valid output extent along x1..x4 (row validity for the statistics) */
+  int32_t n_tiles_n;      /* tiles along N */
+  int32_t block_n;        /* 16, 32, 64, 128 or 256 */
+  int32_t n_total;        /* valid output columns */
+  int32_t bz_sel[2];      /* B coords z1, z2: 0 -> 0, 1 -> class, 2..5 -> tile index along x1..x4 */
+  int32_t sample_dim;     /* 1..4: which x dim is the sample (batch) index; 0 = none */
+  int32_t out_f32;        /* 0: bf16 output, 1: fp32 output */
+  const float* bias;      /* [n_total] or NULL */
+  const float* bias_m;    /* [ext[0]] bias along x1 (rows) or NULL */
+  const float* rowbias;   /* [samples][rowbias_ld] or NULL (time-embedding projection) */
+  int32_t rowbias_ld;
+  float* stats;           /* [samples][stats_ld][2] accumulated with atomics, or NULL */
+  int32_t stats_ld;       /* statistics groups per sample */
+  int32_t stats_cpg;      /* channels per statistics group (multiple of 8) */
+  int32_t stages;         /* TMA ring depth (2..8) */
+  int32_t reserved;
+} MriGemmArgs;
+
+/* dynamic shared memory one CTA needs for (block_n, stages) */
+int mri_gemm_smem_bytes(int block_n, int stages);
+int mri_gemm_launch(const MriGemmArgs* args_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GroupNorm (+SiLU, + time-embedding add, + residual add), channels-last bf16.
+ * Replaces nn.GroupNorm + nn.SiLU + the broadcast adds of
+ *   slice_cond_2d_ddpm/unet.py:43-56,194-197 (post-norm: h = silu(gn(h)); h += silu(lin(t));
+ *   return h + res), ddpm_3d_ldm/unet_attention.py:38,79-85,199 (pre-norm).
+ * x, y: [samples][spatial][C] bf16.  stats: [samples][stats_ld][2] (sum, sumsq) over fine groups
+ * of stats_cpg channels starting at group index stats_g0; `groups` normalisation groups of
+ * C/groups channels each are formed by summing adjacent fine groups.
+ * y = act(gn(x)*gamma+beta) + rowbias[sample][c] + residual ;  act = SiLU if silu != 0.
+ * ------------------------------------------------------------------------------------------ */
+int mri_gn_stats(const void* x, float* stats, int samples, int64_t spatial, int C, int stats_ld,
+                 int stats_g0, int stats_cpg, void* stream);
+int mri_gn_apply(const void* x, void* y, const float* stats, const float* gamma,
+                 const float* beta, const float* rowbias, int rowbias_ld, const void* residual,
+                 int samples, int64_t spatial, int C, int groups, int stats_ld, int stats_g0,
+                 int stats_cpg, float eps, int silu, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Time / slice-position embedding path (tiny GEMMs, fp32).
+ * mri_sinusoidal: SinusoidalPosEmb.forward, slice_cond_2d_ddpm/unet.py:12-25 (identical copies
+ *   in ddpm_25d_all_modalities/unet.py:13-26, ddpm_3d_ldm/unet.py:12-25, unet_attention.py:12-25).
+ * mri_linear: y[b,o] = act(bias[o] + sum_i x[b,i] W[o,i]) (+ addend[b,o]); act: 0 none, 1 SiLU.
+ *   nn.Linear sites: unet.py:124-136 (time_mlp, slice_mlp), :34,48-49 (per-block projection, SiLU
+ *   applied to the projection in 2D), unet_attention.py:68,81-83 (no SiLU in 3D).
+ * ------------------------------------------------------------------------------------------ */
+int mri_sinusoidal(const int64_t* t, float* out, int batch, int dim, void* stream);
+int mri_linear(const float* x, const float* W, const float* bias, const float* addend, float* y,
+               int batch, int in_f, int out_f, int act, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout edges.
+ * mri_im2col: explicit patch matrix for the thin-channel first convolution (Cin = 1, 3, 20):
+ *   src is NC[D]HW fp32 (src_f32=1) ; dst [samples*D*H*W][kpad] bf16 with column
+ *   ((kd*kh_+kh)*kw_+kw)*cin + c, zero padded to kpad.  `ksize` cubic/square kernel, pad = ksize/2.
+ *   A second source (src2, cin2 channels, may be NULL) is concatenated on channels
+ *   (ddpm_25d_all_modalities/unet.py:198-199).
+ * mri_nhwc_to_nchw: dst[n][c][s] fp32 = src[n][s][c] bf16 for c < C (src row pitch ldc).
+ * mri_nchw_to_nhwc: dst[n][s][c] bf16 = src[n][c][s] fp32.
+ * ------------------------------------------------------------------------------------------ */
+int mri_im2col(const float* src, const float* src2, void* dst, int samples, int cin, int cin2,
+               int D, int H, int W, int ksize, int ndim, int kpad, void* stream);
+int mri_nhwc_to_nchw(const void* src, float* dst, int samples, int64_t spatial, int C, int ldc,
+                     void* stream);
+int mri_nchw_to_nhwc(const float* src, void* dst, int samples, int64_t spatial, int C, int ldc,
+                     void* stream);
+
+/* Row softmax for the bottleneck attention (unet_attention.py:50): P = softmax(S * scale),
+ * S fp32 [rows][ld_s], P bf16 [rows][ld_p], `cols` valid columns (padding columns written 0). */
+int mri_softmax_rows(const float* S, void* P, int64_t rows, int cols, int ld_s, int ld_p,
+                     float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * DDPM arithmetic, fp32, bit-exact w.r.t. the reference's eager association order.
+ * All take x as [samples][per_sample] fp32 (NC[D]HW flattened) and t as int64[samples].
+ *
+ * mri_q_sample:  out = sqrt_ac[t]*x0 + sqrt_1mac[t]*noise
+ *   (slice_cond_2d_ddpm/diffusion.py:60-75, ddpm_25d_all_modalities/diffusion.py:59-74,
+ *    ddpm_3d_ldm/diffusion.py:68-82)
+ * mri_ddpm_step: out = c1[t]*(x - (beta[t]/s[t])*eps) + ((t!=0) * sqrt(pv[t])) * noise
+ *   (p_sample: slice_cond_2d_ddpm/diffusion.py:115-132, ddpm_25d.../diffusion.py:96-112,
+ *    ddpm_3d_ldm/diffusion.py:106-126).  eps is either fp32 in x's layout (eps_nhwc_ldc = 0) or
+ *    the bf16 channels-last UNet output with row pitch eps_nhwc_ldc and `channels` channels.
+ * mri_ddim_step: x0=(x-sqrt(1-a_t)*eps)/max(sqrt(a_t),1e-8); out=sqrt(a_p)*x0+sqrt(1-a_p)*eps
+ *   (ddpm_3d_ldm/diffusion.py:168-186)
+ * mri_minsnr_loss: per-sample mean((pred-noise)^2) weighted by min(snr[t],gamma)/snr[t], mean
+ *   over samples (ddpm_3d_ldm/diffusion.py:91-99); gamma <= 0 means plain MSE (F.mse_loss,
+ *   ddpm_25d_all_modalities/diffusion.py:89).  loss_out: float[1]; per_sample: float[samples].
+ * ------------------------------------------------------------------------------------------ */
+int mri_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_ac,
+                 const float* sqrt_1mac, float* out, int samples, int64_t per_sample, void* stream);
+int mri_ddpm_step(const float* x, const void* eps, int eps_nhwc_ldc, int channels,
+                  const float* noise, const int64_t* t, const float* betas, const float* sqrt_1mac,
+                  const float* sqrt_recip_alphas, const float* post_var, float* out, int samples,
+                  int64_t per_sample, void* stream);
+int mri_ddim_step(const float* x, const void* eps, int eps_nhwc_ldc, int channels,
+                  const int64_t* t, const int64_t* t_prev, const float* alphas_cumprod, float* out,
+                  int samples, int64_t per_sample, void* stream);
+int mri_minsnr_loss(const float* pred, const float* noise, const int64_t* t, const float* snr,
+                    float gamma, float* per_sample_out, float* loss_out, int samples,
+                    int64_t per_sample, void* stream);
+/* t[i] += delta for i < n (advances the device-resident timestep inside a CUDA graph) */
+int mri_add_i64(int64_t* t, int n, int64_t delta, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRI_B200_H */

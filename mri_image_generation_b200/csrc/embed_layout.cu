@@ -1,0 +1,250 @@
+// Small kernels around the tensor-core path: timestep embedding + the tiny fp32 linears,
+// the explicit patch matrix for thin-channel first convolutions, layout converters at the
+// public NC[D]HW fp32 edge, and the attention row softmax.
+// Reference call sites: see include/mri_b200.h.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/mri_b200.h"
+#include "common.h"
+
+namespace mri {
+
+// emb[b, j] = sin(t_b * f_j), emb[b, half + j] = cos(t_b * f_j), f_j = exp(j * -(ln(1e4)/(half-1)))
+// (fp32 products rounded exactly as torch does; odd dim is zero padded)
+__global__ void sinusoidal_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int batch,
+                                  int dim) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * dim) return;
+  const int b = i / dim, j = i % dim;
+  if (j >= 2 * half) {
+    out[i] = 0.f;
+    return;
+  }
+  const float neg = -(float)(9.210340371976184 / (double)(half - 1));  // -(ln 1e4)/(half-1)
+  const int jj = j < half ? j : j - half;
+  const float f = expf(__fmul_rn((float)jj, neg));
+  const float arg = __fmul_rn((float)t[b], f);
+  out[i] = j < half ? sinf(arg) : cosf(arg);
+}
+
+// y[b, o] = act(bias[o] + sum_i x[b, i] W[o, i]) + addend[b, o]; one warp per output feature.
+template <int kMaxB>
+__global__ void __launch_bounds__(256)
+linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
+              const float* __restrict__ bias, const float* __restrict__ addend,
+              float* __restrict__ y, int batch, int in_f, int out_f, int act, int b0) {
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (o >= out_f) return;
+  float acc[kMaxB];
+#pragma unroll
+  for (int b = 0; b < kMaxB; ++b) acc[b] = 0.f;
+  const float* w = W + (size_t)o * in_f;
+  for (int i = lane; i < in_f; i += 32) {
+    const float wv = __ldg(w + i);
+#pragma unroll
+    for (int b = 0; b < kMaxB; ++b)
+      if (b0 + b < batch) acc[b] = fmaf(wv, __ldg(x + (size_t)(b0 + b) * in_f + i), acc[b]);
+  }
+#pragma unroll
+  for (int b = 0; b < kMaxB; ++b) {
+    float v = acc[b];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if (lane == 0 && b0 + b < batch) {
+      v += bias != nullptr ? __ldg(bias + o) : 0.f;
+      if (act == 1) v = v / (1.0f + expf(-v));
+      if (addend != nullptr) v += addend[(size_t)(b0 + b) * out_f + o];
+      y[(size_t)(b0 + b) * out_f + o] = v;
+    }
+  }
+}
+
+// Patch matrix of a thin-channel input (fp32 NC[D]HW) for a ksize^ndim, pad ksize/2 convolution.
+// dst[m][((kd*k+kh)*k+kw)*cin_total + c]; one thread per (m, tap).
+__global__ void __launch_bounds__(256)
+im2col_kernel(const float* __restrict__ src, const float* __restrict__ src2,
+              __nv_bfloat16* __restrict__ dst, int samples, int cin, int cin2, int D, int H, int W,
+              int k, int ndim, int kpad) {
+  const int taps = ndim == 3 ? k * k * k : k * k;
+  const int ct = cin + cin2;
+  const int64_t spatial = (int64_t)D * H * W;
+  const int64_t M = (int64_t)samples * spatial;
+  const int slots = taps + 1;  // last slot zero-fills the padding columns
+  const int64_t total = M * slots;
+  const int pad = k / 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / slots;
+    const int tap = (int)(i % slots);
+    __nv_bfloat16* row = dst + m * kpad;
+    if (tap == taps) {
+      for (int c = taps * ct; c < kpad; ++c) row[c] = __float2bfloat16(0.f);
+      continue;
+    }
+    const int n = (int)(m / spatial);
+    int64_t s = m % spatial;
+    const int w0 = (int)(s % W);
+    s /= W;
+    const int h0 = (int)(s % H);
+    const int d0 = (int)(s / H);
+    int kw = tap % k, kh = (tap / k) % k, kd = ndim == 3 ? tap / (k * k) : 0;
+    const int w = w0 + kw - pad, h = h0 + kh - pad, d = ndim == 3 ? d0 + kd - pad : d0;
+    const bool in = w >= 0 && w < W && h >= 0 && h < H && d >= 0 && d < D;
+    const int64_t sp = ((int64_t)d * H + h) * W + w;
+    for (int c = 0; c < ct; ++c) {
+      float v = 0.f;
+      if (in) {
+        v = c < cin ? __ldg(src + ((size_t)n * cin + c) * spatial + sp)
+                    : __ldg(src2 + ((size_t)n * cin2 + (c - cin)) * spatial + sp);
+      }
+      row[tap * ct + c] = __float2bfloat16(v);
+    }
+  }
+}
+
+// dst[n][c][s] (fp32) = src[n][s][c] (bf16, row pitch ldc); small C (<= 32) at the output edge.
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int samples,
+                    int64_t spatial, int C, int ldc) {
+  const int64_t total = (int64_t)samples * C * spatial;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = i % spatial;
+    const int c = (int)((i / spatial) % C);
+    const int n = (int)(i / (spatial * C));
+    dst[i] = __bfloat162float(src[((size_t)n * spatial + s) * ldc + c]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int samples,
+                    int64_t spatial, int C, int ldc) {
+  const int64_t total = (int64_t)samples * spatial * ldc;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ldc);
+    const int64_t s = (i / ldc) % spatial;
+    const int n = (int)(i / ((int64_t)ldc * spatial));
+    const float v = c < C ? __ldg(src + ((size_t)n * C + c) * spatial + s) : 0.f;
+    dst[i] = __float2bfloat16(v);
+  }
+}
+
+// One block per row: P = softmax(S * scale) in fp32, stored bf16.
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P, int cols, int ld_s,
+                    int ld_p, float scale) {
+  const int64_t row = blockIdx.x;
+  const float* s = S + row * ld_s;
+  __nv_bfloat16* p = P + row * ld_p;
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) mx = fmaxf(mx, s[c] * scale);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[wid] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+    for (int i = 1; i < nw; ++i) m = fmaxf(m, red[i]);
+    bcast = m;
+  }
+  __syncthreads();
+  mx = bcast;
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) sum += expf(s[c] * scale - mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncthreads();
+  if (lane == 0) red[wid] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < nw; ++i) t += red[i];
+    bcast = 1.0f / t;
+  }
+  __syncthreads();
+  const float inv = bcast;
+  for (int c = threadIdx.x; c < ld_p; c += blockDim.x)
+    p[c] = __float2bfloat16(c < cols ? expf(s[c] * scale - mx) * inv : 0.f);
+}
+
+static inline unsigned grid_for(int64_t total) {
+  int64_t b = (total + 255) / 256;
+  const int64_t cap = 148 * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace mri
+
+using namespace mri;
+
+extern "C" int mri_sinusoidal(const int64_t* t, float* out, int batch, int dim, void* stream) {
+  if (batch < 1 || dim < 4) return set_error(-2, "mri_sinusoidal: bad shape");
+  const int total = batch * dim;
+  sinusoidal_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, out, batch, dim);
+  return check_launch("sinusoidal_kernel");
+}
+
+extern "C" int mri_linear(const float* x, const float* W, const float* bias, const float* addend,
+                          float* y, int batch, int in_f, int out_f, int act, void* stream) {
+  if (batch < 1 || in_f < 1 || out_f < 1) return set_error(-2, "mri_linear: bad shape");
+  constexpr int kB = 8;
+  const int warps = 8;
+  const unsigned grid = (out_f + warps - 1) / warps;
+  for (int b0 = 0; b0 < batch; b0 += kB) {
+    linear_kernel<kB><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(x, W, bias, addend, y, batch,
+                                                                     in_f, out_f, act, b0);
+    int rc = check_launch("linear_kernel");
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int mri_im2col(const float* src, const float* src2, void* dst, int samples, int cin,
+                          int cin2, int D, int H, int W, int ksize, int ndim, int kpad,
+                          void* stream) {
+  const int taps = ndim == 3 ? ksize * ksize * ksize : ksize * ksize;
+  if (ndim != 2 && ndim != 3) return set_error(-2, "mri_im2col: ndim must be 2 or 3");
+  if ((cin + cin2) * taps > kpad || kpad % 64 != 0)
+    return set_error(-2, "mri_im2col: kpad must be a multiple of 64 and >= taps*cin");
+  if (cin2 > 0 && src2 == nullptr) return set_error(-2, "mri_im2col: src2 missing");
+  const int64_t total = (int64_t)samples * D * H * W * (taps + 1);
+  im2col_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+      src, src2, reinterpret_cast<__nv_bfloat16*>(dst), samples, cin, cin2, D, H, W, ksize, ndim,
+      kpad);
+  return check_launch("im2col_kernel");
+}
+
+extern "C" int mri_nhwc_to_nchw(const void* src, float* dst, int samples, int64_t spatial, int C,
+                                int ldc, void* stream) {
+  const int64_t total = (int64_t)samples * C * spatial;
+  nhwc_to_nchw_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), dst, samples, spatial, C, ldc);
+  return check_launch("nhwc_to_nchw_kernel");
+}
+
+extern "C" int mri_nchw_to_nhwc(const float* src, void* dst, int samples, int64_t spatial, int C,
+                                int ldc, void* stream) {
+  const int64_t total = (int64_t)samples * spatial * ldc;
+  nchw_to_nhwc_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst), samples, spatial, C, ldc);
+  return check_launch("nchw_to_nhwc_kernel");
+}
+
+extern "C" int mri_softmax_rows(const float* S, void* P, int64_t rows, int cols, int ld_s, int ld_p,
+                                float scale, void* stream) {
+  if (rows < 1 || cols < 1 || ld_s < cols || ld_p < cols)
+    return set_error(-2, "mri_softmax_rows: bad shape");
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(
+      S, reinterpret_cast<__nv_bfloat16*>(P), cols, ld_s, ld_p, scale);
+  return check_launch("softmax_rows_kernel");
+}

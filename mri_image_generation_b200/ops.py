@@ -1,0 +1,122 @@
+"""Thin torch-tensor wrappers over the C ABI (include/mri_b200.h).
+
+Each function takes CUDA tensors, passes raw device pointers and the current CUDA stream to
+libmri_b200.so and returns nothing (outputs are caller-allocated).  No wrapper has a fallback:
+a CPU tensor or a missing library raises.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.MriError("mri_image_generation_b200 ops need CUDA tensors (no CPU path)")
+    return t.data_ptr()
+
+
+def _s() -> int:
+    return _lib.current_stream_ptr()
+
+
+def _chk_contig(*ts):
+    for t in ts:
+        if t is not None and not t.is_contiguous():
+            raise _lib.MriError("non-contiguous tensor passed to a libmri_b200 op")
+
+
+def gn_stats(x: torch.Tensor, stats: torch.Tensor, samples: int, spatial: int, C: int,
+             stats_cpg: int, stats_g0: int = 0) -> None:
+    _chk_contig(x, stats)
+    _lib.check(_lib.load().mri_gn_stats(_p(x), _p(stats), samples, spatial, C, stats.shape[1],
+                                        stats_g0, stats_cpg, _s()), "mri_gn_stats")
+
+
+def gn_apply(x, y, stats, gamma, beta, samples: int, spatial: int, C: int, groups: int,
+             stats_cpg: int, eps: float, silu: bool, rowbias=None, rowbias_ld: int = 0,
+             residual=None, stats_g0: int = 0) -> None:
+    _chk_contig(x, y, stats, residual)
+    _lib.check(_lib.load().mri_gn_apply(_p(x), _p(y), _p(stats), _p(gamma), _p(beta), _p(rowbias),
+                                        rowbias_ld, _p(residual), samples, spatial, C, groups,
+                                        stats.shape[1], stats_g0, stats_cpg, eps, 1 if silu else 0,
+                                        _s()), "mri_gn_apply")
+
+
+def sinusoidal(t: torch.Tensor, out: torch.Tensor) -> None:
+    assert t.dtype == torch.int64 and out.dtype == torch.float32
+    _lib.check(_lib.load().mri_sinusoidal(_p(t), _p(out), out.shape[0], out.shape[1], _s()),
+               "mri_sinusoidal")
+
+
+def linear(x, W, bias, y, act: int = 0, addend=None) -> None:
+    _chk_contig(x, W, y, addend)
+    assert x.dtype == W.dtype == y.dtype == torch.float32
+    _lib.check(_lib.load().mri_linear(_p(x), _p(W), _p(bias), _p(addend), _p(y), x.shape[0],
+                                      W.shape[1], W.shape[0], act, _s()), "mri_linear")
+
+
+def im2col(src, dst, samples, cin, D, H, W, ksize, ndim, kpad, src2=None, cin2: int = 0) -> None:
+    _chk_contig(src, src2, dst)
+    _lib.check(_lib.load().mri_im2col(_p(src), _p(src2), _p(dst), samples, cin, cin2, D, H, W,
+                                      ksize, ndim, kpad, _s()), "mri_im2col")
+
+
+def nhwc_to_nchw(src, dst, samples, spatial, C, ldc) -> None:
+    _chk_contig(src, dst)
+    _lib.check(_lib.load().mri_nhwc_to_nchw(_p(src), _p(dst), samples, spatial, C, ldc, _s()),
+               "mri_nhwc_to_nchw")
+
+
+def nchw_to_nhwc(src, dst, samples, spatial, C, ldc) -> None:
+    _chk_contig(src, dst)
+    _lib.check(_lib.load().mri_nchw_to_nhwc(_p(src), _p(dst), samples, spatial, C, ldc, _s()),
+               "mri_nchw_to_nhwc")
+
+
+def softmax_rows(S, P, rows, cols, ld_s, ld_p, scale) -> None:
+    _lib.check(_lib.load().mri_softmax_rows(_p(S), _p(P), rows, cols, ld_s, ld_p, scale, _s()),
+               "mri_softmax_rows")
+
+
+def q_sample(x0, noise, t, sqrt_ac, sqrt_1mac, out) -> None:
+    _chk_contig(x0, noise, out)
+    n = x0.shape[0]
+    _lib.check(_lib.load().mri_q_sample(_p(x0), _p(noise), _p(t), _p(sqrt_ac), _p(sqrt_1mac),
+                                        _p(out), n, x0.numel() // n, _s()), "mri_q_sample")
+
+
+def ddpm_step(x, eps, noise, t, betas, sqrt_1mac, sqrt_recip_alphas, post_var, out,
+              eps_nhwc_ldc: int = 0, channels: int = 0) -> None:
+    _chk_contig(x, eps, noise, out)
+    n = x.shape[0]
+    _lib.check(_lib.load().mri_ddpm_step(_p(x), _p(eps), eps_nhwc_ldc, channels, _p(noise), _p(t),
+                                         _p(betas), _p(sqrt_1mac), _p(sqrt_recip_alphas),
+                                         _p(post_var), _p(out), n, x.numel() // n, _s()),
+               "mri_ddpm_step")
+
+
+def ddim_step(x, eps, t, t_prev, alphas_cumprod, out, eps_nhwc_ldc: int = 0,
+              channels: int = 0) -> None:
+    _chk_contig(x, eps, out)
+    n = x.shape[0]
+    _lib.check(_lib.load().mri_ddim_step(_p(x), _p(eps), eps_nhwc_ldc, channels, _p(t), _p(t_prev),
+                                         _p(alphas_cumprod), _p(out), n, x.numel() // n, _s()),
+               "mri_ddim_step")
+
+
+def minsnr_loss(pred, noise, t, snr, gamma: float, per_sample_out, loss_out) -> None:
+    _chk_contig(pred, noise)
+    n = pred.shape[0]
+    _lib.check(_lib.load().mri_minsnr_loss(_p(pred), _p(noise), _p(t), _p(snr), gamma,
+                                           _p(per_sample_out), _p(loss_out), n, pred.numel() // n,
+                                           _s()), "mri_minsnr_loss")
+
+
+def add_i64(t: torch.Tensor, delta: int) -> None:
+    _lib.check(_lib.load().mri_add_i64(_p(t), t.numel(), delta, _s()), "mri_add_i64")

@@ -1,0 +1,142 @@
+"""tcgen05 implicit-GEMM kernel vs torch convolutions on the same bf16-rounded operands (GPU).
+
+Tolerance: outputs are bf16 (8 mantissa bits) of an fp32-accumulated sum -> rel-L2 <= 4e-3
+against the fp32 result of the same rounded operands; GroupNorm partial sums (fp32 atomics of
+the un-rounded accumulators) rel <= 1e-3."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = 4e-3
+
+
+def nhwc(x):
+    nd = x.dim() - 2
+    return x.permute(0, *range(2, 2 + nd), 1).contiguous().to(torch.bfloat16)
+
+
+def nchw(y):
+    nd = y.dim() - 2
+    return y.permute(0, nd + 1, *range(1, nd + 1)).float()
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+
+def conv_fn(nd):
+    return F.conv3d if nd == 3 else F.conv2d
+
+
+@pytest.fixture(scope="module")
+def P():
+    from mri_image_generation_b200 import _lib, plan
+    _lib.require_device()
+    return plan
+
+
+CASES = [
+    # nd, spatial, N, [Cin sources], Cout, k
+    (3, (8, 12, 10), 2, [128], 128, 3),
+    (3, (40, 48, 40), 1, [128], 128, 3),
+    (3, (10, 12, 10), 2, [512], 512, 3),
+    (3, (20, 24, 20), 1, [256, 256], 256, 3),
+    (2, (32, 32), 4, [64], 64, 3),
+    (2, (30, 30), 3, [192], 128, 3),
+    (3, (10, 12, 10), 2, [512], 1024, 1),
+    (3, (8, 8, 8), 1, [128], 16, 3),
+]
+
+
+@pytest.mark.parametrize("nd,sp,N,cins,cout,k", CASES)
+def test_conv_stride1(P, nd, sp, N, cins, cout, k):
+    torch.manual_seed(1)
+    dev = "cuda"
+    xs = [torch.randn(N, c, *sp, device=dev) for c in cins]
+    acts = [nhwc(x) for x in xs]
+    cin = sum(cins)
+    w = torch.randn(cout, cin, *([k] * nd), device=dev) / (cin * k ** nd) ** 0.5
+    bias = torch.randn(cout, device=dev)
+    rb = torch.randn(N, cout + 8, device=dev)
+    res = nhwc(torch.randn(N, cout, *sp, device=dev))
+    xin = torch.cat([nchw(a) for a in acts], 1)
+    ref = conv_fn(nd)(xin, w.to(torch.bfloat16).float(), bias, padding=k // 2)
+    ref = ref + rb[:, :cout].reshape(N, cout, *[1] * nd) + nchw(res)
+    wm = P.pack_conv_weight(w, splits=cins)
+    y = torch.zeros(N, *sp, cout, dtype=torch.bfloat16, device=dev)
+    groups = 8 if cout % 64 == 0 else 2
+    stats = torch.zeros(N, groups, 2, device=dev)
+    pl = P.conv_plan([P.ConvSource(a) for a in acts], wm, y, k, bias=bias, rowbias=rb,
+                     rowbias_ld=cout + 8, residual=res, stats=stats, stats_cpg=cout // groups)
+    pl.materialize(dev)
+    pl.launch()
+    torch.cuda.synchronize()
+    assert rel(nchw(y), ref) < TOL
+    r = ref.reshape(N, groups, -1)
+    assert rel(stats[:, :, 0], r.sum(-1)) < 1e-3 or (stats[:, :, 0] - r.sum(-1)).abs().max() < 0.05 * r.abs().sum(-1).max() ** 0.5
+    assert rel(stats[:, :, 1], (r ** 2).sum(-1)) < 1e-3
+
+
+@pytest.mark.parametrize("nd,sp,N,cin,cout", [(3, (8, 12, 8), 2, 128, 256), (2, (32, 48), 2, 64, 64),
+                                                (3, (40, 48, 40), 1, 128, 256)])
+def test_down_conv(P, nd, sp, N, cin, cout):
+    torch.manual_seed(2)
+    dev = "cuda"
+    a = nhwc(torch.randn(N, cin, *sp, device=dev))
+    w = torch.randn(cout, cin, *([4] * nd), device=dev) / (cin * 4 ** nd) ** 0.5
+    bias = torch.randn(cout, device=dev)
+    ref = conv_fn(nd)(nchw(a), w.to(torch.bfloat16).float(), bias, stride=2, padding=1)
+    y = torch.zeros(N, *[s // 2 for s in sp], cout, dtype=torch.bfloat16, device=dev)
+    stats = torch.zeros(N, 8, 2, device=dev)
+    pl = P.down_conv_plan(a, P.pack_conv_weight(w), y, bias=bias, stats=stats, stats_cpg=cout // 8)
+    pl.materialize(dev)
+    pl.launch()
+    torch.cuda.synchronize()
+    assert rel(nchw(y), ref) < TOL
+    assert rel(stats[:, :, 1], (ref.reshape(N, 8, -1) ** 2).sum(-1)) < 1e-3
+
+
+@pytest.mark.parametrize("nd,sp,N,cin,cout", [(3, (4, 6, 4), 2, 128, 64), (2, (16, 24), 2, 128, 64),
+                                                (3, (20, 24, 20), 1, 256, 128)])
+def test_up_conv(P, nd, sp, N, cin, cout):
+    torch.manual_seed(3)
+    dev = "cuda"
+    a = nhwc(torch.randn(N, cin, *sp, device=dev))
+    w = torch.randn(cin, cout, *([4] * nd), device=dev) / (cin * 2 ** nd) ** 0.5
+    bias = torch.randn(cout, device=dev)
+    ct = F.conv_transpose3d if nd == 3 else F.conv_transpose2d
+    ref = ct(nchw(a), w.to(torch.bfloat16).float(), bias, stride=2, padding=1)
+    y = torch.zeros(N, *[s * 2 for s in sp], cout, dtype=torch.bfloat16, device=dev)
+    stats = torch.zeros(N, 8, 2, device=dev)
+    pl = P.up_conv_plan(a, P.pack_convT_weight(w), y, bias=bias, stats=stats, stats_cpg=cout // 8)
+    pl.materialize(dev)
+    pl.launch()
+    torch.cuda.synchronize()
+    assert rel(nchw(y), ref) < TOL
+    assert rel(stats[:, :, 1], (ref.reshape(N, 8, -1) ** 2).sum(-1)) < 1e-3
+
+
+def test_matrix_fp32_out(P):
+    """Batched Q K^T with fp32 output (the attention logits GEMM)."""
+    torch.manual_seed(4)
+    dev = "cuda"
+    B, heads, n, d = 2, 4, 200, 128
+    C = heads * d
+    qk = torch.randn(B, n, 2 * C, device=dev).to(torch.bfloat16)
+    npad = (n + 7) // 8 * 8
+    S = torch.zeros(B, heads, n, npad, device=dev)
+    a = P.TView(qk, (d, n, heads, B, 1), (1, 2 * C, d, n * 2 * C, B * n * 2 * C))
+    b = P.TView(qk, (d, n, heads, B), (1, 2 * C, d, n * 2 * C), offset=C)
+    o = P.TView(S, (npad, n, heads, B, 1), (1, npad, n * npad, heads * n * npad, B * heads * n * npad))
+    pl = P.matrix_plan(a, (128, 1, 1, 1), b, o, K=d, n_total=npad, block_n=128,
+                       ext=(n, heads, B, 1), tiles=(-(-n // 128), heads, B, 1), bz_sel=(3, 4),
+                       out_f32=True)
+    pl.materialize(dev)
+    pl.launch()
+    torch.cuda.synchronize()
+    q = qk[:, :, :C].float().reshape(B, n, heads, d).permute(0, 2, 1, 3)
+    k = qk[:, :, C:].float().reshape(B, n, heads, d).permute(0, 2, 1, 3)
+    ref = q @ k.transpose(-1, -2)
+    assert rel(S[..., :n], ref) < 1e-5
