@@ -1,0 +1,465 @@
+"""Static-shape execution engine for the denoising UNets.
+
+A :class:`UNetProgram` is built once per (model, batch, spatial size): it packs the weights into
+the K-major bf16 matrices the tensor-core kernel wants, allocates every activation buffer
+(channels-last bf16), builds one GemmPlan (TMA descriptors + k-table) per convolution and
+records the launch sequence.  Running the program is a fixed list of C-ABI kernel launches on
+the current CUDA stream, so it can be captured in a CUDA graph (see diffusion wrappers).
+
+Fusions: conv epilogues add bias, the per-sample time-embedding projection and
+the residual, and emit GroupNorm partial sums for the next norm; torch.cat is virtual (two TMA
+sources in one K loop); the 1x1 skip convolutions of the 3D ResBlocks ride on conv2's K loop;
+GroupNorm-apply + SiLU (+ time-embedding add + residual add for the 2D post-norm blocks) is one
+bf16 pass.
+
+Reference graphs: ddpm_3d_ldm/unet_attention.py:157-200 (UNet3DModelWithAttention.forward),
+ddpm_3d_ldm/unet.py:115-158, slice_cond_2d_ddpm/unet.py:169-199,
+ddpm_25d_all_modalities/unet.py:174-218.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib, ops
+from . import plan as P
+
+
+def _rup(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+@dataclass
+class Act:
+    """Channels-last bf16 activation [N, *spatial, C] (+ GroupNorm partial sums of its producer)."""
+    t: torch.Tensor
+    stats: Optional[torch.Tensor] = None  # fp32 [N, G, 2]
+    cpg: int = 0                          # channels per statistics group
+
+    @property
+    def C(self) -> int:
+        return self.t.shape[-1]
+
+    @property
+    def spatial(self) -> int:
+        n = 1
+        for s in self.t.shape[1:-1]:
+            n *= s
+        return n
+
+
+class _Pool:
+    """Recycles activation buffers by shape (the program is straight-line, so a buffer released
+    by the builder is free for every later op in program order)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free: Dict[Tuple, List[torch.Tensor]] = {}
+        self.bytes = 0
+
+    def get(self, shape, dtype=torch.bfloat16) -> torch.Tensor:
+        key = (tuple(shape), dtype)
+        lst = self.free.get(key)
+        if lst:
+            return lst.pop()
+        t = torch.zeros(*shape, dtype=dtype, device=self.device)
+        self.bytes += t.numel() * t.element_size()
+        return t
+
+    def release(self, t: torch.Tensor) -> None:
+        self.free.setdefault((tuple(t.shape), t.dtype), []).append(t)
+
+
+class UNetProgram:
+    """Common builder machinery; subclasses lay out a concrete UNet."""
+
+    STATS_ARENA = 1 << 18  # floats
+
+    def __init__(self, device, batch: int, spatial: Sequence[int], groups: int = 8):
+        _lib.require_device()
+        self.device = device
+        self.B = batch
+        self.sp = tuple(int(s) for s in spatial)
+        self.ndim = len(self.sp)
+        self.groups = groups
+        self.pool = _Pool(device)
+        self.ops: List[Callable[[], None]] = []
+        self.op_names: List[str] = []
+        self.plans: List[P.GemmPlan] = []
+        self.refresh: List[Callable[[], None]] = []  # re-pack weights after a parameter update
+        self._arena = torch.zeros(self.STATS_ARENA, dtype=torch.float32, device=device)
+        self._arena_used = 0
+        self.gemm_flops = 0
+        self.hbm_bytes_elementwise = 0
+        self._param_versions: Optional[Tuple] = None
+        self._params: List[torch.Tensor] = []
+
+    # ------------------------------------------------------------------ bookkeeping
+    def _add(self, name: str, fn: Callable[[], None]) -> None:
+        self.op_names.append(name)
+        self.ops.append(fn)
+
+    def new_stats(self, n_groups: int) -> torch.Tensor:
+        n = self.B * n_groups * 2
+        if self._arena_used + n > self.STATS_ARENA:
+            raise _lib.MriError("statistics arena exhausted")
+        s = self._arena[self._arena_used:self._arena_used + n].view(self.B, n_groups, 2)
+        self._arena_used += _rup(n, 4)
+        return s
+
+    def new_act(self, sp: Sequence[int], C: int, with_stats: bool = True) -> Act:
+        t = self.pool.get((self.B, *sp, C))
+        if with_stats and C % (8 * self.groups) == 0:
+            return Act(t, self.new_stats(self.groups), C // self.groups)
+        return Act(t)
+
+    def track(self, *params: torch.Tensor) -> None:
+        self._params.extend(params)
+
+    def packed(self, make: Callable[[], torch.Tensor]) -> torch.Tensor:
+        """A derived weight buffer that is re-computed in place when parameters change."""
+        buf = make()
+        self.refresh.append(lambda: buf.copy_(make()))
+        return buf
+
+    def params_changed(self) -> bool:
+        v = tuple(p._version for p in self._params)
+        if self._param_versions is None:
+            self._param_versions = v
+            return False
+        if v != self._param_versions:
+            self._param_versions = v
+            return True
+        return False
+
+    def run(self) -> None:
+        """Enqueue the whole forward on the current stream."""
+        self._arena[:max(self._arena_used, 4)].zero_()
+        for fn in self.ops:
+            fn()
+
+    # ------------------------------------------------------------------ op emitters
+    def gemm(self, pl: P.GemmPlan) -> None:
+        pl.materialize(self.device)
+        self.plans.append(pl)
+        self.gemm_flops += pl.flops
+        self._add(f"gemm:{pl.name}", pl.launch)
+
+    def gn(self, x: Act, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float,
+           silu: bool, rowbias: Optional[torch.Tensor] = None, rowbias_ld: int = 0,
+           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+           name: str = "gn") -> torch.Tensor:
+        """y = act(GroupNorm(x)) (+ rowbias[n, c]) (+ residual).  Uses x.stats (fine groups)."""
+        assert x.stats is not None, f"{name}: input has no statistics"
+        y = out if out is not None else self.pool.get(tuple(x.t.shape))
+        B, S, C = self.B, x.spatial, x.C
+        xs, st, cpg = x.t, x.stats, x.cpg
+        self.hbm_bytes_elementwise += 2 * xs.numel() * 2 + (residual.numel() * 2 if residual is not None else 0)
+
+        def fn():
+            ops.gn_apply(xs, y, st, gamma, beta, B, S, C, groups, cpg, eps, silu, rowbias=rowbias,
+                         rowbias_ld=rowbias_ld, residual=residual)
+
+        self._add(name, fn)
+        return y
+
+    def stats_of(self, x: Act, name: str = "gn_stats") -> None:
+        """Standalone statistics pass for a tensor whose producer did not emit them."""
+        x.stats = self.new_stats(self.groups)
+        x.cpg = x.C // self.groups
+        B, S, C, xs, st, cpg = self.B, x.spatial, x.C, x.t, x.stats, x.cpg
+        self.hbm_bytes_elementwise += xs.numel() * 2
+        self._add(name, lambda: ops.gn_stats(xs, st, B, S, C, cpg))
+
+    def conv(self, sources: Sequence[P.ConvSource], wmat: torch.Tensor, cout: int, ksize: int,
+             bias: Optional[torch.Tensor], *, rowbias=None, rowbias_ld=0, residual=None,
+             with_stats=True, name="conv") -> Act:
+        sp = sources[0].x.shape[1:-1]
+        y = self.new_act(sp, cout, with_stats)
+        pl = P.conv_plan(sources, wmat, y.t, ksize, bias=bias, rowbias=rowbias, rowbias_ld=rowbias_ld,
+                         residual=residual, stats=y.stats, stats_cpg=y.cpg, name=name)
+        self.gemm(pl)
+        return y
+
+    # ------------------------------------------------------------------ time embedding
+    def time_embedding(self, t_in: torch.Tensor, time_mlp, dim: int) -> torch.Tensor:
+        """SinusoidalPosEmb -> Linear -> SiLU -> Linear  (unet.py:124-129 / unet_attention.py:103-108)."""
+        B, dev = self.B, self.device
+        sin = torch.zeros(B, dim, device=dev)
+        h1 = torch.zeros(B, dim * 4, device=dev)
+        temb = torch.zeros(B, dim, device=dev)
+        l1, l2 = time_mlp[1], time_mlp[3]
+        self.track(l1.weight, l1.bias, l2.weight, l2.bias)
+        self._add("sinusoidal", lambda: ops.sinusoidal(t_in, sin))
+        self._add("time_mlp.1", lambda: ops.linear(sin, l1.weight, l1.bias, h1, act=1))
+        self._add("time_mlp.3", lambda: ops.linear(h1, l2.weight, l2.bias, temb))
+        return temb
+
+    def block_projections(self, temb: torch.Tensor, blocks: Sequence, act: int) -> Tuple[torch.Tensor, List[int], int]:
+        """All per-ResBlock Linear(t_dim, Cout) projections as ONE concatenated linear."""
+        Ws = [b.time_mlp.weight for b in blocks]
+        bs = [b.time_mlp.bias for b in blocks]
+        self.track(*Ws, *bs)
+        W_all = self.packed(lambda: torch.cat([w.detach() for w in Ws], 0).contiguous())
+        b_all = self.packed(lambda: torch.cat([b.detach() for b in bs], 0).contiguous())
+        total = W_all.shape[0]
+        out = torch.zeros(self.B, total, device=self.device)
+        self._add("time_proj_all", lambda: ops.linear(temb, W_all, b_all, out, act=act))
+        offs, o = [], 0
+        for w in Ws:
+            offs.append(o)
+            o += w.shape[0]
+        return out, offs, total
+
+
+# ==========================================================================================
+# 3D latent UNet (pre-norm ResBlocks, optional bottleneck attention)
+# ==========================================================================================
+class UNet3DProgram(UNetProgram):
+    """ddpm_3d_ldm/unet_attention.py:88-200 and ddpm_3d_ldm/unet.py:57-158."""
+
+    def __init__(self, model, batch: int, spatial: Sequence[int]):
+        dev = next(model.parameters()).device
+        super().__init__(dev, batch, spatial, groups=model.out_norm.num_groups)
+        self.model = model
+        B, (D, H, W) = batch, self.sp
+        cin = model.in_channels
+        chs = list(model.chs)
+        L = len(chs)
+        for s in self.sp:
+            if s % (2 ** (L - 1)) != 0:
+                raise _lib.MriError(f"spatial size {self.sp} must be divisible by {2 ** (L - 1)}")
+        eps = model.out_norm.eps
+        self.x_in = torch.zeros(B, cin, D, H, W, device=dev)
+        self.t_in = torch.zeros(B, dtype=torch.int64, device=dev)
+
+        # ---- time embedding + all block projections ---------------------------------------
+        tdim = model.time_mlp[1].in_features
+        temb = self.time_embedding(self.t_in, model.time_mlp, tdim)
+        blocks = []
+        for blk in model.downs:
+            blocks += [blk["res1"], blk["res2"]]
+        blocks += [model.mid1, model.mid2]
+        for blk in model.ups:
+            blocks += [blk["res1"], blk["res2"]]
+        tproj, toffs, tld = self.block_projections(temb, blocks, act=0)
+        self._tproj = {id(b): (tproj[:, o:], tld) for b, o in zip(blocks, toffs)}
+
+        # ---- in_conv: thin Cin -> explicit patch matrix + GEMM ------------------------------
+        S = D * H * W
+        kpad = _rup(27 * cin, 64)
+        col = torch.zeros(B * S, kpad, dtype=torch.bfloat16, device=dev)
+        x_in = self.x_in
+        self._add("im2col", lambda: ops.im2col(x_in, col, B, cin, D, H, W, 3, 3, kpad))
+        ic = model.in_conv
+        self.track(ic.weight, ic.bias)
+        w_in = self.packed(lambda: _pad_k(P.pack_conv_weight(ic.weight.detach()), kpad))
+        h = self.new_act(self.sp, chs[0])
+        self.gemm(self._matrix_conv(col, w_in, h, S, kpad, ic.bias, "in_conv"))
+
+        # ---- down path -----------------------------------------------------------------------
+        skips: List[Act] = []
+        for i, blk in enumerate(model.downs):
+            h = self.resblock(h, None, blk["res1"], eps, f"downs.{i}.res1")
+            h = self.resblock(h, None, blk["res2"], eps, f"downs.{i}.res2")
+            skips.append(h)
+            if i != L - 1:
+                dn = blk["down"]
+                self.track(dn.weight, dn.bias)
+                wd = self.packed(lambda dn=dn: P.pack_conv_weight(dn.weight.detach()))
+                y = self.new_act([s // 2 for s in h.t.shape[1:-1]], chs[i + 1])
+                self.gemm(P.down_conv_plan(h.t, wd, y.t, bias=dn.bias, stats=y.stats, stats_cpg=y.cpg,
+                                           name=f"downs.{i}.down"))
+                h = y
+
+        # ---- bottleneck ------------------------------------------------------------------------
+        h = self.resblock(h, None, model.mid1, eps, "mid1", release_in=False)
+        if hasattr(model, "mid_attn"):
+            h = self.attention(h, model.mid_attn, "mid_attn")
+        h = self.resblock(h, None, model.mid2, eps, "mid2")
+
+        # ---- up path -----------------------------------------------------------------------------
+        for j, blk in enumerate(model.ups):
+            i = L - 1 - j
+            if i != L - 1:
+                up = blk["up"]
+                self.track(up.weight, up.bias)
+                wu = self.packed(lambda up=up: P.pack_convT_weight(up.weight.detach()))
+                u = self.new_act([s * 2 for s in h.t.shape[1:-1]], chs[i])
+                self.gemm(P.up_conv_plan(h.t, wu, u.t, bias=up.bias, stats=u.stats, stats_cpg=u.cpg,
+                                         name=f"ups.{j}.up"))
+                self.pool.release(h.t)
+                h = u
+            skip = skips.pop()
+            if tuple(skip.t.shape[1:-1]) != tuple(h.t.shape[1:-1]):
+                raise _lib.MriError("skip/upsample shape mismatch (centre-crop path not supported "
+                                    "for sizes not divisible by the down-sampling factor)")
+            h = self.resblock(h, skip, blk["res1"], eps, f"ups.{j}.res1")
+            h = self.resblock(h, None, blk["res2"], eps, f"ups.{j}.res2")
+
+        # ---- head --------------------------------------------------------------------------------
+        on, oc = model.out_norm, model.out_conv
+        self.track(on.weight, on.bias, oc.weight, oc.bias)
+        a = self.gn(h, on.weight, on.bias, self.groups, eps, True, name="out_norm")
+        self.cout = oc.weight.shape[0]
+        self.cout_pad = _rup(self.cout, 16)
+        w_out = self.packed(lambda: P.pack_conv_weight(oc.weight.detach(), cout_pad=self.cout_pad))
+        b_out = self.packed(lambda: _pad_vec(oc.bias.detach(), self.cout_pad))
+        y = self.conv([P.ConvSource(a)], w_out, self.cout_pad, 3, b_out, with_stats=False,
+                      name="out_conv")
+        self.eps_nhwc = y.t  # [B, D, H, W, cout_pad] bf16
+        self.out = torch.zeros(B, self.cout, D, H, W, device=dev)
+        self.params_changed()
+
+    # -------------------------------------------------------------------------------------------
+    def _matrix_conv(self, col, wmat, y: Act, S: int, kpad: int, bias, name) -> P.GemmPlan:
+        B, C = self.B, y.C
+        a = P.TView(col, (kpad, S, B, 1, 1), (1, kpad, S * kpad, B * S * kpad, B * S * kpad))
+        b = P.TView(wmat, (kpad, C, 1, 1), (1, kpad, kpad * C, kpad * C))
+        o = P.TView(y.t, (C, S, B, 1, 1), (1, C, S * C, B * S * C, B * S * C))
+        bn = P.pick_block_n(C)
+        return P.matrix_plan(a, (128, 1, 1, 1), b, o, K=kpad, n_total=C, block_n=bn,
+                             ext=(S, B, 1, 1), tiles=(-(-S // 128), B, 1, 1), sample_dim=2,
+                             bias=bias, stats=y.stats, stats_cpg=y.cpg, name=name,
+                             flops=2 * B * S * C * kpad)
+
+    def resblock(self, x: Act, skip: Optional[Act], blk, eps: float, name: str,
+                 release_in: bool = True) -> Act:
+        """ResidualBlock3D (unet_attention.py:59-85).  With `skip`, the block input is the
+        virtual concatenation [x, skip] (unet_attention.py:195)."""
+        n1, n2, c1, c2 = blk.norm1, blk.norm2, blk.conv1, blk.conv2
+        self.track(n1.weight, n1.bias, n2.weight, n2.bias, c1.weight, c1.bias, c2.weight, c2.bias)
+        cout = c1.weight.shape[0]
+        rowbias, rb_ld = self._tproj[id(blk)]
+        srcs = [x] if skip is None else [x, skip]
+        cins = [s.C for s in srcs]
+        g_each = self.groups // len(srcs)  # GN(8, 2C) over a concat == GN(4)+GN(4) over halves
+        normed, c0 = [], 0
+        for k, s in enumerate(srcs):
+            normed.append(self.gn(s, n1.weight[c0:c0 + s.C], n1.bias[c0:c0 + s.C], g_each, eps, True,
+                                  name=f"{name}.norm1.{k}"))
+            c0 += s.C
+        w1 = self.packed(lambda: P.pack_conv_weight(c1.weight.detach(), splits=cins))
+        h = self.conv([P.ConvSource(a) for a in normed], w1, cout, 3, c1.bias, rowbias=rowbias,
+                      rowbias_ld=rb_ld, name=f"{name}.conv1")
+        for a in normed:
+            self.pool.release(a)
+        a2 = self.gn(h, n2.weight, n2.bias, self.groups, eps, True, name=f"{name}.norm2")
+        self.pool.release(h.t)
+        has_skip_conv = not isinstance(blk.skip, torch.nn.Identity)
+        if has_skip_conv:
+            sk = blk.skip
+            self.track(sk.weight, sk.bias)
+            extras = []
+            c0 = 0
+            for s in srcs:
+                extras.append((c0, s.C))
+                c0 += s.C
+            w2 = self.packed(lambda: P.pack_conv_weight(
+                c2.weight.detach(),
+                extra=[sk.weight.detach().reshape(cout, -1)[:, a:a + n] for a, n in extras]))
+            b2 = self.packed(lambda: (c2.bias.detach() + sk.bias.detach()).contiguous())
+            sources = [P.ConvSource(a2)] + [P.ConvSource(s.t, taps=False) for s in srcs]
+            out = self.conv(sources, w2, cout, 3, b2, name=f"{name}.conv2+skip")
+        else:
+            assert skip is None and x.C == cout
+            w2 = self.packed(lambda: P.pack_conv_weight(c2.weight.detach()))
+            out = self.conv([P.ConvSource(a2)], w2, cout, 3, c2.bias, residual=x.t,
+                            name=f"{name}.conv2")
+        self.pool.release(a2)
+        if release_in:
+            for s in srcs:
+                self.pool.release(s.t)
+        return out
+
+    def attention(self, x: Act, blk, name: str) -> Act:
+        """AttentionBlock3D (unet_attention.py:28-56): GN -> qkv 1x1 -> softmax(q^T k / sqrt(d)) v
+        -> proj 1x1 -> + x.  Token-major layouts: q,k as [B, n, 2C]; v transposed [B, C, n]."""
+        B, C, dev = self.B, x.C, self.device
+        heads = blk.num_heads
+        d = C // heads
+        assert d % 64 == 0 and d <= 256
+        n = x.spatial
+        npad = _rup(n, 8)
+        sp = tuple(x.t.shape[1:-1])
+        self.track(blk.norm.weight, blk.norm.bias, blk.qkv.weight, blk.qkv.bias, blk.proj.weight,
+                   blk.proj.bias)
+        hn = self.gn(x, blk.norm.weight, blk.norm.bias, self.groups, blk.norm.eps, False,
+                     name=f"{name}.norm")
+        # q, k: 1x1 conv with the first 2C output channels
+        wqk = self.packed(lambda: P.pack_conv_weight(blk.qkv.weight.detach()[:2 * C]))
+        bqk = self.packed(lambda: blk.qkv.bias.detach()[:2 * C].contiguous())
+        qk = self.conv([P.ConvSource(hn)], wqk, 2 * C, 1, bqk, with_stats=False, name=f"{name}.qk")
+        # v^T[b] = Wv . hn[b]^T  (+ bias along rows): classes = samples
+        wv = self.packed(lambda: blk.qkv.weight.detach()[2 * C:].reshape(C, C).to(torch.bfloat16).contiguous())
+        bv = self.packed(lambda: blk.qkv.bias.detach()[2 * C:].contiguous())
+        vT = torch.zeros(B, C, npad, dtype=torch.bfloat16, device=dev)
+        a = P.TView(wv, (C, C, 1, 1, 1), (1, C, C * C, C * C, C * C))
+        b = P.TView(hn, (C, n, B, 1), (1, C, n * C, B * n * C))
+        o_views = [P.TView(vT, (npad, C, 1, 1, 1), (1, npad, C * npad, C * npad, C * npad),
+                           offset=bi * C * npad) for bi in range(B)]
+        pl = P.matrix_plan(a, (128, 1, 1, 1), b, o_views[0], K=C, n_total=npad, block_n=128,
+                           ext=(C, 1, 1, 1), tiles=(C // 128, 1, 1, 1), bz_sel=(1, 0), bias_m=bv,
+                           name=f"{name}.vT", flops=2 * B * n * C * C)
+        chunk_box = pl.o_maps[0].box
+        swz = pl.o_maps[0].swizzle
+        pl.o_maps = [P.MapSpec(v, chunk_box, swz) for v in o_views]
+        pl.ktable = pl.ktable.repeat(B, axis=0)
+        self.gemm(pl)
+        # S = q k^T  (fp32 logits)
+        S = torch.zeros(B, heads, n, npad, dtype=torch.float32, device=dev)
+        qa = P.TView(qk.t, (d, n, heads, B, 1), (1, 2 * C, d, n * 2 * C, B * n * 2 * C))
+        kb = P.TView(qk.t, (d, n, heads, B), (1, 2 * C, d, n * 2 * C), offset=C)
+        so = P.TView(S, (npad, n, heads, B, 1),
+                     (1, npad, n * npad, heads * n * npad, B * heads * n * npad))
+        self.gemm(P.matrix_plan(qa, (128, 1, 1, 1), kb, so, K=d, n_total=npad, block_n=128,
+                                ext=(n, heads, B, 1), tiles=(-(-n // 128), heads, B, 1),
+                                bz_sel=(3, 4), out_f32=True, name=f"{name}.qk^T",
+                                flops=2 * B * heads * n * n * d))
+        Pm = torch.zeros(B, heads, n, npad, dtype=torch.bfloat16, device=dev)
+        scale = float(d) ** -0.5
+        self._add(f"{name}.softmax",
+                  lambda: ops.softmax_rows(S, Pm, B * heads * n, n, npad, npad, scale))
+        # O = P v  (token-major [B, n, C])
+        O = self.pool.get(tuple(x.t.shape))
+        pa = P.TView(Pm, (npad, n, heads, B, 1),
+                     (1, npad, n * npad, heads * n * npad, B * heads * n * npad))
+        vb = P.TView(vT, (npad, d, heads, B), (1, npad, d * npad, C * npad))
+        oo = P.TView(O, (d, n, heads, B, 1), (1, C, d, n * C, B * n * C))
+        self.gemm(P.matrix_plan(pa, (128, 1, 1, 1), vb, oo, K=npad, n_total=d, block_n=min(d, 128),
+                                ext=(n, heads, B, 1), tiles=(-(-n // 128), heads, B, 1),
+                                bz_sel=(3, 4), name=f"{name}.pv", flops=2 * B * heads * n * n * d))
+        wp = self.packed(lambda: P.pack_conv_weight(blk.proj.weight.detach()))
+        out = self.conv([P.ConvSource(O)], wp, C, 1, blk.proj.bias, residual=x.t, name=f"{name}.proj")
+        self.pool.release(hn)
+        self.pool.release(qk.t)
+        self.pool.release(O)
+        self.pool.release(x.t)
+        return out
+
+    # -------------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """Eager entry: copy inputs into the static buffers, run, return fp32 NCDHW eps."""
+        if self.params_changed():
+            for fn in self.refresh:
+                fn()
+        self.x_in.copy_(x)
+        self.t_in.copy_(t)
+        self.run()
+        S = self.sp[0] * self.sp[1] * self.sp[2]
+        ops.nhwc_to_nchw(self.eps_nhwc, self.out, self.B, S, self.cout, self.cout_pad)
+        return self.out
+
+
+def _pad_k(w: torch.Tensor, kpad: int) -> torch.Tensor:
+    out = torch.zeros(w.shape[0], kpad, dtype=w.dtype, device=w.device)
+    out[:, :w.shape[1]] = w
+    return out
+
+
+def _pad_vec(v: torch.Tensor, n: int) -> torch.Tensor:
+    out = torch.zeros(n, dtype=v.dtype, device=v.device)
+    out[:v.numel()] = v
+    return out

@@ -1,0 +1,71 @@
+"""Shared host-side pieces of the drop-in model classes.
+
+The classes in mri_image_generation_b200.model_scripts.* keep the reference's constructor
+signatures, attribute names and state_dict keys, so they hold their parameters in the same
+torch.nn containers (nn.Conv3d, nn.GroupNorm, nn.Linear ...) the reference uses -- as parameter
+holders only.  Their forward never calls those containers: it runs the UNetProgram (engine.py),
+i.e. the sm_100a kernels behind the C ABI.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class SinusoidalHolder(nn.Module):
+    """Parameter-free placeholder for index 0 of `time_mlp` (SinusoidalPosEmb,
+    slice_cond_2d_ddpm/unet.py:7-25).  The embedding itself is computed by mri_sinusoidal."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.dim = dim
+
+    def forward(self, t):  # pragma: no cover - never part of the product path
+        raise _lib.MriError("SinusoidalHolder is a placeholder; the embedding runs in mri_sinusoidal")
+
+
+class EngineModule(nn.Module):
+    """Base for the drop-in UNets: caches one UNetProgram per (batch, spatial...) key."""
+
+    def _programs(self) -> Dict[Tuple, object]:
+        progs = self.__dict__.get("_mri_programs")
+        if progs is None:
+            progs = {}
+            self.__dict__["_mri_programs"] = progs
+        return progs
+
+    def __getstate__(self):
+        # programs hold ctypes handles / device tables: never pickled (mlflow.pytorch.log_model,
+        # slice_cond_2d_ddpm/model.py:320, pickles the module)
+        state = self.__dict__.copy()
+        state.pop("_mri_programs", None)
+        return state
+
+    def _apply(self, fn, *args, **kwargs):
+        # .to()/.cuda()/.half() may re-allocate parameter storage: drop cached programs
+        self.__dict__.pop("_mri_programs", None)
+        return super()._apply(fn, *args, **kwargs)
+
+    def _check_input(self, x: torch.Tensor) -> None:
+        if not x.is_cuda:
+            raise _lib.MriError(
+                f"{type(self).__name__} runs on B200 GPUs only (input is on {x.device}); this "
+                "framework has no CPU fallback -- the reference implementation covers CPU.")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise _lib.MriError(
+                f"{type(self).__name__}: the backward pass (dgrad/wgrad kernels) is not part of this "
+                "build yet; call under torch.no_grad() (sampling / evaluation).")
+
+    def get_program(self, key: Tuple, build):
+        progs = self._programs()
+        prog = progs.get(key)
+        if prog is None:
+            if len(progs) >= 4:  # static-shape programs own their activation memory: keep few
+                progs.pop(next(iter(progs)))
+            prog = build()
+            progs[key] = prog
+        return prog

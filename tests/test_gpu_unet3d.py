@@ -1,0 +1,122 @@
+"""3D latent UNet + DDPM step on the B200 kernels vs the CPU oracle (same weights, inputs).
+
+Tolerances (stated per SURVEY.md 8c): the CUDA path rounds conv operands and inter-layer
+activations to bf16 with fp32 accumulation (what torch autocast(bf16) does in the reference's
+training path); against the fp32 oracle the noise prediction must satisfy rel-L2 <= 2e-2.
+q_sample / p_sample / DDIM arithmetic with injected eps and noise: bit-exact."""
+import contextlib
+import io
+
+import pytest
+import torch
+
+from helpers import load_gold, rel_l2, shapes_of, synthetic_state_dict
+from oracle import reference_oracle as O
+
+pytestmark = pytest.mark.gpu
+EPS_TOL = 2e-2
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def make(cls_name, **kw):
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm import unet, unet_attention
+    cls = getattr(unet_attention, cls_name, None) or getattr(unet, cls_name)
+    m = cls(**kw)
+    sd = synthetic_state_dict(shapes_of(m), seed=7)
+    m.load_state_dict(sd)
+    return m.cuda().eval(), sd
+
+
+@pytest.mark.parametrize("cls,kw,B,sp", [
+    ("UNet3DModelWithAttention", dict(in_channels=3, base_channels=64, time_emb_dim=64), 2, (8, 8, 8)),
+    ("UNet3DModel", dict(in_channels=3, base_channels=64, time_emb_dim=64), 1, (8, 12, 8)),
+    ("UNet3DModelWithAttention", dict(in_channels=3, base_channels=128, time_emb_dim=256), 1, (16, 16, 12)),
+])
+def test_unet3d_forward_vs_oracle(cls, kw, B, sp):
+    m, sd = make(cls, **kw)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, 3, *sp, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    with torch.no_grad():
+        ref = O.unet3d_forward(sd, x, t)
+        out = m(x.cuda(), t.cuda())
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    err = rel_l2(out, ref)
+    print(f"{cls} {kw} B={B} sp={sp}: rel-L2 {err:.3e}")
+    assert err < EPS_TOL
+    # second call (cached program, same buffers) is reproducible up to atomics ordering
+    with torch.no_grad():
+        out2 = m(x.cuda(), t.cuda())
+    assert rel_l2(out2, out) < 1e-3
+
+
+def test_diffusion_arithmetic_bit_exact_vs_golden():
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.diffusion import GaussianDiffusionLatent3D
+    d = load_gold("diffusion.pt")
+
+    class Stub(torch.nn.Module):
+        def forward(self, x, t):
+            return 0.1 * x + 0.01 * t.float().view(-1, 1, 1, 1, 1)
+
+    diff = quiet(GaussianDiffusionLatent3D, Stub(), 3, timesteps=1000).cuda()
+    x, noise, t = d["x"].cuda(), d["noise"].cuda(), d["t"].cuda()
+    assert torch.equal(diff.q_sample(x, t, noise=noise).cpu(), d["q_sample_3d"])
+    out = diff._p_update(x, t, d["eps"].cuda(), d["p_sample_noise"].cuda())
+    assert torch.equal(out.cpu(), d["p_sample_3d"])
+    out = diff._ddim_update(x, t, d["t_prev"].cuda(), d["eps"].cuda())
+    assert torch.equal(out.cpu(), d["ddim_3d"])
+    # loss (reduction order differs -> tolerance 1e-6 relative)
+    loss = diff.p_losses(x, t, noise=noise, min_snr_gamma=5.0)
+    assert abs(loss.item() - d["p_losses_3d"].item()) <= 2e-6 * abs(d["p_losses_3d"].item())
+    # p_sample through the public method: eps from the (stub) model, noise from torch's RNG
+    torch.manual_seed(5)
+    got = diff.p_sample(x, t)
+    torch.manual_seed(5)
+    z = torch.randn_like(x)
+    buf = O.schedule_buffers(O.cosine_betas(1000))
+    eps_gpu = Stub()(x, t)  # elementwise fp32 on the GPU: may differ from CPU by FMA contraction
+    want = O.p_sample_update(buf, d["x"], d["t"], eps_gpu.cpu(), z.cpu())
+    assert torch.equal(got.cpu(), want)
+
+
+def test_sampling_loop_graph_equals_eager_and_teacher_forced_oracle():
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.diffusion import GaussianDiffusionLatent3D
+    m, sd = make("UNet3DModelWithAttention", in_channels=3, base_channels=64, time_emb_dim=64)
+    T = 12
+    diff = quiet(GaussianDiffusionLatent3D, m, 3, timesteps=T).cuda()
+    B, sp = 2, (8, 8, 8)
+    # (a) public sample(): graph-replayed loop == step-by-step p_sample with the same seed
+    torch.manual_seed(123)
+    a = diff.sample(B, sp)
+    torch.manual_seed(123)
+    img = torch.randn(B, 3, *sp, device="cuda")
+    buf = O.schedule_buffers(O.cosine_betas(T))
+    worst = 0.0
+    for i in reversed(range(T)):
+        t = torch.full((B,), i, device="cuda", dtype=torch.long)
+        eps = m(img, t)
+        # teacher-forced parity of the network at every step of the trajectory
+        ref_eps = O.unet3d_forward(sd, img.cpu(), t.cpu())
+        worst = max(worst, rel_l2(eps, ref_eps))
+        noise = torch.randn_like(img)
+        nxt = diff._p_update(img, t, eps, noise)
+        # the fused update is bit-exact given (x, eps, z)
+        assert torch.equal(nxt.cpu(), O.p_sample_update(buf, img.cpu(), t.cpu(), eps.cpu(), noise.cpu()))
+        img = nxt
+    print(f"teacher-forced worst eps rel-L2 over {T} steps: {worst:.3e}")
+    assert worst < EPS_TOL
+    assert torch.isfinite(a).all()
+    # eager loop reads eps through fp32 NCDHW, graph loop reads the bf16 buffer directly: same values
+    assert rel_l2(a, img) < 5e-3, rel_l2(a, img)
+    # (b) DDIM partial reverse
+    x9 = torch.randn(B, 3, *sp, device="cuda")
+    y = diff.sample_from_ddim(x9, 5)
+    img = x9
+    for i in reversed(range(1, 6)):
+        t = torch.full((B,), i, device="cuda", dtype=torch.long)
+        img = diff.p_sample_ddim(img, t, t - 1)
+    assert rel_l2(y, img) < 5e-3

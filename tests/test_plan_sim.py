@@ -1,0 +1,90 @@
+"""GemmPlan tables executed by the CPU emulator (plan.simulate) vs torch convolutions: checks
+taps, parity views, weight packing, virtual concat, folded 1x1 skip, residual, time-embedding
+bias and the GroupNorm partial sums -- the addressing logic of the tensor-core kernel."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mri_image_generation_b200 import plan as P
+
+TOL = 4e-3  # bf16 output rounding
+
+
+def nhwc(x):
+    nd = x.dim() - 2
+    return x.permute(0, *range(2, 2 + nd), 1).contiguous().to(torch.bfloat16)
+
+
+def nchw(y):
+    nd = y.dim() - 2
+    return y.permute(0, nd + 1, *range(1, nd + 1)).float()
+
+
+def rel(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+@pytest.mark.parametrize("nd,sp", [(3, (6, 8, 10)), (2, (12, 20)), (3, (4, 4, 6))])
+def test_conv_concat_skipfold_residual(nd, sp):
+    torch.manual_seed(0)
+    N, C1, C2, Co = 2, 64, 128, 64
+    conv = F.conv3d if nd == 3 else F.conv2d
+    a1, a2 = nhwc(torch.randn(N, C1, *sp)), nhwc(torch.randn(N, C2, *sp))
+    w = torch.randn(Co, C1 + C2, *([3] * nd)) * 0.05
+    ws = torch.randn(Co, C1, *([1] * nd)) * 0.1
+    b = torch.randn(Co)
+    rb = torch.randn(N, Co + 5)
+    res = nhwc(torch.randn(N, Co, *sp))
+    ref = conv(torch.cat([nchw(a1), nchw(a2)], 1), w.to(torch.bfloat16).float(), b, padding=1)
+    ref = ref + conv(nchw(a1), ws.to(torch.bfloat16).float()) + rb[:, :Co].reshape(N, Co, *[1] * nd) + nchw(res)
+    wm = P.pack_conv_weight(w, splits=[C1, C2], extra=[ws])
+    y = torch.zeros(N, *sp, Co, dtype=torch.bfloat16)
+    stats = torch.zeros(N, 8, 2)
+    pl = P.conv_plan([P.ConvSource(a1), P.ConvSource(a2), P.ConvSource(a1, taps=False)], wm, y, 3,
+                     bias=b, rowbias=rb, rowbias_ld=Co + 5, residual=res, stats=stats, stats_cpg=8)
+    pl.simulate()
+    assert rel(nchw(y), ref) < TOL
+    r = ref.reshape(N, 8, -1)
+    assert rel(stats[:, :, 0], r.sum(-1)) < 1e-4
+    assert rel(stats[:, :, 1], (r ** 2).sum(-1)) < 1e-4
+
+
+@pytest.mark.parametrize("nd,sp", [(3, (4, 8, 6)), (2, (12, 20))])
+def test_down_and_up(nd, sp):
+    torch.manual_seed(1)
+    N, C, Co = 2, 64, 128
+    a = nhwc(torch.randn(N, C, *sp))
+    conv = F.conv3d if nd == 3 else F.conv2d
+    convT = F.conv_transpose3d if nd == 3 else F.conv_transpose2d
+    w = torch.randn(Co, C, *([4] * nd)) * 0.05
+    b = torch.randn(Co)
+    ref = conv(nchw(a), w.to(torch.bfloat16).float(), b, stride=2, padding=1)
+    y = torch.zeros(N, *[s // 2 for s in sp], Co, dtype=torch.bfloat16)
+    P.down_conv_plan(a, P.pack_conv_weight(w), y, bias=b).simulate()
+    assert rel(nchw(y), ref) < TOL
+    wt = torch.randn(C, Co, *([4] * nd)) * 0.05
+    ref = convT(nchw(a), wt.to(torch.bfloat16).float(), b, stride=2, padding=1)
+    y = torch.zeros(N, *[s * 2 for s in sp], Co, dtype=torch.bfloat16)
+    st = torch.zeros(N, 8, 2)
+    P.up_conv_plan(a, P.pack_convT_weight(wt), y, bias=b, stats=st, stats_cpg=16).simulate()
+    assert rel(nchw(y), ref) < TOL
+    assert rel(st[:, :, 0], ref.reshape(N, 8, -1).sum(-1)) < 1e-4
+
+
+def test_choose_box():
+    assert P.choose_box((40, 48, 40, 1))[3] == 1
+    b = P.choose_box((40, 48, 40, 1))
+    assert b[0] * b[1] * b[2] == 128
+    assert P.choose_box((10, 12, 10, 4)) == (10, 12, 1, 1)
+    b = P.choose_box((240, 240, 64, 1))
+    assert b[0] * b[1] * b[2] * b[3] == 128 and 240 % b[0] == 0 and 240 % b[1] == 0
+    b = P.choose_box((2, 2, 2, 2))
+    assert b == (2, 2, 2, 2)
+
+
+def test_pick_stages_fits_staging():
+    y = torch.zeros(1, 8, 8, 8, 128, dtype=torch.bfloat16)
+    a = torch.zeros(1, 8, 8, 8, 64, dtype=torch.bfloat16)
+    pl = P.conv_plan([P.ConvSource(a)], torch.zeros(128, 27 * 64, dtype=torch.bfloat16), y, 3)
+    s = pl.pick_stages()
+    assert 2 <= s <= 8 and s * (128 * 128 + pl.block_n * 128) >= 128 * pl.block_n * 2
