@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Headline benchmark: volumes/sec of 3D-LDM DDPM sampling (BASELINE.json cfg4).
+
+Workload (config.workload = "ddpm_3d_ldm_sampling"): UNet3DModelWithAttention(in=3, base 128,
+mults (1,2,4), time_emb 256, groups 8, heads 4) on 3x40x48x40 latents, cosine schedule,
+T = 1000 reverse steps per volume, random-init weights, synthetic latents.
+
+A "step" = one reverse step (UNet forward + fused DDPM update) over this rank's batch of
+volumes.  value = (volumes in flight over all ranks) / (T * seconds per step): every reverse
+step does identical work, so timing K consecutive steps of a real trajectory (t = T-1, T-2, ...)
+measures the loop; `--steps 1000` times complete volumes.  Sampling shards the batch across
+ranks with no communication (scaling = "weak": per-GPU batch fixed).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+  torchrun ... bench.py --gpus N ...            (one rank per GPU; rank 0 prints ONE JSON line)
+
+--impl reference times the reference's own algorithm for the same path on the host CPU cores
+(the oracle port of the reference modules, all threads; /root/reference does not exist on the
+GPU box and a Python reference cannot be compiled into oracle/_ref).
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_STEPS = 1000
+LATENT = (3, 40, 48, 40)
+MODEL_KW = dict(in_channels=3, base_channels=128, channel_mults=(1, 2, 4), time_emb_dim=256,
+                groups=8, num_heads=4)
+CONV_FLOPS_PER_SAMPLE = 1273.4e9  # conv part of one UNet forward at cfg4
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops": d.get("bf16_tflops_sustained", 1371.0), "hbm": d.get("hbm_gbs", 6555.2),
+                "source": "measured"}
+    return {"tflops": 1590.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_reference_rate(n_forwards: int, threads: int):
+    """Reference algorithm (oracle port) on the host cores: seconds per reverse step at B = 1."""
+    import torch
+    from oracle import reference_oracle as O
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.unet_attention import \
+        UNet3DModelWithAttention
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    sd = {k: v.detach() for k, v in UNet3DModelWithAttention(**MODEL_KW).state_dict().items()}
+    buf = O.schedule_buffers(O.cosine_betas(T_STEPS))
+    x = torch.randn(1, *LATENT)
+    times = []
+    with torch.no_grad():
+        for i in range(n_forwards + 1):
+            t = torch.full((1,), T_STEPS - 1 - i, dtype=torch.long)
+            t0 = time.perf_counter()
+            eps = O.unet3d_forward(sd, x, t)
+            x = O.p_sample_update(buf, x, t, eps, torch.randn_like(x))
+            times.append(time.perf_counter() - t0)
+    return sum(times[1:]) / n_forwards  # first call = warm-up
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    n = max(1, args.steps)
+    w = max(1, args.warmup)
+    # bounded sample: `steps` timed reverse steps at B = 1 after `warmup` untimed ones
+    from oracle import reference_oracle as O
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.unet_attention import \
+        UNet3DModelWithAttention
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    sd = {k: v.detach() for k, v in UNet3DModelWithAttention(**MODEL_KW).state_dict().items()}
+    buf = O.schedule_buffers(O.cosine_betas(T_STEPS))
+    x = torch.randn(1, *LATENT)
+    n = min(n, 5)
+    w = min(w, 1)
+    t_total = 0.0
+    with torch.no_grad():
+        for i in range(w + n):
+            t = torch.full((1,), T_STEPS - 1 - i, dtype=torch.long)
+            t0 = time.perf_counter()
+            x = O.p_sample_update(buf, x, t, O.unet3d_forward(sd, x, t), torch.randn_like(x))
+            if i >= w:
+                t_total += time.perf_counter() - t0
+    sec_per_step = t_total / n
+    value = 1.0 / (T_STEPS * sec_per_step)
+    sample = f"{n} reverse steps at batch 1 after {w} warm-up, extrapolated x{T_STEPS // 1} per volume"
+    line = {
+        "impl": "reference", "metric": "volumes/sec (3D LDM DDPM sampling)", "value": value,
+        "unit": "volumes/s", "n_gpus": args.gpus, "steps": n, "warmup": w,
+        "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ddpm_3d_ldm_sampling", "latent": list(LATENT), "timesteps": T_STEPS,
+                   "model": "UNet3DModelWithAttention(base 128, mults 1-2-4)", "batch_per_step": 1,
+                   "device": "host CPU"},
+        "cpu_baseline": {"value": value, "unit": "volumes/s", "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from mri_image_generation_b200 import _lib, ops
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.diffusion import GaussianDiffusionLatent3D
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.unet_attention import \
+        UNet3DModelWithAttention
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.require_device()
+    B, K, W = args.batch, args.steps, max(3, args.warmup)
+
+    torch.manual_seed(0)  # identical random-init weights on every rank
+    model = UNet3DModelWithAttention(**MODEL_KW).to(dev).eval()
+    diff = quiet(GaussianDiffusionLatent3D, model, LATENT[0], timesteps=T_STEPS).to(dev)
+    torch.manual_seed(1234 + rank)
+    prog = model.program(B, LATENT[1:])
+    x_T = torch.randn(B, *LATENT, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing: K replays of the captured reverse step --------------------
+    with torch.no_grad():
+        diff._reverse_loop(prog, x_T, T_STEPS - 1, W, "ddpm")  # builds + captures + W warm-up steps
+        graph = diff._graphs()[(id(prog), "ddpm")]
+        prog.x_in.copy_(x_T)
+        prog.t_in.fill_(T_STEPS - 1)
+        sampler = ClockSampler(local_rank)
+        barrier()
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        finite = bool(torch.isfinite(prog.x_in).all().item())
+
+        # ---- end to end through the public API with host buffers, every step ---------------
+        x_host = torch.randn(B, *LATENT).pin_memory()
+        out_host = torch.empty(B, *LATENT).pin_memory()
+        x_dev = torch.empty(B, *LATENT, device=dev)
+        Ke = min(K, 20)
+        for i in range(2):
+            diff.p_sample(x_dev.copy_(x_host, non_blocking=True),
+                          torch.full((B,), T_STEPS - 1 - i, device=dev, dtype=torch.long))
+        barrier()
+        e0.record()
+        for i in range(Ke):
+            x_dev.copy_(x_host, non_blocking=True)
+            t = torch.full((B,), T_STEPS - 1 - i, device=dev, dtype=torch.long)
+            y = diff.p_sample(x_dev, t)
+            out_host.copy_(y, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms_e2e = e0.elapsed_time(e1)
+
+        # ---- per-kernel timing of the dominant kernel (tcgen05 implicit GEMM), CUDA events ---
+        gemm_idx = [i for i, n in enumerate(prog.op_names) if n.startswith("gemm:")]
+        evs = []
+        reps = 3
+        stream = torch.cuda.current_stream(dev)
+        for r in range(reps + 1):
+            prog._arena[:max(prog._arena_used, 4)].zero_()
+            for i, fn in enumerate(prog.ops):
+                if i in gemm_idx and r > 0:
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(stream)
+                    fn()
+                    b.record(stream)
+                    evs.append((a, b))
+                else:
+                    fn()
+        torch.cuda.synchronize(dev)
+        gemm_ms = sum(a.elapsed_time(b) for a, b in evs) / reps
+
+    t_ms = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t_ms.tolist()
+    if rank != 0:
+        return
+
+    ms_per_step = ms / K
+    value = world * B / (T_STEPS * ms_per_step / 1e3)
+    e2e_val = world * B / (T_STEPS * (ms_e2e / Ke) / 1e3)
+    peaks = load_peaks()
+    conv_flops = prog.gemm_flops  # all tensor-core GEMM launches of one step (conv + attention)
+    achieved = conv_flops / (gemm_ms * 1e-3) / 1e12
+    x_bytes = x_host.numel() * 4
+    launches_per_step = len(prog.ops) + 4  # + arena memset, noise draw, fused update, t -= 1
+    cpu = None
+    if world == 1 or rank == 0:
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            nfw = 3
+            sec = cpu_reference_rate(nfw, threads)
+            cpu = {"value": 1.0 / (T_STEPS * sec), "unit": "volumes/s", "cores": threads,
+                   "kind": "port",
+                   "sample": f"{nfw} reverse steps at batch 1 ({sec:.2f} s each) x {T_STEPS} per volume"}
+    line = {
+        "metric": "volumes/sec (3D LDM DDPM sampling)", "value": value, "unit": "volumes/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "ddpm_3d_ldm_sampling", "latent": list(LATENT), "timesteps": T_STEPS,
+                   "model": "UNet3DModelWithAttention(base 128, mults 1-2-4, 136.4M params)",
+                   "batch_per_gpu": B, "parallelism": f"batch-sharded x{world}, no collective",
+                   "l2": "per-step working set (273 MB bf16 weights + activations) exceeds the 126 MB L2",
+                   "step": "one reverse step (UNet fwd + fused DDPM update) in a replayed CUDA graph",
+                   "outputs_finite": finite},
+        "e2e": {"value": e2e_val, "unit": "volumes/s", "h2d_bytes_per_step": x_bytes,
+                "d2h_bytes_per_step": x_bytes, "steps": Ke,
+                "path": "pinned host x_t -> GaussianDiffusionLatent3D.p_sample -> pinned host x_{t-1}"},
+        "gpu_launches": launches_per_step * K,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM, all convs + attention GEMMs)",
+                     "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["tflops"], "traffic": None,
+                     "peak_source": peaks["source"] + " (bf16_tflops_sustained)",
+                     "flops_per_step": conv_flops, "kernel_ms_per_step": gemm_ms,
+                     "share_of_step": gemm_ms / ms_per_step},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=4, help="volumes per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

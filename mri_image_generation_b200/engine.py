@@ -87,6 +87,7 @@ class UNetProgram:
         self.pool = _Pool(device)
         self.ops: List[Callable[[], None]] = []
         self.op_names: List[str] = []
+        self.op_outs: List[List[torch.Tensor]] = []
         self.plans: List[P.GemmPlan] = []
         self.refresh: List[Callable[[], None]] = []  # re-pack weights after a parameter update
         self._arena = torch.zeros(self.STATS_ARENA, dtype=torch.float32, device=device)
@@ -97,9 +98,20 @@ class UNetProgram:
         self._params: List[torch.Tensor] = []
 
     # ------------------------------------------------------------------ bookkeeping
-    def _add(self, name: str, fn: Callable[[], None]) -> None:
+    def _add(self, name: str, fn: Callable[[], None], outs: Sequence[torch.Tensor] = ()) -> None:
         self.op_names.append(name)
         self.ops.append(fn)
+        self.op_outs.append([o for o in outs if o is not None])
+
+    def run_traced(self) -> List[Tuple[str, List[torch.Tensor]]]:
+        """Debug: run op by op (synchronising) and return a copy of every op's outputs."""
+        trace = []
+        self._arena[:max(self._arena_used, 4)].zero_()
+        for name, fn, outs in zip(self.op_names, self.ops, self.op_outs):
+            fn()
+            torch.cuda.synchronize(self.device)
+            trace.append((name, [o.detach().clone() for o in outs]))
+        return trace
 
     def new_stats(self, n_groups: int) -> torch.Tensor:
         n = self.B * n_groups * 2
@@ -145,7 +157,7 @@ class UNetProgram:
         pl.materialize(self.device)
         self.plans.append(pl)
         self.gemm_flops += pl.flops
-        self._add(f"gemm:{pl.name}", pl.launch)
+        self._add(f"gemm:{pl.name}", pl.launch, [m.view.base for m in pl.o_maps[:1]] + [pl.stats])
 
     def gn(self, x: Act, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float,
            silu: bool, rowbias: Optional[torch.Tensor] = None, rowbias_ld: int = 0,
@@ -162,7 +174,7 @@ class UNetProgram:
             ops.gn_apply(xs, y, st, gamma, beta, B, S, C, groups, cpg, eps, silu, rowbias=rowbias,
                          rowbias_ld=rowbias_ld, residual=residual)
 
-        self._add(name, fn)
+        self._add(name, fn, [y])
         return y
 
     def stats_of(self, x: Act, name: str = "gn_stats") -> None:
@@ -171,7 +183,7 @@ class UNetProgram:
         x.cpg = x.C // self.groups
         B, S, C, xs, st, cpg = self.B, x.spatial, x.C, x.t, x.stats, x.cpg
         self.hbm_bytes_elementwise += xs.numel() * 2
-        self._add(name, lambda: ops.gn_stats(xs, st, B, S, C, cpg))
+        self._add(name, lambda: ops.gn_stats(xs, st, B, S, C, cpg), [st])
 
     def conv(self, sources: Sequence[P.ConvSource], wmat: torch.Tensor, cout: int, ksize: int,
              bias: Optional[torch.Tensor], *, rowbias=None, rowbias_ld=0, residual=None,
@@ -192,9 +204,9 @@ class UNetProgram:
         temb = torch.zeros(B, dim, device=dev)
         l1, l2 = time_mlp[1], time_mlp[3]
         self.track(l1.weight, l1.bias, l2.weight, l2.bias)
-        self._add("sinusoidal", lambda: ops.sinusoidal(t_in, sin))
-        self._add("time_mlp.1", lambda: ops.linear(sin, l1.weight, l1.bias, h1, act=1))
-        self._add("time_mlp.3", lambda: ops.linear(h1, l2.weight, l2.bias, temb))
+        self._add("sinusoidal", lambda: ops.sinusoidal(t_in, sin), [sin])
+        self._add("time_mlp.1", lambda: ops.linear(sin, l1.weight, l1.bias, h1, act=1), [h1])
+        self._add("time_mlp.3", lambda: ops.linear(h1, l2.weight, l2.bias, temb), [temb])
         return temb
 
     def block_projections(self, temb: torch.Tensor, blocks: Sequence, act: int) -> Tuple[torch.Tensor, List[int], int]:
@@ -206,7 +218,7 @@ class UNetProgram:
         b_all = self.packed(lambda: torch.cat([b.detach() for b in bs], 0).contiguous())
         total = W_all.shape[0]
         out = torch.zeros(self.B, total, device=self.device)
-        self._add("time_proj_all", lambda: ops.linear(temb, W_all, b_all, out, act=act))
+        self._add("time_proj_all", lambda: ops.linear(temb, W_all, b_all, out, act=act), [out])
         offs, o = [], 0
         for w in Ws:
             offs.append(o)
@@ -252,7 +264,7 @@ class UNet3DProgram(UNetProgram):
         kpad = _rup(27 * cin, 64)
         col = torch.zeros(B * S, kpad, dtype=torch.bfloat16, device=dev)
         x_in = self.x_in
-        self._add("im2col", lambda: ops.im2col(x_in, col, B, cin, D, H, W, 3, 3, kpad))
+        self._add("im2col", lambda: ops.im2col(x_in, col, B, cin, D, H, W, 3, 3, kpad), [col])
         ic = model.in_conv
         self.track(ic.weight, ic.bias)
         w_in = self.packed(lambda: _pad_k(P.pack_conv_weight(ic.weight.detach()), kpad))
@@ -421,7 +433,7 @@ class UNet3DProgram(UNetProgram):
         Pm = torch.zeros(B, heads, n, npad, dtype=torch.bfloat16, device=dev)
         scale = float(d) ** -0.5
         self._add(f"{name}.softmax",
-                  lambda: ops.softmax_rows(S, Pm, B * heads * n, n, npad, npad, scale))
+                  lambda: ops.softmax_rows(S, Pm, B * heads * n, n, npad, npad, scale), [Pm])
         # O = P v  (token-major [B, n, C])
         O = self.pool.get(tuple(x.t.shape))
         pa = P.TView(Pm, (npad, n, heads, B, 1),
