@@ -55,56 +55,62 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled through NVML DURING the timed region."""
 
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, index: int):
-        self.index = index
-        self.proc = None
-        self.lines = []
+    def __init__(self, index: int, period_s: float = 0.05):
+        self.index, self.period = index, period_s
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.thread = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(get_reasons(self.h))
+                for n, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(n)
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
+                return
+            time.sleep(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
-            except ValueError:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        sm = sorted(self.sm)
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(sm)}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -258,6 +264,18 @@ def run_ours(args, rank, world, local_rank):
                     fn()
         torch.cuda.synchronize(dev)
         gemm_ms = sum(a.elapsed_time(b) for a, b in evs) / reps
+        if args.per_op and rank == 0:
+            per = {}
+            for j, (a, b) in enumerate(evs):
+                per.setdefault(gemm_idx[j % len(gemm_idx)], []).append(a.elapsed_time(b))
+            rows = []
+            for i, pl in zip(gemm_idx, prog.plans):
+                msi = sum(per[i]) / len(per[i])
+                rows.append((prog.op_names[i], msi, pl.flops / (msi * 1e-3) / 1e12, pl.grid(), pl.block_n,
+                             pl.n_kb, pl.box, pl._args.stages))
+            with open(args.per_op, "w") as f:
+                for r_ in rows:
+                    f.write("%-34s %8.3f ms %8.1f TF/s grid %6d bn %3d n_kb %4d box %s stages %d\n" % r_)
 
     t_ms = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -270,7 +288,10 @@ def run_ours(args, rank, world, local_rank):
     value = world * B / (T_STEPS * ms_per_step / 1e3)
     e2e_val = world * B / (T_STEPS * (ms_e2e / Ke) / 1e3)
     peaks = load_peaks()
-    conv_flops = prog.gemm_flops  # all tensor-core GEMM launches of one step (conv + attention)
+    # algorithmic FLOPs of one step: SURVEY.md 8(d) figure for the reference graph (conv 1273.4 G +
+    # attention bmm 2.95 G per sample), not the padded shapes the kernel executes
+    conv_flops = B * 1276.4e9
+    executed_flops = prog.gemm_flops
     achieved = conv_flops / (gemm_ms * 1e-3) / 1e12
     x_bytes = x_host.numel() * 4
     launches_per_step = len(prog.ops) + 4  # + arena memset, noise draw, fused update, t -= 1
@@ -303,7 +324,8 @@ def run_ours(args, rank, world, local_rank):
                      "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["tflops"], "traffic": None,
                      "peak_source": peaks["source"] + " (bf16_tflops_sustained)",
-                     "flops_per_step": conv_flops, "kernel_ms_per_step": gemm_ms,
+                     "flops_per_step": conv_flops, "executed_flops_per_step": executed_flops,
+                     "kernel_ms_per_step": gemm_ms,
                      "share_of_step": gemm_ms / ms_per_step},
         "cpu_baseline": cpu,
     }
@@ -318,6 +340,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4, help="volumes per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-op", default="", help="write per-GEMM timings (CUDA events) to this file")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -82,7 +82,8 @@ typedef struct MriGemmArgs {
   const float* bias_m;    /* [ext[0]] bias along x1 (rows) or NULL */
   const float* rowbias;   /* [samples][rowbias_ld] or NULL (time-embedding projection) */
   int32_t rowbias_ld;
-  float* stats;           /* [samples][stats_ld][2] accumulated with atomics, or NULL */
+  double* stats;          /* [samples][stats_ld][2] (sum, sumsq) accumulated with fp64 atomics
+                             (order-insensitive to ~1e-16, i.e. reproducible), or NULL */
   int32_t stats_ld;       /* statistics groups per sample */
   int32_t stats_cpg;      /* channels per statistics group (multiple of 8) */
   int32_t stages;         /* TMA ring depth (2..8) */
@@ -92,20 +93,22 @@ typedef struct MriGemmArgs {
 /* dynamic shared memory one CTA needs for (block_n, stages) */
 int mri_gemm_smem_bytes(int block_n, int stages);
 int mri_gemm_launch(const MriGemmArgs* args_host, void* stream);
+/* resident CTAs per SM the kernel reaches for (block_n, stages); <0 on error */
+int mri_gemm_occupancy(int block_n, int stages);
 
 /* ------------------------------------------------------------------------------------------
  * GroupNorm (+SiLU, + time-embedding add, + residual add), channels-last bf16.
  * Replaces nn.GroupNorm + nn.SiLU + the broadcast adds of
  *   slice_cond_2d_ddpm/unet.py:43-56,194-197 (post-norm: h = silu(gn(h)); h += silu(lin(t));
  *   return h + res), ddpm_3d_ldm/unet_attention.py:38,79-85,199 (pre-norm).
- * x, y: [samples][spatial][C] bf16.  stats: [samples][stats_ld][2] (sum, sumsq) over fine groups
+ * x, y: [samples][spatial][C] bf16.  stats: fp64 [samples][stats_ld][2] (sum, sumsq) over fine groups
  * of stats_cpg channels starting at group index stats_g0; `groups` normalisation groups of
  * C/groups channels each are formed by summing adjacent fine groups.
  * y = act(gn(x)*gamma+beta) + rowbias[sample][c] + residual ;  act = SiLU if silu != 0.
  * ------------------------------------------------------------------------------------------ */
-int mri_gn_stats(const void* x, float* stats, int samples, int64_t spatial, int C, int stats_ld,
+int mri_gn_stats(const void* x, double* stats, int samples, int64_t spatial, int C, int stats_ld,
                  int stats_g0, int stats_cpg, void* stream);
-int mri_gn_apply(const void* x, void* y, const float* stats, const float* gamma,
+int mri_gn_apply(const void* x, void* y, const double* stats, const float* gamma,
                  const float* beta, const float* rowbias, int rowbias_ld, const void* residual,
                  int samples, int64_t spatial, int C, int groups, int stats_ld, int stats_g0,
                  int stats_cpg, float eps, int silu, void* stream);

@@ -53,6 +53,7 @@ SIGNATURES = {
                              C.POINTER(C.c_uint32), _i]),
     "mri_gemm_smem_bytes": (_i, [_i, _i]),
     "mri_gemm_launch": (_i, [C.POINTER(MriGemmArgs), _vp]),
+    "mri_gemm_occupancy": (_i, [_i, _i]),
     "mri_gn_stats": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _i, _vp]),
     "mri_gn_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i64, _i, _i, _i, _i, _i, _f,
                           _i, _vp]),

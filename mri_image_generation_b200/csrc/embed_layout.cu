@@ -63,45 +63,54 @@ linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
 }
 
 // Patch matrix of a thin-channel input (fp32 NC[D]HW) for a ksize^ndim, pad ksize/2 convolution.
-// dst[m][((kd*k+kh)*k+kw)*cin_total + c]; one thread per (m, tap).
+// dst[m][((kd*k+kh)*k+kw)*cin_total + c]; one thread per (m, 8 output columns) -> one 16-byte
+// store; the (tiny) source stays L1/L2 resident.
 __global__ void __launch_bounds__(256)
 im2col_kernel(const float* __restrict__ src, const float* __restrict__ src2,
-              __nv_bfloat16* __restrict__ dst, int samples, int cin, int cin2, int D, int H, int W,
+              uint4* __restrict__ dst, int samples, int cin, int cin2, int D, int H, int W,
               int k, int ndim, int kpad) {
   const int taps = ndim == 3 ? k * k * k : k * k;
   const int ct = cin + cin2;
+  const int kvalid = taps * ct;
   const int64_t spatial = (int64_t)D * H * W;
   const int64_t M = (int64_t)samples * spatial;
-  const int slots = taps + 1;  // last slot zero-fills the padding columns
-  const int64_t total = M * slots;
+  const int vec_per_row = kpad >> 3;
+  const int64_t total = M * vec_per_row;
   const int pad = k / 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t m = i / slots;
-    const int tap = (int)(i % slots);
-    __nv_bfloat16* row = dst + m * kpad;
-    if (tap == taps) {
-      for (int c = taps * ct; c < kpad; ++c) row[c] = __float2bfloat16(0.f);
-      continue;
-    }
+    const int64_t m = i / vec_per_row;
+    const int col0 = (int)(i % vec_per_row) * 8;
     const int n = (int)(m / spatial);
     int64_t s = m % spatial;
     const int w0 = (int)(s % W);
     s /= W;
     const int h0 = (int)(s % H);
     const int d0 = (int)(s / H);
-    int kw = tap % k, kh = (tap / k) % k, kd = ndim == 3 ? tap / (k * k) : 0;
-    const int w = w0 + kw - pad, h = h0 + kh - pad, d = ndim == 3 ? d0 + kd - pad : d0;
-    const bool in = w >= 0 && w < W && h >= 0 && h < H && d >= 0 && d < D;
-    const int64_t sp = ((int64_t)d * H + h) * W + w;
-    for (int c = 0; c < ct; ++c) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = col0 + j;
       float v = 0.f;
-      if (in) {
-        v = c < cin ? __ldg(src + ((size_t)n * cin + c) * spatial + sp)
-                    : __ldg(src2 + ((size_t)n * cin2 + (c - cin)) * spatial + sp);
+      if (col < kvalid) {
+        const int tap = col / ct, c = col - tap * ct;
+        const int kw = tap % k, kh = (tap / k) % k, kd = ndim == 3 ? tap / (k * k) : 0;
+        const int w = w0 + kw - pad, h = h0 + kh - pad, d = ndim == 3 ? d0 + kd - pad : d0;
+        if (w >= 0 && w < W && h >= 0 && h < H && d >= 0 && d < D) {
+          const int64_t sp = ((int64_t)d * H + h) * W + w;
+          v = c < cin ? __ldg(src + ((size_t)n * cin + c) * spatial + sp)
+                      : __ldg(src2 + ((size_t)n * cin2 + (c - cin)) * spatial + sp);
+        }
       }
-      row[tap * ct + c] = __float2bfloat16(v);
+      f[j] = v;
     }
+    uint32_t wd[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+      wd[j] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    dst[i] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
   }
 }
 
@@ -133,46 +142,42 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ d
   }
 }
 
-// One block per row: P = softmax(S * scale) in fp32, stored bf16.
+// One warp per row: P = softmax(S * scale) in fp32, stored bf16.  The row lives in registers
+// (up to kMaxPerLane * 32 columns), so S is read exactly once.
+constexpr int kSoftmaxMaxPerLane = 64;
+template <int kPerLane>
 __global__ void __launch_bounds__(256)
-softmax_rows_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P, int cols, int ld_s,
-                    int ld_p, float scale) {
-  const int64_t row = blockIdx.x;
+softmax_rows_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P, int64_t rows,
+                    int cols, int ld_s, int ld_p, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
   const float* s = S + row * ld_s;
   __nv_bfloat16* p = P + row * ld_p;
-  __shared__ float red[8];
-  __shared__ float bcast;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-
+  float v[kPerLane];
   float mx = -INFINITY;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) mx = fmaxf(mx, s[c] * scale);
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    const int c = lane + 32 * j;
+    v[j] = c < cols ? __ldg(s + c) * scale : -INFINITY;
+    mx = fmaxf(mx, v[j]);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if (lane == 0) red[wid] = mx;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float m = red[0];
-    for (int i = 1; i < nw; ++i) m = fmaxf(m, red[i]);
-    bcast = m;
-  }
-  __syncthreads();
-  mx = bcast;
   float sum = 0.f;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) sum += expf(s[c] * scale - mx);
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    v[j] = __expf(v[j] - mx);  // exp(-inf) = 0 for the padding columns
+    sum += v[j];
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  __syncthreads();
-  if (lane == 0) red[wid] = sum;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int i = 0; i < nw; ++i) t += red[i];
-    bcast = 1.0f / t;
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    const int c = lane + 32 * j;
+    if (c < ld_p) p[c] = __float2bfloat16(v[j] * inv);
   }
-  __syncthreads();
-  const float inv = bcast;
-  for (int c = threadIdx.x; c < ld_p; c += blockDim.x)
-    p[c] = __float2bfloat16(c < cols ? expf(s[c] * scale - mx) * inv : 0.f);
 }
 
 static inline unsigned grid_for(int64_t total) {
@@ -217,10 +222,9 @@ extern "C" int mri_im2col(const float* src, const float* src2, void* dst, int sa
   if ((cin + cin2) * taps > kpad || kpad % 64 != 0)
     return set_error(-2, "mri_im2col: kpad must be a multiple of 64 and >= taps*cin");
   if (cin2 > 0 && src2 == nullptr) return set_error(-2, "mri_im2col: src2 missing");
-  const int64_t total = (int64_t)samples * D * H * W * (taps + 1);
+  const int64_t total = (int64_t)samples * D * H * W * (kpad / 8);
   im2col_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
-      src, src2, reinterpret_cast<__nv_bfloat16*>(dst), samples, cin, cin2, D, H, W, ksize, ndim,
-      kpad);
+      src, src2, reinterpret_cast<uint4*>(dst), samples, cin, cin2, D, H, W, ksize, ndim, kpad);
   return check_launch("im2col_kernel");
 }
 
@@ -244,7 +248,15 @@ extern "C" int mri_softmax_rows(const float* S, void* P, int64_t rows, int cols,
                                 float scale, void* stream) {
   if (rows < 1 || cols < 1 || ld_s < cols || ld_p < cols)
     return set_error(-2, "mri_softmax_rows: bad shape");
-  softmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(
-      S, reinterpret_cast<__nv_bfloat16*>(P), cols, ld_s, ld_p, scale);
+  if (ld_p > kSoftmaxMaxPerLane * 32)
+    return set_error(-2, "mri_softmax_rows: more than 2048 columns unsupported");
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  __nv_bfloat16* Pp = reinterpret_cast<__nv_bfloat16*>(P);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int per_lane = (ld_p + 31) / 32;
+  if (per_lane <= 8) softmax_rows_kernel<8><<<grid, 256, 0, st>>>(S, Pp, rows, cols, ld_s, ld_p, scale);
+  else if (per_lane <= 16) softmax_rows_kernel<16><<<grid, 256, 0, st>>>(S, Pp, rows, cols, ld_s, ld_p, scale);
+  else if (per_lane <= 40) softmax_rows_kernel<40><<<grid, 256, 0, st>>>(S, Pp, rows, cols, ld_s, ld_p, scale);
+  else softmax_rows_kernel<64><<<grid, 256, 0, st>>>(S, Pp, rows, cols, ld_s, ld_p, scale);
   return check_launch("softmax_rows_kernel");
 }

@@ -199,7 +199,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
                                ? p.rowbias + (size_t)sample * p.rowbias_ld
                                : nullptr;
     const float bias_m = (p.bias_m != nullptr && valid) ? __ldg(p.bias_m + org[0] + rl[0]) : 0.f;
-    float* stats = p.stats;
+    double* stats = p.stats;
     const int cpg = p.stats_cpg;
     int cur_g = -1;
     float s_sum = 0.f, s_sq = 0.f;
@@ -214,14 +214,14 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
         }
         if (lane == 0) {
           const int smp = sd > 0 ? org[sd - 1] : 0;
-          float* dst = stats + ((size_t)smp * p.stats_ld + cur_g) * 2;
-          atomicAdd(dst, s_sum);
-          atomicAdd(dst + 1, s_sq);
+          double* dst = stats + ((size_t)smp * p.stats_ld + cur_g) * 2;
+          atomicAdd(dst, (double)s_sum);
+          atomicAdd(dst + 1, (double)s_sq);
         }
       } else if (valid) {
-        float* dst = stats + ((size_t)sample * p.stats_ld + cur_g) * 2;
-        atomicAdd(dst, s_sum);
-        atomicAdd(dst + 1, s_sq);
+        double* dst = stats + ((size_t)sample * p.stats_ld + cur_g) * 2;
+        atomicAdd(dst, (double)s_sum);
+        atomicAdd(dst + 1, (double)s_sq);
       }
       s_sum = 0.f;
       s_sq = 0.f;
@@ -354,6 +354,18 @@ extern "C" int mri_gemm_smem_bytes(int block_n, int stages) {
   return stages * stage_bytes(block_n) + 1024;
 }
 
+extern "C" int mri_gemm_occupancy(int block_n, int stages) {
+  const int smem = mri_gemm_smem_bytes(block_n, stages);
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm_tc_kernel)");
+  (void)cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+  int nb = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gemm_tc_kernel, kThreads, smem);
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  return nb;
+}
+
 extern "C" int mri_gemm_launch(const MriGemmArgs* a, void* stream) {
   if (a == nullptr) return set_error(-1, "mri_gemm_launch: null args");
   const int bn = a->block_n;
@@ -386,6 +398,10 @@ extern "C" int mri_gemm_launch(const MriGemmArgs* a, void* stream) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          smem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm_tc_kernel)");
+    // ask for the full shared-memory carveout so that two CTAs (2 x ~100 KB) can share an SM
+    e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(carveout)");
     configured_smem = smem;
   }
   gemm_tc_kernel<<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(*a);

@@ -34,16 +34,16 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // and added to stats with one atomic pair per fine group.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-gn_stats_kernel(const uint4* __restrict__ x, float* __restrict__ stats, int64_t spatial, int C,
+gn_stats_kernel(const uint4* __restrict__ x, double* __restrict__ stats, int64_t spatial, int C,
                 int stats_ld, int stats_g0, int stats_cpg, int rows_per_block) {
-  extern __shared__ float red[];  // [n_fine][2]
+  extern __shared__ double red[];  // [n_fine][2] (fp64: summation order does not matter)
   const int vec_per_row = C >> 3;
   const int n_fine = C / stats_cpg;
   const int sample = blockIdx.y;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   int64_t r1 = r0 + rows_per_block;
   if (r1 > spatial) r1 = spatial;
-  for (int i = threadIdx.x; i < n_fine * 2; i += blockDim.x) red[i] = 0.f;
+  for (int i = threadIdx.x; i < n_fine * 2; i += blockDim.x) red[i] = 0.0;
   __syncthreads();
 
   const int rows_step = blockDim.x / vec_per_row;  // host guarantees blockDim % vec_per_row == 0
@@ -62,8 +62,8 @@ gn_stats_kernel(const uint4* __restrict__ x, float* __restrict__ stats, int64_t 
     }
   }
   const int g = (cv * 8) / stats_cpg;
-  atomicAdd(&red[2 * g], s);
-  atomicAdd(&red[2 * g + 1], ss);
+  atomicAdd(&red[2 * g], (double)s);
+  atomicAdd(&red[2 * g + 1], (double)ss);
   __syncthreads();
   for (int i = threadIdx.x; i < n_fine * 2; i += blockDim.x) {
     const int gi = i >> 1;
@@ -72,65 +72,84 @@ gn_stats_kernel(const uint4* __restrict__ x, float* __restrict__ stats, int64_t 
 }
 
 // ---------------------------------------------------------------------------------------
-// Apply.  One thread per 8-channel vector; grid-stride.  mean / rstd are derived on the fly
-// from the fine-group partial sums (a handful of cached loads per vector).
+// Apply.  grid (chunks, samples).  A thread owns one 8-channel vector position (fixed channel
+// group), so mean / rstd / gamma / beta collapse into 8 (scale, shift) pairs computed once;
+// the thread then streams rows with 4 independent 16-byte loads in flight.
 // ---------------------------------------------------------------------------------------
+template <bool kSilu, bool kResidual>
 __global__ void __launch_bounds__(256)
-gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ stats,
+gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double* __restrict__ stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta,
                 const float* __restrict__ rowbias, int rowbias_ld, const uint4* __restrict__ residual,
                 int64_t spatial, int C, int groups, int stats_ld, int stats_g0, int stats_cpg,
-                float eps, int silu, int64_t total_vec) {
+                float eps, int rows_per_block) {
   const int vec_per_row = C >> 3;
-  const int cpg = C / groups;           // channels per normalisation group
-  const int comb = cpg / stats_cpg;     // fine groups per normalisation group
-  const float inv_cnt = 1.0f / ((float)cpg * (float)spatial);
-  const int64_t vec_per_sample = spatial * vec_per_row;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int sample = (int)(i / vec_per_sample);
-    const int cv = (int)(i % vec_per_row);
-    const int c = cv * 8;
-    const int g = c / cpg;
-    const float* st = stats + ((size_t)sample * stats_ld + stats_g0 + g * comb) * 2;
-    float s = 0.f, ss = 0.f;
-    for (int j = 0; j < comb; ++j) {
-      s += __ldg(st + 2 * j);
-      ss += __ldg(st + 2 * j + 1);
-    }
-    const float mean = s * inv_cnt;
-    float var = ss * inv_cnt - mean * mean;
-    var = var < 0.f ? 0.f : var;
-    const float rstd = rsqrtf(var + eps);
+  const int cpg = C / groups;        // channels per normalisation group
+  const int comb = cpg / stats_cpg;  // fine groups per normalisation group
+  const int sample = blockIdx.y;
+  const int cv = threadIdx.x % vec_per_row;
+  const int rsub = threadIdx.x / vec_per_row;
+  const int rows_step = blockDim.x / vec_per_row;
+  const int c = cv * 8;
+  const int g = c / cpg;
 
-    float f[8];
-    unpack8(__ldg(x + i), f);
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
-    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
-    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const double* st = stats + ((size_t)sample * stats_ld + stats_g0 + g * comb) * 2;
+  double s = 0.0, ss = 0.0;
+  for (int j = 0; j < comb; ++j) {
+    s += __ldg(st + 2 * j);
+    ss += __ldg(st + 2 * j + 1);
+  }
+  const double inv_cnt = 1.0 / ((double)cpg * (double)spatial);
+  const double mean_d = s * inv_cnt;
+  double var_d = ss * inv_cnt - mean_d * mean_d;  // fp64: no cancellation problem
+  var_d = var_d < 0.0 ? 0.0 : var_d;
+  const float mean = (float)mean_d;
+  const float rstd = rsqrtf((float)var_d + eps);
+  float sc[8], sh[8], rb[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float v = (f[k] - mean) * rstd * gm[k] + bt[k];
-      if (silu) v = v / (1.0f + __expf(-v));
-      f[k] = v;
-    }
-    if (rowbias != nullptr) {
-      const float* rb = rowbias + (size_t)sample * rowbias_ld + c;
-      const float4 r0 = __ldg(reinterpret_cast<const float4*>(rb));
-      const float4 r1 = __ldg(reinterpret_cast<const float4*>(rb + 4));
-      f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
-      f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
-    }
-    if (residual != nullptr) {
-      float rr[8];
-      unpack8(__ldg(residual + i), rr);
+  for (int k = 0; k < 8; ++k) {
+    const float gm = __ldg(gamma + c + k), bt = __ldg(beta + c + k);
+    sc[k] = rstd * gm;
+    sh[k] = bt - mean * rstd * gm;
+    rb[k] = rowbias != nullptr ? __ldg(rowbias + (size_t)sample * rowbias_ld + c + k) : 0.f;
+  }
+
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > spatial) r1 = spatial;
+  const size_t base = (size_t)sample * spatial * vec_per_row + cv;
+  constexpr int U = 4;
+  for (int64_t r = r0 + rsub; r < r1; r += (int64_t)rows_step * U) {
+    uint4 v[U], rr[U];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] += rr[k];
+    for (int u = 0; u < U; ++u) {
+      const int64_t ru = r + (int64_t)u * rows_step;
+      if (ru < r1) {
+        v[u] = __ldg(x + base + ru * vec_per_row);
+        if (kResidual) rr[u] = __ldg(residual + base + ru * vec_per_row);
+      }
     }
-    y[i] = pack8(f);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t ru = r + (int64_t)u * rows_step;
+      if (ru < r1) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float t = fmaf(f[k], sc[k], sh[k]);
+          if (kSilu) t = t / (1.0f + __expf(-t));
+          f[k] = t + rb[k];
+        }
+        if (kResidual) {
+          float q[8];
+          unpack8(rr[u], q);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] += q[k];
+        }
+        y[base + ru * vec_per_row] = pack8(f);
+      }
+    }
   }
 }
 
@@ -138,7 +157,7 @@ gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float*
 
 using namespace mri;
 
-extern "C" int mri_gn_stats(const void* x, float* stats, int samples, int64_t spatial, int C,
+extern "C" int mri_gn_stats(const void* x, double* stats, int samples, int64_t spatial, int C,
                             int stats_ld, int stats_g0, int stats_cpg, void* stream) {
   if (C % 8 != 0 || stats_cpg % 8 != 0 || C % stats_cpg != 0)
     return set_error(-2, "mri_gn_stats: C and stats_cpg must be multiples of 8");
@@ -153,27 +172,43 @@ extern "C" int mri_gn_stats(const void* x, float* stats, int samples, int64_t sp
   if (rows_per < rows_step * 4) rows_per = rows_step * 4;
   const int chunks = (int)((spatial + rows_per - 1) / rows_per);
   const int n_fine = C / stats_cpg;
-  gn_stats_kernel<<<dim3(chunks, samples), threads, n_fine * 2 * sizeof(float),
+  gn_stats_kernel<<<dim3(chunks, samples), threads, n_fine * 2 * sizeof(double),
                     (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(x), stats, spatial, C,
                                             stats_ld, stats_g0, stats_cpg, (int)rows_per);
   return check_launch("gn_stats_kernel");
 }
 
-extern "C" int mri_gn_apply(const void* x, void* y, const float* stats, const float* gamma,
+extern "C" int mri_gn_apply(const void* x, void* y, const double* stats, const float* gamma,
                             const float* beta, const float* rowbias, int rowbias_ld,
                             const void* residual, int samples, int64_t spatial, int C, int groups,
                             int stats_ld, int stats_g0, int stats_cpg, float eps, int silu,
                             void* stream) {
   if (C % 8 != 0 || groups < 1 || C % groups != 0 || (C / groups) % stats_cpg != 0)
     return set_error(-2, "mri_gn_apply: bad channel / group configuration");
-  const int64_t total_vec = (int64_t)samples * spatial * (C / 8);
-  int64_t blocks = (total_vec + 255) / 256;
-  const int64_t cap = 148 * 16;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  gn_apply_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), stats, gamma, beta, rowbias,
-      rowbias_ld, reinterpret_cast<const uint4*>(residual), spatial, C, groups, stats_ld, stats_g0,
-      stats_cpg, eps, silu, total_vec);
+  const int vec_per_row = C / 8;
+  if (vec_per_row > 256) return set_error(-2, "mri_gn_apply: C > 2048 unsupported");
+  const int threads = (256 / vec_per_row) * vec_per_row;
+  const int rows_step = threads / vec_per_row;
+  // ~8 blocks per SM over the whole grid, each covering a multiple of 4*rows_step rows
+  int64_t want_blocks = (148 * 8 + samples - 1) / samples;
+  int64_t rows_per = (spatial + want_blocks - 1) / want_blocks;
+  const int64_t quantum = (int64_t)rows_step * 4;
+  rows_per = (rows_per + quantum - 1) / quantum * quantum;
+  const int chunks = (int)((spatial + rows_per - 1) / rows_per);
+  dim3 grid(chunks, samples);
+  const uint4* xp = reinterpret_cast<const uint4*>(x);
+  uint4* yp = reinterpret_cast<uint4*>(y);
+  const uint4* rp = reinterpret_cast<const uint4*>(residual);
+  cudaStream_t st = (cudaStream_t)stream;
+#define MRI_GN_LAUNCH(S, R)                                                                     \
+  gn_apply_kernel<S, R><<<grid, threads, 0, st>>>(xp, yp, stats, gamma, beta, rowbias,          \
+                                                  rowbias_ld, rp, spatial, C, groups, stats_ld, \
+                                                  stats_g0, stats_cpg, eps, (int)rows_per)
+  if (silu) {
+    if (residual) MRI_GN_LAUNCH(true, true); else MRI_GN_LAUNCH(true, false);
+  } else {
+    if (residual) MRI_GN_LAUNCH(false, true); else MRI_GN_LAUNCH(false, false);
+  }
+#undef MRI_GN_LAUNCH
   return check_launch("gn_apply_kernel");
 }

@@ -35,7 +35,7 @@ def _rup(n: int, m: int) -> int:
 class Act:
     """Channels-last bf16 activation [N, *spatial, C] (+ GroupNorm partial sums of its producer)."""
     t: torch.Tensor
-    stats: Optional[torch.Tensor] = None  # fp32 [N, G, 2]
+    stats: Optional[torch.Tensor] = None  # fp64 [N, G, 2]
     cpg: int = 0                          # channels per statistics group
 
     @property
@@ -75,7 +75,7 @@ class _Pool:
 class UNetProgram:
     """Common builder machinery; subclasses lay out a concrete UNet."""
 
-    STATS_ARENA = 1 << 18  # floats
+    STATS_ARENA = 1 << 17  # doubles
 
     def __init__(self, device, batch: int, spatial: Sequence[int], groups: int = 8):
         _lib.require_device()
@@ -90,7 +90,7 @@ class UNetProgram:
         self.op_outs: List[List[torch.Tensor]] = []
         self.plans: List[P.GemmPlan] = []
         self.refresh: List[Callable[[], None]] = []  # re-pack weights after a parameter update
-        self._arena = torch.zeros(self.STATS_ARENA, dtype=torch.float32, device=device)
+        self._arena = torch.zeros(self.STATS_ARENA, dtype=torch.float64, device=device)
         self._arena_used = 0
         self.gemm_flops = 0
         self.hbm_bytes_elementwise = 0
@@ -475,3 +475,165 @@ def _pad_vec(v: torch.Tensor, n: int) -> torch.Tensor:
     out = torch.zeros(n, dtype=v.dtype, device=v.device)
     out[:v.numel()] = v
     return out
+
+
+# ==========================================================================================
+# 2D / 2.5D UNet (post-norm ResBlocks, slice-position conditioning, optional context channels)
+# ==========================================================================================
+class UNet2DProgram(UNetProgram):
+    """slice_cond_2d_ddpm/unet.py:108-199 and ddpm_25d_all_modalities/unet.py:109-218."""
+
+    def __init__(self, model, batch: int, spatial: Sequence[int], x_channels: int, ctx_channels: int):
+        dev = next(model.parameters()).device
+        super().__init__(dev, batch, spatial, groups=model.out_norm.num_groups)
+        self.model = model
+        B, (H, W) = batch, self.sp
+        chs = list(model.chs)
+        n_down = len(model.downs)
+        if H % (2 ** n_down) or W % (2 ** n_down):
+            raise _lib.MriError(f"image size {self.sp} must be divisible by {2 ** n_down} (the bilinear "
+                                "resize branch of UpBlock, unet.py:98-99, is not implemented)")
+        eps = model.out_norm.eps
+        cin = model.init_conv.weight.shape[1]
+        if x_channels + ctx_channels != cin:
+            raise _lib.MriError(f"init_conv expects {cin} input channels, got {x_channels} + "
+                                f"{ctx_channels} context")
+        self.x_in = torch.zeros(B, x_channels, H, W, device=dev)
+        self.ctx_in = torch.zeros(B, ctx_channels, H, W, device=dev) if ctx_channels else None
+        self.t_in = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.z_in = torch.zeros(B, 1, device=dev)
+
+        # ---- conditioning: cond = time_mlp(t) + slice_mlp(z)  (unet.py:173-183) -----------------
+        tdim = model.time_mlp[1].in_features
+        temb = self.time_embedding(self.t_in, model.time_mlp, tdim)
+        s0, s2 = model.slice_mlp[0], model.slice_mlp[2]
+        self.track(s0.weight, s0.bias, s2.weight, s2.bias)
+        zh = torch.zeros(B, s0.weight.shape[0], device=dev)
+        cond = torch.zeros(B, tdim, device=dev)
+        z_in = self.z_in
+        self._add("slice_mlp.0", lambda: ops.linear(z_in, s0.weight, s0.bias, zh, act=1), [zh])
+        self._add("slice_mlp.2", lambda: ops.linear(zh, s2.weight, s2.bias, cond, addend=temb), [cond])
+        blocks = []
+        for d in model.downs:
+            blocks += [d.res1, d.res2]
+        blocks += [model.mid_block1, model.mid_block2]
+        for u in model.ups:
+            blocks += [u.res1, u.res2]
+        # the 2D block applies SiLU to the projected embedding (unet.py:48-50)
+        tproj, toffs, tld = self.block_projections(cond, blocks, act=1)
+        self._tproj = {id(b): (tproj[:, o:], tld) for b, o in zip(blocks, toffs)}
+
+        # ---- init_conv: thin Cin -> patch matrix + GEMM --------------------------------------------
+        S = H * W
+        kpad = _rup(9 * cin, 64)
+        col = torch.zeros(B * S, kpad, dtype=torch.bfloat16, device=dev)
+        x_in, ctx_in = self.x_in, self.ctx_in
+        self._add("im2col", lambda: ops.im2col(x_in, col, B, x_channels, 1, H, W, 3, 2, kpad,
+                                               src2=ctx_in, cin2=ctx_channels), [col])
+        ic = model.init_conv
+        self.track(ic.weight, ic.bias)
+        w_in = self.packed(lambda: _pad_k(P.pack_conv_weight(ic.weight.detach()), kpad))
+        h = self.new_act(self.sp, chs[0], with_stats=False)
+        self.gemm(self._matrix_conv2d(col, w_in, h, S, kpad, ic.bias, "init_conv"))
+
+        skips: List[Act] = []
+        for i, d in enumerate(model.downs):
+            h = self.resblock2d(h, None, d.res1, eps, f"downs.{i}.res1")
+            h = self.resblock2d(h, None, d.res2, eps, f"downs.{i}.res2")
+            skips.append(h)
+            dn = d.down
+            self.track(dn.weight, dn.bias)
+            wd = self.packed(lambda dn=dn: P.pack_conv_weight(dn.weight.detach()))
+            y = self.new_act([s // 2 for s in h.t.shape[1:-1]], dn.weight.shape[0], with_stats=False)
+            self.gemm(P.down_conv_plan(h.t, wd, y.t, bias=dn.bias, name=f"downs.{i}.down"))
+            h = y
+        h = self.resblock2d(h, None, model.mid_block1, eps, "mid_block1")
+        h = self.resblock2d(h, None, model.mid_block2, eps, "mid_block2")
+        for j, u in enumerate(model.ups):
+            skip = skips.pop()
+            up = u.up
+            self.track(up.weight, up.bias)
+            wu = self.packed(lambda up=up: P.pack_convT_weight(up.weight.detach()))
+            y = self.new_act([s * 2 for s in h.t.shape[1:-1]], up.weight.shape[1], with_stats=False)
+            self.gemm(P.up_conv_plan(h.t, wu, y.t, bias=up.bias, name=f"ups.{j}.up"))
+            self.pool.release(h.t)
+            if tuple(y.t.shape[1:-1]) != tuple(skip.t.shape[1:-1]):
+                raise _lib.MriError("UpBlock bilinear-resize branch (unet.py:98-99) not implemented")
+            h = self.resblock2d(y, skip, u.res1, eps, f"ups.{j}.res1")
+            h = self.resblock2d(h, None, u.res2, eps, f"ups.{j}.res2")
+
+        on, oc = model.out_norm, model.out_conv
+        self.track(on.weight, on.bias, oc.weight, oc.bias)
+        self.stats_of(h, "out_norm.stats")
+        a = self.gn(h, on.weight, on.bias, self.groups, eps, True, name="out_norm")
+        self.cout = oc.weight.shape[0]
+        self.cout_pad = _rup(self.cout, 16)
+        w_out = self.packed(lambda: P.pack_conv_weight(oc.weight.detach(), cout_pad=self.cout_pad))
+        b_out = self.packed(lambda: _pad_vec(oc.bias.detach(), self.cout_pad))
+        y = self.conv([P.ConvSource(a)], w_out, self.cout_pad, 3, b_out, with_stats=False,
+                      name="out_conv")
+        self.eps_nhwc = y.t
+        self.out = torch.zeros(B, self.cout, H, W, device=dev)
+        self.params_changed()
+
+    def _matrix_conv2d(self, col, wmat, y: Act, S: int, kpad: int, bias, name) -> P.GemmPlan:
+        B, C = self.B, y.C
+        a = P.TView(col, (kpad, S, B, 1, 1), (1, kpad, S * kpad, B * S * kpad, B * S * kpad))
+        b = P.TView(wmat, (kpad, C, 1, 1), (1, kpad, kpad * C, kpad * C))
+        o = P.TView(y.t, (C, S, B, 1, 1), (1, C, S * C, B * S * C, B * S * C))
+        return P.matrix_plan(a, (128, 1, 1, 1), b, o, K=kpad, n_total=C, block_n=P.pick_block_n(C),
+                             ext=(S, B, 1, 1), tiles=(-(-S // 128), B, 1, 1), sample_dim=2,
+                             bias=bias, stats=y.stats, stats_cpg=y.cpg, name=name,
+                             flops=2 * B * S * C * kpad)
+
+    def resblock2d(self, x: Act, skip: Optional[Act], blk, eps: float, name: str) -> Act:
+        """ResidualBlock (slice_cond_2d_ddpm/unet.py:42-56), post-norm:
+        h = silu(gn1(conv1(x))) + silu(lin(cond)); h = silu(gn2(conv2(h))); return h + res_conv(x).
+        With `skip`, x is the virtual concatenation [x, skip] (unet.py:101)."""
+        n1, n2, c1, c2 = blk.norm1, blk.norm2, blk.conv1, blk.conv2
+        self.track(n1.weight, n1.bias, n2.weight, n2.bias, c1.weight, c1.bias, c2.weight, c2.bias)
+        cout = c1.weight.shape[0]
+        rowbias, rb_ld = self._tproj[id(blk)]
+        srcs = [x] if skip is None else [x, skip]
+        cins = [s.C for s in srcs]
+        w1 = self.packed(lambda: P.pack_conv_weight(c1.weight.detach(), splits=cins))
+        h1 = self.conv([P.ConvSource(s.t) for s in srcs], w1, cout, 3, c1.bias, name=f"{name}.conv1")
+        a1 = self.gn(h1, n1.weight, n1.bias, self.groups, eps, True, rowbias=rowbias, rowbias_ld=rb_ld,
+                     name=f"{name}.norm1+temb")
+        self.pool.release(h1.t)
+        w2 = self.packed(lambda: P.pack_conv_weight(c2.weight.detach()))
+        h2 = self.conv([P.ConvSource(a1)], w2, cout, 3, c2.bias, name=f"{name}.conv2")
+        self.pool.release(a1)
+        if isinstance(blk.res_conv, torch.nn.Identity):
+            assert skip is None and x.C == cout
+            res = x.t
+            res_tmp = None
+        else:
+            rc = blk.res_conv
+            self.track(rc.weight, rc.bias)
+            wr = self.packed(lambda: P.pack_conv_weight(rc.weight.detach(), splits=cins))
+            res_tmp = self.conv([P.ConvSource(s.t) for s in srcs], wr, cout, 1, rc.bias,
+                                with_stats=False, name=f"{name}.res_conv")
+            res = res_tmp.t
+        out = self.gn(h2, n2.weight, n2.bias, self.groups, eps, True, residual=res,
+                      name=f"{name}.norm2+res")
+        self.pool.release(h2.t)
+        if res_tmp is not None:
+            self.pool.release(res_tmp.t)
+        for s in srcs:
+            self.pool.release(s.t)
+        return Act(out)
+
+    def forward(self, x, t, z_pos, context=None) -> torch.Tensor:
+        if self.params_changed():
+            for fn in self.refresh:
+                fn()
+        self.x_in.copy_(x)
+        self.t_in.copy_(t)
+        self.z_in.copy_(z_pos.reshape(-1, 1))
+        if self.ctx_in is not None:
+            self.ctx_in.copy_(context)
+        self.run()
+        ops.nhwc_to_nchw(self.eps_nhwc, self.out, self.B, self.sp[0] * self.sp[1], self.cout,
+                         self.cout_pad)
+        return self.out

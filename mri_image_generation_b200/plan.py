@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import itertools
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -140,7 +141,7 @@ class GemmPlan:
     bias_m: Optional[torch.Tensor] = None     # fp32 [ext[0]]
     rowbias: Optional[torch.Tensor] = None    # fp32 view [samples, >= n]; row stride = rowbias_ld
     rowbias_ld: int = 0
-    stats: Optional[torch.Tensor] = None      # fp32 [samples, stats_ld, 2]
+    stats: Optional[torch.Tensor] = None      # fp64 [samples, stats_ld, 2]
     stats_ld: int = 0
     stats_cpg: int = 0
     stages: int = 0
@@ -168,6 +169,9 @@ class GemmPlan:
     def pick_stages(self) -> int:
         if self.stages:
             return self.stages
+        env = os.environ.get("MRI_GEMM_STAGES")  # tuning experiments only
+        if env:
+            return int(env)
         stage = BLOCK_M * 128 + self.block_n * 128
         stag = BLOCK_M * self.block_n * (4 if self.out_f32 else 2)
         # two CTAs per SM (one's epilogue overlaps the other's main loop) when >= 3 stages fit

@@ -67,7 +67,7 @@ def test_conv_stride1(P, nd, sp, N, cins, cout, k):
     wm = P.pack_conv_weight(w, splits=cins)
     y = torch.zeros(N, *sp, cout, dtype=torch.bfloat16, device=dev)
     groups = 8 if cout % 64 == 0 else 2
-    stats = torch.zeros(N, groups, 2, device=dev)
+    stats = torch.zeros(N, groups, 2, device=dev, dtype=torch.float64)
     pl = P.conv_plan([P.ConvSource(a) for a in acts], wm, y, k, bias=bias, rowbias=rb,
                      rowbias_ld=cout + 8, residual=res, stats=stats, stats_cpg=cout // groups)
     pl.materialize(dev)
@@ -89,7 +89,7 @@ def test_down_conv(P, nd, sp, N, cin, cout):
     bias = torch.randn(cout, device=dev)
     ref = conv_fn(nd)(nchw(a), w.to(torch.bfloat16).float(), bias, stride=2, padding=1)
     y = torch.zeros(N, *[s // 2 for s in sp], cout, dtype=torch.bfloat16, device=dev)
-    stats = torch.zeros(N, 8, 2, device=dev)
+    stats = torch.zeros(N, 8, 2, device=dev, dtype=torch.float64)
     pl = P.down_conv_plan(a, P.pack_conv_weight(w), y, bias=bias, stats=stats, stats_cpg=cout // 8)
     pl.materialize(dev)
     pl.launch()
@@ -109,7 +109,7 @@ def test_up_conv(P, nd, sp, N, cin, cout):
     ct = F.conv_transpose3d if nd == 3 else F.conv_transpose2d
     ref = ct(nchw(a), w.to(torch.bfloat16).float(), bias, stride=2, padding=1)
     y = torch.zeros(N, *[s * 2 for s in sp], cout, dtype=torch.bfloat16, device=dev)
-    stats = torch.zeros(N, 8, 2, device=dev)
+    stats = torch.zeros(N, 8, 2, device=dev, dtype=torch.float64)
     pl = P.up_conv_plan(a, P.pack_convT_weight(w), y, bias=bias, stats=stats, stats_cpg=cout // 8)
     pl.materialize(dev)
     pl.launch()

@@ -39,7 +39,7 @@ def test_conv_concat_skipfold_residual(nd, sp):
     ref = ref + conv(nchw(a1), ws.to(torch.bfloat16).float()) + rb[:, :Co].reshape(N, Co, *[1] * nd) + nchw(res)
     wm = P.pack_conv_weight(w, splits=[C1, C2], extra=[ws])
     y = torch.zeros(N, *sp, Co, dtype=torch.bfloat16)
-    stats = torch.zeros(N, 8, 2)
+    stats = torch.zeros(N, 8, 2, dtype=torch.float64)
     pl = P.conv_plan([P.ConvSource(a1), P.ConvSource(a2), P.ConvSource(a1, taps=False)], wm, y, 3,
                      bias=b, rowbias=rb, rowbias_ld=Co + 5, residual=res, stats=stats, stats_cpg=8)
     pl.simulate()
@@ -65,7 +65,7 @@ def test_down_and_up(nd, sp):
     wt = torch.randn(C, Co, *([4] * nd)) * 0.05
     ref = convT(nchw(a), wt.to(torch.bfloat16).float(), b, stride=2, padding=1)
     y = torch.zeros(N, *[s * 2 for s in sp], Co, dtype=torch.bfloat16)
-    st = torch.zeros(N, 8, 2)
+    st = torch.zeros(N, 8, 2, dtype=torch.float64)
     P.up_conv_plan(a, P.pack_convT_weight(wt), y, bias=b, stats=st, stats_cpg=16).simulate()
     assert rel(nchw(y), ref) < TOL
     assert rel(st[:, :, 0], ref.reshape(N, 8, -1).sum(-1)) < 1e-4
