@@ -117,11 +117,13 @@ int mri_gn_apply(const void* x, void* y, const double* stats, const float* gamma
  * Time / slice-position embedding path (tiny GEMMs, fp32).
  * mri_sinusoidal: SinusoidalPosEmb.forward, slice_cond_2d_ddpm/unet.py:12-25 (identical copies
  *   in ddpm_25d_all_modalities/unet.py:13-26, ddpm_3d_ldm/unet.py:12-25, unet_attention.py:12-25).
+ *   freqs[dim/2] = exp(arange(dim/2) * -(ln 1e4 / (dim/2 - 1))) in fp32, built on the host.
  * mri_linear: y[b,o] = act(bias[o] + sum_i x[b,i] W[o,i]) (+ addend[b,o]); act: 0 none, 1 SiLU.
  *   nn.Linear sites: unet.py:124-136 (time_mlp, slice_mlp), :34,48-49 (per-block projection, SiLU
  *   applied to the projection in 2D), unet_attention.py:68,81-83 (no SiLU in 3D).
  * ------------------------------------------------------------------------------------------ */
-int mri_sinusoidal(const int64_t* t, float* out, int batch, int dim, void* stream);
+int mri_sinusoidal(const int64_t* t, const float* freqs, float* out, int batch, int dim,
+                   void* stream);
 int mri_linear(const float* x, const float* W, const float* bias, const float* addend, float* y,
                int batch, int in_f, int out_f, int act, void* stream);
 

@@ -57,7 +57,7 @@ SIGNATURES = {
     "mri_gn_stats": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _i, _vp]),
     "mri_gn_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i64, _i, _i, _i, _i, _i, _f,
                           _i, _vp]),
-    "mri_sinusoidal": (_i, [_vp, _vp, _i, _i, _vp]),
+    "mri_sinusoidal": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "mri_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mri_im2col": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mri_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i64, _i, _i, _vp]),

@@ -10,10 +10,11 @@
 
 namespace mri {
 
-// emb[b, j] = sin(t_b * f_j), emb[b, half + j] = cos(t_b * f_j), f_j = exp(j * -(ln(1e4)/(half-1)))
-// (fp32 products rounded exactly as torch does; odd dim is zero padded)
-__global__ void sinusoidal_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int batch,
-                                  int dim) {
+// emb[b, j] = sin(t_b * f_j), emb[b, half + j] = cos(t_b * f_j); the frequency table
+// f_j = exp(j * -(ln(1e4)/(half-1))) is built once on the host exactly as the reference builds
+// it (fp32), so the products t*f are bit-identical; odd dim is zero padded.
+__global__ void sinusoidal_kernel(const int64_t* __restrict__ t, const float* __restrict__ freqs,
+                                  float* __restrict__ out, int batch, int dim) {
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch * dim) return;
@@ -22,10 +23,8 @@ __global__ void sinusoidal_kernel(const int64_t* __restrict__ t, float* __restri
     out[i] = 0.f;
     return;
   }
-  const float neg = -(float)(9.210340371976184 / (double)(half - 1));  // -(ln 1e4)/(half-1)
   const int jj = j < half ? j : j - half;
-  const float f = expf(__fmul_rn((float)jj, neg));
-  const float arg = __fmul_rn((float)t[b], f);
+  const float arg = __fmul_rn((float)t[b], __ldg(freqs + jj));
   out[i] = j < half ? sinf(arg) : cosf(arg);
 }
 
@@ -192,10 +191,11 @@ static inline unsigned grid_for(int64_t total) {
 
 using namespace mri;
 
-extern "C" int mri_sinusoidal(const int64_t* t, float* out, int batch, int dim, void* stream) {
-  if (batch < 1 || dim < 4) return set_error(-2, "mri_sinusoidal: bad shape");
+extern "C" int mri_sinusoidal(const int64_t* t, const float* freqs, float* out, int batch, int dim,
+                              void* stream) {
+  if (batch < 1 || dim < 4 || freqs == nullptr) return set_error(-2, "mri_sinusoidal: bad arguments");
   const int total = batch * dim;
-  sinusoidal_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, out, batch, dim);
+  sinusoidal_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, freqs, out, batch, dim);
   return check_launch("sinusoidal_kernel");
 }
 

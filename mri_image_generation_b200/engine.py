@@ -204,7 +204,8 @@ class UNetProgram:
         temb = torch.zeros(B, dim, device=dev)
         l1, l2 = time_mlp[1], time_mlp[3]
         self.track(l1.weight, l1.bias, l2.weight, l2.bias)
-        self._add("sinusoidal", lambda: ops.sinusoidal(t_in, sin), [sin])
+        freqs = ops.sinusoidal_freqs(dim, dev)
+        self._add("sinusoidal", lambda: ops.sinusoidal(t_in, freqs, sin), [sin])
         self._add("time_mlp.1", lambda: ops.linear(sin, l1.weight, l1.bias, h1, act=1), [h1])
         self._add("time_mlp.3", lambda: ops.linear(h1, l2.weight, l2.bias, temb), [temb])
         return temb

@@ -48,10 +48,19 @@ def gn_apply(x, y, stats, gamma, beta, samples: int, spatial: int, C: int, group
                                         _s()), "mri_gn_apply")
 
 
-def sinusoidal(t: torch.Tensor, out: torch.Tensor) -> None:
-    assert t.dtype == torch.int64 and out.dtype == torch.float32
-    _lib.check(_lib.load().mri_sinusoidal(_p(t), _p(out), out.shape[0], out.shape[1], _s()),
-               "mri_sinusoidal")
+def sinusoidal_freqs(dim: int, device) -> torch.Tensor:
+    """Frequency table of SinusoidalPosEmb, built on the host with the reference's own fp32
+    expression (slice_cond_2d_ddpm/unet.py:18-20) so that t * f is bit-identical."""
+    import math
+    half = dim // 2
+    f = math.log(10000) / (half - 1)
+    return torch.exp(torch.arange(half) * -f).to(device)
+
+
+def sinusoidal(t: torch.Tensor, freqs: torch.Tensor, out: torch.Tensor) -> None:
+    assert t.dtype == torch.int64 and out.dtype == torch.float32 and freqs.dtype == torch.float32
+    _lib.check(_lib.load().mri_sinusoidal(_p(t), _p(freqs), _p(out), out.shape[0], out.shape[1],
+                                          _s()), "mri_sinusoidal")
 
 
 def linear(x, W, bias, y, act: int = 0, addend=None) -> None:
