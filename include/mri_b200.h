@@ -181,6 +181,66 @@ int mri_minsnr_loss(const float* pred, const float* noise, const int64_t* t, con
 /* t[i] += delta for i < n (advances the device-resident timestep inside a CUDA graph) */
 int mri_add_i64(int64_t* t, int n, int64_t delta, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Backward pass (training): what autograd computes for the modules above.
+ *
+ * Data gradients of every convolution re-use mri_gemm_launch with transposed/flipped packed
+ * weights (the adjoint of a stride-2 convolution is the parity-decomposed transposed
+ * convolution and vice versa).  Weight gradients run on mri_wgrad_launch:
+ *     dW[class][co][b_k + c] += sum over output positions m of dY[m, co] * A_kb[m, c]
+ * for every k-table entry kb of the FORWARD plan (same a_maps, ktable, tiles, box).  dW is an
+ * fp32 matrix in the packed-weight layout ([n_class][dw_rows][dw_ld]), accumulated with
+ * red.global.add -- zero it first.  dy_maps: CUtensorMap[n_class], rank 5, bf16, box
+ * {64, box[0..3]}, 128B swizzle (the output-gradient tensor through the forward output view).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MriWgradArgs {
+  const void* a_maps;
+  const void* dy_maps;
+  const int32_t* ktable;  /* [n_class][n_kb][8], as in MriGemmArgs */
+  int32_t n_kb;
+  int32_t n_class;
+  int32_t tiles[4];
+  int32_t box[4];
+  int32_t n_total;        /* valid output channels (rows of dW) */
+  int32_t co_blocks;      /* ceil(n_total / 128) */
+  int32_t splits;         /* CTAs sharing one dW tile (strided split of the M tiles) */
+  int32_t group;          /* k-table entries per CTA, 1..4 */
+  float* dw;
+  int32_t dw_rows;
+  int32_t dw_ld;
+  int32_t stages;         /* 2..6 */
+  int32_t reserved;
+} MriWgradArgs;
+int mri_wgrad_launch(const MriWgradArgs* args_host, void* stream);
+
+/* GroupNorm(+SiLU) backward, y = act(gn(x)*gamma+beta):
+ * mri_gn_bwd_reduce: sums[3][samples][C] (fp32, accumulated with atomics -- zero first):
+ *   [0] = sum_s dy, [1] = sum_s du, [2] = sum_s du*xhat  (du = dy*act'(u)); x == NULL: only [0]
+ *   (plain per-(sample, channel) column sum: bias and time-embedding-projection gradients).
+ *   dgamma = sum_n sums[2], dbeta = sum_n sums[1].
+ * mri_gn_bwd_apply: dx = rstd*(gamma*du - mean_g(gamma*du) - xhat*mean_g(gamma*du*xhat)) (+ add). */
+int mri_gn_bwd_reduce(const void* x, const void* dy, const double* stats, const float* gamma,
+                      const float* beta, float* sums, int samples, int64_t spatial, int C,
+                      int groups, int stats_ld, int stats_cpg, float eps, int silu, void* stream);
+int mri_gn_bwd_apply(const void* x, const void* dy, const void* add, void* dx, const double* stats,
+                     const float* gamma, const float* beta, const float* sums, int samples,
+                     int64_t spatial, int C, int groups, int stats_ld, int stats_cpg, float eps,
+                     int silu, void* stream);
+/* out = a + b, bf16, n elements (multiple of 8) */
+int mri_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
+/* attention: dS = scale * P * (dP - rowsum(dP * P)); P, dS bf16 [rows][ld_p], dP fp32 [rows][ld_dp] */
+int mri_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int cols, int ld_p,
+                    int ld_dp, float scale, void* stream);
+/* nn.Linear backward (fp32): dX = dZ W (if dX), dW = dZ^T X and db = sum_b dZ (if dW; overwrite) */
+int mri_linear_bwd(const float* dZ, const float* X, const float* W, float* dX, float* dW, float* db,
+                   int batch, int in_f, int out_f, void* stream);
+int mri_silu(const float* z, float* y, int64_t n, void* stream);
+int mri_silu_bwd(const float* z, const float* dy, float* dz, int64_t n, void* stream);
+/* d pred of mri_minsnr_loss, scaled by the upstream gradient upstream[0] (device scalar) */
+int mri_minsnr_loss_bwd(const float* pred, const float* noise, const int64_t* t, const float* snr,
+                        float gamma, const float* upstream, float* dpred, int samples,
+                        int64_t per_sample, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

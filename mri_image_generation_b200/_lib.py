@@ -43,6 +43,27 @@ class MriGemmArgs(C.Structure):
     ]
 
 
+class MriWgradArgs(C.Structure):
+    _fields_ = [
+        ("a_maps", C.c_void_p),
+        ("dy_maps", C.c_void_p),
+        ("ktable", C.c_void_p),
+        ("n_kb", C.c_int32),
+        ("n_class", C.c_int32),
+        ("tiles", C.c_int32 * 4),
+        ("box", C.c_int32 * 4),
+        ("n_total", C.c_int32),
+        ("co_blocks", C.c_int32),
+        ("splits", C.c_int32),
+        ("group", C.c_int32),
+        ("dw", C.c_void_p),
+        ("dw_rows", C.c_int32),
+        ("dw_ld", C.c_int32),
+        ("stages", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/mri_b200.h one to one
 _vp, _i, _i64, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
 SIGNATURES = {
@@ -68,6 +89,16 @@ SIGNATURES = {
     "mri_ddim_step": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "mri_minsnr_loss": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i64, _vp]),
     "mri_add_i64": (_i, [_vp, _i, _i64, _vp]),
+    "mri_wgrad_launch": (_i, [C.POINTER(MriWgradArgs), _vp]),
+    "mri_gn_bwd_reduce": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _i, _f, _i, _vp]),
+    "mri_gn_bwd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _i, _f,
+                              _i, _vp]),
+    "mri_add_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "mri_softmax_bwd": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _f, _vp]),
+    "mri_linear_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "mri_silu": (_i, [_vp, _vp, _i64, _vp]),
+    "mri_silu_bwd": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "mri_minsnr_loss_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i64, _vp]),
 }
 
 

@@ -1,0 +1,436 @@
+// HBM-bound backward kernels: GroupNorm(+SiLU) backward (two passes), per-(sample, channel)
+// column sums (bias / time-embedding gradients), attention softmax backward, the tiny linear
+// layers' backward, the loss gradient and a bf16 accumulate.  Channels-last bf16 activations,
+// fp32 accumulation.  Reference semantics: autograd of the modules cited in include/mri_b200.h.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/mri_b200.h"
+#include "common.h"
+
+namespace mri {
+
+__device__ __forceinline__ void unpack8b(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[2 * j] = __uint_as_float(w[j] << 16);
+    f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8b(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    w[j] = *reinterpret_cast<uint32_t*>(&h2);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+struct GnCoef {
+  float mean, rstd;
+};
+__device__ __forceinline__ GnCoef gn_coef(const double* stats, int sample, int stats_ld, int g,
+                                          int comb, int cpg, int64_t spatial, float eps) {
+  const double* st = stats + ((size_t)sample * stats_ld + g * comb) * 2;
+  double s = 0.0, ss = 0.0;
+  for (int j = 0; j < comb; ++j) {
+    s += __ldg(st + 2 * j);
+    ss += __ldg(st + 2 * j + 1);
+  }
+  const double inv_cnt = 1.0 / ((double)cpg * (double)spatial);
+  const double mean = s * inv_cnt;
+  double var = ss * inv_cnt - mean * mean;
+  var = var < 0.0 ? 0.0 : var;
+  GnCoef c;
+  c.mean = (float)mean;
+  c.rstd = rsqrtf((float)var + eps);
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------
+// Pass A.  Per (sample, channel): S0 = sum dy, S1 = sum du, S2 = sum du * xhat, where
+// u = xhat*gamma+beta, du = dy * silu'(u) (or dy when !silu).  With x == nullptr only S0 is
+// produced (plain column sum).  grid (chunks, samples); thread = fixed 8-channel vector.
+// sums: fp32 [3][samples][C]
+// ---------------------------------------------------------------------------------------
+template <bool kSilu>
+__global__ void __launch_bounds__(256)
+gn_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
+                     const double* __restrict__ stats, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float* __restrict__ sums, int samples,
+                     int64_t spatial, int C, int groups, int stats_ld, int stats_cpg, float eps,
+                     int rows_per_block) {
+  extern __shared__ float red[];  // [3][C]
+  const int vec_per_row = C >> 3;
+  const int sample = blockIdx.y;
+  const int cv = threadIdx.x % vec_per_row;
+  const int rsub = threadIdx.x / vec_per_row;
+  const int rows_step = blockDim.x / vec_per_row;
+  const int c = cv * 8;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+
+  float sc[8], sh[8], mean = 0.f, rstd = 1.f;
+  if (x != nullptr) {
+    const int cpg = C / groups;
+    const GnCoef k = gn_coef(stats, sample, stats_ld, c / cpg, cpg / stats_cpg, cpg, spatial, eps);
+    mean = k.mean;
+    rstd = k.rstd;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = __ldg(gamma + c + j);
+      sh[j] = __ldg(beta + c + j);
+    }
+  }
+  float s0[8], s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s0[j] = s1[j] = s2[j] = 0.f;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > spatial) r1 = spatial;
+  const size_t base = (size_t)sample * spatial * vec_per_row + cv;
+  for (int64_t r = r0 + rsub; r < r1; r += rows_step) {
+    float d[8];
+    unpack8b(__ldg(dy + base + r * vec_per_row), d);
+    if (x == nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s0[j] += d[j];
+      continue;
+    }
+    float f[8];
+    unpack8b(__ldg(x + base + r * vec_per_row), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (f[j] - mean) * rstd;
+      float du = d[j];
+      if (kSilu) {
+        const float u = fmaf(xh, sc[j], sh[j]);
+        const float sg = 1.0f / (1.0f + __expf(-u));
+        du *= sg * (1.0f + u * (1.0f - sg));
+      }
+      s0[j] += d[j];
+      s1[j] += du;
+      s2[j] = fmaf(du, xh, s2[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&red[c + j], s0[j]);
+    if (x != nullptr) {
+      atomicAdd(&red[C + c + j], s1[j]);
+      atomicAdd(&red[2 * C + c + j], s2[j]);
+    }
+  }
+  __syncthreads();
+  const int nq = x != nullptr ? 3 : 1;
+  for (int i = threadIdx.x; i < nq * C; i += blockDim.x) {
+    const int qi = i / C, ci = i % C;
+    atomicAdd(sums + ((size_t)qi * samples + sample) * C + ci, red[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Pass B.  dx = rstd * (gamma*du - m1 - xhat*m2) (+ add), with per (sample, group)
+// m1 = mean(gamma*du), m2 = mean(gamma*du*xhat) from the pass-A sums.
+// ---------------------------------------------------------------------------------------
+template <bool kSilu>
+__global__ void __launch_bounds__(256)
+gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
+                    const uint4* __restrict__ add, uint4* __restrict__ dx,
+                    const double* __restrict__ stats, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const float* __restrict__ sums, int samples,
+                    int64_t spatial, int C, int groups, int stats_ld, int stats_cpg, float eps,
+                    int rows_per_block) {
+  const int vec_per_row = C >> 3;
+  const int sample = blockIdx.y;
+  const int cv = threadIdx.x % vec_per_row;
+  const int rsub = threadIdx.x / vec_per_row;
+  const int rows_step = blockDim.x / vec_per_row;
+  const int c = cv * 8;
+  const int cpg = C / groups;
+  const int g = c / cpg;
+  const GnCoef k = gn_coef(stats, sample, stats_ld, g, cpg / stats_cpg, cpg, spatial, eps);
+  const float* S1 = sums + ((size_t)1 * samples + sample) * C;
+  const float* S2 = sums + ((size_t)2 * samples + sample) * C;
+  float m1 = 0.f, m2 = 0.f;
+  for (int j = g * cpg; j < (g + 1) * cpg; ++j) {
+    const float gm = __ldg(gamma + j);
+    m1 = fmaf(gm, __ldg(S1 + j), m1);
+    m2 = fmaf(gm, __ldg(S2 + j), m2);
+  }
+  const float inv_cnt = 1.0f / ((float)cpg * (float)spatial);
+  m1 *= inv_cnt;
+  m2 *= inv_cnt;
+  float gmv[8], btv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    gmv[j] = __ldg(gamma + c + j);
+    btv[j] = __ldg(beta + c + j);
+  }
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > spatial) r1 = spatial;
+  const size_t base = (size_t)sample * spatial * vec_per_row + cv;
+  for (int64_t r = r0 + rsub; r < r1; r += rows_step) {
+    float f[8], d[8], o[8];
+    unpack8b(__ldg(x + base + r * vec_per_row), f);
+    unpack8b(__ldg(dy + base + r * vec_per_row), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (f[j] - k.mean) * k.rstd;
+      float du = d[j];
+      if (kSilu) {
+        const float u = fmaf(xh, gmv[j], btv[j]);
+        const float sg = 1.0f / (1.0f + __expf(-u));
+        du *= sg * (1.0f + u * (1.0f - sg));
+      }
+      o[j] = k.rstd * (gmv[j] * du - m1 - xh * m2);
+    }
+    if (add != nullptr) {
+      float a[8];
+      unpack8b(__ldg(add + base + r * vec_per_row), a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += a[j];
+    }
+    dx[base + r * vec_per_row] = pack8b(o);
+  }
+}
+
+// out = a + b (bf16, 8 per thread)
+__global__ void __launch_bounds__(256)
+add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
+                int64_t nvec) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float x[8], y[8];
+    unpack8b(__ldg(a + i), x);
+    unpack8b(__ldg(b + i), y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += y[j];
+    out[i] = pack8b(x);
+  }
+}
+
+// dS = scale * P * (dP - sum_j dP_j P_j), one warp per row (fp32 dP, bf16 P -> bf16 dS)
+template <int kPerLane>
+__global__ void __launch_bounds__(256)
+softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P, const float* __restrict__ dP,
+                   __nv_bfloat16* __restrict__ dS, int64_t rows, int cols, int ld_p, int ld_dp,
+                   float scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const __nv_bfloat16* p = P + row * ld_p;
+  const float* dp = dP + row * ld_dp;
+  __nv_bfloat16* ds = dS + row * ld_p;
+  float pv[kPerLane], dv[kPerLane];
+  float dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    const int c = lane + 32 * j;
+    pv[j] = c < cols ? __bfloat162float(p[c]) : 0.f;
+    dv[j] = c < cols ? __ldg(dp + c) : 0.f;
+    dot = fmaf(pv[j], dv[j], dot);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    const int c = lane + 32 * j;
+    if (c < ld_p) ds[c] = __float2bfloat16(c < cols ? scale * pv[j] * (dv[j] - dot) : 0.f);
+  }
+}
+
+// ---- tiny fp32 linear layers ------------------------------------------------------------
+// dX[b, i] = sum_o dZ[b, o] W[o, i]     (one thread per (b, i))
+__global__ void linear_bwd_input_kernel(const float* __restrict__ dZ, const float* __restrict__ W,
+                                        float* __restrict__ dX, int batch, int in_f, int out_f) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= batch * in_f) return;
+  const int b = idx / in_f, i = idx % in_f;
+  float acc = 0.f;
+  for (int o = 0; o < out_f; ++o) acc = fmaf(__ldg(dZ + (size_t)b * out_f + o), __ldg(W + (size_t)o * in_f + i), acc);
+  dX[idx] = acc;
+}
+// dW[o, i] = sum_b dZ[b, o] X[b, i];  db[o] = sum_b dZ[b, o]   (overwrite)
+__global__ void linear_bwd_weight_kernel(const float* __restrict__ dZ, const float* __restrict__ X,
+                                         float* __restrict__ dW, float* __restrict__ db, int batch,
+                                         int in_f, int out_f) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)out_f * in_f) return;
+  const int o = (int)(idx / in_f), i = (int)(idx % in_f);
+  float acc = 0.f, bs = 0.f;
+  for (int b = 0; b < batch; ++b) {
+    const float dz = __ldg(dZ + (size_t)b * out_f + o);
+    acc = fmaf(dz, __ldg(X + (size_t)b * in_f + i), acc);
+    bs += dz;
+  }
+  dW[idx] = acc;
+  if (i == 0 && db != nullptr) db[o] = bs;
+}
+// SiLU forward / backward on small fp32 tensors (time-embedding MLP)
+__global__ void silu_kernel(const float* __restrict__ z, float* __restrict__ y, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float v = z[i];
+    y[i] = v / (1.0f + expf(-v));
+  }
+}
+__global__ void silu_bwd_kernel(const float* __restrict__ z, const float* __restrict__ dy,
+                                float* __restrict__ dz, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float v = z[i];
+    const float sg = 1.0f / (1.0f + expf(-v));
+    dz[i] = dy[i] * sg * (1.0f + v * (1.0f - sg));
+  }
+}
+
+// d pred = upstream * 2 w_b / (B * P) * (pred - noise), w_b = min(snr, gamma)/snr (1 if gamma<=0)
+__global__ void __launch_bounds__(256)
+loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ noise,
+                const int64_t* __restrict__ t, const float* __restrict__ snr, float gamma,
+                const float* __restrict__ upstream, float* __restrict__ dpred, int samples,
+                int64_t per_sample) {
+  const int sample = blockIdx.y;
+  float w = 1.0f;
+  if (gamma > 0.f) {
+    const float s = snr[t[sample]];
+    w = fminf(s, gamma) / s;
+  }
+  const float coef = upstream[0] * 2.0f * w / ((float)samples * (float)per_sample);
+  const size_t base = (size_t)sample * per_sample;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < per_sample;
+       j += (int64_t)gridDim.x * blockDim.x)
+    dpred[base + j] = coef * (pred[base + j] - noise[base + j]);
+}
+
+static inline int rows_per_block_for(int samples, int64_t spatial, int rows_step, dim3* grid) {
+  int64_t want_blocks = (148 * 8 + samples - 1) / samples;
+  int64_t rows_per = (spatial + want_blocks - 1) / want_blocks;
+  const int64_t quantum = (int64_t)rows_step * 4;
+  rows_per = (rows_per + quantum - 1) / quantum * quantum;
+  *grid = dim3((unsigned)((spatial + rows_per - 1) / rows_per), (unsigned)samples);
+  return (int)rows_per;
+}
+
+}  // namespace mri
+
+using namespace mri;
+
+extern "C" int mri_gn_bwd_reduce(const void* x, const void* dy, const double* stats,
+                                 const float* gamma, const float* beta, float* sums, int samples,
+                                 int64_t spatial, int C, int groups, int stats_ld, int stats_cpg,
+                                 float eps, int silu, void* stream) {
+  if (C % 8 != 0 || C / 8 > 256) return set_error(-2, "mri_gn_bwd_reduce: bad C");
+  if (x != nullptr && (groups < 1 || C % groups != 0 || (C / groups) % stats_cpg != 0))
+    return set_error(-2, "mri_gn_bwd_reduce: bad group configuration");
+  const int vpr = C / 8;
+  const int threads = (256 / vpr) * vpr;
+  dim3 grid;
+  const int rpb = rows_per_block_for(samples, spatial, threads / vpr, &grid);
+  const size_t smem = 3 * C * sizeof(float);
+  const uint4* xp = reinterpret_cast<const uint4*>(x);
+  const uint4* dp = reinterpret_cast<const uint4*>(dy);
+  if (silu)
+    gn_bwd_reduce_kernel<true><<<grid, threads, smem, (cudaStream_t)stream>>>(
+        xp, dp, stats, gamma, beta, sums, samples, spatial, C, groups, stats_ld, stats_cpg, eps, rpb);
+  else
+    gn_bwd_reduce_kernel<false><<<grid, threads, smem, (cudaStream_t)stream>>>(
+        xp, dp, stats, gamma, beta, sums, samples, spatial, C, groups, stats_ld, stats_cpg, eps, rpb);
+  return check_launch("gn_bwd_reduce_kernel");
+}
+
+extern "C" int mri_gn_bwd_apply(const void* x, const void* dy, const void* add, void* dx,
+                                const double* stats, const float* gamma, const float* beta,
+                                const float* sums, int samples, int64_t spatial, int C, int groups,
+                                int stats_ld, int stats_cpg, float eps, int silu, void* stream) {
+  if (C % 8 != 0 || C / 8 > 256 || groups < 1 || C % groups != 0 || (C / groups) % stats_cpg != 0)
+    return set_error(-2, "mri_gn_bwd_apply: bad channel / group configuration");
+  const int vpr = C / 8;
+  const int threads = (256 / vpr) * vpr;
+  dim3 grid;
+  const int rpb = rows_per_block_for(samples, spatial, threads / vpr, &grid);
+  const uint4* xp = reinterpret_cast<const uint4*>(x);
+  const uint4* dp = reinterpret_cast<const uint4*>(dy);
+  const uint4* ap = reinterpret_cast<const uint4*>(add);
+  uint4* op = reinterpret_cast<uint4*>(dx);
+  if (silu)
+    gn_bwd_apply_kernel<true><<<grid, threads, 0, (cudaStream_t)stream>>>(
+        xp, dp, ap, op, stats, gamma, beta, sums, samples, spatial, C, groups, stats_ld, stats_cpg,
+        eps, rpb);
+  else
+    gn_bwd_apply_kernel<false><<<grid, threads, 0, (cudaStream_t)stream>>>(
+        xp, dp, ap, op, stats, gamma, beta, sums, samples, spatial, C, groups, stats_ld, stats_cpg,
+        eps, rpb);
+  return check_launch("gn_bwd_apply_kernel");
+}
+
+extern "C" int mri_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream) {
+  if (n % 8 != 0) return set_error(-2, "mri_add_bf16: n must be a multiple of 8");
+  const int64_t nvec = n / 8;
+  int64_t blocks = (nvec + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  add_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b),
+      reinterpret_cast<uint4*>(out), nvec);
+  return check_launch("add_bf16_kernel");
+}
+
+extern "C" int mri_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int cols,
+                               int ld_p, int ld_dp, float scale, void* stream) {
+  if (rows < 1 || cols < 1 || ld_p < cols || ld_dp < cols || ld_p > 2048)
+    return set_error(-2, "mri_softmax_bwd: bad shape");
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const __nv_bfloat16* Pp = reinterpret_cast<const __nv_bfloat16*>(P);
+  __nv_bfloat16* Sp = reinterpret_cast<__nv_bfloat16*>(dS);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int per_lane = (ld_p + 31) / 32;
+  if (per_lane <= 8) softmax_bwd_kernel<8><<<grid, 256, 0, st>>>(Pp, dP, Sp, rows, cols, ld_p, ld_dp, scale);
+  else if (per_lane <= 40) softmax_bwd_kernel<40><<<grid, 256, 0, st>>>(Pp, dP, Sp, rows, cols, ld_p, ld_dp, scale);
+  else softmax_bwd_kernel<64><<<grid, 256, 0, st>>>(Pp, dP, Sp, rows, cols, ld_p, ld_dp, scale);
+  return check_launch("softmax_bwd_kernel");
+}
+
+extern "C" int mri_linear_bwd(const float* dZ, const float* X, const float* W, float* dX, float* dW,
+                              float* db, int batch, int in_f, int out_f, void* stream) {
+  if (batch < 1 || in_f < 1 || out_f < 1) return set_error(-2, "mri_linear_bwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dX != nullptr) {
+    const int n = batch * in_f;
+    linear_bwd_input_kernel<<<(n + 127) / 128, 128, 0, st>>>(dZ, W, dX, batch, in_f, out_f);
+    int rc = check_launch("linear_bwd_input_kernel");
+    if (rc) return rc;
+  }
+  if (dW != nullptr) {
+    const int64_t n = (int64_t)out_f * in_f;
+    linear_bwd_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dZ, X, dW, db, batch, in_f,
+                                                                         out_f);
+    return check_launch("linear_bwd_weight_kernel");
+  }
+  return 0;
+}
+
+extern "C" int mri_silu(const float* z, float* y, int64_t n, void* stream) {
+  silu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(z, y, n);
+  return check_launch("silu_kernel");
+}
+extern "C" int mri_silu_bwd(const float* z, const float* dy, float* dz, int64_t n, void* stream) {
+  silu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(z, dy, dz, n);
+  return check_launch("silu_bwd_kernel");
+}
+
+extern "C" int mri_minsnr_loss_bwd(const float* pred, const float* noise, const int64_t* t,
+                                   const float* snr, float gamma, const float* upstream,
+                                   float* dpred, int samples, int64_t per_sample, void* stream) {
+  if (samples < 1 || per_sample < 1) return set_error(-2, "mri_minsnr_loss_bwd: empty input");
+  int64_t bx = (per_sample + 255) / 256;
+  int64_t cap = (148 * 8 + samples - 1) / samples;
+  if (bx > cap) bx = cap;
+  loss_bwd_kernel<<<dim3((unsigned)bx, (unsigned)samples), 256, 0, (cudaStream_t)stream>>>(
+      pred, noise, t, snr, gamma, upstream, dpred, samples, per_sample);
+  return check_launch("loss_bwd_kernel");
+}

@@ -1,0 +1,242 @@
+// Weight-gradient GEMM on tcgen05:   dW[co, kb*64 + c] += sum_m dY[m, co] * A_kb[m, c]
+//
+// It re-uses the forward plan's k-table and activation TMA maps: for every k-table entry (one
+// filter tap x 64 input channels) the matching 64-wide slab of dW is the product of the dY tile
+// transposed and the same shifted activation box the forward pass multiplied.  The reduction
+// runs over the output positions m, i.e. over the ROWS of both TMA tiles, so both operands are
+// "MN-major" UMMA operands -- exactly what the 128-byte-swizzled TMA tiles already are when
+// read along the other axis.  No transposition pass exists anywhere.
+//
+// One CTA owns (class, 128-wide co block, group of `group` k-table entries) and a strided
+// share (`splits`) of the M tiles; partial sums are added to the fp32 dW matrix with vectorised
+// reductions (red.global.add.v4.f32).  Replaces autograd's conv weight gradients for every
+// nn.Conv*/ConvTranspose* of the UNets (reference sites: include/mri_b200.h, MriGemmArgs) and,
+// with per-class maps, the dV / dK products of the attention backward.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/mri_b200.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mri {
+
+constexpr int kWgThreads = 192;
+constexpr int kWgMaxStages = 6;
+constexpr int kTileBytes = 128 * 128;  // one [128 rows x 64 ch] bf16 box
+constexpr int kWgMaxGroup = 4;
+
+// MN-major operand, 128B swizzle: 64 MN elements contiguous (128 B) per K row, 8 K rows per
+// 1024-byte atom; lbo = distance between 64-element MN blocks, sbo = distance between atoms.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes,
+                                                       uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kWgMaxStages + 1];
+  __shared__ uint32_t tmem_holder;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int S = p.stages;
+  const int G = p.group;
+  const int stage_bytes = (2 + G) * kTileBytes;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kWgMaxStages + s); };
+  const uint32_t tmem_full_bar = bar0 + 8u * (2 * kWgMaxStages);
+
+  // ---- work decode: blockIdx.x = ((cls * co_blocks + cb) * kb_groups + kg) * splits + split
+  const int kb_groups = (p.n_kb + G - 1) / G;
+  int w = blockIdx.x;
+  const int split = w % p.splits;
+  w /= p.splits;
+  const int kg = w % kb_groups;
+  w /= kb_groups;
+  const int cb = w % p.co_blocks;
+  const int cls = w / p.co_blocks;
+  const int kb0 = kg * G;
+  const int gact = (p.n_kb - kb0) < G ? (p.n_kb - kb0) : G;
+  const int co0 = cb * 128;
+  const int rows_in_box = p.box[0] * p.box[1] * p.box[2] * p.box[3];
+  const int total_mt = p.tiles[0] * p.tiles[1] * p.tiles[2] * p.tiles[3];
+  const int my_tiles = split < total_mt ? (total_mt - split + p.splits - 1) / p.splits : 0;
+
+  uint32_t tmem_cols = 64;
+  while ((int)tmem_cols < 64 * G) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_holder), tmem_cols);
+    tmem_relinquish();
+  }
+  // rows beyond the box are never written by TMA: they must read as zero (they are summed)
+  if (rows_in_box < 128) {
+    const int tiles_total = S * (2 + G);
+    const int tail_bytes = (128 - rows_in_box) * 128;
+    for (int t = 0; t < tiles_total; ++t) {
+      const uint32_t base = smem_base + t * kTileBytes + rows_in_box * 128;
+      for (int o = threadIdx.x * 16; o < tail_bytes; o += kWgThreads * 16)
+        asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(base + o), "r"(0u) : "memory");
+    }
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_holder;
+
+  const CUtensorMap* a_maps = reinterpret_cast<const CUtensorMap*>(p.a_maps);
+  const CUtensorMap* dy_map = reinterpret_cast<const CUtensorMap*>(p.dy_maps) + cls;
+
+  if (warp == 0) {
+    if (lane == 0 && my_tiles > 0) {
+      // k-table entries of this group (registers)
+      int4 e0[kWgMaxGroup], e1[kWgMaxGroup];
+      const int4* kt = reinterpret_cast<const int4*>(p.ktable) + ((size_t)cls * p.n_kb + kb0) * 2;
+#pragma unroll
+      for (int g = 0; g < kWgMaxGroup; ++g) {
+        if (g < gact) {
+          e0[g] = __ldg(kt + 2 * g);
+          e1[g] = __ldg(kt + 2 * g + 1);
+        }
+      }
+      const uint32_t tx = (uint32_t)rows_in_box * 128u * (2u + (uint32_t)gact);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        int mt = split + it * p.splits;
+        int org[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          org[i] = (mt % p.tiles[i]) * p.box[i];
+          mt /= p.tiles[i];
+        }
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t base = smem_base + stage * stage_bytes;
+        mbar_arrive_expect_tx(full_bar(stage), tx);
+        tma_load_5d(base, dy_map, full_bar(stage), co0, org[0], org[1], org[2], org[3]);
+        tma_load_5d(base + kTileBytes, dy_map, full_bar(stage), co0 + 64, org[0], org[1], org[2],
+                    org[3]);
+#pragma unroll
+        for (int g = 0; g < kWgMaxGroup; ++g) {
+          if (g < gact)
+            tma_load_5d(base + (2 + g) * kTileBytes, a_maps + e0[g].x, full_bar(stage), e0[g].y,
+                        org[0] + e0[g].z, org[1] + e0[g].w, org[2] + e1[g].x, org[3] + e1[g].y);
+        }
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && my_tiles > 0) {
+      // D = f32, A = B = bf16, both MN-major (bits 15, 16), M = 128, N = 64
+      const uint32_t idesc = umma_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t base = smem_base + stage * stage_bytes;
+        for (int g = 0; g < gact; ++g) {
+          const uint32_t b_addr = base + (2 + g) * kTileBytes;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {  // 16 rows (K) per MMA = 2 swizzle atoms = 2048 B
+            const uint64_t a_desc = umma_desc_mn_sw128(base + ks * 2048, kTileBytes, 1024);
+            const uint64_t b_desc = umma_desc_mn_sw128(b_addr + ks * 2048, kTileBytes, 1024);
+            umma_bf16(tmem_base + (uint32_t)(g * 64), a_desc, b_desc, idesc,
+                      (it | ks) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else if (my_tiles > 0) {
+    // ---- epilogue: TMEM (lane = co row) -> fp32 reductions into dW ----
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int4* kt = reinterpret_cast<const int4*>(p.ktable) + ((size_t)cls * p.n_kb + kb0) * 2;
+    float* dw_row = p.dw + ((size_t)cls * p.dw_rows + co) * p.dw_ld;
+    for (int g = 0; g < gact; ++g) {
+      const int bk = __ldg(kt + 2 * g + 1).z;
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64 + c0), v);
+        tmem_ld_wait();
+        if (co < p.n_total) {
+          float* dst = dw_row + bk + c0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 4 * u),
+                         "f"(__uint_as_float(v[4 * u])), "f"(__uint_as_float(v[4 * u + 1])),
+                         "f"(__uint_as_float(v[4 * u + 2])), "f"(__uint_as_float(v[4 * u + 3]))
+                         : "memory");
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace mri
+
+using namespace mri;
+
+extern "C" int mri_wgrad_launch(const MriWgradArgs* a, void* stream) {
+  if (a == nullptr) return set_error(-1, "mri_wgrad_launch: null args");
+  if (a->group < 1 || a->group > kWgMaxGroup) return set_error(-2, "mri_wgrad_launch: group must be 1..4");
+  if (a->stages < 2 || a->stages > kWgMaxStages) return set_error(-2, "mri_wgrad_launch: stages must be 2..6");
+  if (a->n_kb < 1 || a->n_class < 1 || a->splits < 1 || a->co_blocks < 1)
+    return set_error(-2, "mri_wgrad_launch: empty problem");
+  long rows = 1;
+  for (int i = 0; i < 4; ++i) {
+    if (a->box[i] < 1 || a->tiles[i] < 1) return set_error(-2, "mri_wgrad_launch: bad box/tiles");
+    rows *= a->box[i];
+  }
+  if (rows > 128) return set_error(-2, "mri_wgrad_launch: box has more than 128 rows");
+  if (a->dw_ld % 4 != 0) return set_error(-2, "mri_wgrad_launch: dw_ld must be a multiple of 4");
+  const int smem = a->stages * (2 + a->group) * kTileBytes + 1024;
+  if (smem > 227 * 1024) return set_error(-2, "mri_wgrad_launch: shared memory over 227 KB");
+  static int configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm_wgrad_kernel)");
+    configured = smem;
+  }
+  const int kb_groups = (a->n_kb + a->group - 1) / a->group;
+  const long grid = (long)a->n_class * a->co_blocks * kb_groups * a->splits;
+  gemm_wgrad_kernel<<<(unsigned)grid, kWgThreads, smem, (cudaStream_t)stream>>>(*a);
+  return check_launch("gemm_wgrad_kernel");
+}

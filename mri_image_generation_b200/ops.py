@@ -129,3 +129,61 @@ def minsnr_loss(pred, noise, t, snr, gamma: float, per_sample_out, loss_out) -> 
 
 def add_i64(t: torch.Tensor, delta: int) -> None:
     _lib.check(_lib.load().mri_add_i64(_p(t), t.numel(), delta, _s()), "mri_add_i64")
+
+
+# ------------------------------------------------------------------------------ backward
+def gn_bwd_reduce(x, dy, stats, gamma, beta, sums, samples, spatial, C, groups, stats_cpg, eps,
+                  silu: bool) -> None:
+    _chk_contig(x, dy, sums)
+    _lib.check(_lib.load().mri_gn_bwd_reduce(_p(x), _p(dy), _p(stats), _p(gamma), _p(beta), _p(sums),
+                                             samples, spatial, C, groups,
+                                             stats.shape[1] if stats is not None else 0, stats_cpg,
+                                             eps, 1 if silu else 0, _s()), "mri_gn_bwd_reduce")
+
+
+def colsum(dy, sums, samples, spatial, C) -> None:
+    """sums[0][n][c] += sum_s dy[n, s, c]"""
+    _chk_contig(dy, sums)
+    _lib.check(_lib.load().mri_gn_bwd_reduce(None, _p(dy), None, None, None, _p(sums), samples,
+                                             spatial, C, 1, 0, 8, 0.0, 0, _s()), "mri_gn_bwd_reduce")
+
+
+def gn_bwd_apply(x, dy, add, dx, stats, gamma, beta, sums, samples, spatial, C, groups, stats_cpg,
+                 eps, silu: bool) -> None:
+    _chk_contig(x, dy, add, dx, sums)
+    _lib.check(_lib.load().mri_gn_bwd_apply(_p(x), _p(dy), _p(add), _p(dx), _p(stats), _p(gamma),
+                                            _p(beta), _p(sums), samples, spatial, C, groups,
+                                            stats.shape[1], stats_cpg, eps, 1 if silu else 0, _s()),
+               "mri_gn_bwd_apply")
+
+
+def add_bf16(a, b, out) -> None:
+    _chk_contig(a, b, out)
+    _lib.check(_lib.load().mri_add_bf16(_p(a), _p(b), _p(out), a.numel(), _s()), "mri_add_bf16")
+
+
+def softmax_bwd(P, dP, dS, rows, cols, ld_p, ld_dp, scale) -> None:
+    _lib.check(_lib.load().mri_softmax_bwd(_p(P), _p(dP), _p(dS), rows, cols, ld_p, ld_dp, scale,
+                                           _s()), "mri_softmax_bwd")
+
+
+def linear_bwd(dZ, X, W, dX=None, dW=None, db=None) -> None:
+    _chk_contig(dZ, X, W, dX, dW, db)
+    _lib.check(_lib.load().mri_linear_bwd(_p(dZ), _p(X), _p(W), _p(dX), _p(dW), _p(db), dZ.shape[0],
+                                          W.shape[1], W.shape[0], _s()), "mri_linear_bwd")
+
+
+def silu(z, y) -> None:
+    _lib.check(_lib.load().mri_silu(_p(z), _p(y), z.numel(), _s()), "mri_silu")
+
+
+def silu_bwd(z, dy, dz) -> None:
+    _lib.check(_lib.load().mri_silu_bwd(_p(z), _p(dy), _p(dz), z.numel(), _s()), "mri_silu_bwd")
+
+
+def minsnr_loss_bwd(pred, noise, t, snr, gamma, upstream, dpred) -> None:
+    _chk_contig(pred, noise, dpred)
+    n = pred.shape[0]
+    _lib.check(_lib.load().mri_minsnr_loss_bwd(_p(pred), _p(noise), _p(t), _p(snr), gamma,
+                                               _p(upstream), _p(dpred), n, pred.numel() // n, _s()),
+               "mri_minsnr_loss_bwd")

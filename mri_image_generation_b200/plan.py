@@ -460,7 +460,8 @@ def _rup8(n: int) -> int:
 
 
 def down_conv_plan(x: torch.Tensor, wmat: torch.Tensor, y: torch.Tensor, *, bias=None, stats=None,
-                   stats_cpg=0, block_n=None, stages=0, name="") -> GemmPlan:
+                   stats_cpg=0, block_n=None, stages=0, name="",
+                   residual: Optional[torch.Tensor] = None) -> GemmPlan:
     """Conv k=4, stride 2, pad 1 (slice_cond_2d_ddpm/unet.py:70, unet_attention.py:123): input
     index 2*o - 1 + k = 2*(o + a) + par with (par, a) = (1,-1), (0,0), (1,0), (0,1) for k = 0..3,
     i.e. tap k reads the parity-`par` sub-lattice shifted by a."""
@@ -488,8 +489,12 @@ def down_conv_plan(x: torch.Tensor, wmat: torch.Tensor, y: torch.Tensor, *, bias
     chunk = _out_chunk(bn, False)
     omap = MapSpec(_act_view(y, ndim), (chunk,) + box, _out_swizzle(chunk * 2))
     tiles = tuple(-(-e // b) for e, b in zip(ext, box))
+    rmaps = None
+    if residual is not None:
+        assert residual.shape == y.shape
+        rmaps = [MapSpec(_act_view(residual, ndim), (chunk,) + box, _out_swizzle(chunk * 2))]
     return GemmPlan(a_maps=a_maps, b_map=MapSpec(bview, (BLOCK_K, bn, 1, 1), 3), o_maps=[omap],
-                    ktable=kt, tiles=tiles, box=box, ext=ext, block_n=bn, n_total=cout_pad,
+                    r_maps=rmaps, ktable=kt, tiles=tiles, box=box, ext=ext, block_n=bn, n_total=cout_pad,
                     sample_dim=sample_dim, bias=bias, stats=stats,
                     stats_ld=(stats.shape[1] if stats is not None else 0), stats_cpg=stats_cpg,
                     stages=stages, name=name, flops=2 * int(np.prod(ext)) * cout_pad * bk)
@@ -500,7 +505,8 @@ _CT_TAPS = {0: [(1, 0), (3, -1)], 1: [(0, 1), (2, 0)]}
 
 
 def up_conv_plan(x: torch.Tensor, wmat: torch.Tensor, y: torch.Tensor, *, bias=None, stats=None,
-                 stats_cpg=0, block_n=None, stages=0, name="") -> GemmPlan:
+                 stats_cpg=0, block_n=None, stages=0, name="",
+                 residual: Optional[torch.Tensor] = None) -> GemmPlan:
     """ConvTranspose k=4, stride 2, pad 1 (slice_cond_2d_ddpm/unet.py:89, unet_attention.py:142)
     as 2^d output-parity classes, each a 2^d-tap stride-1 convolution of the input written to
     the parity sub-lattice of the output.  wmat: [n_class, Cout_pad, 2^d * Cin]."""
@@ -533,8 +539,13 @@ def up_conv_plan(x: torch.Tensor, wmat: torch.Tensor, y: torch.Tensor, *, bias=N
     o_maps = [MapSpec(_parity_view(y, ndim, rho), (chunk,) + box, _out_swizzle(chunk * 2))
               for rho in classes]
     tiles = tuple(-(-e // b) for e, b in zip(in_ext, box))
+    rmaps = None
+    if residual is not None:
+        assert residual.shape == y.shape
+        rmaps = [MapSpec(_parity_view(residual, ndim, rho), (chunk,) + box, _out_swizzle(chunk * 2))
+                 for rho in classes]
     return GemmPlan(a_maps=a_maps, b_map=MapSpec(bview, (BLOCK_K, bn, 1, 1), 3), o_maps=o_maps,
-                    ktable=kt, tiles=tiles, box=box, ext=in_ext, block_n=bn, n_total=cout_pad,
+                    r_maps=rmaps, ktable=kt, tiles=tiles, box=box, ext=in_ext, block_n=bn, n_total=cout_pad,
                     bz_sel=(1, 0), sample_dim=sample_dim, bias=bias, stats=stats,
                     stats_ld=(stats.shape[1] if stats is not None else 0), stats_cpg=stats_cpg,
                     stages=stages, name=name, flops=2 * int(np.prod(in_ext)) * cout_pad * K * ncls)
@@ -561,6 +572,88 @@ def matrix_plan(a: TView, a_box_rows: Tuple[int, int, int, int], b: TView, o: TV
                     out_f32=out_f32, bias=bias, bias_m=bias_m, stats=stats,
                     stats_ld=(stats.shape[1] if stats is not None else 0), stats_cpg=stats_cpg,
                     stages=stages, name=name, flops=flops)
+
+
+@dataclass
+class WgradPlan:
+    """dW[class][co][b_k + c] += sum_m dY[m, co] * A_kb[m, c] over the forward plan's k-table
+    (MriWgradArgs).  `dy` is the gradient of the forward output tensor(s) `fwd.o_maps` view."""
+    fwd: GemmPlan
+    dy: torch.Tensor            # same shape/layout as the forward output base tensor
+    dw: torch.Tensor            # fp32 [n_class, rows, K]
+    n_total: int
+    group: int = 2
+    stages: int = 3
+    splits: int = 0
+    name: str = ""
+    _args: Optional[_lib.MriWgradArgs] = field(default=None, repr=False)
+    _keep: list = field(default_factory=list, repr=False)
+
+    def dy_specs(self) -> List[MapSpec]:
+        out = []
+        for om in self.fwd.o_maps:
+            v = om.view
+            assert v.base.shape == self.dy.shape and v.base.dtype == torch.bfloat16
+            out.append(MapSpec(TView(self.dy, v.dims, v.strides, v.offset),
+                               (BLOCK_K,) + tuple(self.fwd.box), 3))
+        return out
+
+    def pick_splits(self) -> int:
+        if self.splits:
+            return self.splits
+        f = self.fwd
+        co_blocks = -(-self.n_total // 128)
+        base = f.n_class * co_blocks * (-(-f.n_kb // self.group))
+        total_mt = int(np.prod(f.tiles))
+        return max(1, min(total_mt, -(-2 * 148 // base)))
+
+    def materialize(self, device) -> None:
+        f = self.fwd
+        maps = list(f.a_maps) + self.dy_specs()
+        blob = encode_maps(maps, device)
+        kt = torch.from_numpy(np.ascontiguousarray(f.ktable, dtype=np.int32)).to(device)
+        self._keep = [blob, kt]
+        a = _lib.MriWgradArgs()
+        a.a_maps = blob.data_ptr()
+        a.dy_maps = blob.data_ptr() + 128 * len(f.a_maps)
+        a.ktable = kt.data_ptr()
+        a.n_kb, a.n_class = f.n_kb, f.n_class
+        for i in range(4):
+            a.tiles[i], a.box[i] = f.tiles[i], f.box[i]
+        a.n_total = self.n_total
+        a.co_blocks = -(-self.n_total // 128)
+        a.splits = self.pick_splits()
+        a.group = self.group
+        assert self.dw.dtype == torch.float32 and self.dw.is_contiguous() and self.dw.dim() == 3
+        assert self.dw.shape[0] == f.n_class and self.dw.shape[1] >= self.n_total
+        a.dw = self.dw.data_ptr()
+        a.dw_rows, a.dw_ld = self.dw.shape[1], self.dw.shape[2]
+        a.stages = self.stages
+        self._args = a
+
+    def launch(self, stream: Optional[int] = None) -> None:
+        rc = _lib.load().mri_wgrad_launch(C.byref(self._args),
+                                          stream if stream is not None else _lib.current_stream_ptr())
+        _lib.check(rc, f"mri_wgrad_launch[{self.name}]")
+
+    def simulate(self) -> None:
+        """CPU emulation (tests): same tables, TMA zero fill."""
+        f = self.fwd
+        rows = int(np.prod(f.box))
+        dys = self.dy_specs()
+        for cls in range(f.n_class):
+            for tix in itertools.product(*[range(t) for t in reversed(f.tiles)]):
+                tix = tuple(reversed(tix))
+                org = [tix[i] * f.box[i] for i in range(4)]
+                dyt = _load_box(dys[cls].view, [0] + org,
+                                (dys[cls].view.dims[0],) + tuple(f.box)).reshape(rows, -1)
+                for kb in range(f.n_kb):
+                    e = f.ktable[cls, kb]
+                    am = f.a_maps[int(e[0])]
+                    coords = [int(e[1])] + [org[i] + int(e[2 + i]) for i in range(4)]
+                    a = _load_box(am.view, coords, am.box).reshape(rows, BLOCK_K)
+                    bk = int(e[6])
+                    self.dw[cls, :self.n_total, bk:bk + BLOCK_K] += (dyt.t() @ a)[:self.n_total]
 
 
 # ======================================================================================
@@ -607,3 +700,40 @@ def pack_convT_weight(w: torch.Tensor, cout_pad: int = 0) -> torch.Tensor:
             out[ci, :cout, col:col + cin] = sl.t().to(torch.bfloat16)
             col += cin
     return out.contiguous()
+
+
+def unpack_conv_wgrad(dw: torch.Tensor, w_shape, splits: Optional[Sequence[int]] = None,
+                      extra_shapes: Sequence = ()) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+    """Inverse of pack_conv_weight for an fp32 gradient matrix [Cout_pad, K]: returns the gradient
+    in the nn.ConvNd layout [Cout, Cin, *k] and the gradients of the folded 1x1 weights."""
+    cout, cin = w_shape[0], w_shape[1]
+    taps = int(np.prod(w_shape[2:]))
+    splits = list(splits) if splits else [cin]
+    parts, col = [], 0
+    for ci in splits:
+        blk = dw[:cout, col:col + taps * ci].reshape(cout, taps, ci).permute(0, 2, 1)
+        parts.append(blk)
+        col += taps * ci
+    g = torch.cat(parts, dim=1).reshape(w_shape)
+    extras = []
+    for shp in extra_shapes:
+        n = int(np.prod(shp[1:]))
+        extras.append(dw[:cout, col:col + n].reshape(shp))
+        col += n
+    return g, extras
+
+
+def unpack_convT_wgrad(dw: torch.Tensor, w_shape) -> torch.Tensor:
+    """Inverse of pack_convT_weight: dw [2^d, Cout_pad, 2^d * Cin] -> [Cin, Cout, 4, 4(, 4)]."""
+    cin, cout = w_shape[0], w_shape[1]
+    ndim = len(w_shape) - 2
+    g = torch.zeros(w_shape, dtype=dw.dtype, device=dw.device)
+    classes = list(itertools.product((0, 1), repeat=ndim))
+    for ci, rho in enumerate(classes):
+        col = 0
+        for combo in itertools.product((0, 1), repeat=ndim):
+            ks = [_CT_TAPS[rho[i]][combo[i]][0] for i in range(ndim)]
+            idx = tuple(reversed(ks))
+            g[(slice(None), slice(None)) + idx] = dw[ci, :cout, col:col + cin].t()
+            col += cin
+    return g

@@ -140,3 +140,91 @@ def test_matrix_fp32_out(P):
     k = qk[:, :, C:].float().reshape(B, n, heads, d).permute(0, 2, 1, 3)
     ref = q @ k.transpose(-1, -2)
     assert rel(S[..., :n], ref) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+# backward: weight gradients (MN-major tcgen05 GEMM) and data gradients (fprop kernel on the
+# adjoint plan) vs torch autograd on the same bf16-rounded operands
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nd,sp,N", [(3, (8, 12, 10), 2), (2, (30, 30), 3), (3, (10, 12, 10), 1)])
+def test_wgrad_and_dgrad_stride1_concat_skipfold(P, nd, sp, N):
+    torch.manual_seed(5)
+    dev = "cuda"
+    C1, C2, Co = 64, 128, 128
+    conv = conv_fn(nd)
+    a1, a2 = nhwc(torch.randn(N, C1, *sp, device=dev)), nhwc(torch.randn(N, C2, *sp, device=dev))
+    w = (torch.randn(Co, C1 + C2, *([3] * nd), device=dev) * 0.05).requires_grad_()
+    ws = (torch.randn(Co, C1, *([1] * nd), device=dev) * 0.1).requires_grad_()
+    x1, x2 = nchw(a1).requires_grad_(), nchw(a2).requires_grad_()
+    out = conv(torch.cat([x1, x2], 1), w, None, padding=1) + conv(x1, ws)
+    dy = nhwc(torch.randn(N, Co, *sp, device=dev))
+    out.backward(nchw(dy))
+    wm = P.pack_conv_weight(w.detach(), splits=[C1, C2], extra=[ws.detach()])
+    y = torch.zeros(N, *sp, Co, dtype=torch.bfloat16, device=dev)
+    fwd = P.conv_plan([P.ConvSource(a1), P.ConvSource(a2), P.ConvSource(a1, taps=False)], wm, y, 3)
+    dw = torch.zeros(1, Co, wm.shape[1], device=dev)
+    wg = P.WgradPlan(fwd, dy, dw, Co)
+    wg.materialize(dev)
+    wg.launch()
+    torch.cuda.synchronize()
+    g, ex = P.unpack_conv_wgrad(dw[0], w.shape, [C1, C2], [ws.shape])
+    assert rel(g, w.grad) < 1e-4
+    assert rel(ex[0], ws.grad) < 1e-4
+    # data gradient of source 2 through the adjoint plan (flipped, transposed weights)
+    wT = w.detach()[:, C1:].transpose(0, 1).flip(*range(2, 2 + nd)).to(torch.bfloat16).float()
+    gx = torch.zeros(N, *sp, C2, dtype=torch.bfloat16, device=dev)
+    pl = P.conv_plan([P.ConvSource(dy)], P.pack_conv_weight(wT), gx, 3)
+    pl.materialize(dev)
+    pl.launch()
+    torch.cuda.synchronize()
+    ref = conv(nchw(dy), wT, None, padding=1)
+    assert rel(nchw(gx), ref) < TOL
+
+
+@pytest.mark.parametrize("nd,sp,N", [(3, (8, 12, 8), 2), (2, (32, 48), 2)])
+def test_wgrad_and_dgrad_strided(P, nd, sp, N):
+    torch.manual_seed(6)
+    dev = "cuda"
+    C, Cd = 128, 256
+    conv = conv_fn(nd)
+    convT = F.conv_transpose3d if nd == 3 else F.conv_transpose2d
+    a = nhwc(torch.randn(N, C, *sp, device=dev))
+    # ---- down conv
+    wd = (torch.randn(Cd, C, *([4] * nd), device=dev) * 0.05).to(torch.bfloat16).float().requires_grad_()
+    xd = nchw(a).requires_grad_()
+    od = conv(xd, wd, None, stride=2, padding=1)
+    dyd = nhwc(torch.randn(*od.shape, device=dev))
+    od.backward(nchw(dyd))
+    yd = torch.zeros(N, *[s // 2 for s in sp], Cd, dtype=torch.bfloat16, device=dev)
+    fwd = P.down_conv_plan(a, P.pack_conv_weight(wd.detach()), yd)
+    dw = torch.zeros(1, Cd, fwd.n_kb * 64, device=dev)
+    wg = P.WgradPlan(fwd, dyd, dw, Cd)
+    wg.materialize(dev)
+    wg.launch()
+    gx = torch.zeros(N, *sp, C, dtype=torch.bfloat16, device=dev)
+    pl = P.up_conv_plan(dyd, P.pack_convT_weight(wd.detach()), gx)
+    pl.materialize(dev)
+    pl.launch()
+    torch.cuda.synchronize()
+    assert rel(P.unpack_conv_wgrad(dw[0], wd.shape)[0], wd.grad) < 1e-4
+    assert rel(nchw(gx), xd.grad) < TOL
+    # ---- up conv
+    wu = (torch.randn(C, Cd, *([4] * nd), device=dev) * 0.05).to(torch.bfloat16).float().requires_grad_()
+    xu = nchw(a).requires_grad_()
+    ou = convT(xu, wu, None, stride=2, padding=1)
+    dyu = nhwc(torch.randn(*ou.shape, device=dev))
+    ou.backward(nchw(dyu))
+    yu = torch.zeros(N, *[s * 2 for s in sp], Cd, dtype=torch.bfloat16, device=dev)
+    fwd = P.up_conv_plan(a, P.pack_convT_weight(wu.detach()), yu)
+    dw = torch.zeros(fwd.n_class, Cd, fwd.n_kb * 64, device=dev)
+    wg = P.WgradPlan(fwd, dyu, dw, Cd)
+    wg.materialize(dev)
+    wg.launch()
+    gx = torch.zeros(N, *sp, C, dtype=torch.bfloat16, device=dev)
+    res = nhwc(torch.randn(N, C, *sp, device=dev))
+    pl = P.down_conv_plan(dyu, P.pack_conv_weight(wu.detach()), gx, residual=res)
+    pl.materialize(dev)
+    pl.launch()
+    torch.cuda.synchronize()
+    assert rel(P.unpack_convT_wgrad(dw, wu.shape), wu.grad) < 1e-4
+    assert rel(nchw(gx), xu.grad + nchw(res)) < TOL
