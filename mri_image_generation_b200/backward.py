@@ -1,0 +1,449 @@
+"""Backward program of the UNet engines (training).
+
+The forward builder (engine.py) records one tape entry per op; `build_backward()` walks the tape
+in reverse and emits the launch list that computes what autograd computes for the reference
+modules: data gradients on the forward tensor-core kernel through adjoint plans (flipped /
+transposed packed weights; stride-2 <-> parity-decomposed transposed convolution), weight
+gradients on the MN-major tcgen05 kernel (mri_wgrad_launch) over the forward k-tables,
+GroupNorm(+SiLU) backward as two bf16 passes, the attention backward as GEMMs + a fused
+softmax-backward, and the tiny fp32 linears of the time embedding.
+
+Gradient buffers are bf16 channels-last like the activations; parameter gradients are fp32 in
+the reference parameter layout (what `.grad` must hold).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from . import plan as P
+
+
+@dataclass
+class ConvRec:
+    kind: str                      # 'conv' | 'down' | 'up' | 'matrix'
+    plan: P.GemmPlan
+    y: torch.Tensor                # forward output tensor (channels-last bf16)
+    ksize: int
+    sources: List[Tuple[torch.Tensor, bool]]    # (tensor, has_taps)
+    weight: Optional[torch.Tensor]              # nn.Parameter in the reference layout
+    splits: List[int]
+    extra_weight: Optional[torch.Tensor] = None  # folded 1x1 skip weight [Cout, sum(centre srcs)]
+    bias_params: List[torch.Tensor] = field(default_factory=list)
+    residual: Optional[torch.Tensor] = None
+    tproj_off: Optional[int] = None
+    cout: int = 0
+    need_dgrad: bool = True
+    w_rows: Optional[Tuple[int, int]] = None     # use only weight rows [a, b) (qkv slices)
+    kpad: int = 0                                # 'matrix': padded K of the im2col'd weight
+    dgrad_dy: Optional[torch.Tensor] = None      # 64-channel copy of dY when Cout is thin (out_conv)
+    name: str = ""
+
+
+@dataclass
+class GnRec:
+    x: object                      # engine.Act (tensor + statistics)
+    y: torch.Tensor
+    gamma: torch.Tensor            # parameter
+    beta: torch.Tensor
+    c_off: int
+    groups: int
+    eps: float
+    silu: bool
+    tproj_off: Optional[int] = None
+    residual: Optional[torch.Tensor] = None
+    name: str = ""
+
+
+@dataclass
+class AttnRec:
+    x: object
+    hn: torch.Tensor
+    qkv: torch.Tensor
+    kvT: torch.Tensor
+    Pm: torch.Tensor
+    O: torch.Tensor
+    out: torch.Tensor
+    blk: object
+    qkv_plan: P.GemmPlan
+    proj_plan: P.GemmPlan
+    heads: int
+    n: int
+    npad: int
+    name: str = ""
+
+
+@dataclass
+class TimeRec:
+    """time_mlp (+ slice_mlp) + concatenated per-block projections."""
+    sin: torch.Tensor
+    z1: torch.Tensor
+    h1: torch.Tensor
+    temb: torch.Tensor
+    l1: object
+    l2: object
+    cond: torch.Tensor             # input of the block projections (temb, or temb + z_emb in 2D)
+    W_all: torch.Tensor
+    zproj: torch.Tensor            # pre-activation of the projections
+    act: int
+    blocks: Sequence
+    offs: List[int]
+    slice: Optional[dict] = None   # 2D: {"z_in", "zz", "zh", "s0", "s2"}
+
+
+class BackwardMixin:
+    """Mixed into engine.UNetProgram."""
+
+    # ------------------------------------------------------------------ bookkeeping
+    def _binit(self):
+        self.tape: List[object] = []
+        self.grads: Dict[int, torch.Tensor] = {}
+        self.pgrad: Dict[int, torch.Tensor] = {}
+        self.bwd_ops: List[Callable[[], None]] = []
+        self.bwd_names: List[str] = []
+        self._zero_each_bwd: List[torch.Tensor] = []
+        self.dtproj: Optional[torch.Tensor] = None
+        self.bwd_flops = 0
+
+    def badd(self, name: str, fn: Callable[[], None]) -> None:
+        self.bwd_names.append(name)
+        self.bwd_ops.append(fn)
+
+    def bgemm(self, pl, name=None) -> None:
+        pl.materialize(self.device)
+        self.bwd_flops += pl.flops
+        self.badd(f"gemm:{name or pl.name}", pl.launch)
+
+    def zeros_each_bwd(self, *shape, dtype=torch.float32) -> torch.Tensor:
+        t = torch.zeros(*shape, dtype=dtype, device=self.device)
+        self._zero_each_bwd.append(t)
+        return t
+
+    def pg(self, p: torch.Tensor) -> torch.Tensor:
+        g = self.pgrad.get(id(p))
+        if g is None:
+            g = torch.zeros(p.shape, dtype=torch.float32, device=self.device)
+            self.pgrad[id(p)] = g
+        return g
+
+    def emit_grad(self, t: torch.Tensor, produce: Callable[[torch.Tensor, Optional[torch.Tensor]], None]):
+        """grad[t] (+)= contribution; produce(out, add) must emit ops writing contribution + add."""
+        g = self.grads.get(id(t))
+        if g is None:
+            g = torch.zeros(tuple(t.shape), dtype=torch.bfloat16, device=self.device)
+            self.grads[id(t)] = g
+            produce(g, None)
+        else:
+            produce(g, g)
+
+    def pass_grad(self, t: torch.Tensor, dy: torch.Tensor) -> None:
+        """grad[t] += dy for an identity edge (residual); aliases dy when it is the first."""
+        g = self.grads.get(id(t))
+        if g is None:
+            self.grads[id(t)] = dy
+        else:
+            self.badd("add", lambda: ops.add_bf16(g, dy, g))
+
+    # ------------------------------------------------------------------ per-op backward
+    def _bwd_bias_and_tproj(self, dy: torch.Tensor, C: int, bias_params, tproj_off, name):
+        if not bias_params and tproj_off is None:
+            return
+        B = self.B
+        S = dy.numel() // (B * C)
+        cs = self.zeros_each_bwd(1, B, C)
+        self.badd(f"colsum:{name}", lambda: ops.colsum(dy, cs, B, S, C))
+        for bp in bias_params:
+            g = self.pg(bp)
+            n = bp.numel()
+            self.badd("bias_grad", lambda g=g, n=n: g.copy_(cs[0].sum(0)[:n]))
+        if tproj_off is not None:
+            dst = self.dtproj[:, tproj_off:tproj_off + C]
+            self.badd("dtproj", lambda: dst.copy_(cs[0]))
+
+    def bwd_conv(self, r: ConvRec) -> None:
+        dy = self.grads.get(id(r.y))
+        if dy is None:
+            raise _lib.MriError(f"backward: no gradient reached {r.name}")
+        nd = self.ndim
+        C = r.y.shape[-1]
+        if r.residual is not None:
+            self.pass_grad(r.residual, dy)
+        self._bwd_bias_and_tproj(dy, C, r.bias_params, r.tproj_off, r.name)
+        # ---- weight gradient over the forward k-table ------------------------------------
+        if r.weight is not None:
+            pl = r.plan
+            K = pl.n_kb * P.BLOCK_K
+            dw = self.zeros_each_bwd(pl.n_class, max(r.cout, 8), K)
+            wg = P.WgradPlan(pl, dy, dw, r.cout, name=r.name)
+            wg.materialize(self.device)
+            self.bwd_flops += pl.flops
+            self.badd(f"wgrad:{r.name}", wg.launch)
+            gw = self.pg(r.weight)
+            if r.kind == "up":
+                self.badd("unpack", lambda: gw.copy_(P.unpack_convT_wgrad(dw, tuple(r.weight.shape))))
+            else:
+                taps_splits = r.splits
+                extra_shapes = []
+                if r.extra_weight is not None:
+                    cin_e = r.extra_weight.shape[1]
+                    c0 = 0
+                    for (t, has_taps) in r.sources:
+                        if not has_taps:
+                            extra_shapes.append((r.cout, t.shape[-1]))
+                    assert sum(s[1] for s in extra_shapes) == cin_e
+                ge = self.pg(r.extra_weight) if r.extra_weight is not None else None
+                wshape = tuple(r.weight.shape)
+                rows = r.w_rows
+
+                def unpack():
+                    shp = wshape if rows is None else (rows[1] - rows[0],) + wshape[1:]
+                    if r.kind == "matrix":
+                        g, _ = P.unpack_conv_wgrad(dw[0][:, :int(np.prod(shp[1:]))], shp)
+                        ex = []
+                    else:
+                        g, ex = P.unpack_conv_wgrad(dw[0], shp, taps_splits, extra_shapes)
+                    if rows is None:
+                        gw.copy_(g)
+                    else:
+                        gw[rows[0]:rows[1]].copy_(g)
+                    if ge is not None:
+                        ge.copy_(torch.cat(ex, dim=1).reshape(ge.shape))
+
+                self.badd("unpack", unpack)
+        # ---- data gradients through the adjoint plans ---------------------------------------
+        if not r.need_dgrad:
+            return
+        w = r.weight
+        if r.kind == "down":
+            (src, _), = r.sources
+            wT = self.packed(lambda: P.pack_convT_weight(w.detach()))
+            self.emit_grad(src, lambda out, add: self.bgemm(
+                P.up_conv_plan(dy, wT, out, residual=add, name=f"dgrad:{r.name}")))
+            return
+        if r.kind == "up":
+            (src, _), = r.sources
+            wT = self.packed(lambda: P.pack_conv_weight(w.detach()))
+            self.emit_grad(src, lambda out, add: self.bgemm(
+                P.down_conv_plan(dy, wT, out, residual=add, name=f"dgrad:{r.name}")))
+            return
+        assert r.kind == "conv"
+        c0 = 0
+        e0 = 0
+        dyd = r.dgrad_dy if r.dgrad_dy is not None else dy
+        cy = dyd.shape[-1]
+        for (src, has_taps) in r.sources:
+            Ci = src.shape[-1]
+            if has_taps:
+                a, b = c0, c0 + Ci
+                rows = r.w_rows
+
+                def make(a=a, b=b, rows=rows):
+                    ww = w.detach() if rows is None else w.detach()[rows[0]:rows[1]]
+                    wt = ww[:, a:b].transpose(0, 1).flip(*range(2, 2 + nd))  # [Ci, Co, *k]
+                    if wt.shape[1] < cy:  # thin Cout padded to the 64-channel dY copy
+                        pad = torch.zeros(wt.shape[0], cy - wt.shape[1], *wt.shape[2:],
+                                          dtype=wt.dtype, device=wt.device)
+                        wt = torch.cat([wt, pad], dim=1)
+                    return P.pack_conv_weight(wt)
+
+                wT = self.packed(make)
+                self.emit_grad(src, lambda out, add, wT=wT: self.bgemm(
+                    P.conv_plan([P.ConvSource(dyd)], wT, out, r.ksize, residual=add,
+                                name=f"dgrad:{r.name}")))
+                c0 += Ci
+            else:
+                a, b = e0, e0 + Ci
+                ew = r.extra_weight
+
+                def make_e(a=a, b=b):
+                    wt = ew.detach().reshape(ew.shape[0], -1)[:, a:b].t().contiguous()
+                    return P.pack_conv_weight(wt.reshape(b - a, ew.shape[0], *([1] * nd)))
+
+                wTe = self.packed(make_e)
+                self.emit_grad(src, lambda out, add, wTe=wTe: self.bgemm(
+                    P.conv_plan([P.ConvSource(dy)], wTe, out, 1, residual=add,
+                                name=f"dgrad_skip:{r.name}")))
+                e0 += Ci
+
+    def bwd_gn(self, r: GnRec) -> None:
+        dy = self.grads.get(id(r.y))
+        if dy is None:
+            raise _lib.MriError(f"backward: no gradient reached {r.name}")
+        x = r.x
+        B, S, C = self.B, x.spatial, x.C
+        if r.residual is not None:
+            self.pass_grad(r.residual, dy)
+        sums = self.zeros_each_bwd(3, B, C)
+        gamma = r.gamma[r.c_off:r.c_off + C]
+        beta = r.beta[r.c_off:r.c_off + C]
+        xs, st, cpg = x.t, x.stats, x.cpg
+        self.badd(f"gn_bwd_reduce:{r.name}", lambda: ops.gn_bwd_reduce(
+            xs, dy, st, gamma, beta, sums, B, S, C, r.groups, cpg, r.eps, r.silu))
+        gg = self.pg(r.gamma)[r.c_off:r.c_off + C]
+        gb = self.pg(r.beta)[r.c_off:r.c_off + C]
+        self.badd("gn_param_grad", lambda: (gg.copy_(sums[2].sum(0)), gb.copy_(sums[1].sum(0))))
+        if r.tproj_off is not None:
+            dst = self.dtproj[:, r.tproj_off:r.tproj_off + C]
+            self.badd("dtproj", lambda: dst.copy_(sums[0]))
+        self.emit_grad(xs, lambda out, add: self.badd(f"gn_bwd_apply:{r.name}", lambda: ops.gn_bwd_apply(
+            xs, dy, add, out, st, gamma, beta, sums, B, S, C, r.groups, cpg, r.eps, r.silu)))
+
+    def bwd_attention(self, r: AttnRec) -> None:
+        dev, B = self.device, self.B
+        blk = r.blk
+        C = r.x.C
+        heads, n, npad = r.heads, r.n, r.npad
+        d = C // heads
+        dout = self.grads.get(id(r.out))
+        if dout is None:
+            raise _lib.MriError(f"backward: no gradient reached {r.name}")
+        bf = torch.bfloat16
+        sp = tuple(r.out.shape[1:-1])
+        # residual + proj (1x1 conv) -------------------------------------------------------------
+        self.pass_grad(r.x.t, dout)
+        self._bwd_bias_and_tproj(dout, C, [blk.proj.bias], None, f"{r.name}.proj")
+        dwp = self.zeros_each_bwd(1, C, C)
+        wg = P.WgradPlan(r.proj_plan, dout, dwp, C, name=f"{r.name}.proj")
+        wg.materialize(dev)
+        self.badd(f"wgrad:{r.name}.proj", wg.launch)
+        gwp = self.pg(blk.proj.weight)
+        self.badd("unpack", lambda: gwp.copy_(dwp[0].reshape(gwp.shape)))
+        dO = torch.zeros(B, *sp, C, dtype=bf, device=dev)
+        wpT = self.packed(lambda: P.pack_conv_weight(
+            blk.proj.weight.detach().reshape(C, C).t().reshape(C, C, *([1] * self.ndim))))
+        self.bgemm(P.conv_plan([P.ConvSource(dout)], wpT, dO, 1, name=f"dgrad:{r.name}.proj"))
+        # dP = dO v^T (fp32) -------------------------------------------------------------------------
+        dP = torch.zeros(B, heads, n, npad, dtype=torch.float32, device=dev)
+        C3 = 3 * C
+        doa = P.TView(dO, (d, n, heads, B, 1), (1, C, d, n * C, B * n * C))
+        vb = P.TView(r.qkv, (d, n, heads, B), (1, C3, d, n * C3), offset=2 * C)
+        dpo = P.TView(dP, (npad, n, heads, B, 1),
+                      (1, npad, n * npad, heads * n * npad, B * heads * n * npad))
+        tiles = (-(-n // 128), heads, B, 1)
+        self.bgemm(P.matrix_plan(doa, (128, 1, 1, 1), vb, dpo, K=d, n_total=npad, block_n=128,
+                                 ext=(n, heads, B, 1), tiles=tiles, bz_sel=(3, 4), out_f32=True,
+                                 name=f"{r.name}.dP", flops=2 * B * heads * n * n * d))
+        # dS = softmax backward ------------------------------------------------------------------------
+        dS = torch.zeros(B, heads, n, npad, dtype=bf, device=dev)
+        scale = float(d) ** -0.5
+        Pm = r.Pm
+        self.badd(f"{r.name}.softmax_bwd",
+                  lambda: ops.softmax_bwd(Pm, dP, dS, B * heads * n, n, npad, npad, scale))
+        # dqkv assembled token-major [B, n, 3C] ------------------------------------------------------------
+        dqkv = torch.zeros(B, *sp, C3, dtype=bf, device=dev)
+        # dq = dS k  (B operand = k^T rows from kvT)
+        dsa = P.TView(dS, (npad, n, heads, B, 1),
+                      (1, npad, n * npad, heads * n * npad, B * heads * n * npad))
+        ktb = P.TView(r.kvT, (npad, d, heads, B), (1, npad, d * npad, 2 * C * npad))
+        dqo = P.TView(dqkv, (d, n, heads, B, 1), (1, C3, d, n * C3, B * n * C3))
+        self.bgemm(P.matrix_plan(dsa, (128, 1, 1, 1), ktb, dqo, K=npad, n_total=d, block_n=min(d, 128),
+                                 ext=(n, heads, B, 1), tiles=tiles, bz_sel=(3, 4),
+                                 name=f"{r.name}.dq", flops=2 * B * heads * n * n * d))
+        # dk = dS^T q and dv = P^T dO: reductions over the query rows -> MN-major kernel
+        n_tiles = -(-n // 128)
+        mpad = n_tiles * 128
+
+        def rowsum_product(lhs: torch.Tensor, rhs_base: torch.Tensor, rhs_off: int, rhs_ld: int,
+                           dst_slot: int, nm: str):
+            """dst[b, m, slot, h, :] = sum_n lhs[b, h, n, m] * rhs[b, n, h, :]"""
+            ncls = B * heads
+            a_maps, dy_views, kts = [], [], []
+            for b in range(B):
+                for h in range(heads):
+                    cls = b * heads + h
+                    av = P.TView(rhs_base, (d, n, 1, 1, 1), (1, rhs_ld, n * rhs_ld, n * rhs_ld, n * rhs_ld),
+                                 offset=b * n * rhs_ld + rhs_off + h * d)
+                    a_maps.append(P.MapSpec(av, (P.BLOCK_K, 128, 1, 1, 1), 3))
+                    dv_ = P.TView(lhs, (npad, n, 1, 1, 1), (1, npad, n * npad, n * npad, n * npad),
+                                  offset=cls * n * npad)
+                    dy_views.append(dv_)
+                    kts.append([[cls, c0, 0, 0, 0, 0, c0, 0] for c0 in range(0, d, P.BLOCK_K)])
+            fake = P.GemmPlan(a_maps=a_maps, b_map=None, o_maps=[], ktable=np.asarray(kts, dtype=np.int32),
+                              tiles=(n_tiles, 1, 1, 1), box=(128, 1, 1, 1), ext=(n, 1, 1, 1),
+                              block_n=128, n_total=d, name=nm)
+            dwb = self.zeros_each_bwd(ncls, mpad, d)
+            wgp = P.WgradPlan(fake, lhs, dwb, n, name=nm, dy_views=dy_views)
+            wgp.materialize(dev)
+            self.bwd_flops += 2 * B * heads * n * n * d
+            self.badd(f"wgrad:{nm}", wgp.launch)
+            dst = dqkv.view(B, n, 3, heads, d)[:, :, dst_slot]
+
+            def scatter():
+                dst.copy_(dwb.view(B, heads, mpad, d)[:, :, :n].permute(0, 2, 1, 3))
+
+            self.badd(f"scatter:{nm}", scatter)
+
+        rowsum_product(dS, r.qkv, 0, C3, 1, f"{r.name}.dk")
+        rowsum_product(Pm, dO, 0, C, 2, f"{r.name}.dv")
+        # qkv 1x1 conv backward --------------------------------------------------------------------------
+        self._bwd_bias_and_tproj(dqkv, C3, [blk.qkv.bias], None, f"{r.name}.qkv")
+        dwq = self.zeros_each_bwd(1, C3, C)
+        wg2 = P.WgradPlan(r.qkv_plan, dqkv, dwq, C3, name=f"{r.name}.qkv")
+        wg2.materialize(dev)
+        self.badd(f"wgrad:{r.name}.qkv", wg2.launch)
+        gwq = self.pg(blk.qkv.weight)
+        self.badd("unpack", lambda: gwq.copy_(dwq[0].reshape(gwq.shape)))
+        wqT = self.packed(lambda: P.pack_conv_weight(
+            blk.qkv.weight.detach().reshape(C3, C).t().reshape(C, C3, *([1] * self.ndim))))
+        hn = r.hn
+        self.emit_grad(hn, lambda out, add: self.bgemm(
+            P.conv_plan([P.ConvSource(dqkv)], wqT, out, 1, residual=add, name=f"dgrad:{r.name}.qkv")))
+
+    def bwd_time(self, r: TimeRec) -> None:
+        B = self.B
+        dev = self.device
+        dz = self.dtproj
+        if r.act == 1:
+            dzz = torch.zeros_like(self.dtproj)
+            self.badd("silu_bwd:tproj", lambda: ops.silu_bwd(r.zproj, self.dtproj, dzz))
+            dz = dzz
+        total, tdim = r.W_all.shape
+        dW_all = torch.zeros(total, tdim, device=dev)
+        db_all = torch.zeros(total, device=dev)
+        dcond = torch.zeros(B, tdim, device=dev)
+        self.badd("linear_bwd:tproj", lambda: ops.linear_bwd(dz, r.cond, r.W_all, dcond, dW_all, db_all))
+        for blk, o in zip(r.blocks, r.offs):
+            n = blk.time_mlp.weight.shape[0]
+            self.pgrad[id(blk.time_mlp.weight)] = dW_all[o:o + n]
+            self.pgrad[id(blk.time_mlp.bias)] = db_all[o:o + n]
+
+        def mlp_bwd(dout, lin_a, lin_b, x_in, z_mid, h_mid, tag):
+            """out = lin_b(silu(lin_a(x_in)))"""
+            dh = torch.zeros_like(h_mid)
+            gWb, gbb = self.pg(lin_b.weight), self.pg(lin_b.bias)
+            self.badd(f"linear_bwd:{tag}.b", lambda: ops.linear_bwd(dout, h_mid, lin_b.weight, dh, gWb, gbb))
+            dzm = torch.zeros_like(z_mid)
+            self.badd(f"silu_bwd:{tag}", lambda: ops.silu_bwd(z_mid, dh, dzm))
+            gWa, gba = self.pg(lin_a.weight), self.pg(lin_a.bias)
+            self.badd(f"linear_bwd:{tag}.a", lambda: ops.linear_bwd(dzm, x_in, lin_a.weight, None, gWa, gba))
+
+        mlp_bwd(dcond, r.l1, r.l2, r.sin, r.z1, r.h1, "time_mlp")
+        if r.slice is not None:
+            s = r.slice
+            mlp_bwd(dcond, s["s0"], s["s2"], s["z_in"], s["zz"], s["zh"], "slice_mlp")
+
+    # ------------------------------------------------------------------ driver
+    def build_backward(self, dy_seed: Dict[int, torch.Tensor]) -> None:
+        """dy_seed: id(forward tensor) -> gradient buffer filled before the backward ops run."""
+        self.grads.update(dy_seed)
+        for rec in reversed(self.tape):
+            if isinstance(rec, ConvRec):
+                self.bwd_conv(rec)
+            elif isinstance(rec, GnRec):
+                self.bwd_gn(rec)
+            elif isinstance(rec, AttnRec):
+                self.bwd_attention(rec)
+            elif isinstance(rec, TimeRec):
+                self.bwd_time(rec)
+            else:  # pragma: no cover
+                raise _lib.MriError(f"unknown tape record {type(rec)}")
+
+    def run_backward(self) -> None:
+        if self._zero_each_bwd:
+            torch._foreach_zero_(self._zero_each_bwd)
+        for fn in self.bwd_ops:
+            fn()

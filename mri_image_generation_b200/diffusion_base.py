@@ -26,6 +26,27 @@ def _require_cuda(x: torch.Tensor, what: str) -> None:
                             "this framework has no CPU fallback")
 
 
+class _LossFn(torch.autograd.Function):
+    """min-SNR / plain MSE loss with its gradient kernel (ddpm_3d_ldm/diffusion.py:91-99)."""
+
+    @staticmethod
+    def forward(ctx, pred, noise, t, snr, gamma):
+        B = pred.shape[0]
+        per = torch.empty(B, dtype=torch.float32, device=pred.device)
+        loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+        ops.minsnr_loss(pred, noise, t, snr, gamma, per, loss)
+        ctx.save_for_backward(pred, noise, t, snr)
+        ctx.gamma = gamma
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, noise, t, snr = ctx.saved_tensors
+        dpred = torch.empty_like(pred)
+        ops.minsnr_loss_bwd(pred, noise, t, snr, ctx.gamma, g.reshape(1).float().contiguous(), dpred)
+        return dpred, None, None, None, None
+
+
 class DiffusionBase(nn.Module):
     """Host logic common to GaussianDiffusion (2D, 2.5D) and GaussianDiffusionLatent3D."""
 
@@ -80,16 +101,12 @@ class DiffusionBase(nn.Module):
     def _loss(self, pred, noise, t, gamma: float):
         """min-SNR weighted (gamma > 0) or plain (gamma <= 0) MSE, fused reduce."""
         _require_cuda(pred, "p_losses")
-        B = pred.shape[0]
-        per = torch.empty(B, dtype=torch.float32, device=pred.device)
-        loss = torch.empty(1, dtype=torch.float32, device=pred.device)
         snr = getattr(self, "snr", None)
         if gamma > 0 and snr is None:
             raise _lib.MriError("min-SNR loss needs the `snr` buffer")
-        ops.minsnr_loss(pred.float().contiguous(), noise.float().contiguous(),
-                        t.to(pred.device).long().contiguous(),
-                        snr if snr is not None else self.betas, gamma, per, loss)
-        return loss[0]
+        return _LossFn.apply(pred.float().contiguous(), noise.float().contiguous(),
+                             t.to(pred.device).long().contiguous(),
+                             snr if snr is not None else self.betas, float(gamma))
 
     # ------------------------------------------------------------------ graph-replayed loops
     def _engine_model(self) -> Optional[EngineModule]:

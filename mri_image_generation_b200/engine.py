@@ -25,6 +25,7 @@ import torch
 
 from . import _lib, ops
 from . import plan as P
+from .backward import AttnRec, BackwardMixin, ConvRec, GnRec, TimeRec
 
 
 def _rup(n: int, m: int) -> int:
@@ -58,6 +59,7 @@ class _Pool:
         self.device = device
         self.free: Dict[Tuple, List[torch.Tensor]] = {}
         self.bytes = 0
+        self.frozen = False
 
     def get(self, shape, dtype=torch.bfloat16) -> torch.Tensor:
         key = (tuple(shape), dtype)
@@ -69,22 +71,28 @@ class _Pool:
         return t
 
     def release(self, t: torch.Tensor) -> None:
+        if self.frozen:  # training: every forward tensor is needed again by the backward pass
+            return
         self.free.setdefault((tuple(t.shape), t.dtype), []).append(t)
 
 
-class UNetProgram:
+class UNetProgram(BackwardMixin):
     """Common builder machinery; subclasses lay out a concrete UNet."""
 
     STATS_ARENA = 1 << 17  # doubles
 
-    def __init__(self, device, batch: int, spatial: Sequence[int], groups: int = 8):
+    def __init__(self, device, batch: int, spatial: Sequence[int], groups: int = 8,
+                 training: bool = False):
         _lib.require_device()
+        self._binit()
+        self.training = training
         self.device = device
         self.B = batch
         self.sp = tuple(int(s) for s in spatial)
         self.ndim = len(self.sp)
         self.groups = groups
         self.pool = _Pool(device)
+        self.pool.frozen = training
         self.ops: List[Callable[[], None]] = []
         self.op_names: List[str] = []
         self.op_outs: List[List[torch.Tensor]] = []
@@ -162,19 +170,23 @@ class UNetProgram:
     def gn(self, x: Act, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float,
            silu: bool, rowbias: Optional[torch.Tensor] = None, rowbias_ld: int = 0,
            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-           name: str = "gn") -> torch.Tensor:
-        """y = act(GroupNorm(x)) (+ rowbias[n, c]) (+ residual).  Uses x.stats (fine groups)."""
+           name: str = "gn", c_off: int = 0, tproj_off: Optional[int] = None) -> torch.Tensor:
+        """y = act(GroupNorm(x)) (+ rowbias[n, c]) (+ residual).  Uses x.stats (fine groups).
+        gamma / beta are the module parameters; channels [c_off, c_off + C) of them apply."""
         assert x.stats is not None, f"{name}: input has no statistics"
         y = out if out is not None else self.pool.get(tuple(x.t.shape))
         B, S, C = self.B, x.spatial, x.C
         xs, st, cpg = x.t, x.stats, x.cpg
+        gm, bt = gamma[c_off:c_off + C], beta[c_off:c_off + C]
         self.hbm_bytes_elementwise += 2 * xs.numel() * 2 + (residual.numel() * 2 if residual is not None else 0)
 
         def fn():
-            ops.gn_apply(xs, y, st, gamma, beta, B, S, C, groups, cpg, eps, silu, rowbias=rowbias,
+            ops.gn_apply(xs, y, st, gm, bt, B, S, C, groups, cpg, eps, silu, rowbias=rowbias,
                          rowbias_ld=rowbias_ld, residual=residual)
 
         self._add(name, fn, [y])
+        self.tape.append(GnRec(x=x, y=y, gamma=gamma, beta=beta, c_off=c_off, groups=groups, eps=eps,
+                               silu=silu, tproj_off=tproj_off, residual=residual, name=name))
         return y
 
     def stats_of(self, x: Act, name: str = "gn_stats") -> None:
@@ -187,12 +199,24 @@ class UNetProgram:
 
     def conv(self, sources: Sequence[P.ConvSource], wmat: torch.Tensor, cout: int, ksize: int,
              bias: Optional[torch.Tensor], *, rowbias=None, rowbias_ld=0, residual=None,
-             with_stats=True, name="conv") -> Act:
+             with_stats=True, name="conv", rec: Optional[dict] = None) -> Act:
+        """Stride-1 convolution over (virtually concatenated) sources.  `rec` carries what the
+        backward pass needs: weight (parameter), splits, extra_weight, bias_params, tproj_off,
+        valid cout, need_dgrad."""
         sp = sources[0].x.shape[1:-1]
         y = self.new_act(sp, cout, with_stats)
         pl = P.conv_plan(sources, wmat, y.t, ksize, bias=bias, rowbias=rowbias, rowbias_ld=rowbias_ld,
                          residual=residual, stats=y.stats, stats_cpg=y.cpg, name=name)
         self.gemm(pl)
+        if rec is not None:
+            self.tape.append(ConvRec(kind="conv", plan=pl, y=y.t, ksize=ksize,
+                                     sources=[(s_.x, s_.taps) for s_ in sources],
+                                     weight=rec.get("weight"), splits=rec.get("splits", []),
+                                     extra_weight=rec.get("extra_weight"),
+                                     bias_params=rec.get("bias_params", []), residual=residual,
+                                     tproj_off=rec.get("tproj_off"), cout=rec.get("cout", cout),
+                                     need_dgrad=rec.get("need_dgrad", True),
+                                     dgrad_dy=rec.get("dgrad_dy"), name=name))
         return y
 
     # ------------------------------------------------------------------ time embedding
@@ -200,17 +224,24 @@ class UNetProgram:
         """SinusoidalPosEmb -> Linear -> SiLU -> Linear  (unet.py:124-129 / unet_attention.py:103-108)."""
         B, dev = self.B, self.device
         sin = torch.zeros(B, dim, device=dev)
+        z1 = torch.zeros(B, dim * 4, device=dev)
         h1 = torch.zeros(B, dim * 4, device=dev)
         temb = torch.zeros(B, dim, device=dev)
         l1, l2 = time_mlp[1], time_mlp[3]
         self.track(l1.weight, l1.bias, l2.weight, l2.bias)
         freqs = ops.sinusoidal_freqs(dim, dev)
         self._add("sinusoidal", lambda: ops.sinusoidal(t_in, freqs, sin), [sin])
-        self._add("time_mlp.1", lambda: ops.linear(sin, l1.weight, l1.bias, h1, act=1), [h1])
+        if self.training:  # keep the pre-activation for the backward pass
+            self._add("time_mlp.1", lambda: ops.linear(sin, l1.weight, l1.bias, z1), [z1])
+            self._add("time_mlp.silu", lambda: ops.silu(z1, h1), [h1])
+        else:
+            self._add("time_mlp.1", lambda: ops.linear(sin, l1.weight, l1.bias, h1, act=1), [h1])
         self._add("time_mlp.3", lambda: ops.linear(h1, l2.weight, l2.bias, temb), [temb])
+        self._time = dict(sin=sin, z1=z1, h1=h1, temb=temb, l1=l1, l2=l2)
         return temb
 
-    def block_projections(self, temb: torch.Tensor, blocks: Sequence, act: int) -> Tuple[torch.Tensor, List[int], int]:
+    def block_projections(self, cond: torch.Tensor, blocks: Sequence, act: int,
+                          slice_rec: Optional[dict] = None) -> Tuple[torch.Tensor, List[int], int]:
         """All per-ResBlock Linear(t_dim, Cout) projections as ONE concatenated linear."""
         Ws = [b.time_mlp.weight for b in blocks]
         bs = [b.time_mlp.bias for b in blocks]
@@ -219,11 +250,22 @@ class UNetProgram:
         b_all = self.packed(lambda: torch.cat([b.detach() for b in bs], 0).contiguous())
         total = W_all.shape[0]
         out = torch.zeros(self.B, total, device=self.device)
-        self._add("time_proj_all", lambda: ops.linear(temb, W_all, b_all, out, act=act), [out])
+        zproj = torch.zeros(self.B, total, device=self.device)
+        if self.training and act == 1:
+            self._add("time_proj_all", lambda: ops.linear(cond, W_all, b_all, zproj), [zproj])
+            self._add("time_proj_all.silu", lambda: ops.silu(zproj, out), [out])
+        else:
+            self._add("time_proj_all", lambda: ops.linear(cond, W_all, b_all, out, act=act), [out])
         offs, o = [], 0
         for w in Ws:
             offs.append(o)
             o += w.shape[0]
+        self.dtproj = torch.zeros(self.B, total, device=self.device)
+        t = self._time
+        # recorded FIRST on the tape -> processed LAST in the backward pass
+        self.tape.insert(0, TimeRec(sin=t["sin"], z1=t["z1"], h1=t["h1"], temb=t["temb"], l1=t["l1"],
+                                    l2=t["l2"], cond=cond, W_all=W_all, zproj=zproj, act=act,
+                                    blocks=list(blocks), offs=offs, slice=slice_rec))
         return out, offs, total
 
 
@@ -233,9 +275,9 @@ class UNetProgram:
 class UNet3DProgram(UNetProgram):
     """ddpm_3d_ldm/unet_attention.py:88-200 and ddpm_3d_ldm/unet.py:57-158."""
 
-    def __init__(self, model, batch: int, spatial: Sequence[int]):
+    def __init__(self, model, batch: int, spatial: Sequence[int], training: bool = False):
         dev = next(model.parameters()).device
-        super().__init__(dev, batch, spatial, groups=model.out_norm.num_groups)
+        super().__init__(dev, batch, spatial, groups=model.out_norm.num_groups, training=training)
         self.model = model
         B, (D, H, W) = batch, self.sp
         cin = model.in_channels
@@ -258,7 +300,7 @@ class UNet3DProgram(UNetProgram):
         for blk in model.ups:
             blocks += [blk["res1"], blk["res2"]]
         tproj, toffs, tld = self.block_projections(temb, blocks, act=0)
-        self._tproj = {id(b): (tproj[:, o:], tld) for b, o in zip(blocks, toffs)}
+        self._tproj = {id(b): (tproj[:, o:], tld, o) for b, o in zip(blocks, toffs)}
 
         # ---- in_conv: thin Cin -> explicit patch matrix + GEMM ------------------------------
         S = D * H * W
@@ -270,7 +312,11 @@ class UNet3DProgram(UNetProgram):
         self.track(ic.weight, ic.bias)
         w_in = self.packed(lambda: _pad_k(P.pack_conv_weight(ic.weight.detach()), kpad))
         h = self.new_act(self.sp, chs[0])
-        self.gemm(self._matrix_conv(col, w_in, h, S, kpad, ic.bias, "in_conv"))
+        pl = self._matrix_conv(col, w_in, h, S, kpad, ic.bias, "in_conv")
+        self.gemm(pl)
+        self.tape.append(ConvRec(kind="matrix", plan=pl, y=h.t, ksize=3, sources=[(col, True)],
+                                 weight=ic.weight, splits=[cin], bias_params=[ic.bias], cout=chs[0],
+                                 need_dgrad=False, kpad=kpad, name="in_conv"))
 
         # ---- down path -----------------------------------------------------------------------
         skips: List[Act] = []
@@ -283,8 +329,12 @@ class UNet3DProgram(UNetProgram):
                 self.track(dn.weight, dn.bias)
                 wd = self.packed(lambda dn=dn: P.pack_conv_weight(dn.weight.detach()))
                 y = self.new_act([s // 2 for s in h.t.shape[1:-1]], chs[i + 1])
-                self.gemm(P.down_conv_plan(h.t, wd, y.t, bias=dn.bias, stats=y.stats, stats_cpg=y.cpg,
-                                           name=f"downs.{i}.down"))
+                pl = P.down_conv_plan(h.t, wd, y.t, bias=dn.bias, stats=y.stats, stats_cpg=y.cpg,
+                                      name=f"downs.{i}.down")
+                self.gemm(pl)
+                self.tape.append(ConvRec(kind="down", plan=pl, y=y.t, ksize=4, sources=[(h.t, True)],
+                                         weight=dn.weight, splits=[h.C], bias_params=[dn.bias],
+                                         cout=chs[i + 1], name=f"downs.{i}.down"))
                 h = y
 
         # ---- bottleneck ------------------------------------------------------------------------
@@ -301,8 +351,12 @@ class UNet3DProgram(UNetProgram):
                 self.track(up.weight, up.bias)
                 wu = self.packed(lambda up=up: P.pack_convT_weight(up.weight.detach()))
                 u = self.new_act([s * 2 for s in h.t.shape[1:-1]], chs[i])
-                self.gemm(P.up_conv_plan(h.t, wu, u.t, bias=up.bias, stats=u.stats, stats_cpg=u.cpg,
-                                         name=f"ups.{j}.up"))
+                pl = P.up_conv_plan(h.t, wu, u.t, bias=up.bias, stats=u.stats, stats_cpg=u.cpg,
+                                    name=f"ups.{j}.up")
+                self.gemm(pl)
+                self.tape.append(ConvRec(kind="up", plan=pl, y=u.t, ksize=4, sources=[(h.t, True)],
+                                         weight=up.weight, splits=[h.C], bias_params=[up.bias],
+                                         cout=chs[i], name=f"ups.{j}.up"))
                 self.pool.release(h.t)
                 h = u
             skip = skips.pop()
@@ -320,11 +374,18 @@ class UNet3DProgram(UNetProgram):
         self.cout_pad = _rup(self.cout, 16)
         w_out = self.packed(lambda: P.pack_conv_weight(oc.weight.detach(), cout_pad=self.cout_pad))
         b_out = self.packed(lambda: _pad_vec(oc.bias.detach(), self.cout_pad))
+        self.deps64 = torch.zeros(B, D, H, W, 64, dtype=torch.bfloat16, device=dev) if training else None
         y = self.conv([P.ConvSource(a)], w_out, self.cout_pad, 3, b_out, with_stats=False,
-                      name="out_conv")
+                      name="out_conv",
+                      rec=dict(weight=oc.weight, splits=[a.shape[-1]], bias_params=[oc.bias],
+                               cout=self.cout, dgrad_dy=self.deps64))
         self.eps_nhwc = y.t  # [B, D, H, W, cout_pad] bf16
         self.out = torch.zeros(B, self.cout, D, H, W, device=dev)
         self.params_changed()
+        if training:
+            self.dout_in = torch.zeros(B, self.cout, D, H, W, device=dev)
+            self.deps16 = torch.zeros_like(self.eps_nhwc)
+            self.build_backward({id(self.eps_nhwc): self.deps16})
 
     # -------------------------------------------------------------------------------------------
     def _matrix_conv(self, col, wmat, y: Act, S: int, kpad: int, bias, name) -> P.GemmPlan:
@@ -345,18 +406,19 @@ class UNet3DProgram(UNetProgram):
         n1, n2, c1, c2 = blk.norm1, blk.norm2, blk.conv1, blk.conv2
         self.track(n1.weight, n1.bias, n2.weight, n2.bias, c1.weight, c1.bias, c2.weight, c2.bias)
         cout = c1.weight.shape[0]
-        rowbias, rb_ld = self._tproj[id(blk)]
+        rowbias, rb_ld, t_off = self._tproj[id(blk)]
         srcs = [x] if skip is None else [x, skip]
         cins = [s.C for s in srcs]
         g_each = self.groups // len(srcs)  # GN(8, 2C) over a concat == GN(4)+GN(4) over halves
         normed, c0 = [], 0
         for k, s in enumerate(srcs):
-            normed.append(self.gn(s, n1.weight[c0:c0 + s.C], n1.bias[c0:c0 + s.C], g_each, eps, True,
+            normed.append(self.gn(s, n1.weight, n1.bias, g_each, eps, True, c_off=c0,
                                   name=f"{name}.norm1.{k}"))
             c0 += s.C
         w1 = self.packed(lambda: P.pack_conv_weight(c1.weight.detach(), splits=cins))
         h = self.conv([P.ConvSource(a) for a in normed], w1, cout, 3, c1.bias, rowbias=rowbias,
-                      rowbias_ld=rb_ld, name=f"{name}.conv1")
+                      rowbias_ld=rb_ld, name=f"{name}.conv1",
+                      rec=dict(weight=c1.weight, splits=cins, bias_params=[c1.bias], tproj_off=t_off))
         for a in normed:
             self.pool.release(a)
         a2 = self.gn(h, n2.weight, n2.bias, self.groups, eps, True, name=f"{name}.norm2")
@@ -375,12 +437,15 @@ class UNet3DProgram(UNetProgram):
                 extra=[sk.weight.detach().reshape(cout, -1)[:, a:a + n] for a, n in extras]))
             b2 = self.packed(lambda: (c2.bias.detach() + sk.bias.detach()).contiguous())
             sources = [P.ConvSource(a2)] + [P.ConvSource(s.t, taps=False) for s in srcs]
-            out = self.conv(sources, w2, cout, 3, b2, name=f"{name}.conv2+skip")
+            out = self.conv(sources, w2, cout, 3, b2, name=f"{name}.conv2+skip",
+                            rec=dict(weight=c2.weight, splits=[cout], extra_weight=sk.weight,
+                                     bias_params=[c2.bias, sk.bias]))
         else:
             assert skip is None and x.C == cout
             w2 = self.packed(lambda: P.pack_conv_weight(c2.weight.detach()))
             out = self.conv([P.ConvSource(a2)], w2, cout, 3, c2.bias, residual=x.t,
-                            name=f"{name}.conv2")
+                            name=f"{name}.conv2",
+                            rec=dict(weight=c2.weight, splits=[cout], bias_params=[c2.bias]))
         self.pool.release(a2)
         if release_in:
             for s in srcs:
@@ -389,42 +454,43 @@ class UNet3DProgram(UNetProgram):
 
     def attention(self, x: Act, blk, name: str) -> Act:
         """AttentionBlock3D (unet_attention.py:28-56): GN -> qkv 1x1 -> softmax(q^T k / sqrt(d)) v
-        -> proj 1x1 -> + x.  Token-major layouts: q,k as [B, n, 2C]; v transposed [B, C, n]."""
+        -> proj 1x1 -> + x.  Layouts: qkv token-major [B, n, 3C]; k and v additionally transposed
+        ([B, 2C, n], computed by a second GEMM W . hn^T) so that every product is K-major."""
         B, C, dev = self.B, x.C, self.device
         heads = blk.num_heads
         d = C // heads
         assert d % 64 == 0 and d <= 256
         n = x.spatial
         npad = _rup(n, 8)
-        sp = tuple(x.t.shape[1:-1])
+        C3 = 3 * C
         self.track(blk.norm.weight, blk.norm.bias, blk.qkv.weight, blk.qkv.bias, blk.proj.weight,
                    blk.proj.bias)
         hn = self.gn(x, blk.norm.weight, blk.norm.bias, self.groups, blk.norm.eps, False,
                      name=f"{name}.norm")
-        # q, k: 1x1 conv with the first 2C output channels
-        wqk = self.packed(lambda: P.pack_conv_weight(blk.qkv.weight.detach()[:2 * C]))
-        bqk = self.packed(lambda: blk.qkv.bias.detach()[:2 * C].contiguous())
-        qk = self.conv([P.ConvSource(hn)], wqk, 2 * C, 1, bqk, with_stats=False, name=f"{name}.qk")
-        # v^T[b] = Wv . hn[b]^T  (+ bias along rows): classes = samples
-        wv = self.packed(lambda: blk.qkv.weight.detach()[2 * C:].reshape(C, C).to(torch.bfloat16).contiguous())
-        bv = self.packed(lambda: blk.qkv.bias.detach()[2 * C:].contiguous())
-        vT = torch.zeros(B, C, npad, dtype=torch.bfloat16, device=dev)
-        a = P.TView(wv, (C, C, 1, 1, 1), (1, C, C * C, C * C, C * C))
+        wqkv = self.packed(lambda: P.pack_conv_weight(blk.qkv.weight.detach()))
+        qkv = self.conv([P.ConvSource(hn)], wqkv, C3, 1, blk.qkv.bias, with_stats=False,
+                        name=f"{name}.qkv")
+        qkv_plan = self.plans[-1]
+        # [k^T; v^T][b] = W[C:3C] . hn[b]^T  (+ bias along rows): classes = samples
+        wkv = self.packed(lambda: blk.qkv.weight.detach()[C:].reshape(2 * C, C).to(torch.bfloat16).contiguous())
+        bkv = self.packed(lambda: blk.qkv.bias.detach()[C:].contiguous())
+        kvT = torch.zeros(B, 2 * C, npad, dtype=torch.bfloat16, device=dev)
+        a = P.TView(wkv, (C, 2 * C, 1, 1, 1), (1, C, 2 * C * C, 2 * C * C, 2 * C * C))
         b = P.TView(hn, (C, n, B, 1), (1, C, n * C, B * n * C))
-        o_views = [P.TView(vT, (npad, C, 1, 1, 1), (1, npad, C * npad, C * npad, C * npad),
-                           offset=bi * C * npad) for bi in range(B)]
+        sz = 2 * C * npad
+        o_views = [P.TView(kvT, (npad, 2 * C, 1, 1, 1), (1, npad, sz, sz, sz), offset=bi * sz)
+                   for bi in range(B)]
         pl = P.matrix_plan(a, (128, 1, 1, 1), b, o_views[0], K=C, n_total=npad, block_n=128,
-                           ext=(C, 1, 1, 1), tiles=(C // 128, 1, 1, 1), bz_sel=(1, 0), bias_m=bv,
-                           name=f"{name}.vT", flops=2 * B * n * C * C)
-        chunk_box = pl.o_maps[0].box
-        swz = pl.o_maps[0].swizzle
+                           ext=(2 * C, 1, 1, 1), tiles=(2 * C // 128, 1, 1, 1), bz_sel=(1, 0),
+                           bias_m=bkv, name=f"{name}.kvT", flops=2 * B * n * 2 * C * C)
+        chunk_box, swz = pl.o_maps[0].box, pl.o_maps[0].swizzle
         pl.o_maps = [P.MapSpec(v, chunk_box, swz) for v in o_views]
         pl.ktable = pl.ktable.repeat(B, axis=0)
         self.gemm(pl)
         # S = q k^T  (fp32 logits)
         S = torch.zeros(B, heads, n, npad, dtype=torch.float32, device=dev)
-        qa = P.TView(qk.t, (d, n, heads, B, 1), (1, 2 * C, d, n * 2 * C, B * n * 2 * C))
-        kb = P.TView(qk.t, (d, n, heads, B), (1, 2 * C, d, n * 2 * C), offset=C)
+        qa = P.TView(qkv.t, (d, n, heads, B, 1), (1, C3, d, n * C3, B * n * C3))
+        kb = P.TView(qkv.t, (d, n, heads, B), (1, C3, d, n * C3), offset=C)
         so = P.TView(S, (npad, n, heads, B, 1),
                      (1, npad, n * npad, heads * n * npad, B * heads * n * npad))
         self.gemm(P.matrix_plan(qa, (128, 1, 1, 1), kb, so, K=d, n_total=npad, block_n=128,
@@ -435,19 +501,26 @@ class UNet3DProgram(UNetProgram):
         scale = float(d) ** -0.5
         self._add(f"{name}.softmax",
                   lambda: ops.softmax_rows(S, Pm, B * heads * n, n, npad, npad, scale), [Pm])
-        # O = P v  (token-major [B, n, C])
+        # O = P v  (token-major [B, n, C]); B operand = v^T rows of kvT
         O = self.pool.get(tuple(x.t.shape))
         pa = P.TView(Pm, (npad, n, heads, B, 1),
                      (1, npad, n * npad, heads * n * npad, B * heads * n * npad))
-        vb = P.TView(vT, (npad, d, heads, B), (1, npad, d * npad, C * npad))
+        vb = P.TView(kvT, (npad, d, heads, B), (1, npad, d * npad, sz), offset=C * npad)
         oo = P.TView(O, (d, n, heads, B, 1), (1, C, d, n * C, B * n * C))
         self.gemm(P.matrix_plan(pa, (128, 1, 1, 1), vb, oo, K=npad, n_total=d, block_n=min(d, 128),
                                 ext=(n, heads, B, 1), tiles=(-(-n // 128), heads, B, 1),
                                 bz_sel=(3, 4), name=f"{name}.pv", flops=2 * B * heads * n * n * d))
         wp = self.packed(lambda: P.pack_conv_weight(blk.proj.weight.detach()))
         out = self.conv([P.ConvSource(O)], wp, C, 1, blk.proj.bias, residual=x.t, name=f"{name}.proj")
+        proj_plan = self.plans[-1]
+        self.tape.append(AttnRec(x=x, hn=hn, qkv=qkv.t, kvT=kvT, Pm=Pm, O=O, out=out.t, blk=blk,
+                                 qkv_plan=qkv_plan, proj_plan=proj_plan, heads=heads, n=n, npad=npad,
+                                 name=name))
+        # the norm's GnRec was recorded before the attention record; backward order must be
+        # attention first, then the norm: move the norm record after... (tape is reversed, so
+        # the later-recorded AttnRec is already processed first)
         self.pool.release(hn)
-        self.pool.release(qk.t)
+        self.pool.release(qkv.t)
         self.pool.release(O)
         self.pool.release(x.t)
         return out
@@ -464,6 +537,15 @@ class UNet3DProgram(UNetProgram):
         S = self.sp[0] * self.sp[1] * self.sp[2]
         ops.nhwc_to_nchw(self.eps_nhwc, self.out, self.B, S, self.cout, self.cout_pad)
         return self.out
+
+    def backward(self, dout: torch.Tensor) -> None:
+        """Training: gradient of the loss w.r.t. the fp32 NCDHW output -> parameter gradients in
+        self.pgrad (fp32, reference layouts)."""
+        S = self.sp[0] * self.sp[1] * self.sp[2]
+        self.dout_in.copy_(dout)
+        ops.nchw_to_nhwc(self.dout_in, self.deps16, self.B, S, self.cout, self.cout_pad)
+        ops.nchw_to_nhwc(self.dout_in, self.deps64, self.B, S, self.cout, 64)
+        self.run_backward()
 
 
 def _pad_k(w: torch.Tensor, kpad: int) -> torch.Tensor:

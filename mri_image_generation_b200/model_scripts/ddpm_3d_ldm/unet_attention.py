@@ -8,7 +8,7 @@ import torch.nn as nn
 
 from ... import _lib
 from ...engine import UNet3DProgram
-from ...modules import EngineModule, SinusoidalHolder
+from ...modules import EngineModule, SinusoidalHolder, UNetFunction
 
 # name kept for importers of the reference module (unet_attention.py:7)
 SinusoidalPositionEmbeddings = SinusoidalHolder
@@ -91,9 +91,9 @@ class _UNet3DBase(EngineModule):
         self.out_act = nn.SiLU()
         self.out_conv = nn.Conv3d(chs[0], in_channels, 3, padding=1)
 
-    def program(self, batch: int, spatial) -> UNet3DProgram:
-        key = (int(batch), tuple(int(s) for s in spatial))
-        return self.get_program(key, lambda: UNet3DProgram(self, key[0], key[1]))
+    def program(self, batch: int, spatial, training: bool = False) -> UNet3DProgram:
+        key = (int(batch), tuple(int(s) for s in spatial), bool(training))
+        return self.get_program(key, lambda: UNet3DProgram(self, key[0], key[1], training=key[2]))
 
     def forward(self, x, t):
         """x: (B, C, D, H, W) fp32, t: (B,) int64 -> predicted noise (B, C, D, H, W) fp32
@@ -101,9 +101,15 @@ class _UNet3DBase(EngineModule):
         self._check_input(x)
         if x.dim() != 5 or x.shape[1] != self.in_channels:
             raise _lib.MriError(f"expected input (B, {self.in_channels}, D, H, W), got {tuple(x.shape)}")
+        xf, tl = x.float().contiguous(), t.to(x.device).long()
+        if self._needs_grad():
+            # training: forward + backward launch lists behind one autograd node
+            prog = self.program(x.shape[0], x.shape[2:], training=True)
+            prog.param_list = list(self.parameters())
+            return UNetFunction.apply(prog, lambda: prog.forward(xf, tl), len(prog.param_list),
+                                      *prog.param_list)
         prog = self.program(x.shape[0], x.shape[2:])
-        out = prog.forward(x.float().contiguous(), t.to(x.device).long())
-        return out.clone()
+        return prog.forward(xf, tl).clone()
 
 
 class UNet3DModelWithAttention(_UNet3DBase):

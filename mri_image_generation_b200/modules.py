@@ -55,10 +55,9 @@ class EngineModule(nn.Module):
             raise _lib.MriError(
                 f"{type(self).__name__} runs on B200 GPUs only (input is on {x.device}); this "
                 "framework has no CPU fallback -- the reference implementation covers CPU.")
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise _lib.MriError(
-                f"{type(self).__name__}: the backward pass (dgrad/wgrad kernels) is not part of this "
-                "build yet; call under torch.no_grad() (sampling / evaluation).")
+
+    def _needs_grad(self) -> bool:
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
     def get_program(self, key: Tuple, build):
         progs = self._programs()
@@ -69,3 +68,30 @@ class EngineModule(nn.Module):
             prog = build()
             progs[key] = prog
         return prog
+
+
+class UNetFunction(torch.autograd.Function):
+    """Autograd bridge: forward = the training UNetProgram's forward launch list, backward = its
+    backward launch list.  All parameters are passed as inputs so that autograd (and DDP's
+    reducer hooks, ddpm_3d_ldm/train.py:232-233) see their gradients.
+
+    The program owns static activation buffers: exactly one backward may follow each forward
+    (the reference training loops do precisely that, train.py:395-400)."""
+
+    @staticmethod
+    def forward(ctx, prog, run_forward, n_params, *tensors):
+        ctx.prog = prog
+        ctx.n_params = n_params
+        out = run_forward()
+        return out.clone()
+
+    @staticmethod
+    def backward(ctx, dout):
+        prog = ctx.prog
+        prog.backward(dout.contiguous().float())
+        grads = []
+        for p in prog.param_list:
+            g = prog.pgrad.get(id(p))
+            grads.append(g.clone() if (g is not None and p.requires_grad) else None)
+        extra = len(ctx.needs_input_grad) - 3 - len(grads)
+        return (None, None, None, *grads, *([None] * extra))

@@ -125,7 +125,7 @@ def choose_box(ext: Sequence[int], prefer_unit: Sequence[int] = ()) -> Tuple[int
 @dataclass
 class GemmPlan:
     a_maps: List[MapSpec]
-    b_map: MapSpec
+    b_map: Optional[MapSpec]
     o_maps: List[MapSpec]
     ktable: np.ndarray  # int32 [n_class, n_kb, 8]
     tiles: Tuple[int, int, int, int]
@@ -586,10 +586,13 @@ class WgradPlan:
     stages: int = 3
     splits: int = 0
     name: str = ""
+    dy_views: Optional[List[TView]] = None   # explicit per-class dY views (attention products)
     _args: Optional[_lib.MriWgradArgs] = field(default=None, repr=False)
     _keep: list = field(default_factory=list, repr=False)
 
     def dy_specs(self) -> List[MapSpec]:
+        if self.dy_views is not None:
+            return [MapSpec(v, (BLOCK_K,) + tuple(self.fwd.box), 3) for v in self.dy_views]
         out = []
         for om in self.fwd.o_maps:
             v = om.view
