@@ -87,16 +87,29 @@ def test_optimizer_step_changes_output_and_repacks_weights():
     torch.manual_seed(0)
     m = UNet3DModel(3, base_channels=64, time_emb_dim=64).cuda().train()
     diff = quiet(GaussianDiffusionLatent3D, m, 3, timesteps=50).cuda()
-    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
     x0 = torch.randn(2, 3, 8, 8, 8, device="cuda")
     t = torch.tensor([3, 40], device="cuda")
     noise = torch.randn_like(x0)
+    with torch.no_grad():
+        before = diff.p_losses(x0, t, noise=noise).item()  # inference program, packed once
     losses = []
-    for _ in range(4):
+    for _ in range(6):
         opt.zero_grad()
         loss = diff.p_losses(x0, t, noise=noise)
         loss.backward()
         opt.step()
         losses.append(loss.item())
-    print("losses", losses)
-    assert losses[-1] < losses[0]  # same batch, 4 Adam steps: the loss must go down
+    print("losses", before, losses)
+    assert abs(losses[0] - before) <= 1e-3 * abs(before)
+    assert losses[-1] < losses[0]  # same batch, small Adam steps: the loss must go down
+    # both programs must have re-packed the updated weights: compare with the oracle on them
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    buf = O.schedule_buffers(O.cosine_betas(50))
+    xn = O.q_sample(buf, x0.cpu(), t.cpu(), noise.cpu())
+    with torch.no_grad():
+        want = O.minsnr_loss(buf, O.unet3d_forward(sd, xn, t.cpu()), noise.cpu(), t.cpu(), 5.0).item()
+        got_eval = diff.p_losses(x0, t, noise=noise).item()
+    got_train = diff.p_losses(x0, t, noise=noise).item()
+    assert abs(got_eval - want) <= 1e-2 * abs(want), (got_eval, want)
+    assert abs(got_train - want) <= 1e-2 * abs(want), (got_train, want)
