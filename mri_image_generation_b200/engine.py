@@ -566,9 +566,10 @@ def _pad_vec(v: torch.Tensor, n: int) -> torch.Tensor:
 class UNet2DProgram(UNetProgram):
     """slice_cond_2d_ddpm/unet.py:108-199 and ddpm_25d_all_modalities/unet.py:109-218."""
 
-    def __init__(self, model, batch: int, spatial: Sequence[int], x_channels: int, ctx_channels: int):
+    def __init__(self, model, batch: int, spatial: Sequence[int], x_channels: int, ctx_channels: int,
+                 training: bool = False):
         dev = next(model.parameters()).device
-        super().__init__(dev, batch, spatial, groups=model.out_norm.num_groups)
+        super().__init__(dev, batch, spatial, groups=model.out_norm.num_groups, training=training)
         self.model = model
         B, (H, W) = batch, self.sp
         chs = list(model.chs)
@@ -591,10 +592,15 @@ class UNet2DProgram(UNetProgram):
         temb = self.time_embedding(self.t_in, model.time_mlp, tdim)
         s0, s2 = model.slice_mlp[0], model.slice_mlp[2]
         self.track(s0.weight, s0.bias, s2.weight, s2.bias)
+        zz = torch.zeros(B, s0.weight.shape[0], device=dev)
         zh = torch.zeros(B, s0.weight.shape[0], device=dev)
         cond = torch.zeros(B, tdim, device=dev)
         z_in = self.z_in
-        self._add("slice_mlp.0", lambda: ops.linear(z_in, s0.weight, s0.bias, zh, act=1), [zh])
+        if training:
+            self._add("slice_mlp.0", lambda: ops.linear(z_in, s0.weight, s0.bias, zz), [zz])
+            self._add("slice_mlp.silu", lambda: ops.silu(zz, zh), [zh])
+        else:
+            self._add("slice_mlp.0", lambda: ops.linear(z_in, s0.weight, s0.bias, zh, act=1), [zh])
         self._add("slice_mlp.2", lambda: ops.linear(zh, s2.weight, s2.bias, cond, addend=temb), [cond])
         blocks = []
         for d in model.downs:
@@ -603,8 +609,9 @@ class UNet2DProgram(UNetProgram):
         for u in model.ups:
             blocks += [u.res1, u.res2]
         # the 2D block applies SiLU to the projected embedding (unet.py:48-50)
-        tproj, toffs, tld = self.block_projections(cond, blocks, act=1)
-        self._tproj = {id(b): (tproj[:, o:], tld) for b, o in zip(blocks, toffs)}
+        tproj, toffs, tld = self.block_projections(
+            cond, blocks, act=1, slice_rec=dict(z_in=z_in, zz=zz, zh=zh, s0=s0, s2=s2))
+        self._tproj = {id(b): (tproj[:, o:], tld, o) for b, o in zip(blocks, toffs)}
 
         # ---- init_conv: thin Cin -> patch matrix + GEMM --------------------------------------------
         S = H * W
@@ -617,7 +624,11 @@ class UNet2DProgram(UNetProgram):
         self.track(ic.weight, ic.bias)
         w_in = self.packed(lambda: _pad_k(P.pack_conv_weight(ic.weight.detach()), kpad))
         h = self.new_act(self.sp, chs[0], with_stats=False)
-        self.gemm(self._matrix_conv2d(col, w_in, h, S, kpad, ic.bias, "init_conv"))
+        pl = self._matrix_conv2d(col, w_in, h, S, kpad, ic.bias, "init_conv")
+        self.gemm(pl)
+        self.tape.append(ConvRec(kind="matrix", plan=pl, y=h.t, ksize=3, sources=[(col, True)],
+                                 weight=ic.weight, splits=[cin], bias_params=[ic.bias], cout=chs[0],
+                                 need_dgrad=False, kpad=kpad, name="init_conv"))
 
         skips: List[Act] = []
         for i, d in enumerate(model.downs):
@@ -628,7 +639,11 @@ class UNet2DProgram(UNetProgram):
             self.track(dn.weight, dn.bias)
             wd = self.packed(lambda dn=dn: P.pack_conv_weight(dn.weight.detach()))
             y = self.new_act([s // 2 for s in h.t.shape[1:-1]], dn.weight.shape[0], with_stats=False)
-            self.gemm(P.down_conv_plan(h.t, wd, y.t, bias=dn.bias, name=f"downs.{i}.down"))
+            pl = P.down_conv_plan(h.t, wd, y.t, bias=dn.bias, name=f"downs.{i}.down")
+            self.gemm(pl)
+            self.tape.append(ConvRec(kind="down", plan=pl, y=y.t, ksize=4, sources=[(h.t, True)],
+                                     weight=dn.weight, splits=[h.C], bias_params=[dn.bias],
+                                     cout=dn.weight.shape[0], name=f"downs.{i}.down"))
             h = y
         h = self.resblock2d(h, None, model.mid_block1, eps, "mid_block1")
         h = self.resblock2d(h, None, model.mid_block2, eps, "mid_block2")
@@ -638,7 +653,11 @@ class UNet2DProgram(UNetProgram):
             self.track(up.weight, up.bias)
             wu = self.packed(lambda up=up: P.pack_convT_weight(up.weight.detach()))
             y = self.new_act([s * 2 for s in h.t.shape[1:-1]], up.weight.shape[1], with_stats=False)
-            self.gemm(P.up_conv_plan(h.t, wu, y.t, bias=up.bias, name=f"ups.{j}.up"))
+            pl = P.up_conv_plan(h.t, wu, y.t, bias=up.bias, name=f"ups.{j}.up")
+            self.gemm(pl)
+            self.tape.append(ConvRec(kind="up", plan=pl, y=y.t, ksize=4, sources=[(h.t, True)],
+                                     weight=up.weight, splits=[h.C], bias_params=[up.bias],
+                                     cout=up.weight.shape[1], name=f"ups.{j}.up"))
             self.pool.release(h.t)
             if tuple(y.t.shape[1:-1]) != tuple(skip.t.shape[1:-1]):
                 raise _lib.MriError("UpBlock bilinear-resize branch (unet.py:98-99) not implemented")
@@ -653,11 +672,18 @@ class UNet2DProgram(UNetProgram):
         self.cout_pad = _rup(self.cout, 16)
         w_out = self.packed(lambda: P.pack_conv_weight(oc.weight.detach(), cout_pad=self.cout_pad))
         b_out = self.packed(lambda: _pad_vec(oc.bias.detach(), self.cout_pad))
+        self.deps64 = torch.zeros(B, H, W, 64, dtype=torch.bfloat16, device=dev) if training else None
         y = self.conv([P.ConvSource(a)], w_out, self.cout_pad, 3, b_out, with_stats=False,
-                      name="out_conv")
+                      name="out_conv",
+                      rec=dict(weight=oc.weight, splits=[a.shape[-1]], bias_params=[oc.bias],
+                               cout=self.cout, dgrad_dy=self.deps64))
         self.eps_nhwc = y.t
         self.out = torch.zeros(B, self.cout, H, W, device=dev)
         self.params_changed()
+        if training:
+            self.dout_in = torch.zeros(B, self.cout, H, W, device=dev)
+            self.deps16 = torch.zeros_like(self.eps_nhwc)
+            self.build_backward({id(self.eps_nhwc): self.deps16})
 
     def _matrix_conv2d(self, col, wmat, y: Act, S: int, kpad: int, bias, name) -> P.GemmPlan:
         B, C = self.B, y.C
@@ -676,16 +702,18 @@ class UNet2DProgram(UNetProgram):
         n1, n2, c1, c2 = blk.norm1, blk.norm2, blk.conv1, blk.conv2
         self.track(n1.weight, n1.bias, n2.weight, n2.bias, c1.weight, c1.bias, c2.weight, c2.bias)
         cout = c1.weight.shape[0]
-        rowbias, rb_ld = self._tproj[id(blk)]
+        rowbias, rb_ld, t_off = self._tproj[id(blk)]
         srcs = [x] if skip is None else [x, skip]
         cins = [s.C for s in srcs]
         w1 = self.packed(lambda: P.pack_conv_weight(c1.weight.detach(), splits=cins))
-        h1 = self.conv([P.ConvSource(s.t) for s in srcs], w1, cout, 3, c1.bias, name=f"{name}.conv1")
+        h1 = self.conv([P.ConvSource(s.t) for s in srcs], w1, cout, 3, c1.bias, name=f"{name}.conv1",
+                       rec=dict(weight=c1.weight, splits=cins, bias_params=[c1.bias]))
         a1 = self.gn(h1, n1.weight, n1.bias, self.groups, eps, True, rowbias=rowbias, rowbias_ld=rb_ld,
-                     name=f"{name}.norm1+temb")
+                     name=f"{name}.norm1+temb", tproj_off=t_off)
         self.pool.release(h1.t)
         w2 = self.packed(lambda: P.pack_conv_weight(c2.weight.detach()))
-        h2 = self.conv([P.ConvSource(a1)], w2, cout, 3, c2.bias, name=f"{name}.conv2")
+        h2 = self.conv([P.ConvSource(a1)], w2, cout, 3, c2.bias, name=f"{name}.conv2",
+                       rec=dict(weight=c2.weight, splits=[cout], bias_params=[c2.bias]))
         self.pool.release(a1)
         if isinstance(blk.res_conv, torch.nn.Identity):
             assert skip is None and x.C == cout
@@ -696,7 +724,8 @@ class UNet2DProgram(UNetProgram):
             self.track(rc.weight, rc.bias)
             wr = self.packed(lambda: P.pack_conv_weight(rc.weight.detach(), splits=cins))
             res_tmp = self.conv([P.ConvSource(s.t) for s in srcs], wr, cout, 1, rc.bias,
-                                with_stats=False, name=f"{name}.res_conv")
+                                with_stats=False, name=f"{name}.res_conv",
+                                rec=dict(weight=rc.weight, splits=cins, bias_params=[rc.bias]))
             res = res_tmp.t
         out = self.gn(h2, n2.weight, n2.bias, self.groups, eps, True, residual=res,
                       name=f"{name}.norm2+res")
@@ -707,7 +736,7 @@ class UNet2DProgram(UNetProgram):
             self.pool.release(s.t)
         return Act(out)
 
-    def forward(self, x, t, z_pos, context=None) -> torch.Tensor:
+    def _load_inputs(self, x, t, z_pos, context):
         if self.params_changed():
             for fn in self.refresh:
                 fn()
@@ -716,7 +745,17 @@ class UNet2DProgram(UNetProgram):
         self.z_in.copy_(z_pos.reshape(-1, 1))
         if self.ctx_in is not None:
             self.ctx_in.copy_(context)
+
+    def forward(self, x, t, z_pos, context=None) -> torch.Tensor:
+        self._load_inputs(x, t, z_pos, context)
         self.run()
         ops.nhwc_to_nchw(self.eps_nhwc, self.out, self.B, self.sp[0] * self.sp[1], self.cout,
                          self.cout_pad)
         return self.out
+
+    def backward(self, dout: torch.Tensor) -> None:
+        S = self.sp[0] * self.sp[1]
+        self.dout_in.copy_(dout)
+        ops.nchw_to_nhwc(self.dout_in, self.deps16, self.B, S, self.cout, self.cout_pad)
+        ops.nchw_to_nhwc(self.dout_in, self.deps64, self.B, S, self.cout, 64)
+        self.run_backward()

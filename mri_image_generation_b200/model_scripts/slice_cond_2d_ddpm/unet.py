@@ -7,7 +7,7 @@ import torch.nn as nn
 
 from ... import _lib
 from ...engine import UNet2DProgram
-from ...modules import EngineModule, SinusoidalHolder
+from ...modules import EngineModule, SinusoidalHolder, UNetFunction
 
 SinusoidalPosEmb = SinusoidalHolder  # unet.py:7
 
@@ -78,9 +78,12 @@ class _UNet2DBase(EngineModule):
         self.out_norm = nn.GroupNorm(8, self.chs[0])
         self.out_conv = nn.Conv2d(self.chs[0], out_channels, 3, padding=1)
 
-    def program(self, batch: int, spatial, x_channels: int, ctx_channels: int = 0) -> UNet2DProgram:
-        key = (int(batch), tuple(int(s) for s in spatial), int(x_channels), int(ctx_channels))
-        return self.get_program(key, lambda: UNet2DProgram(self, key[0], key[1], key[2], key[3]))
+    def program(self, batch: int, spatial, x_channels: int, ctx_channels: int = 0,
+                training: bool = False) -> UNet2DProgram:
+        key = (int(batch), tuple(int(s) for s in spatial), int(x_channels), int(ctx_channels),
+               bool(training))
+        return self.get_program(key, lambda: UNet2DProgram(self, key[0], key[1], key[2], key[3],
+                                                           training=key[4]))
 
     def _forward(self, x, t, z_pos, context=None):
         self._check_input(x)
@@ -89,9 +92,15 @@ class _UNet2DBase(EngineModule):
         t = t.to(x.device).long()
         z_pos = z_pos.to(x.device).float()
         cc = 0 if context is None else context.shape[1]
-        prog = self.program(x.shape[0], x.shape[2:], x.shape[1], cc)
         ctx = None if context is None else context.to(x.device).float().contiguous()
-        return prog.forward(x.float().contiguous(), t, z_pos, ctx).clone()
+        xf = x.float().contiguous()
+        if self._needs_grad():
+            prog = self.program(x.shape[0], x.shape[2:], x.shape[1], cc, training=True)
+            prog.param_list = list(self.parameters())
+            return UNetFunction.apply(prog, lambda: prog.forward(xf, t, z_pos, ctx),
+                                      len(prog.param_list), *prog.param_list)
+        prog = self.program(x.shape[0], x.shape[2:], x.shape[1], cc)
+        return prog.forward(xf, t, z_pos, ctx).clone()
 
 
 class UNet(_UNet2DBase):
