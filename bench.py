@@ -332,6 +332,76 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def run_train(args, rank, world, local_rank):
+    """Secondary workload (BASELINE.json cfg5): one DDP training step of the 3D LDM UNet --
+    q_sample + UNet fwd + min-SNR loss + bwd (+ NCCL gradient all-reduce through torch DDP when
+    world > 1) + Adam -- at `--batch` latents per GPU.  Prints samples/s; not the headline."""
+    import torch
+    import torch.distributed as dist
+    from mri_image_generation_b200 import _lib
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.diffusion import GaussianDiffusionLatent3D
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.unet_attention import \
+        UNet3DModelWithAttention
+    from mri_image_generation_b200.parallel import wrap_ddp
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.require_device()
+    B, K, W = args.batch, args.steps, max(3, args.warmup)
+    torch.manual_seed(0)
+    model = UNet3DModelWithAttention(**MODEL_KW).to(dev).train()
+    net = wrap_ddp(model, dev) if world > 1 else model
+    diff = quiet(GaussianDiffusionLatent3D, net, LATENT[0], timesteps=T_STEPS).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=2e-4)
+    torch.manual_seed(1234 + rank)
+    z = torch.randn(B, *LATENT, device=dev)
+
+    def step():
+        t = torch.randint(1, T_STEPS, (B,), device=dev)
+        opt.zero_grad(set_to_none=True)
+        loss = diff.p_losses(z, t, cond=None, min_snr_gamma=5.0)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(W):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return
+    ms_per_step = ms.item() / K
+    prog = model.program(B, LATENT[1:], training=True)
+    flops = B * 3 * 1276.4e9  # fwd + bwd = 3 x fwd (SURVEY.md 8d: 30.62 TFLOP per 8-sample step)
+    peaks = load_peaks()
+    line = {
+        "metric": "training samples/sec (3D LDM UNet DDP step)", "value": world * B / (ms_per_step / 1e3),
+        "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "ddpm_3d_ldm_train_step", "latent": list(LATENT), "batch_per_gpu": B,
+                   "model": "UNet3DModelWithAttention(base 128, mults 1-2-4, 136.4M params)",
+                   "step": "q_sample + fwd + min-SNR loss + bwd + DDP all-reduce + Adam",
+                   "loss": float(loss.item())},
+        "roofline": {"bound": "tensor", "achieved": flops / (ms_per_step * 1e-3) / 1e12,
+                     "peak": peaks["tflops"], "unit": "TFLOP/s",
+                     "frac": flops / (ms_per_step * 1e-3) / 1e12 / peaks["tflops"],
+                     "note": "whole step (all kernels + optimizer + all-reduce), algorithmic conv+attention FLOPs",
+                     "executed_gemm_flops": prog.gemm_flops + prog.bwd_flops},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -339,6 +409,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=4, help="volumes per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="sample", choices=["sample", "train"],
+                    help="sample = headline (cfg4); train = DDP training step (cfg5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-op", default="", help="write per-GEMM timings (CUDA events) to this file")
     args = ap.parse_args()
@@ -356,7 +428,10 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.mode == "train":
+            run_train(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -1,0 +1,95 @@
+"""Multi-GPU checks (run under torchrun on a multi-GPU box; not collected by pytest):
+
+  torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_check.py
+
+1. batch-sharded sampling: every rank's volumes equal a single-process run with that rank's seed
+   (no data-path collective; gather only for the comparison);
+2. DDP training step (NCCL gradient all-reduce through torch DDP, train.py:232-233): 2 ranks x
+   batch b == single process batch 2b, gradient by gradient.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def main():
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.diffusion import GaussianDiffusionLatent3D
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.unet_attention import UNet3DModelWithAttention
+    from mri_image_generation_b200.parallel import sample_sharded, shard_bounds, wrap_ddp
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+
+    def rel(a, b):
+        return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30)).item()
+
+    torch.manual_seed(0)
+    model = UNet3DModelWithAttention(3, base_channels=64, time_emb_dim=64).to(dev)
+    diff = quiet(GaussianDiffusionLatent3D, model, 3, timesteps=6).to(dev)
+
+    # ---- 1. sharded sampling --------------------------------------------------------------
+    model.eval()
+    total = 2 * world + 1  # ragged on purpose
+    out = sample_sharded(diff, total, (8, 8, 8), base_seed=500)
+    if rank == 0:
+        parts = []
+        for r in range(world):
+            lo, hi = shard_bounds(total, world, r)
+            torch.manual_seed(500 + r)
+            parts.append(diff.sample(hi - lo, (8, 8, 8)).cpu())
+        want = torch.cat(parts, 0)
+        assert out.shape == want.shape
+        assert torch.equal(out, want), rel(out, want)
+        print(f"[dist_check] sharded sampling over {world} ranks == per-seed single-process runs (bit-exact)")
+
+    # ---- 2. DDP gradient equality ---------------------------------------------------------------
+    model.train()
+    b = 2
+    g = torch.Generator().manual_seed(3)
+    x0 = torch.randn(b * world, 3, 8, 8, 8, generator=g)
+    noise = torch.randn(b * world, 3, 8, 8, 8, generator=g)
+    t = torch.randint(1, 6, (b * world,), generator=g)
+    ddp = wrap_ddp(model, dev)
+    diff_ddp = quiet(GaussianDiffusionLatent3D, ddp, 3, timesteps=6).to(dev)
+    sl = slice(rank * b, (rank + 1) * b)
+    loss = diff_ddp.p_losses(x0[sl].to(dev), t[sl].to(dev), noise=noise[sl].to(dev))
+    loss.backward()
+    grads_ddp = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+    for p in model.parameters():
+        p.grad = None
+    loss_full = diff.p_losses(x0.to(dev), t.to(dev), noise=noise.to(dev))
+    loss_full.backward()
+    worst = 0.0
+    for n, p in model.named_parameters():
+        worst = max(worst, rel(grads_ddp[n], p.grad))
+    lt = loss.detach().clone()
+    dist.all_reduce(lt)
+    assert abs(lt.item() / world - loss_full.item()) < 1e-4 * abs(loss_full.item())
+    assert worst < 5e-3, worst
+    if rank == 0:
+        print(f"[dist_check] DDP x{world} gradients == single-process large-batch gradients "
+              f"(worst rel-L2 {worst:.2e}); mean loss {lt.item() / world:.6f} vs {loss_full.item():.6f}")
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("[dist_check] OK")
+
+
+if __name__ == "__main__":
+    main()
