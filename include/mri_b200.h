@@ -214,16 +214,17 @@ typedef struct MriWgradArgs {
 int mri_wgrad_launch(const MriWgradArgs* args_host, void* stream);
 
 /* GroupNorm(+SiLU) backward, y = act(gn(x)*gamma+beta):
- * mri_gn_bwd_reduce: sums[3][samples][C] (fp32, accumulated with atomics -- zero first):
+ * mri_gn_bwd_reduce: sums[3][samples][C] (fp64, accumulated with fp64 atomics so that the result
+ *   does not depend on arrival order -- zero first):
  *   [0] = sum_s dy, [1] = sum_s du, [2] = sum_s du*xhat  (du = dy*act'(u)); x == NULL: only [0]
  *   (plain per-(sample, channel) column sum: bias and time-embedding-projection gradients).
  *   dgamma = sum_n sums[2], dbeta = sum_n sums[1].
  * mri_gn_bwd_apply: dx = rstd*(gamma*du - mean_g(gamma*du) - xhat*mean_g(gamma*du*xhat)) (+ add). */
 int mri_gn_bwd_reduce(const void* x, const void* dy, const double* stats, const float* gamma,
-                      const float* beta, float* sums, int samples, int64_t spatial, int C,
+                      const float* beta, double* sums, int samples, int64_t spatial, int C,
                       int groups, int stats_ld, int stats_cpg, float eps, int silu, void* stream);
 int mri_gn_bwd_apply(const void* x, const void* dy, const void* add, void* dx, const double* stats,
-                     const float* gamma, const float* beta, const float* sums, int samples,
+                     const float* gamma, const float* beta, const double* sums, int samples,
                      int64_t spatial, int C, int groups, int stats_ld, int stats_cpg, float eps,
                      int silu, void* stream);
 /* out = a + b, bf16, n elements (multiple of 8) */

@@ -154,7 +154,7 @@ class BackwardMixin:
             return
         B = self.B
         S = dy.numel() // (B * C)
-        cs = self.zeros_each_bwd(1, B, C)
+        cs = self.zeros_each_bwd(1, B, C, dtype=torch.float64)
         self.badd(f"colsum:{name}", lambda: ops.colsum(dy, cs, B, S, C))
         for bp in bias_params:
             g = self.pg(bp)
@@ -277,7 +277,7 @@ class BackwardMixin:
         B, S, C = self.B, x.spatial, x.C
         if r.residual is not None:
             self.pass_grad(r.residual, dy)
-        sums = self.zeros_each_bwd(3, B, C)
+        sums = self.zeros_each_bwd(3, B, C, dtype=torch.float64)
         gamma = r.gamma[r.c_off:r.c_off + C]
         beta = r.beta[r.c_off:r.c_off + C]
         xs, st, cpg = x.t, x.stats, x.cpg

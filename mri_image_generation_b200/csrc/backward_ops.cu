@@ -53,23 +53,23 @@ __device__ __forceinline__ GnCoef gn_coef(const double* stats, int sample, int s
 // Pass A.  Per (sample, channel): S0 = sum dy, S1 = sum du, S2 = sum du * xhat, where
 // u = xhat*gamma+beta, du = dy * silu'(u) (or dy when !silu).  With x == nullptr only S0 is
 // produced (plain column sum).  grid (chunks, samples); thread = fixed 8-channel vector.
-// sums: fp32 [3][samples][C]
+// sums: fp64 [3][samples][C] (fp64 atomics: the result does not depend on arrival order)
 // ---------------------------------------------------------------------------------------
 template <bool kSilu>
 __global__ void __launch_bounds__(256)
 gn_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
                      const double* __restrict__ stats, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, float* __restrict__ sums, int samples,
+                     const float* __restrict__ beta, double* __restrict__ sums, int samples,
                      int64_t spatial, int C, int groups, int stats_ld, int stats_cpg, float eps,
                      int rows_per_block) {
-  extern __shared__ float red[];  // [3][C]
+  extern __shared__ double red[];  // [3][C]
   const int vec_per_row = C >> 3;
   const int sample = blockIdx.y;
   const int cv = threadIdx.x % vec_per_row;
   const int rsub = threadIdx.x / vec_per_row;
   const int rows_step = blockDim.x / vec_per_row;
   const int c = cv * 8;
-  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.0;
   __syncthreads();
 
   float sc[8], sh[8], mean = 0.f, rstd = 1.f;
@@ -117,10 +117,10 @@ gn_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    atomicAdd(&red[c + j], s0[j]);
+    atomicAdd(&red[c + j], (double)s0[j]);
     if (x != nullptr) {
-      atomicAdd(&red[C + c + j], s1[j]);
-      atomicAdd(&red[2 * C + c + j], s2[j]);
+      atomicAdd(&red[C + c + j], (double)s1[j]);
+      atomicAdd(&red[2 * C + c + j], (double)s2[j]);
     }
   }
   __syncthreads();
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256)
 gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
                     const uint4* __restrict__ add, uint4* __restrict__ dx,
                     const double* __restrict__ stats, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, const float* __restrict__ sums, int samples,
+                    const float* __restrict__ beta, const double* __restrict__ sums, int samples,
                     int64_t spatial, int C, int groups, int stats_ld, int stats_cpg, float eps,
                     int rows_per_block) {
   const int vec_per_row = C >> 3;
@@ -152,17 +152,17 @@ gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
   const int cpg = C / groups;
   const int g = c / cpg;
   const GnCoef k = gn_coef(stats, sample, stats_ld, g, cpg / stats_cpg, cpg, spatial, eps);
-  const float* S1 = sums + ((size_t)1 * samples + sample) * C;
-  const float* S2 = sums + ((size_t)2 * samples + sample) * C;
-  float m1 = 0.f, m2 = 0.f;
+  const double* S1 = sums + ((size_t)1 * samples + sample) * C;
+  const double* S2 = sums + ((size_t)2 * samples + sample) * C;
+  double m1d = 0.0, m2d = 0.0;
   for (int j = g * cpg; j < (g + 1) * cpg; ++j) {
-    const float gm = __ldg(gamma + j);
-    m1 = fmaf(gm, __ldg(S1 + j), m1);
-    m2 = fmaf(gm, __ldg(S2 + j), m2);
+    const double gm = (double)__ldg(gamma + j);
+    m1d += gm * __ldg(S1 + j);
+    m2d += gm * __ldg(S2 + j);
   }
-  const float inv_cnt = 1.0f / ((float)cpg * (float)spatial);
-  m1 *= inv_cnt;
-  m2 *= inv_cnt;
+  const double inv_cnt = 1.0 / ((double)cpg * (double)spatial);
+  const float m1 = (float)(m1d * inv_cnt);
+  const float m2 = (float)(m2d * inv_cnt);
   float gmv[8], btv[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -321,7 +321,7 @@ static inline int rows_per_block_for(int samples, int64_t spatial, int rows_step
 using namespace mri;
 
 extern "C" int mri_gn_bwd_reduce(const void* x, const void* dy, const double* stats,
-                                 const float* gamma, const float* beta, float* sums, int samples,
+                                 const float* gamma, const float* beta, double* sums, int samples,
                                  int64_t spatial, int C, int groups, int stats_ld, int stats_cpg,
                                  float eps, int silu, void* stream) {
   if (C % 8 != 0 || C / 8 > 256) return set_error(-2, "mri_gn_bwd_reduce: bad C");
@@ -331,7 +331,7 @@ extern "C" int mri_gn_bwd_reduce(const void* x, const void* dy, const double* st
   const int threads = (256 / vpr) * vpr;
   dim3 grid;
   const int rpb = rows_per_block_for(samples, spatial, threads / vpr, &grid);
-  const size_t smem = 3 * C * sizeof(float);
+  const size_t smem = 3 * C * sizeof(double);
   const uint4* xp = reinterpret_cast<const uint4*>(x);
   const uint4* dp = reinterpret_cast<const uint4*>(dy);
   if (silu)
@@ -345,7 +345,7 @@ extern "C" int mri_gn_bwd_reduce(const void* x, const void* dy, const double* st
 
 extern "C" int mri_gn_bwd_apply(const void* x, const void* dy, const void* add, void* dx,
                                 const double* stats, const float* gamma, const float* beta,
-                                const float* sums, int samples, int64_t spatial, int C, int groups,
+                                const double* sums, int samples, int64_t spatial, int C, int groups,
                                 int stats_ld, int stats_cpg, float eps, int silu, void* stream) {
   if (C % 8 != 0 || C / 8 > 256 || groups < 1 || C % groups != 0 || (C / groups) % stats_cpg != 0)
     return set_error(-2, "mri_gn_bwd_apply: bad channel / group configuration");
