@@ -272,10 +272,10 @@ def run_ours(args, rank, world, local_rank):
             for i, pl in zip(gemm_idx, prog.plans):
                 msi = sum(per[i]) / len(per[i])
                 rows.append((prog.op_names[i], msi, pl.flops / (msi * 1e-3) / 1e12, pl.grid(), pl.block_n,
-                             pl.n_kb, pl.box, pl._args.stages))
+                             pl.n_kb, pl.box, pl._args.sched))
             with open(args.per_op, "w") as f:
                 for r_ in rows:
-                    f.write("%-34s %8.3f ms %8.1f TF/s grid %6d bn %3d n_kb %4d box %s stages %d\n" % r_)
+                    f.write("%-34s %8.3f ms %8.1f TF/s grid %6d bn %3d n_kb %4d box %s sched %d\n" % r_)
 
     t_ms = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:

@@ -65,7 +65,6 @@ typedef struct MriGemmArgs {
   const void* a_maps;     /* device: CUtensorMap[], rank-5 bf16, box {64, box[0..3]}, swizzle 128B */
   const void* b_map;      /* device: CUtensorMap, rank-4 bf16 {K, rows, z1, z2}, box {64, block_n,1,1} */
   const void* o_maps;     /* device: CUtensorMap[n_class], rank-5 output, box {chunk, box[0..3]} */
-  const void* r_maps;     /* device: CUtensorMap[n_class] residual (bf16, same boxes) or NULL */
   const int32_t* ktable;  /* device: [n_class][n_kb][8] */
   int32_t n_kb;
   int32_t n_class;
@@ -86,15 +85,33 @@ typedef struct MriGemmArgs {
                              (order-insensitive to ~1e-16, i.e. reproducible), or NULL */
   int32_t stats_ld;       /* statistics groups per sample */
   int32_t stats_cpg;      /* channels per statistics group (multiple of 8) */
-  int32_t stages;         /* TMA ring depth (2..8) */
+  int32_t stages;         /* TMA ring depth; 0 = as deep as shared memory allows (4..8) */
+  int32_t sched;          /* 0: every tile's K loop stays in one CTA; 1: the tiles that do not fill a
+                             whole wave of the persistent grid are split along K across all CTAs
+                             ("stream-K", needs the workspace), the rest run as whole tiles */
+  const void* r_maps;     /* device: CUtensorMap[n_class] residual tensor (bf16) through the output
+                             view, boxes as o_maps, or NULL.  Used when swap_ab = 1 ... */
+  const void* r_base;     /* ... and the same residual as a plain pointer (swap_ab = 0): the element
+                             added to output (class c, box position x, column n) is
+                             r_base[r_cls_off[c] + sum_i x_i * r_stride[i] + n]  (n_class <= 8).
+                             Both are set or both NULL. */
+  int64_t r_cls_off[8];
+  int64_t r_stride[4];
+  float* sk_partials;     /* stream-K workspace (mri_gemm_workspace_bytes), shared by all launches */
+  int32_t* sk_flags;      /* [sk_ctas] zero-initialised once; the kernel resets what it raises */
+  int32_t sk_ctas;
+  int32_t swap_ab;        /* 1: weights are the M = 128 MMA operand, two boxes of positions the N = 256
+                             operand (needs block_n 128, n_total % 128 == 0, bf16 output) */
   int32_t reserved;
+  uint64_t* trace;        /* profiling only (normally NULL): [grid][8] per-CTA timestamps, see gemm_tc.cu */
 } MriGemmArgs;
 
-/* dynamic shared memory one CTA needs for (block_n, stages) */
-int mri_gemm_smem_bytes(int block_n, int stages);
+/* dynamic shared memory one CTA uses for (block_n, swap_ab, requested stages; 0 = maximum) */
+int mri_gemm_smem_bytes(int block_n, int swap_ab, int stages);
+/* bytes of the stream-K workspace for the current device: [n_ctas][128][256] fp32 partial tiles
+ * followed by 1 KB holding int32 flags[n_ctas] (the caller zeroes the flags once). */
+int mri_gemm_workspace_bytes(int* n_ctas_out);
 int mri_gemm_launch(const MriGemmArgs* args_host, void* stream);
-/* resident CTAs per SM the kernel reaches for (block_n, stages); <0 on error */
-int mri_gemm_occupancy(int block_n, int stages);
 
 /* ------------------------------------------------------------------------------------------
  * GroupNorm (+SiLU, + time-embedding add, + residual add), channels-last bf16.

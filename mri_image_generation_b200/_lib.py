@@ -18,7 +18,6 @@ class MriGemmArgs(C.Structure):
         ("a_maps", C.c_void_p),
         ("b_map", C.c_void_p),
         ("o_maps", C.c_void_p),
-        ("r_maps", C.c_void_p),
         ("ktable", C.c_void_p),
         ("n_kb", C.c_int32),
         ("n_class", C.c_int32),
@@ -39,7 +38,17 @@ class MriGemmArgs(C.Structure):
         ("stats_ld", C.c_int32),
         ("stats_cpg", C.c_int32),
         ("stages", C.c_int32),
+        ("sched", C.c_int32),
+        ("r_maps", C.c_void_p),
+        ("r_base", C.c_void_p),
+        ("r_cls_off", C.c_int64 * 8),
+        ("r_stride", C.c_int64 * 4),
+        ("sk_partials", C.c_void_p),
+        ("sk_flags", C.c_void_p),
+        ("sk_ctas", C.c_int32),
+        ("swap_ab", C.c_int32),
         ("reserved", C.c_int32),
+        ("trace", C.c_void_p),
     ]
 
 
@@ -72,9 +81,9 @@ SIGNATURES = {
     "mri_device_ok": (_i, []),
     "mri_tmap_encode": (_i, [_vp, _u64, _i, _i, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                              C.POINTER(C.c_uint32), _i]),
-    "mri_gemm_smem_bytes": (_i, [_i, _i]),
+    "mri_gemm_smem_bytes": (_i, [_i, _i, _i]),
     "mri_gemm_launch": (_i, [C.POINTER(MriGemmArgs), _vp]),
-    "mri_gemm_occupancy": (_i, [_i, _i]),
+    "mri_gemm_workspace_bytes": (_i, [C.POINTER(C.c_int)]),
     "mri_gn_stats": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _i, _vp]),
     "mri_gn_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i64, _i, _i, _i, _i, _i, _f,
                           _i, _vp]),

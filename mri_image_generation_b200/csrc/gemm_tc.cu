@@ -1,14 +1,34 @@
-// Implicit-GEMM convolution / GEMM on Blackwell tensor cores (tcgen05 + TMEM + TMA).
+// Implicit-GEMM convolution / GEMM on Blackwell tensor cores (tcgen05 + TMEM + TMA), revision B:
+// persistent CTAs, stream-K work split, epilogue overlapped with the next tile's main loop.
 //
 //   D[m, n] = sum_k A[m, k] * B[n, k]      A, B bf16 (K-major, 128B swizzle), D fp32 in TMEM
+//   m = output position (a box of up to 128 positions), n = output channel, k = (tap, channel)
 //
-// One CTA = one 128 x block_n output tile.  Warp roles (192 threads):
-//   warp 0     TMA producer: walks the k-table, one 64-channel A slab + B slab per stage
-//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2-5  epilogue: tcgen05.ld -> bias / time-embedding / residual / GroupNorm partial
-//              sums -> bf16|fp32 -> swizzled smem staging -> TMA store
-// The 128 rows of a tile are a box of output positions; every filter tap is the same box
-// shifted by (o1..o4), loaded by TMA with hardware zero fill outside the tensor (= padding).
+// One CTA per SM (grid <= #SMs), each walking its share of the tiles (see "schedule" below):
+// whole tiles, plus -- for the tiles that would leave the last wave under-filled -- an equal
+// share of their K loops ("stream-K").
+//
+// Two tile shapes (measured on B200: one tcgen05.mma with M = 128 occupies the tensor pipe for
+// ~137 cycles whatever N <= 128 is, and ~150 cycles at N = 256, so only N = 256 instructions
+// come near the pipe's peak):
+//   swap_ab = 1  (convolutions with Cout % 128 == 0): the WEIGHTS are the M = 128 operand and
+//                two boxes of positions are the N = 256 operand; the accumulator holds D^T
+//                (lane = channel, column = position) and the epilogue transposes on its way
+//                to the channels-last output;
+//   swap_ab = 0  (thin / odd shapes, fp32 outputs): positions are M, block_n channels are N.
+// Warp roles (192 threads):
+//   warp 0     TMA producer: walks the k-table, one stage = activation slab(s) + weight slab
+//   warp 1     TMEM allocator + tcgen05.mma issuer (whole warp walks the loop converged, one
+//              elected lane issues: operands stay in uniform registers).  TMEM holds two tile
+//              buffers of 256 columns, so tile i+1 accumulates while tile i drains
+//   warps 2-5  epilogue: tcgen05.ld -> (+ partial sums of the CTAs that share the tile) ->
+//              bias / time-embedding / residual / GroupNorm partial sums -> bf16|fp32 ->
+//              swizzled staging (2 x 16 KB) -> TMA store
+// Split tiles: every CTA but the one holding a tile's first k-step writes its fp32 partial
+// tile to a workspace and raises a flag; the head CTA (which reaches that tile LAST in its own
+// range) adds the partials in fixed order and runs the fused epilogue -> deterministic.
+// Every filter tap is the same box of positions shifted by (o1..o4), loaded by TMA with
+// hardware zero fill outside the tensor (= the convolution's zero padding).
 // See include/mri_b200.h (MriGemmArgs) for the contract and the reference call sites.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -24,50 +44,225 @@ namespace mri {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // bf16 -> 128-byte rows = one swizzle span
 constexpr int kUmmaK = 16;
-constexpr int kAStageBytes = kBlockM * 128;
+constexpr int kSlabBytes = kBlockM * 128;        // 128 rows x 64 bf16
 constexpr int kThreads = 192;
 constexpr int kMaxStages = 8;
+constexpr int kChunkBytes = kBlockM * 128;       // one staging buffer: 128 rows x 128 bytes
+constexpr int kStagingBytes = 2 * kChunkBytes;
+constexpr int kPartialLd = 256;                  // floats per row of a stream-K partial tile
+constexpr int kMaxStatGroups = 32;
+constexpr int kSmemLimit = 227 * 1024;
 
-__host__ __device__ inline int stage_bytes(int block_n) { return kAStageBytes + block_n * 128; }
+__host__ __device__ inline int stage_bytes(int block_n, int swap_ab) {
+  return swap_ab ? 3 * kSlabBytes : kSlabBytes + block_n * 128;
+}
 
-__global__ void __launch_bounds__(kThreads, 2)
+// One tile of work: 1 (normal) or 2 (swap_ab) boxes of positions x one block of channels.
+struct Work {
+  int cls, n0, nbox;
+  int tix[2][4], org[2][4];
+};
+
+struct Geom {
+  int boxes_per_class;   // boxes of positions per output class
+  int groups_per_class;  // tiles along the position axis per class (box pairs when swap_ab)
+  long long n_tiles;
+};
+
+__device__ __forceinline__ Geom make_geom(const MriGemmArgs& p) {
+  Geom g;
+  g.boxes_per_class = p.tiles[0] * p.tiles[1] * p.tiles[2] * p.tiles[3];
+  g.groups_per_class = p.swap_ab ? (g.boxes_per_class + 1) / 2 : g.boxes_per_class;
+  g.n_tiles = (long long)p.n_tiles_n * p.n_class * g.groups_per_class;
+  return g;
+}
+
+__device__ __forceinline__ void decode_tile(const MriGemmArgs& p, const Geom& g, int tile, Work& w) {
+  const int nt = tile % p.n_tiles_n;
+  int pr = tile / p.n_tiles_n;
+  w.cls = pr / g.groups_per_class;
+  pr -= w.cls * g.groups_per_class;
+  w.n0 = nt * p.block_n;
+  int b0 = pr;
+  w.nbox = 1;
+  if (p.swap_ab) {
+    b0 = 2 * pr;
+    w.nbox = (b0 + 1 < g.boxes_per_class) ? 2 : 1;
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    int b = b0 + h;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      w.tix[h][i] = b % p.tiles[i];
+      b /= p.tiles[i];
+      w.org[h][i] = w.tix[h][i] * p.box[i];
+    }
+  }
+}
+
+// ---- schedule ------------------------------------------------------------------------------
+// sched 0: CTA with range index r owns the whole tiles [n_tiles*r/G, n_tiles*(r+1)/G).
+// sched 1: n_tiles = q*G + rem.  Phase A ("stream-K"): the K loops of the first `rem` tiles are
+//          one linear space of rem*n_kb k-steps cut into GA equal ranges (GA <= G CTAs take
+//          part), so a tile may be shared by neighbouring ranges.  Phase B: q whole tiles per
+//          CTA.  The split tiles come FIRST so that the exchange of partial sums is hidden
+//          behind the whole tiles that follow.
+struct Sched {
+  int n_kb, G, GA, q;
+  long long rem_units;  // rem * n_kb
+  long long n_tiles, rem;
+};
+
+__device__ __forceinline__ Sched make_sched(const MriGemmArgs& p, long long n_tiles, int G) {
+  Sched s;
+  s.n_kb = p.n_kb;
+  s.G = G;
+  s.n_tiles = n_tiles;
+  if (p.sched == 0) {
+    s.q = 0;
+    s.rem = 0;
+    s.rem_units = 0;
+    s.GA = 0;
+  } else {
+    s.q = (int)(n_tiles / G);
+    s.rem = n_tiles - (long long)s.q * G;
+    s.rem_units = s.rem * p.n_kb;
+    // a tile is shared by at most ~4 CTAs (its head CTA reads every other share back from L2)
+    // and a share is at least 8 k-steps
+    const int min_share = (p.n_kb + 3) / 4 > 8 ? (p.n_kb + 3) / 4 : 8;
+    const long long ga = s.rem_units / min_share;
+    s.GA = (int)(ga < 1 ? (s.rem > 0 ? 1 : 0) : (ga > G ? G : ga));
+  }
+  return s;
+}
+
+// phase-A unit range of range index r
+__device__ __forceinline__ void range_a(const Sched& s, int r, long long& u0, long long& u1) {
+  if (r >= s.GA) {
+    u0 = u1 = s.rem_units;
+    return;
+  }
+  u0 = s.rem_units * r / s.GA;
+  u1 = s.rem_units * (r + 1) / s.GA;
+}
+
+struct SegIter {
+  long long u, u1;  // phase A
+  long long tb, tb1;  // phase B (whole tiles)
+  int n_kb;
+  __device__ __forceinline__ void init(const MriGemmArgs& p, const Sched& s, int r) {
+    n_kb = s.n_kb;
+    if (p.sched == 0) {
+      u = u1 = 0;
+      tb = s.n_tiles * r / s.G;
+      tb1 = s.n_tiles * (r + 1) / s.G;
+    } else {
+      range_a(s, r, u, u1);
+      tb = s.rem + (long long)r * s.q;
+      tb1 = tb + s.q;
+    }
+  }
+  // next segment: tile, first k-step, number of k-steps; false when the CTA's work is done
+  __device__ __forceinline__ bool next(int& tile, int& kb0, int& len, long long& seg_end) {
+    if (u < u1) {
+      tile = (int)(u / n_kb);
+      kb0 = (int)(u - (long long)tile * n_kb);
+      const long long left = u1 - u;
+      len = (int)(left < (long long)(n_kb - kb0) ? left : (long long)(n_kb - kb0));
+      u += len;
+      seg_end = u;
+      return true;
+    }
+    if (tb < tb1) {
+      tile = (int)tb++;
+      kb0 = 0;
+      len = n_kb;
+      seg_end = -1;
+      return true;
+    }
+    return false;
+  }
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const int32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Contributors of a split tile: the phase-A ranges after `my_r` that cover [pos, tile_end).
+__device__ __forceinline__ int count_contributors(const Sched& s, int my_r, long long pos,
+                                                  long long tile_end) {
+  int n = 0;
+  int rr = my_r + 1;
+  while (pos < tile_end) {
+    long long a, b;
+    range_a(s, rr, a, b);
+    pos = b < tile_end ? b : tile_end;
+    ++rr;
+    ++n;
+  }
+  return n;
+}
+
+__device__ __forceinline__ void wait_contributors(const MriGemmArgs& p, int first_cta, int n) {
+  for (int j = 0; j < n; ++j) {
+    const int32_t* f = p.sk_flags + (first_cta - j);
+    const uint64_t t0 = globaltimer_ns();
+    while (ld_acquire_gpu(f) == 0u) {
+      if (globaltimer_ns() - t0 > 4000000000ull) {
+        printf("mri_b200: stream-K partial wait timeout (block %d waits for %d)\n",
+               (int)blockIdx.x, first_cta - j);
+        __trap();
+      }
+    }
+  }
+}
+
+// Partial tiles live in the workspace as [cta][column / 4][lane 0..127][4 floats]: the 32 lanes
+// of a warp touch 512 contiguous bytes per access.
+__device__ __forceinline__ float4* partial_ptr(const MriGemmArgs& p, int cta, int lane128, int col) {
+  return reinterpret_cast<float4*>(p.sk_partials) +
+         ((size_t)cta * (kPartialLd / 4) + (size_t)(col >> 2)) * kBlockM + lane128;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 2];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 5];
   __shared__ uint32_t tmem_holder;
+  __shared__ double s_stats[kMaxStatGroups * 2];
+  __shared__ int s_pos_info[kBlockM];       // swap_ab: sample index, or -1 for an invalid position
+  __shared__ uint32_t s_vmask[4];           // swap_ab: validity bits of the box's 128 positions
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform((int)(threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int S = p.stages;
   const int block_n = p.block_n;
-  const int sbytes = stage_bytes(block_n);
+  const bool swap = p.swap_ab != 0;
+  const int sbytes = stage_bytes(block_n, p.swap_ab);
+  const uint32_t stag = smem_base + (uint32_t)(S * sbytes);  // staging follows the ring
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
-  const uint32_t tmem_full_bar = bar0 + 8u * (2 * kMaxStages);
-  const uint32_t resid_bar = bar0 + 8u * (2 * kMaxStages + 1);
+  auto tmem_full_bar = [&](int b) { return bar0 + 8u * (2 * kMaxStages + b); };
+  auto tmem_empty_bar = [&](int b) { return bar0 + 8u * (2 * kMaxStages + 2 + b); };
+  const uint32_t resid_bar = bar0 + 8u * (2 * kMaxStages + 4);
 
-  // ---- tile decode -------------------------------------------------------------------
-  int tile = blockIdx.x;
-  const int nt = tile % p.n_tiles_n;
-  tile /= p.n_tiles_n;
-  int tix[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    tix[i] = tile % p.tiles[i];
-    tile /= p.tiles[i];
-  }
-  const int cls = tile;
-  int org[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) org[i] = tix[i] * p.box[i];
-  const int n0 = nt * block_n;
+  const int n_kb = p.n_kb;
+  const int G = (int)gridDim.x;
+  const int my_r = G - 1 - (int)blockIdx.x;  // waiters (tile heads) wait on LOWER block indices
+  const Geom geom = make_geom(p);
+  const long long n_tiles = geom.n_tiles;
+  const Sched sch = make_sched(p, n_tiles, G);
   const int rows_in_box = p.box[0] * p.box[1] * p.box[2] * p.box[3];
-
-  uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < block_n) tmem_cols <<= 1;
+  const bool dual = !swap && block_n <= 128;  // two accumulators per tile (k-step parity)
 
   // ---- one-time setup ------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
@@ -75,84 +270,139 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full_bar(b), 1);
+      mbar_init(tmem_empty_bar(b), 4);  // one arrive per epilogue warp
+    }
     mbar_init(resid_bar, 1);
     mbar_fence_init();
+    tma_prefetch_desc(p.b_map);
+    tma_prefetch_desc(p.a_maps);
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_holder), tmem_cols);
+    tmem_alloc(smem_u32(&tmem_holder), 512);
     tmem_relinquish();
   }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * kMaxStatGroups) s_stats[threadIdx.x - 64] = 0.0;
+  static_assert(2 * kMaxStatGroups <= 128, "statistics table is zeroed by the epilogue threads");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_holder;
+  // profiling: [0] kernel entry (globaltimer ns), [1] setup done, [2] first stage landed,
+  // [3] last MMA issued, [4] last accumulator complete, [5] epilogue done (clock64 cycles)
+  uint64_t* trace = p.trace != nullptr ? p.trace + (size_t)blockIdx.x * 8 : nullptr;
+  if (trace != nullptr && threadIdx.x == 0) {
+    trace[0] = globaltimer_ns();
+    trace[1] = (uint64_t)clock64();
+  }
 
   const CUtensorMap* a_maps = reinterpret_cast<const CUtensorMap*>(p.a_maps);
   const CUtensorMap* b_map = reinterpret_cast<const CUtensorMap*>(p.b_map);
 
   if (warp == 0) {
     // ================================ TMA producer ==================================
-    if (lane == 0) {
-      auto sel = [&](int s) { return s == 0 ? 0 : (s == 1 ? cls : tix[s - 2]); };
-      const int bz1 = sel(p.bz_sel[0]);
-      const int bz2 = sel(p.bz_sel[1]);
-      const uint32_t tx_bytes = (uint32_t)rows_in_box * 128u + (uint32_t)block_n * 128u;
-      const int4* kt = reinterpret_cast<const int4*>(p.ktable) + (size_t)cls * p.n_kb * 2;
-      int4 e0 = __ldg(kt), e1 = __ldg(kt + 1);
+    // The whole warp walks the loop (converged, warp-uniform values); one elected lane issues.
+    {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.n_kb; ++kb) {
-        int4 f0 = e0, f1 = e1;
-        if (kb + 1 < p.n_kb) {  // prefetch the next table entry ahead of the barrier wait
-          f0 = __ldg(kt + 2 * (kb + 1));
-          f1 = __ldg(kt + 2 * (kb + 1) + 1);
-        }
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t a_dst = smem_base + stage * sbytes;
-        const uint32_t b_dst = a_dst + kAStageBytes;
-        mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-        tma_load_5d(a_dst, a_maps + e0.x, full_bar(stage), e0.y, org[0] + e0.z, org[1] + e0.w,
-                    org[2] + e1.x, org[3] + e1.y);
-        tma_load_4d(b_dst, b_map, full_bar(stage), e1.z, n0, bz1, bz2);
-        e0 = f0;
-        e1 = f1;
-        if (++stage == S) {
-          stage = 0;
-          phase ^= 1u;
+      SegIter it;
+      it.init(p, sch, my_r);
+      int tile, kb0, len;
+      long long seg_end;
+      while (it.next(tile, kb0, len, seg_end)) {
+        Work t;
+        decode_tile(p, geom, tile, t);
+        auto sel = [&](int s) { return s == 0 ? 0 : (s == 1 ? t.cls : t.tix[0][s - 2]); };
+        const int bz1 = sel(p.bz_sel[0]);
+        const int bz2 = sel(p.bz_sel[1]);
+        const uint32_t tx_bytes = (uint32_t)(rows_in_box * t.nbox) * 128u + (uint32_t)block_n * 128u;
+        const int4* kt = reinterpret_cast<const int4*>(p.ktable) + ((size_t)t.cls * n_kb + kb0) * 2;
+        int4 e0 = __ldg(kt), e1 = __ldg(kt + 1);
+        for (int i = 0; i < len; ++i) {
+          int4 f0 = e0, f1 = e1;
+          if (i + 1 < len) {  // prefetch the next table entry ahead of the barrier wait
+            f0 = __ldg(kt + 2 * (i + 1));
+            f1 = __ldg(kt + 2 * (i + 1) + 1);
+          }
+          // every lane loaded the same entry; tell the compiler so
+          const int am = uniform(e0.x), c0 = uniform(e0.y), o1 = uniform(e0.z), o2 = uniform(e0.w);
+          const int o3 = uniform(e1.x), o4 = uniform(e1.y), bk = uniform(e1.z);
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          // stage layout: normal [positions 16K][weights block_n x 128B];
+          //               swap_ab [weights 16K][positions box0 16K][positions box1 16K]
+          const uint32_t s0 = smem_base + stage * sbytes;
+          const uint32_t x_dst = swap ? s0 + kSlabBytes : s0;
+          const uint32_t w_dst = swap ? s0 : s0 + kSlabBytes;
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+            tma_load_5d(x_dst, a_maps + am, full_bar(stage), c0, t.org[0][0] + o1, t.org[0][1] + o2,
+                        t.org[0][2] + o3, t.org[0][3] + o4);
+            if (t.nbox == 2)
+              tma_load_5d(x_dst + kSlabBytes, a_maps + am, full_bar(stage), c0, t.org[1][0] + o1,
+                          t.org[1][1] + o2, t.org[1][2] + o3, t.org[1][3] + o4);
+            tma_load_4d(w_dst, b_map, full_bar(stage), bk, t.n0, bz1, bz2);
+          }
+          __syncwarp();
+          e0 = f0;
+          e1 = f1;
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ====================================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(kBlockM, (uint32_t)block_n);
+    {
+      const uint32_t idesc = umma_idesc_bf16(kBlockM, swap ? 256u : (uint32_t)block_n);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.n_kb; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+      int seg = 0;
+      SegIter it;
+      it.init(p, sch, my_r);
+      int tile, kb0, len;
+      long long seg_end;
+      while (it.next(tile, kb0, len, seg_end)) {
+        const int buf = seg & 1;
+        mbar_wait(tmem_empty_bar(buf), (((uint32_t)seg >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t a_addr = smem_base + stage * sbytes;
-        const uint32_t b_addr = a_addr + kAStageBytes;
-        const uint64_t a_desc = umma_desc_k_sw128(a_addr, 1024);
-        const uint64_t b_desc = umma_desc_k_sw128(b_addr, 1024);
+        const uint32_t d0 = tmem_base + (uint32_t)(buf * 256);
+        for (int i = 0; i < len; ++i) {
+          mbar_wait(full_bar(stage), phase);
+          if (trace != nullptr && lane == 0 && seg == 0 && i == 0) trace[2] = (uint64_t)clock64();
+          tc_fence_after();
+          // the M = 128 operand is always the first slab of the stage
+          const uint32_t m_addr = smem_base + stage * sbytes;
+          const uint32_t n_addr = m_addr + kSlabBytes;
+          const uint64_t a_desc = umma_desc_k_sw128(m_addr, 1024);
+          const uint64_t b_desc = umma_desc_k_sw128(n_addr, 1024);
+          const uint32_t d = d0 + ((dual && (i & 1)) ? 128u : 0u);
+          const uint32_t acc_first = (dual ? (i >= 2) : (i >= 1)) ? 1u : 0u;
+          if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-          // advance 16 bf16 = 32 bytes inside the 128B swizzle span: +2 in 16-byte units
-          umma_bf16(tmem_base, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              // advance 16 bf16 = 32 bytes inside the 128B swizzle span: +2 in 16-byte units
+              umma_bf16(d, a_desc + 2u * k, b_desc + 2u * k, idesc, (k != 0) ? 1u : acc_first);
+            }
+            umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs have read it
+            if (i == len - 1) umma_commit(tmem_full_bar(buf));  // segment complete -> epilogue
+          }
+          __syncwarp();
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
-        umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs have read it
-        if (++stage == S) {
-          stage = 0;
-          phase ^= 1u;
-        }
+        ++seg;
       }
-      umma_commit(tmem_full_bar);  // accumulator complete -> epilogue
+      if (trace != nullptr && lane == 0) trace[3] = (uint64_t)clock64();
     }
   } else {
     // ================================ epilogue ======================================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    const int r = q * 32 + lane;
+    const int r = q * 32 + lane;  // TMEM lane: position (normal) or channel (swap_ab) of this thread
     const int epi_tid = (warp - 2) * 32 + lane;
     const int esize = p.out_f32 ? 4 : 2;
     const int chunk_cols_full = p.out_f32 ? 32 : 64;
@@ -160,9 +410,16 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
     const int chunk_bytes = chunk_cols * esize;
     const bool swz = (chunk_bytes == 128);
     const int n_chunks = block_n / chunk_cols;
-    const uint32_t stag = smem_base;  // staging aliases the (drained) pipeline stages
+    const int sd = p.sample_dim;
+    const bool uniform_sample = (sd == 0) || (p.box[sd - 1] == 1);
+    const bool smem_stats = p.stats != nullptr && uniform_sample && p.stats_ld <= kMaxStatGroups;
+    const int cpg = p.stats_cpg;
+    const float* bias = p.bias;
+    int cur_sample = -1;       // sample whose statistics s_stats currently accumulates
+    uint32_t chunk_ctr = 0;    // staging buffer alternation across tiles (normal mode)
+    uint32_t resid_phase = 0;  // swap_ab: parity of the residual-tile barrier
 
-    // row -> box-local coordinates
+    // TMEM-lane index -> box-local coordinates (normal mode: fixed for the whole kernel)
     int rl[4];
     {
       int rr = r;
@@ -172,177 +429,426 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
         rr /= p.box[i];
       }
     }
-    bool valid = r < rows_in_box;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) valid = valid && (org[i] + rl[i] < p.ext[i]);
-    const int sd = p.sample_dim;
-    const int sample = sd > 0 ? org[sd - 1] + rl[sd - 1] : 0;
-    const bool uniform_sample = (sd == 0) || (p.box[sd - 1] == 1);
 
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-
-    const CUtensorMap* o_map = reinterpret_cast<const CUtensorMap*>(p.o_maps) + cls;
-    if (p.r_maps != nullptr) {
-      if (epi_tid == 0) {
-        const CUtensorMap* r_map = reinterpret_cast<const CUtensorMap*>(p.r_maps) + cls;
-        mbar_arrive_expect_tx(resid_bar, (uint32_t)(rows_in_box * chunk_bytes * n_chunks));
-        for (int c = 0; c < n_chunks; ++c)
-          tma_load_5d(stag + c * (kBlockM * chunk_bytes), r_map, resid_bar, n0 + c * chunk_cols,
-                      org[0], org[1], org[2], org[3]);
+    auto flush_smem_stats = [&]() {  // all 128 epilogue threads
+      named_bar_sync(1, 128);
+      if (cur_sample >= 0 && epi_tid < 2 * p.stats_ld) {
+        const double v = s_stats[epi_tid];
+        if (v != 0.0) atomicAdd(p.stats + (size_t)cur_sample * p.stats_ld * 2 + epi_tid, v);
+        s_stats[epi_tid] = 0.0;
       }
-      mbar_wait(resid_bar, 0);
-    }
-
-    const float* bias = p.bias;
-    const float* rowbias = (p.rowbias != nullptr && valid)
-                               ? p.rowbias + (size_t)sample * p.rowbias_ld
-                               : nullptr;
-    const float bias_m = (p.bias_m != nullptr && valid) ? __ldg(p.bias_m + org[0] + rl[0]) : 0.f;
-    double* stats = p.stats;
-    const int cpg = p.stats_cpg;
-    int cur_g = -1;
-    float s_sum = 0.f, s_sq = 0.f;
-
-    auto flush_stats = [&]() {
-      if (cur_g < 0) return;
-      if (uniform_sample) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          s_sum += __shfl_xor_sync(0xffffffffu, s_sum, o);
-          s_sq += __shfl_xor_sync(0xffffffffu, s_sq, o);
-        }
-        if (lane == 0) {
-          const int smp = sd > 0 ? org[sd - 1] : 0;
-          double* dst = stats + ((size_t)smp * p.stats_ld + cur_g) * 2;
-          atomicAdd(dst, (double)s_sum);
-          atomicAdd(dst + 1, (double)s_sq);
-        }
-      } else if (valid) {
-        double* dst = stats + ((size_t)sample * p.stats_ld + cur_g) * 2;
-        atomicAdd(dst, (double)s_sum);
-        atomicAdd(dst + 1, (double)s_sq);
-      }
-      s_sum = 0.f;
-      s_sq = 0.f;
+      named_bar_sync(1, 128);
     };
 
-    for (int c0 = 0; c0 < block_n; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
-      float f[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + bias_m;
-      const int nb = n0 + c0;
-      if (nb < p.n_total) {  // n_total is a multiple of 8; 16-col groups may straddle the end
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (nb + h * 8 < p.n_total) {
-            if (bias != nullptr) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + nb + h * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + nb + h * 8 + 4));
-              f[h * 8 + 0] += b0.x; f[h * 8 + 1] += b0.y; f[h * 8 + 2] += b0.z; f[h * 8 + 3] += b0.w;
-              f[h * 8 + 4] += b1.x; f[h * 8 + 5] += b1.y; f[h * 8 + 6] += b1.z; f[h * 8 + 7] += b1.w;
-            }
-            if (rowbias != nullptr) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(rowbias + nb + h * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(rowbias + nb + h * 8 + 4));
-              f[h * 8 + 0] += b0.x; f[h * 8 + 1] += b0.y; f[h * 8 + 2] += b0.z; f[h * 8 + 3] += b0.w;
-              f[h * 8 + 4] += b1.x; f[h * 8 + 5] += b1.y; f[h * 8 + 6] += b1.z; f[h * 8 + 7] += b1.w;
-            }
-          }
-        }
-      }
-      // staging address of this thread's 16 columns
-      const int chunk = c0 / chunk_cols;
-      const int within = c0 - chunk * chunk_cols;
-      const uint32_t row_base = stag + chunk * (kBlockM * chunk_bytes) + r * chunk_bytes;
-      const int unit0 = (within * esize) >> 4;
-      const int xr = swz ? (r & 7) : 0;
+    int seg = 0;
+    SegIter it;
+    it.init(p, sch, my_r);
+    int tile, kb0, len;
+    long long seg_end;
+    while (it.next(tile, kb0, len, seg_end)) {
+      const int buf = seg & 1;
+      const bool head = (kb0 == 0);
+      const bool two_acc = dual && len >= 2;
+      const int acc_cols = swap ? 256 : block_n;
+      Work t;
+      decode_tile(p, geom, tile, t);
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
 
-      if (p.r_maps != nullptr) {  // residual tile (bf16) sits in the staging buffer
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const uint32_t addr = row_base + (uint32_t)(((unit0 + u) ^ xr) << 4);
-          uint32_t w0, w1, w2, w3;
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                       : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                       : "r"(addr));
-          const uint32_t w[4] = {w0, w1, w2, w3};
+      mbar_wait(tmem_full_bar(buf), ((uint32_t)seg >> 1) & 1u);
+      tc_fence_after();
+      if (trace != nullptr && epi_tid == 0) trace[4] = (uint64_t)clock64();
+
+      if (!head) {
+        // ---------- partial tile: raw fp32 sums -> workspace, flag -> the tile's head CTA ------
+        for (int c0 = 0; c0 < acc_cols; c0 += 16) {
+          float4* dst = partial_ptr(p, (int)blockIdx.x, r, c0);
+          uint32_t v[16], w[16];
+          tmem_ld16(tacc + (uint32_t)c0, v);
+          if (two_acc) tmem_ld16(tacc + 128u + (uint32_t)c0, w);
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            f[u * 8 + 2 * j] += __uint_as_float(w[j] << 16);
-            f[u * 8 + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+            float4 o;
+            o.x = __uint_as_float(v[4 * j + 0]);
+            o.y = __uint_as_float(v[4 * j + 1]);
+            o.z = __uint_as_float(v[4 * j + 2]);
+            o.w = __uint_as_float(v[4 * j + 3]);
+            if (two_acc) {
+              o.x += __uint_as_float(w[4 * j + 0]);
+              o.y += __uint_as_float(w[4 * j + 1]);
+              o.z += __uint_as_float(w[4 * j + 2]);
+              o.w += __uint_as_float(w[4 * j + 3]);
+            }
+            __stcg(dst + (size_t)j * kBlockM, o);
           }
         }
-      }
-
-      if (stats != nullptr) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
+        __threadfence();
+        named_bar_sync(1, 128);
+        if (epi_tid == 0) st_release_gpu(p.sk_flags + blockIdx.x, 1u);
+      } else {
+        // ---------- head of the tile: gather partials (if split), fused epilogue --------------
+        int n_contrib = 0;
+        const int contrib_cta0 = G - 2 - my_r;  // block index of range my_r + 1
+        if (len < n_kb) {
+          n_contrib = count_contributors(sch, my_r, seg_end, (long long)(tile + 1) * n_kb);
+          if (epi_tid == 0) wait_contributors(p, contrib_cta0, n_contrib);
+          named_bar_sync(1, 128);
+          // add the partial tiles into accumulator 0 (fixed order -> deterministic); loads of the
+          // next 16 columns are in flight while the current ones are folded into TMEM
+          for (int j = 0; j < n_contrib; ++j) {
+            const int cta = contrib_cta0 - j;
+            float4 nx[4];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int n = nb + h * 8;
-          if (n < p.n_total) {
-            const int g = n / cpg;
-            if (g != cur_g) {
-              flush_stats();
-              cur_g = g;
+            for (int k4 = 0; k4 < 4; ++k4) nx[k4] = __ldcg(partial_ptr(p, cta, r, 0) + (size_t)k4 * kBlockM);
+            for (int c0 = 0; c0 < acc_cols; c0 += 16) {
+              float4 cur[4];
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) cur[k4] = nx[k4];
+              if (c0 + 16 < acc_cols) {
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4)
+                  nx[k4] = __ldcg(partial_ptr(p, cta, r, c0 + 16) + (size_t)k4 * kBlockM);
+              }
+              uint32_t v[16];
+              tmem_ld16(tacc + (uint32_t)c0, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                v[4 * k4 + 0] = __float_as_uint(__uint_as_float(v[4 * k4 + 0]) + cur[k4].x);
+                v[4 * k4 + 1] = __float_as_uint(__uint_as_float(v[4 * k4 + 1]) + cur[k4].y);
+                v[4 * k4 + 2] = __float_as_uint(__uint_as_float(v[4 * k4 + 2]) + cur[k4].z);
+                v[4 * k4 + 3] = __float_as_uint(__uint_as_float(v[4 * k4 + 3]) + cur[k4].w);
+              }
+              tmem_st16(tacc + (uint32_t)c0, v);
             }
-            if (valid) {
+            tmem_st_wait();
+          }
+        }
+        const CUtensorMap* o_map = reinterpret_cast<const CUtensorMap*>(p.o_maps) + t.cls;
+
+        if (!swap) {
+          // ======================= normal: lane = position, columns = channels ================
+          bool valid = r < rows_in_box;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float x = f[h * 8 + i];
-                s_sum += x;
-                s_sq = fmaf(x, x, s_sq);
+          for (int i = 0; i < 4; ++i) valid = valid && (t.org[0][i] + rl[i] < p.ext[i]);
+          const int sample = sd > 0 ? t.org[0][sd - 1] + rl[sd - 1] : 0;
+          const int tile_sample = sd > 0 ? t.org[0][sd - 1] : 0;
+          if (smem_stats && tile_sample != cur_sample) {
+            flush_smem_stats();
+            cur_sample = tile_sample;
+          }
+          const float* rowbias = (p.rowbias != nullptr && valid)
+                                     ? p.rowbias + (size_t)sample * p.rowbias_ld
+                                     : nullptr;
+          const float bias_m =
+              (p.bias_m != nullptr && valid) ? __ldg(p.bias_m + t.org[0][0] + rl[0]) : 0.f;
+          const __nv_bfloat16* resid = nullptr;
+          if (p.r_base != nullptr && valid) {
+            long long off = p.r_cls_off[t.cls];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) off += (long long)(t.org[0][i] + rl[i]) * p.r_stride[i];
+            resid = reinterpret_cast<const __nv_bfloat16*>(p.r_base) + off + t.n0;
+          }
+
+          int cur_g = -1;
+          float s_sum = 0.f, s_sq = 0.f;
+          auto flush_stats = [&]() {
+            if (cur_g < 0) return;
+            if (uniform_sample) {
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                s_sum += __shfl_xor_sync(0xffffffffu, s_sum, o);
+                s_sq += __shfl_xor_sync(0xffffffffu, s_sq, o);
+              }
+              if (lane == 0) {
+                if (smem_stats) {
+                  atomicAdd(&s_stats[cur_g * 2], (double)s_sum);
+                  atomicAdd(&s_stats[cur_g * 2 + 1], (double)s_sq);
+                } else {
+                  double* dstp = p.stats + ((size_t)tile_sample * p.stats_ld + cur_g) * 2;
+                  atomicAdd(dstp, (double)s_sum);
+                  atomicAdd(dstp + 1, (double)s_sq);
+                }
+              }
+            } else if (valid) {
+              double* dstp = p.stats + ((size_t)sample * p.stats_ld + cur_g) * 2;
+              atomicAdd(dstp, (double)s_sum);
+              atomicAdd(dstp + 1, (double)s_sq);
+            }
+            s_sum = 0.f;
+            s_sq = 0.f;
+          };
+
+          for (int ch = 0; ch < n_chunks; ++ch) {
+            const int cbase = ch * chunk_cols;
+            if (t.n0 + cbase >= p.n_total) break;  // whole chunk beyond the valid columns
+            const uint32_t sbuf = stag + (chunk_ctr & 1u) * kChunkBytes;
+            // the TMA store that last used this buffer (two chunks ago) must have read it out
+            if (epi_tid == 0) tma_store_wait_read1();
+            named_bar_sync(1, 128);
+            for (int c0 = cbase; c0 < cbase + chunk_cols; c0 += 16) {
+              uint32_t v[16], w[16];
+              tmem_ld16(tacc + (uint32_t)c0, v);
+              if (two_acc) tmem_ld16(tacc + 128u + (uint32_t)c0, w);
+              tmem_ld_wait();
+              float f[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+              if (two_acc) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] += __uint_as_float(w[i]);
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] += bias_m;
+              const int nb = t.n0 + c0;
+              if (nb < p.n_total) {  // n_total is a multiple of 8; 16-col groups may straddle the end
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  if (nb + h * 8 < p.n_total) {
+                    if (bias != nullptr) {
+                      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + nb + h * 8));
+                      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + nb + h * 8 + 4));
+                      f[h * 8 + 0] += b0.x; f[h * 8 + 1] += b0.y; f[h * 8 + 2] += b0.z; f[h * 8 + 3] += b0.w;
+                      f[h * 8 + 4] += b1.x; f[h * 8 + 5] += b1.y; f[h * 8 + 6] += b1.z; f[h * 8 + 7] += b1.w;
+                    }
+                    if (rowbias != nullptr) {
+                      const float4 b0 = __ldg(reinterpret_cast<const float4*>(rowbias + nb + h * 8));
+                      const float4 b1 = __ldg(reinterpret_cast<const float4*>(rowbias + nb + h * 8 + 4));
+                      f[h * 8 + 0] += b0.x; f[h * 8 + 1] += b0.y; f[h * 8 + 2] += b0.z; f[h * 8 + 3] += b0.w;
+                      f[h * 8 + 4] += b1.x; f[h * 8 + 5] += b1.y; f[h * 8 + 6] += b1.z; f[h * 8 + 7] += b1.w;
+                    }
+                    if (resid != nullptr) {
+                      const uint4 rv = *reinterpret_cast<const uint4*>(resid + c0 + h * 8);
+                      const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                      for (int j = 0; j < 4; ++j) {
+                        f[h * 8 + 2 * j] += __uint_as_float(rw[j] << 16);
+                        f[h * 8 + 2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
+                      }
+                    }
+                  }
+                }
+              }
+
+              if (p.stats != nullptr) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const int n = nb + h * 8;
+                  if (n < p.n_total) {
+                    const int g = n / cpg;
+                    if (g != cur_g) {
+                      flush_stats();
+                      cur_g = g;
+                    }
+                    if (valid) {
+#pragma unroll
+                      for (int i = 0; i < 8; ++i) {
+                        const float x = f[h * 8 + i];
+                        s_sum += x;
+                        s_sq = fmaf(x, x, s_sq);
+                      }
+                    }
+                  }
+                }
+              }
+
+              // staging address of this thread's 16 columns
+              const int within = c0 - cbase;
+              const uint32_t row_base = sbuf + r * chunk_bytes;
+              const int unit0 = (within * esize) >> 4;
+              const int xr = swz ? (r & 7) : 0;
+              if (p.out_f32) {
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu) {
+                  const uint32_t addr = row_base + (uint32_t)(((unit0 + uu) ^ xr) << 4);
+                  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(f[uu * 4 + 0]),
+                               "f"(f[uu * 4 + 1]), "f"(f[uu * 4 + 2]), "f"(f[uu * 4 + 3])
+                               : "memory");
+                }
+              } else {
+#pragma unroll
+                for (int uu = 0; uu < 2; ++uu) {
+                  uint32_t wv[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[uu * 8 + 2 * j], f[uu * 8 + 2 * j + 1]);
+                    wv[j] = *reinterpret_cast<uint32_t*>(&h2);
+                  }
+                  const uint32_t addr = row_base + (uint32_t)(((unit0 + uu) ^ xr) << 4);
+                  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(wv[0]),
+                               "r"(wv[1]), "r"(wv[2]), "r"(wv[3])
+                               : "memory");
+                }
               }
             }
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (epi_tid == 0) {
+              tma_store_5d(o_map, sbuf, t.n0 + cbase, t.org[0][0], t.org[0][1], t.org[0][2],
+                           t.org[0][3]);
+              tma_store_commit();
+            }
+            ++chunk_ctr;
+          }
+          if (p.stats != nullptr) flush_stats();
+        } else {
+          // ============ swap_ab: lane = channel, columns = positions of box 0 | box 1 ============
+          const int ch = t.n0 + r;              // this thread's output channel
+          const float bias_c = bias != nullptr ? __ldg(bias + ch) : 0.f;
+          const int grp = p.stats != nullptr ? ch / cpg : 0;
+          const bool has_res = p.r_maps != nullptr;
+          const bool per_pos_sample = !uniform_sample && (p.rowbias != nullptr || p.stats != nullptr);
+          // staging: chunk buffer (q >> 1) holds channels [64*(q>>1), +64); 128B rows, swizzled.
+          // Position c0 + i (c0 % 16 == 0) lives in row c0 + i, 16-byte unit (cunit ^ (i & 7)).
+          const uint32_t sbuf = stag + (uint32_t)(q >> 1) * kChunkBytes;
+          const uint32_t cbyte = (uint32_t)(((q & 1) * 32 + lane) * 2);
+          uint32_t swz8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) swz8[j] = sbuf + ((((cbyte >> 4) ^ (uint32_t)j) << 4) | (cbyte & 15u));
+          for (int h = 0; h < t.nbox; ++h) {
+            int oh[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) oh[i] = h ? t.org[1][i] : t.org[0][i];
+            // per-position tables of this box (thread epi_tid describes position epi_tid)
+            {
+              int pl[4], rr = epi_tid;
+              bool ok = epi_tid < rows_in_box;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                pl[i] = rr % p.box[i];
+                rr /= p.box[i];
+                ok = ok && (oh[i] + pl[i] < p.ext[i]);
+              }
+              const int smp = sd > 0 ? oh[sd - 1] + pl[sd - 1] : 0;
+              s_pos_info[epi_tid] = ok ? smp : -1;
+              const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+              if (lane == 0) s_vmask[warp - 2] = bal;  // positions 32*(warp-2) .. +31
+            }
+            const int tile_sample = sd > 0 ? oh[sd - 1] : 0;
+            if (smem_stats && tile_sample != cur_sample) {
+              flush_smem_stats();
+              cur_sample = tile_sample;
+            }
+            // both staging buffers must have been read out by the previous box's stores
+            if (epi_tid == 0) tma_store_wait_read0();
+            named_bar_sync(1, 128);  // also publishes the position tables
+            if (has_res) {
+              // residual box -> the staging buffers (same layout as the output), by TMA
+              if (epi_tid == 0) {
+                const CUtensorMap* r_map = reinterpret_cast<const CUtensorMap*>(p.r_maps) + t.cls;
+                mbar_arrive_expect_tx(resid_bar, (uint32_t)rows_in_box * 256u);
+                tma_load_5d(stag, r_map, resid_bar, t.n0, oh[0], oh[1], oh[2], oh[3]);
+                tma_load_5d(stag + kChunkBytes, r_map, resid_bar, t.n0 + 64, oh[0], oh[1], oh[2], oh[3]);
+              }
+              mbar_wait(resid_bar, resid_phase);
+              resid_phase ^= 1u;
+            }
+            const float add_c = bias_c + ((p.rowbias != nullptr && uniform_sample)
+                                              ? __ldg(p.rowbias + (size_t)tile_sample * p.rowbias_ld + ch)
+                                              : 0.f);
+            float s_sum = 0.f, s_sq = 0.f;
+            for (int c0 = 0; c0 < kBlockM; c0 += 16) {
+              if (c0 >= rows_in_box) break;
+              uint32_t v[16];
+              tmem_ld16(tacc + (uint32_t)(h * 128 + c0), v);
+              tmem_ld_wait();
+              float f[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + add_c;
+              const uint32_t vm = (s_vmask[c0 >> 5] >> (c0 & 31)) & 0xffffu;  // valid positions
+              const uint32_t rowb = (uint32_t)c0 * 128u;
+              if (has_res) {  // TMA zero-filled the positions outside the tensor
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  uint16_t rv;
+                  asm volatile("ld.shared.u16 %0, [%1];"
+                               : "=h"(rv)
+                               : "r"(swz8[i & 7] + rowb + (uint32_t)i * 128u));
+                  f[i] += __uint_as_float((uint32_t)rv << 16);
+                }
+              }
+              if (per_pos_sample) {  // rare: a box spans several samples
+                for (int i = 0; i < 16; ++i) {
+                  const int info = s_pos_info[c0 + i];
+                  if (info < 0) continue;
+                  if (p.rowbias != nullptr) f[i] += __ldg(p.rowbias + (size_t)info * p.rowbias_ld + ch);
+                  if (p.stats != nullptr) {
+                    double* dstp = p.stats + ((size_t)info * p.stats_ld + grp) * 2;
+                    atomicAdd(dstp, (double)f[i]);
+                    atomicAdd(dstp + 1, (double)f[i] * (double)f[i]);
+                  }
+                }
+              } else if (vm == 0xffffu) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  s_sum += f[i];
+                  s_sq = fmaf(f[i], f[i], s_sq);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float x = ((vm >> i) & 1u) ? f[i] : 0.f;
+                  s_sum += x;
+                  s_sq = fmaf(x, x, s_sq);
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const __nv_bfloat16 o = __float2bfloat16_rn(f[i]);
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(swz8[i & 7] + rowb + (uint32_t)i * 128u),
+                             "h"(*reinterpret_cast<const uint16_t*>(&o))
+                             : "memory");
+              }
+            }
+            if (p.stats != nullptr && uniform_sample) {
+              // reduce the lanes that share a statistics group, then one atomic per group
+              const bool pow2 = (cpg & (cpg - 1)) == 0 && cpg <= 32;
+              const int span = pow2 ? cpg : (cpg % 32 == 0 ? 32 : 1);
+              for (int o = span >> 1; o > 0; o >>= 1) {
+                s_sum += __shfl_xor_sync(0xffffffffu, s_sum, o);
+                s_sq += __shfl_xor_sync(0xffffffffu, s_sq, o);
+              }
+              if ((lane & (span - 1)) == 0) {
+                double* dstp = smem_stats ? &s_stats[grp * 2]
+                                          : p.stats + ((size_t)tile_sample * p.stats_ld + grp) * 2;
+                atomicAdd(dstp, (double)s_sum);
+                atomicAdd(dstp + 1, (double)s_sq);
+              }
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (epi_tid == 0) {
+              tma_store_5d(o_map, stag, t.n0, oh[0], oh[1], oh[2], oh[3]);
+              tma_store_5d(o_map, stag + kChunkBytes, t.n0 + 64, oh[0], oh[1], oh[2], oh[3]);
+              tma_store_commit();
+            }
           }
         }
-      }
-
-      if (p.out_f32) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t addr = row_base + (uint32_t)(((unit0 + u) ^ xr) << 4);
-          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(f[u * 4 + 0]),
-                       "f"(f[u * 4 + 1]), "f"(f[u * 4 + 2]), "f"(f[u * 4 + 3])
-                       : "memory");
-        }
-      } else {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          uint32_t w[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[u * 8 + 2 * j], f[u * 8 + 2 * j + 1]);
-            w[j] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-          const uint32_t addr = row_base + (uint32_t)(((unit0 + u) ^ xr) << 4);
-          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[0]), "r"(w[1]),
-                       "r"(w[2]), "r"(w[3])
-                       : "memory");
+        // TMEM buffer drained -> the MMA warp may start the tile after next in it
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
+        if (n_contrib > 0 && epi_tid == 0) {  // consume the flags: the next launch starts clean
+          for (int j = 0; j < n_contrib; ++j) p.sk_flags[contrib_cta0 - j] = 0;
         }
       }
+      ++seg;
     }
-    if (stats != nullptr) flush_stats();
-
-    fence_proxy_async_smem();
-    named_bar_sync(1, 128);
-    if (epi_tid == 0) {
-      for (int c = 0; c < n_chunks; ++c) {
-        if (n0 + c * chunk_cols < p.n_total)
-          tma_store_5d(o_map, stag + c * (kBlockM * chunk_bytes), n0 + c * chunk_cols, org[0],
-                       org[1], org[2], org[3]);
-      }
-      tma_store_commit();
-      tma_store_wait_all();
+    if (smem_stats) flush_smem_stats();
+    if (epi_tid == 0) tma_store_wait_all();
+    if (trace != nullptr && epi_tid == 0) {
+      trace[5] = (uint64_t)clock64();
+      trace[6] = globaltimer_ns();
     }
   }
 
   // ---- teardown ------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace mri
@@ -350,20 +856,27 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
 // =============================== host side =============================================
 using namespace mri;
 
-extern "C" int mri_gemm_smem_bytes(int block_n, int stages) {
-  return stages * stage_bytes(block_n) + 1024;
+static int pick_stages(int block_n, int swap_ab, int requested) {
+  const int budget = kSmemLimit - 1024 - kStagingBytes;
+  int s = budget / stage_bytes(block_n, swap_ab);
+  if (s > kMaxStages) s = kMaxStages;
+  if (requested >= 2 && requested < s) s = requested;
+  return s;
 }
 
-extern "C" int mri_gemm_occupancy(int block_n, int stages) {
-  const int smem = mri_gemm_smem_bytes(block_n, stages);
-  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm_tc_kernel)");
-  (void)cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-  int nb = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gemm_tc_kernel, kThreads, smem);
-  if (e != cudaSuccess) return set_cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-  return nb;
+extern "C" int mri_gemm_smem_bytes(int block_n, int swap_ab, int stages) {
+  return pick_stages(block_n, swap_ab, stages) * stage_bytes(block_n, swap_ab) + kStagingBytes + 1024;
+}
+
+extern "C" int mri_gemm_workspace_bytes(int* n_ctas_out) {
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return set_cuda_error(e, "mri_gemm_workspace_bytes");
+  if (n_ctas_out) *n_ctas_out = sms;
+  // [sms][128][256] fp32 partial tiles, then [sms] int32 flags (padded to 1 KB)
+  const long long bytes = (long long)sms * kBlockM * kPartialLd * 4 + 1024;
+  return (int)bytes;
 }
 
 extern "C" int mri_gemm_launch(const MriGemmArgs* a, void* stream) {
@@ -371,40 +884,70 @@ extern "C" int mri_gemm_launch(const MriGemmArgs* a, void* stream) {
   const int bn = a->block_n;
   if (!(bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256))
     return set_error(-2, "mri_gemm_launch: block_n must be 16/32/64/128/256");
-  if (a->stages < 2 || a->stages > kMaxStages)
-    return set_error(-2, "mri_gemm_launch: stages must be in [2, 8]");
   if (a->n_kb < 1 || a->n_class < 1) return set_error(-2, "mri_gemm_launch: empty K loop");
-  long rows = 1;
-  long grid = (long)a->n_tiles_n * a->n_class;
+  long long rows = 1;
+  long long boxes = 1;
   for (int i = 0; i < 4; ++i) {
     if (a->box[i] < 1 || a->tiles[i] < 1) return set_error(-2, "mri_gemm_launch: bad box/tiles");
     rows *= a->box[i];
-    grid *= a->tiles[i];
+    boxes *= a->tiles[i];
   }
+  const int swap = a->swap_ab != 0;
+  if (swap && (bn != 128 || a->n_total % 128 != 0 || a->out_f32 || a->bias_m != nullptr ||
+               a->bz_sel[0] > 1 || a->bz_sel[1] > 1))
+    return set_error(-2, "mri_gemm_launch: swap_ab needs block_n 128, n_total % 128 == 0, bf16 "
+                         "output, no bias_m and class-only weight selection");
+  if (a->r_base != nullptr) {  // 16-byte residual loads / 8-element offset units
+    bool ok = true;
+    for (int i = 0; i < 4; ++i) ok = ok && (a->r_stride[i] % 8 == 0);
+    for (int c = 0; c < a->n_class && c < 8; ++c) ok = ok && (a->r_cls_off[c] % 8 == 0);
+    if (!ok) return set_error(-2, "mri_gemm_launch: residual strides/offsets must be multiples of 8");
+  }
+  const long long tiles = (long long)a->n_tiles_n * a->n_class * (swap ? (boxes + 1) / 2 : boxes);
   if (rows > kBlockM) return set_error(-2, "mri_gemm_launch: box has more than 128 rows");
+  if (tiles > 0x7fffffffLL / a->n_kb) return set_error(-2, "mri_gemm_launch: too many work units");
   if (a->n_total % 8 != 0) return set_error(-2, "mri_gemm_launch: n_total must be a multiple of 8");
   if (a->stats != nullptr && (a->stats_cpg < 8 || a->stats_cpg % 8 != 0))
     return set_error(-2, "mri_gemm_launch: statistics need channel groups in multiples of 8");
-  if (a->r_maps != nullptr && a->out_f32)
+  if (a->r_base != nullptr && a->out_f32)
     return set_error(-2, "mri_gemm_launch: residual input requires bf16 output");
-  const int smem = mri_gemm_smem_bytes(bn, a->stages);
-  // staging (aliases the stages) must fit
-  const int stag_bytes = kBlockM * bn * (a->out_f32 ? 4 : 2);
-  if (stag_bytes > a->stages * stage_bytes(bn))
-    return set_error(-2, "mri_gemm_launch: staging does not fit the stage ring");
-  if (smem > 227 * 1024) return set_error(-2, "mri_gemm_launch: shared memory over 227 KB");
+  if (a->r_base != nullptr && a->n_class > 8)
+    return set_error(-2, "mri_gemm_launch: residual supports at most 8 output classes");
+  if ((a->r_base != nullptr) != (a->r_maps != nullptr))
+    return set_error(-2, "mri_gemm_launch: residual needs both r_maps and r_base");
+  if (a->out_f32 && bn > 128)
+    return set_error(-2, "mri_gemm_launch: fp32 output needs block_n <= 128");
+  static int n_sms = 0;
+  if (n_sms == 0) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaDeviceGetAttribute(SM count)");
+  }
+  MriGemmArgs k = *a;
+  k.stages = pick_stages(bn, swap, a->stages);
+  const int smem = k.stages * stage_bytes(bn, swap) + kStagingBytes + 1024;
+  long long grid = tiles < n_sms ? tiles : n_sms;
+  if (k.sched != 0) {
+    if (k.sk_partials == nullptr || k.sk_flags == nullptr)
+      return set_error(-2, "mri_gemm_launch: stream-K schedule needs the workspace");
+    if (tiles < n_sms) {
+      // fewer tiles than SMs: split K loops into shares of >= max(8, n_kb / 4) k-steps
+      const long long units = tiles * k.n_kb;
+      const int min_share = (k.n_kb + 3) / 4 > 8 ? (k.n_kb + 3) / 4 : 8;
+      const long long want = units / min_share > tiles ? units / min_share : tiles;
+      grid = want < n_sms ? want : n_sms;
+    }
+    if (grid > k.sk_ctas) return set_error(-2, "mri_gemm_launch: stream-K workspace too small");
+  }
   static int configured_smem = 0;
   if (smem > configured_smem) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          smem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm_tc_kernel)");
-    // ask for the full shared-memory carveout so that two CTAs (2 x ~100 KB) can share an SM
-    e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(carveout)");
     configured_smem = smem;
   }
-  gemm_tc_kernel<<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(*a);
+  gemm_tc_kernel<<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(k);
   return check_launch("gemm_tc_kernel");
 }
 

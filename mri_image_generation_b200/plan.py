@@ -92,6 +92,34 @@ def encode_maps(specs: Sequence[MapSpec], device) -> torch.Tensor:
     return torch.from_numpy(host).to(device)
 
 
+class _Workspace:
+    """Stream-K scratch of one device: fp32 partial tiles + self-resetting flags."""
+
+    def __init__(self, device):
+        n = C.c_int(0)
+        nbytes = _lib.load().mri_gemm_workspace_bytes(C.byref(n))
+        if nbytes <= 0:
+            _lib.check(nbytes, "mri_gemm_workspace_bytes")
+        self.n_ctas = n.value
+        self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        self.partials_ptr = self.buf.data_ptr()
+        self.flags_ptr = self.buf.data_ptr() + nbytes - 1024
+
+
+_WORKSPACES = {}
+
+
+def gemm_workspace(device) -> _Workspace:
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    ws = _WORKSPACES.get(idx)
+    if ws is None:
+        with torch.cuda.device(idx):
+            ws = _Workspace(torch.device("cuda", idx))
+        _WORKSPACES[idx] = ws
+    return ws
+
+
 def choose_box(ext: Sequence[int], prefer_unit: Sequence[int] = ()) -> Tuple[int, int, int, int]:
     """Pick box extents (product <= 128) over up to four output dims maximising tile fill.
 
@@ -145,6 +173,9 @@ class GemmPlan:
     stats_ld: int = 0
     stats_cpg: int = 0
     stages: int = 0
+    sched: Optional[int] = None
+    swap_ab: Optional[bool] = None
+    trace: Optional[torch.Tensor] = None     # int64 [grid, 8]: per-CTA timestamps (profiling only)
     name: str = ""
     flops: int = 0
     _args: Optional[_lib.MriGemmArgs] = field(default=None, repr=False)
@@ -162,24 +193,44 @@ class GemmPlan:
     def n_tiles_n(self) -> int:
         return -(-self.n_total // self.block_n)
 
+    def pick_swap(self) -> bool:
+        """Weights as the M = 128 MMA operand, two boxes of positions as N = 256 (gemm_tc.cu):
+        every bf16 convolution whose output channels fill whole 128-channel tiles."""
+        if self.swap_ab is not None:
+            return self.swap_ab
+        env = os.environ.get("MRI_GEMM_SWAP")  # tuning experiments only
+        if env:
+            return bool(int(env)) and self.block_n == 128 and self.n_total % 128 == 0
+        return (self.block_n == 128 and self.n_total % 128 == 0 and not self.out_f32
+                and self.bias_m is None and max(self.bz_sel) <= 1 and self.n_kb >= 4)
+
     def grid(self) -> int:
+        """Number of tiles (work items of n_kb k-steps each)."""
         t = self.tiles
-        return t[0] * t[1] * t[2] * t[3] * self.n_tiles_n * self.n_class
+        boxes = t[0] * t[1] * t[2] * t[3]
+        groups = -(-boxes // 2) if self.pick_swap() else boxes
+        return groups * self.n_tiles_n * self.n_class
 
     def pick_stages(self) -> int:
+        """Requested TMA ring depth: 0 lets the library take what shared memory allows."""
         if self.stages:
             return self.stages
         env = os.environ.get("MRI_GEMM_STAGES")  # tuning experiments only
+        return int(env) if env else 0
+
+    def pick_sched(self, n_sms: int) -> int:
+        """1 = stream-K (split K loops across neighbouring CTAs) when whole tiles would leave
+        the last wave of the persistent grid under-filled; 0 = tile-aligned ranges."""
+        if self.sched is not None:
+            return self.sched
+        env = os.environ.get("MRI_GEMM_SCHED")  # tuning experiments only
         if env:
             return int(env)
-        stage = BLOCK_M * 128 + self.block_n * 128
-        stag = BLOCK_M * self.block_n * (4 if self.out_f32 else 2)
-        # two CTAs per SM (one's epilogue overlaps the other's main loop) when >= 3 stages fit
-        budget = 100 * 1024 if 3 * stage <= 100 * 1024 else 200 * 1024
-        s = max(2, min(8, budget // stage))
-        while s * stage < stag:
-            s += 1
-        return s
+        tiles = self.grid()
+        if self.n_kb < 8:
+            return 0
+        waves = tiles / n_sms
+        return 1 if -(-tiles // n_sms) / waves > 1.02 else 0
 
     # ------------------------------------------------------------------ GPU
     def materialize(self, device) -> None:
@@ -193,7 +244,22 @@ class GemmPlan:
         a.a_maps = base
         a.b_map = base + 128 * na
         a.o_maps = base + 128 * (na + 1)
-        a.r_maps = base + 128 * (na + 1 + no) if self.r_maps else None
+        if self.r_maps:
+            # the residual is read with plain loads: base pointer + per-class offset + strides
+            if len(self.r_maps) > 8:
+                raise _lib.MriError("residual input supports at most 8 output classes")
+            v0 = self.r_maps[0].view
+            assert v0.base.dtype == torch.bfloat16
+            a.r_maps = base + 128 * (na + 1 + no)
+            a.r_base = v0.base.data_ptr()
+            for ci, m in enumerate(self.r_maps):
+                assert m.view.base is v0.base and m.view.strides == v0.strides
+                a.r_cls_off[ci] = m.view.offset
+            for i in range(4):
+                a.r_stride[i] = v0.strides[1 + i]
+        else:
+            a.r_maps = None
+            a.r_base = None
         a.ktable = kt.data_ptr()
         a.n_kb, a.n_class = self.n_kb, self.n_class
         for i in range(4):
@@ -209,6 +275,11 @@ class GemmPlan:
         a.stats = self.stats.data_ptr() if self.stats is not None else None
         a.stats_ld, a.stats_cpg = self.stats_ld, self.stats_cpg
         a.stages = self.pick_stages()
+        ws = gemm_workspace(device)
+        a.sk_partials, a.sk_flags, a.sk_ctas = ws.partials_ptr, ws.flags_ptr, ws.n_ctas
+        a.sched = self.pick_sched(ws.n_ctas)
+        a.swap_ab = 1 if self.pick_swap() else 0
+        a.trace = self.trace.data_ptr() if self.trace is not None else None
         self._args = a
 
     def launch(self, stream: Optional[int] = None) -> None:

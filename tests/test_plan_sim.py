@@ -82,9 +82,19 @@ def test_choose_box():
     assert b == (2, 2, 2, 2)
 
 
-def test_pick_stages_fits_staging():
+def test_schedule_choice_and_smem_budget():
+    """Stream-K is chosen when whole tiles would under-fill the last wave of a 148-CTA grid; the
+    library's stage count keeps ring + staging inside 227 KB of shared memory."""
     y = torch.zeros(1, 8, 8, 8, 128, dtype=torch.bfloat16)
     a = torch.zeros(1, 8, 8, 8, 64, dtype=torch.bfloat16)
     pl = P.conv_plan([P.ConvSource(a)], torch.zeros(128, 27 * 64, dtype=torch.bfloat16), y, 3)
-    s = pl.pick_stages()
-    assert 2 <= s <= 8 and s * (128 * 128 + pl.block_n * 128) >= 128 * pl.block_n * 2
+    assert pl.pick_stages() == 0            # library decides
+    assert pl.pick_swap() and pl.grid() == 2 and pl.pick_sched(148) == 1   # 2 box pairs x 27 k-steps
+    pl.ktable = pl.ktable[:, :4]
+    assert pl.pick_sched(148) == 0          # short K loops are never split
+    from mri_image_generation_b200 import _lib
+    lib = _lib.load()
+    for bn in (16, 64, 128, 256):
+        assert lib.mri_gemm_smem_bytes(bn, 0, 0) <= 227 * 1024
+        assert lib.mri_gemm_smem_bytes(bn, 0, 2) == 2 * (128 * 128 + bn * 128) + 2 * 16384 + 1024
+    assert lib.mri_gemm_smem_bytes(128, 1, 0) == 4 * 3 * 16384 + 2 * 16384 + 1024
