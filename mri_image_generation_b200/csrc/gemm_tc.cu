@@ -750,6 +750,24 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
                                               ? __ldg(p.rowbias + (size_t)tile_sample * p.rowbias_ld + ch)
                                               : 0.f);
             float s_sum = 0.f, s_sq = 0.f;
+            int pp_sample = -1;  // per_pos_sample: sample the register sums belong to
+            const bool pow2 = (cpg & (cpg - 1)) == 0 && cpg <= 32;
+            const int span = pow2 ? cpg : (cpg % 32 == 0 ? 32 : 1);  // lanes sharing a stats group
+            auto flush_pp = [&](float& a, float& b, int smp) {  // warp-uniform call
+              if (p.stats != nullptr && smp >= 0) {
+                for (int o = span >> 1; o > 0; o >>= 1) {
+                  a += __shfl_xor_sync(0xffffffffu, a, o);
+                  b += __shfl_xor_sync(0xffffffffu, b, o);
+                }
+                if ((lane & (span - 1)) == 0) {
+                  double* dstp = p.stats + ((size_t)smp * p.stats_ld + grp) * 2;
+                  atomicAdd(dstp, (double)a);
+                  atomicAdd(dstp + 1, (double)b);
+                }
+              }
+              a = 0.f;
+              b = 0.f;
+            };
             for (int c0 = 0; c0 < kBlockM; c0 += 16) {
               if (c0 >= rows_in_box) break;
               uint32_t v[16];
@@ -770,15 +788,44 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
                   f[i] += __uint_as_float((uint32_t)rv << 16);
                 }
               }
-              if (per_pos_sample) {  // rare: a box spans several samples
+              if (per_pos_sample) {
+                // the box spans several samples (sample = slowest box coordinate): a 16-position
+                // chunk normally lies inside one sample -> register sums, flushed on change
+                int smp = -1;
+                bool same = true;
+#pragma unroll
                 for (int i = 0; i < 16; ++i) {
                   const int info = s_pos_info[c0 + i];
-                  if (info < 0) continue;
-                  if (p.rowbias != nullptr) f[i] += __ldg(p.rowbias + (size_t)info * p.rowbias_ld + ch);
-                  if (p.stats != nullptr) {
-                    double* dstp = p.stats + ((size_t)info * p.stats_ld + grp) * 2;
-                    atomicAdd(dstp, (double)f[i]);
-                    atomicAdd(dstp + 1, (double)f[i] * (double)f[i]);
+                  if (info >= 0) {
+                    same = same && (smp < 0 || smp == info);
+                    smp = info;
+                  }
+                }
+                if (smp >= 0 && same) {
+                  if (smp != pp_sample) {
+                    flush_pp(s_sum, s_sq, pp_sample);
+                    pp_sample = smp;
+                  }
+                  const float rbv = p.rowbias != nullptr
+                                        ? __ldg(p.rowbias + (size_t)smp * p.rowbias_ld + ch)
+                                        : 0.f;
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    f[i] += rbv;
+                    const float x = ((vm >> i) & 1u) ? f[i] : 0.f;
+                    s_sum += x;
+                    s_sq = fmaf(x, x, s_sq);
+                  }
+                } else if (smp >= 0) {  // chunk straddles a sample boundary: element-wise
+                  for (int i = 0; i < 16; ++i) {
+                    const int info = s_pos_info[c0 + i];
+                    if (info < 0) continue;
+                    if (p.rowbias != nullptr) f[i] += __ldg(p.rowbias + (size_t)info * p.rowbias_ld + ch);
+                    if (p.stats != nullptr) {
+                      double* dstp = p.stats + ((size_t)info * p.stats_ld + grp) * 2;
+                      atomicAdd(dstp, (double)f[i]);
+                      atomicAdd(dstp + 1, (double)f[i] * (double)f[i]);
+                    }
                   }
                 }
               } else if (vm == 0xffffu) {
@@ -803,10 +850,9 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
                              : "memory");
               }
             }
+            if (per_pos_sample) flush_pp(s_sum, s_sq, pp_sample);
             if (p.stats != nullptr && uniform_sample) {
               // reduce the lanes that share a statistics group, then one atomic per group
-              const bool pow2 = (cpg & (cpg - 1)) == 0 && cpg <= 32;
-              const int span = pow2 ? cpg : (cpg % 32 == 0 ? 32 : 1);
               for (int o = span >> 1; o > 0; o >>= 1) {
                 s_sum += __shfl_xor_sync(0xffffffffu, s_sum, o);
                 s_sq += __shfl_xor_sync(0xffffffffu, s_sq, o);

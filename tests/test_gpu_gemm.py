@@ -47,6 +47,9 @@ CASES = [
     (2, (30, 30), 3, [192], 128, 3),
     (3, (10, 12, 10), 2, [512], 1024, 1),
     (3, (8, 8, 8), 1, [128], 16, 3),
+    (3, (10, 12, 10), 8, [128], 256, 3),   # 128-row boxes spanning all 8 samples (2,4,2,8)
+    (3, (6, 6, 6), 5, [64], 128, 3),        # odd box count per class, ragged boxes
+    (2, (24, 24), 3, [64, 64], 384, 3),     # cpg = 48 (not a power of two)
 ]
 
 
