@@ -156,6 +156,13 @@ int mri_linear(const float* x, const float* W, const float* bias, const float* a
  * ------------------------------------------------------------------------------------------ */
 int mri_im2col(const float* src, const float* src2, void* dst, int samples, int cin, int cin2,
                int D, int H, int W, int ksize, int ndim, int kpad, void* stream);
+/* Thin-Cout convolution (out_conv: 128 -> 3 / 64 -> 1 / 64 -> 4 channels,
+ * slice_cond_2d_ddpm/unet.py:167, unet_attention.py:155) finished from the per-tap products
+ * Y[q][tap*cout + co] = W[tap][co] . x[q] (one tensor-core GEMM, K = Cin):
+ *   out[o][co] = bias[co] + sum_tap Y[o + tap - ksize/2][tap*cout + co]   (zero outside the volume)
+ * y: [samples][D][H][W][ldy] bf16, out: [samples][D][H][W][ldo] bf16 (channels >= cout written 0). */
+int mri_tap_gather(const void* y, void* out, const float* bias, int samples, int D, int H, int W,
+                   int ksize, int ndim, int cout, int ldy, int ldo, void* stream);
 int mri_nhwc_to_nchw(const void* src, float* dst, int samples, int64_t spatial, int C, int ldc,
                      void* stream);
 int mri_nchw_to_nhwc(const float* src, void* dst, int samples, int64_t spatial, int C, int ldc,

@@ -63,42 +63,54 @@ linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
 
 // Patch matrix of a thin-channel input (fp32 NC[D]HW) for a ksize^ndim, pad ksize/2 convolution.
 // dst[m][((kd*k+kh)*k+kw)*cin_total + c]; one thread per (m, 8 output columns) -> one 16-byte
-// store; the (tiny) source stays L1/L2 resident.
+// store; the (tiny) source stays L1/L2 resident.  The column -> (tap shift, channel) decode is a
+// shared-memory table built once per block, so the inner loop has no divisions.
 __global__ void __launch_bounds__(256)
 im2col_kernel(const float* __restrict__ src, const float* __restrict__ src2,
               uint4* __restrict__ dst, int samples, int cin, int cin2, int D, int H, int W,
               int k, int ndim, int kpad) {
+  extern __shared__ int col_tab[];  // per column: (dd+8) | (dh+8)<<4 | (dw+8)<<8 | c<<12, or -1
   const int taps = ndim == 3 ? k * k * k : k * k;
   const int ct = cin + cin2;
   const int kvalid = taps * ct;
+  const int pad = k / 2;
+  for (int col = threadIdx.x; col < kpad; col += blockDim.x) {
+    int e = -1;
+    if (col < kvalid) {
+      const int tap = col / ct, c = col - tap * ct;
+      const int kw = tap % k, kh = (tap / k) % k, kd = ndim == 3 ? tap / (k * k) : pad;
+      e = (kd - pad + 8) | ((kh - pad + 8) << 4) | ((kw - pad + 8) << 8) | (c << 12);
+    }
+    col_tab[col] = e;
+  }
+  __syncthreads();
   const int64_t spatial = (int64_t)D * H * W;
   const int64_t M = (int64_t)samples * spatial;
   const int vec_per_row = kpad >> 3;
   const int64_t total = M * vec_per_row;
-  const int pad = k / 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = i / vec_per_row;
-    const int col0 = (int)(i % vec_per_row) * 8;
+    const int col0 = (int)(i - m * vec_per_row) * 8;
     const int n = (int)(m / spatial);
-    int64_t s = m % spatial;
-    const int w0 = (int)(s % W);
+    int s = (int)(m - (int64_t)n * spatial);
+    const int w0 = s % W;
     s /= W;
-    const int h0 = (int)(s % H);
-    const int d0 = (int)(s / H);
+    const int h0 = s % H;
+    const int d0 = s / H;
+    const float* s1 = src + (size_t)n * cin * spatial;
+    const float* s2 = src2 != nullptr ? src2 + (size_t)n * cin2 * spatial : nullptr;
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int col = col0 + j;
+      const int e = col_tab[col0 + j];
       float v = 0.f;
-      if (col < kvalid) {
-        const int tap = col / ct, c = col - tap * ct;
-        const int kw = tap % k, kh = (tap / k) % k, kd = ndim == 3 ? tap / (k * k) : 0;
-        const int w = w0 + kw - pad, h = h0 + kh - pad, d = ndim == 3 ? d0 + kd - pad : d0;
-        if (w >= 0 && w < W && h >= 0 && h < H && d >= 0 && d < D) {
+      if (e >= 0) {
+        const int d = d0 + (e & 15) - 8, h = h0 + ((e >> 4) & 15) - 8, w = w0 + ((e >> 8) & 15) - 8;
+        const int c = e >> 12;
+        if ((unsigned)w < (unsigned)W && (unsigned)h < (unsigned)H && (unsigned)d < (unsigned)D) {
           const int64_t sp = ((int64_t)d * H + h) * W + w;
-          v = c < cin ? __ldg(src + ((size_t)n * cin + c) * spatial + sp)
-                      : __ldg(src2 + ((size_t)n * cin2 + (c - cin)) * spatial + sp);
+          v = c < cin ? __ldg(s1 + (size_t)c * spatial + sp) : __ldg(s2 + (size_t)(c - cin) * spatial + sp);
         }
       }
       f[j] = v;
@@ -110,6 +122,50 @@ im2col_kernel(const float* __restrict__ src, const float* __restrict__ src2,
       wd[j] = *reinterpret_cast<uint32_t*>(&h2);
     }
     dst[i] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+  }
+}
+
+// Thin-Cout convolution as "GEMM over taps, then gather": Y[q][tap*cout + co] = W[tap][co] . x[q]
+// was computed for every position q by the tensor-core kernel; the convolution output is
+//   out[o][co] = bias[co] + sum_tap Y[o + tap - pad][tap*cout + co]      (zero outside the volume)
+// One thread per (output position, channel): reads 2 bytes from each of the k^ndim neighbouring
+// rows of Y (L2-resident), writes bf16 channels-last with row pitch ldo (padding channels = 0).
+__global__ void __launch_bounds__(256)
+tap_gather_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ out,
+                  const float* __restrict__ bias, int samples, int D, int H, int W, int k, int ndim,
+                  int cout, int ldy, int ldo) {
+  const int64_t spatial = (int64_t)D * H * W;
+  const int64_t total = (int64_t)samples * spatial * ldo;
+  const int pad = k / 2;
+  const int kd_n = ndim == 3 ? k : 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / ldo;
+    const int co = (int)(i - m * ldo);
+    float acc = 0.f;
+    if (co < cout) {
+      const int n = (int)(m / spatial);
+      int s = (int)(m - (int64_t)n * spatial);
+      const int w0 = s % W;
+      s /= W;
+      const int h0 = s % H;
+      const int d0 = s / H;
+      acc = bias != nullptr ? __ldg(bias + co) : 0.f;
+      const __nv_bfloat16* yn = y + (size_t)n * spatial * ldy;
+      int tap = 0;
+      for (int kd = 0; kd < kd_n; ++kd) {
+        const int d = ndim == 3 ? d0 + kd - pad : d0;
+        for (int kh = 0; kh < k; ++kh) {
+          const int h = h0 + kh - pad;
+          for (int kw = 0; kw < k; ++kw, ++tap) {
+            const int w = w0 + kw - pad;
+            if ((unsigned)w < (unsigned)W && (unsigned)h < (unsigned)H && (unsigned)d < (unsigned)D)
+              acc += __bfloat162float(yn[(((size_t)d * H + h) * W + w) * ldy + tap * cout + co]);
+          }
+        }
+      }
+    }
+    out[i] = __float2bfloat16_rn(acc);
   }
 }
 
@@ -223,9 +279,22 @@ extern "C" int mri_im2col(const float* src, const float* src2, void* dst, int sa
     return set_error(-2, "mri_im2col: kpad must be a multiple of 64 and >= taps*cin");
   if (cin2 > 0 && src2 == nullptr) return set_error(-2, "mri_im2col: src2 missing");
   const int64_t total = (int64_t)samples * D * H * W * (kpad / 8);
-  im2col_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+  if (ksize > 15 || cin + cin2 >= (1 << 18)) return set_error(-2, "mri_im2col: kernel size / channels too large");
+  im2col_kernel<<<grid_for(total), 256, kpad * sizeof(int), (cudaStream_t)stream>>>(
       src, src2, reinterpret_cast<uint4*>(dst), samples, cin, cin2, D, H, W, ksize, ndim, kpad);
   return check_launch("im2col_kernel");
+}
+
+extern "C" int mri_tap_gather(const void* y, void* out, const float* bias, int samples, int D, int H,
+                              int W, int ksize, int ndim, int cout, int ldy, int ldo, void* stream) {
+  const int taps = ndim == 3 ? ksize * ksize * ksize : ksize * ksize;
+  if (ndim != 2 && ndim != 3) return set_error(-2, "mri_tap_gather: ndim must be 2 or 3");
+  if (cout < 1 || cout > ldo || taps * cout > ldy) return set_error(-2, "mri_tap_gather: bad channel layout");
+  const int64_t total = (int64_t)samples * D * H * W * ldo;
+  tap_gather_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<__nv_bfloat16*>(out), bias, samples,
+      D, H, W, ksize, ndim, cout, ldy, ldo);
+  return check_launch("tap_gather_kernel");
 }
 
 extern "C" int mri_nhwc_to_nchw(const void* src, float* dst, int samples, int64_t spatial, int C,

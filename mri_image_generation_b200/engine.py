@@ -219,6 +219,28 @@ class UNetProgram(BackwardMixin):
                                      dgrad_dy=rec.get("dgrad_dy"), name=name))
         return y
 
+    def thin_out_conv(self, a: torch.Tensor, oc, name: str = "out_conv") -> None:
+        """Inference head for a k^d convolution with 1..4 output channels (out_conv): one GEMM
+        computes every tap's product Y[q][tap*cout + co] = W[tap][co] . a[q] (K = Cin, the
+        activation is read once instead of once per tap), mri_tap_gather sums the shifted taps.
+        Sets self.eps_nhwc / self.cout / self.cout_pad."""
+        cout = oc.weight.shape[0]
+        ksize = oc.weight.shape[2]
+        taps = ksize ** self.ndim
+        n_y = _rup(taps * cout, 16) if taps * cout <= 64 else _rup(taps * cout, 128)
+        self.track(oc.weight, oc.bias)
+        w_exp = self.packed(lambda: P.pack_tap_weight(oc.weight.detach(), n_y))
+        y = self.conv([P.ConvSource(a)], w_exp, n_y, 1, None, with_stats=False, name=f"{name}.taps")
+        ldo = _rup(cout, 4)
+        eps = self.pool.get((self.B, *self.sp, ldo))
+        sp3 = (1,) * (3 - self.ndim) + self.sp
+        B, nd, bias = self.B, self.ndim, oc.bias
+        self._add(f"{name}.gather",
+                  lambda: ops.tap_gather(y.t, eps, bias, B, sp3[0], sp3[1], sp3[2], ksize, nd, cout,
+                                         n_y, ldo), [eps])
+        self.cout, self.cout_pad, self.eps_nhwc = cout, ldo, eps
+        self.hbm_bytes_elementwise += y.t.numel() * 2 + eps.numel() * 2
+
     # ------------------------------------------------------------------ time embedding
     def time_embedding(self, t_in: torch.Tensor, time_mlp, dim: int) -> torch.Tensor:
         """SinusoidalPosEmb -> Linear -> SiLU -> Linear  (unet.py:124-129 / unet_attention.py:103-108)."""
@@ -371,15 +393,20 @@ class UNet3DProgram(UNetProgram):
         self.track(on.weight, on.bias, oc.weight, oc.bias)
         a = self.gn(h, on.weight, on.bias, self.groups, eps, True, name="out_norm")
         self.cout = oc.weight.shape[0]
-        self.cout_pad = _rup(self.cout, 16)
-        w_out = self.packed(lambda: P.pack_conv_weight(oc.weight.detach(), cout_pad=self.cout_pad))
-        b_out = self.packed(lambda: _pad_vec(oc.bias.detach(), self.cout_pad))
-        self.deps64 = torch.zeros(B, D, H, W, 64, dtype=torch.bfloat16, device=dev) if training else None
-        y = self.conv([P.ConvSource(a)], w_out, self.cout_pad, 3, b_out, with_stats=False,
-                      name="out_conv",
-                      rec=dict(weight=oc.weight, splits=[a.shape[-1]], bias_params=[oc.bias],
-                               cout=self.cout, dgrad_dy=self.deps64))
-        self.eps_nhwc = y.t  # [B, D, H, W, cout_pad] bf16
+        self.deps64 = None
+        if not training and self.cout <= 4:
+            self.thin_out_conv(a, oc)
+        else:
+            self.cout_pad = _rup(self.cout, 16)
+            w_out = self.packed(lambda: P.pack_conv_weight(oc.weight.detach(), cout_pad=self.cout_pad))
+            b_out = self.packed(lambda: _pad_vec(oc.bias.detach(), self.cout_pad))
+            if training:
+                self.deps64 = torch.zeros(B, D, H, W, 64, dtype=torch.bfloat16, device=dev)
+            y = self.conv([P.ConvSource(a)], w_out, self.cout_pad, 3, b_out, with_stats=False,
+                          name="out_conv",
+                          rec=dict(weight=oc.weight, splits=[a.shape[-1]], bias_params=[oc.bias],
+                                   cout=self.cout, dgrad_dy=self.deps64))
+            self.eps_nhwc = y.t  # [B, D, H, W, cout_pad] bf16
         self.out = torch.zeros(B, self.cout, D, H, W, device=dev)
         self.params_changed()
         if training:
@@ -669,15 +696,20 @@ class UNet2DProgram(UNetProgram):
         self.stats_of(h, "out_norm.stats")
         a = self.gn(h, on.weight, on.bias, self.groups, eps, True, name="out_norm")
         self.cout = oc.weight.shape[0]
-        self.cout_pad = _rup(self.cout, 16)
-        w_out = self.packed(lambda: P.pack_conv_weight(oc.weight.detach(), cout_pad=self.cout_pad))
-        b_out = self.packed(lambda: _pad_vec(oc.bias.detach(), self.cout_pad))
-        self.deps64 = torch.zeros(B, H, W, 64, dtype=torch.bfloat16, device=dev) if training else None
-        y = self.conv([P.ConvSource(a)], w_out, self.cout_pad, 3, b_out, with_stats=False,
-                      name="out_conv",
-                      rec=dict(weight=oc.weight, splits=[a.shape[-1]], bias_params=[oc.bias],
-                               cout=self.cout, dgrad_dy=self.deps64))
-        self.eps_nhwc = y.t
+        self.deps64 = None
+        if not training and self.cout <= 4:
+            self.thin_out_conv(a, oc)
+        else:
+            self.cout_pad = _rup(self.cout, 16)
+            w_out = self.packed(lambda: P.pack_conv_weight(oc.weight.detach(), cout_pad=self.cout_pad))
+            b_out = self.packed(lambda: _pad_vec(oc.bias.detach(), self.cout_pad))
+            if training:
+                self.deps64 = torch.zeros(B, H, W, 64, dtype=torch.bfloat16, device=dev)
+            y = self.conv([P.ConvSource(a)], w_out, self.cout_pad, 3, b_out, with_stats=False,
+                          name="out_conv",
+                          rec=dict(weight=oc.weight, splits=[a.shape[-1]], bias_params=[oc.bias],
+                                   cout=self.cout, dgrad_dy=self.deps64))
+            self.eps_nhwc = y.t
         self.out = torch.zeros(B, self.cout, H, W, device=dev)
         self.params_changed()
         if training:

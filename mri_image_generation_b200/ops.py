@@ -76,6 +76,12 @@ def im2col(src, dst, samples, cin, D, H, W, ksize, ndim, kpad, src2=None, cin2: 
                                       ksize, ndim, kpad, _s()), "mri_im2col")
 
 
+def tap_gather(y, out, bias, samples, D, H, W, ksize, ndim, cout, ldy, ldo) -> None:
+    _chk_contig(y, out, bias)
+    _lib.check(_lib.load().mri_tap_gather(_p(y), _p(out), _p(bias), samples, D, H, W, ksize, ndim,
+                                          cout, ldy, ldo, _s()), "mri_tap_gather")
+
+
 def nhwc_to_nchw(src, dst, samples, spatial, C, ldc) -> None:
     _chk_contig(src, dst)
     _lib.check(_lib.load().mri_nhwc_to_nchw(_p(src), _p(dst), samples, spatial, C, ldc, _s()),

@@ -202,7 +202,7 @@ class GemmPlan:
         if env:
             return bool(int(env)) and self.block_n == 128 and self.n_total % 128 == 0
         return (self.block_n == 128 and self.n_total % 128 == 0 and not self.out_f32
-                and self.bias_m is None and max(self.bz_sel) <= 1 and self.n_kb >= 4)
+                and self.bias_m is None and max(self.bz_sel) <= 1)
 
     def grid(self) -> int:
         """Number of tiles (work items of n_kb k-steps each)."""
@@ -754,6 +754,18 @@ def pack_conv_weight(w: torch.Tensor, splits: Optional[Sequence[int]] = None, co
     cp = cout_pad or cout
     out = torch.zeros(cp, m.shape[1], dtype=torch.bfloat16, device=w.device)
     out[:cout] = m.to(torch.bfloat16)
+    return out.contiguous()
+
+
+def pack_tap_weight(w: torch.Tensor, rows_pad: int) -> torch.Tensor:
+    """nn.ConvNd weight [Cout, Cin, *k] -> [rows_pad, Cin] bf16 with row (tap * Cout + co), tap in
+    (kd, kh, kw) order: the B operand of the "GEMM over taps" used for thin-Cout convolutions
+    (mri_tap_gather finishes the convolution)."""
+    cout, cin = w.shape[0], w.shape[1]
+    taps = int(np.prod(w.shape[2:]))
+    m = w.reshape(cout, cin, taps).permute(2, 0, 1).reshape(taps * cout, cin)
+    out = torch.zeros(rows_pad, cin, dtype=torch.bfloat16, device=w.device)
+    out[:taps * cout] = m.to(torch.bfloat16)
     return out.contiguous()
 
 
