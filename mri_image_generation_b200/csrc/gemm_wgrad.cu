@@ -7,9 +7,13 @@
 // "MN-major" UMMA operands -- exactly what the 128-byte-swizzled TMA tiles already are when
 // read along the other axis.  No transposition pass exists anywhere.
 //
-// One CTA owns (class, 128-wide co block, group of `group` k-table entries) and a strided
-// share (`splits`) of the M tiles; partial sums are added to the fp32 dW matrix with vectorised
-// reductions (red.global.add.v4.f32).  Replaces autograd's conv weight gradients for every
+// One CTA owns (class, 128-wide co block, group of `group` <= 4 k-table entries) and a strided
+// share (`splits`) of the M tiles.  The `group` activation boxes of a stage sit back to back in
+// shared memory and form ONE MN-major B operand of N = 64 * group columns, so every 16 positions
+// cost a single tcgen05.mma of shape 128 x (64*group) x 16 (measured: an M = 128 instruction
+// occupies the tensor pipe ~137 cycles for any N <= 128 and ~150 cycles at N = 256, so N = 256
+// is the only shape near the pipe's peak).  Partial sums are added to the fp32 dW matrix with
+// vectorised reductions (red.global.add.v4.f32).  Replaces autograd's conv weight gradients for every
 // nn.Conv*/ConvTranspose* of the UNets (reference sites: include/mri_b200.h, MriGemmArgs) and,
 // with per-class maps, the dV / dK products of the attention backward.
 #include <cuda.h>
@@ -46,7 +50,7 @@ gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
   __shared__ __align__(8) uint64_t bars[2 * kWgMaxStages + 1];
   __shared__ uint32_t tmem_holder;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform((int)(threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int S = p.stages;
@@ -108,15 +112,21 @@ gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
   const CUtensorMap* dy_map = reinterpret_cast<const CUtensorMap*>(p.dy_maps) + cls;
 
   if (warp == 0) {
-    if (lane == 0 && my_tiles > 0) {
-      // k-table entries of this group (registers)
-      int4 e0[kWgMaxGroup], e1[kWgMaxGroup];
+    // whole warp converged, one elected lane issues (operands stay in uniform registers)
+    if (my_tiles > 0) {
+      // k-table entries of this group (registers; every lane loads the same values)
+      int em[kWgMaxGroup], ec[kWgMaxGroup], eo[kWgMaxGroup][4];
       const int4* kt = reinterpret_cast<const int4*>(p.ktable) + ((size_t)cls * p.n_kb + kb0) * 2;
 #pragma unroll
       for (int g = 0; g < kWgMaxGroup; ++g) {
         if (g < gact) {
-          e0[g] = __ldg(kt + 2 * g);
-          e1[g] = __ldg(kt + 2 * g + 1);
+          const int4 e0 = __ldg(kt + 2 * g), e1 = __ldg(kt + 2 * g + 1);
+          em[g] = uniform(e0.x);
+          ec[g] = uniform(e0.y);
+          eo[g][0] = uniform(e0.z);
+          eo[g][1] = uniform(e0.w);
+          eo[g][2] = uniform(e1.x);
+          eo[g][3] = uniform(e1.y);
         }
       }
       const uint32_t tx = (uint32_t)rows_in_box * 128u * (2u + (uint32_t)gact);
@@ -132,16 +142,19 @@ gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
         }
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t base = smem_base + stage * stage_bytes;
-        mbar_arrive_expect_tx(full_bar(stage), tx);
-        tma_load_5d(base, dy_map, full_bar(stage), co0, org[0], org[1], org[2], org[3]);
-        tma_load_5d(base + kTileBytes, dy_map, full_bar(stage), co0 + 64, org[0], org[1], org[2],
-                    org[3]);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(full_bar(stage), tx);
+          tma_load_5d(base, dy_map, full_bar(stage), co0, org[0], org[1], org[2], org[3]);
+          tma_load_5d(base + kTileBytes, dy_map, full_bar(stage), co0 + 64, org[0], org[1], org[2],
+                      org[3]);
 #pragma unroll
-        for (int g = 0; g < kWgMaxGroup; ++g) {
-          if (g < gact)
-            tma_load_5d(base + (2 + g) * kTileBytes, a_maps + e0[g].x, full_bar(stage), e0[g].y,
-                        org[0] + e0[g].z, org[1] + e0[g].w, org[2] + e1[g].x, org[3] + e1[g].y);
+          for (int g = 0; g < kWgMaxGroup; ++g) {
+            if (g < gact)
+              tma_load_5d(base + (2 + g) * kTileBytes, a_maps + em[g], full_bar(stage), ec[g],
+                          org[0] + eo[g][0], org[1] + eo[g][1], org[2] + eo[g][2], org[3] + eo[g][3]);
+          }
         }
+        __syncwarp();
         if (++stage == S) {
           stage = 0;
           phase ^= 1u;
@@ -149,32 +162,32 @@ gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && my_tiles > 0) {
-      // D = f32, A = B = bf16, both MN-major (bits 15, 16), M = 128, N = 64
-      const uint32_t idesc = umma_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);
+    if (my_tiles > 0) {
+      // D = f32, A = B = bf16, both MN-major (bits 15, 16), M = 128 (co), N = 64 * gact (channels)
+      const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)(64 * gact)) | (1u << 15) | (1u << 16);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < my_tiles; ++it) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint32_t base = smem_base + stage * stage_bytes;
-        for (int g = 0; g < gact; ++g) {
-          const uint32_t b_addr = base + (2 + g) * kTileBytes;
+        const uint32_t b_addr = base + 2 * kTileBytes;
+        if (elect_one_sync()) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {  // 16 rows (K) per MMA = 2 swizzle atoms = 2048 B
             const uint64_t a_desc = umma_desc_mn_sw128(base + ks * 2048, kTileBytes, 1024);
             const uint64_t b_desc = umma_desc_mn_sw128(b_addr + ks * 2048, kTileBytes, 1024);
-            umma_bf16(tmem_base + (uint32_t)(g * 64), a_desc, b_desc, idesc,
-                      (it | ks) != 0 ? 1u : 0u);
+            umma_bf16(tmem_base, a_desc, b_desc, idesc, (it | ks) != 0 ? 1u : 0u);
           }
+          umma_commit(empty_bar(stage));
+          if (it == my_tiles - 1) umma_commit(tmem_full_bar);
         }
-        umma_commit(empty_bar(stage));
+        __syncwarp();
         if (++stage == S) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      umma_commit(tmem_full_bar);
     }
   } else if (my_tiles > 0) {
     // ---- epilogue: TMEM (lane = co row) -> fp32 reductions into dW ----

@@ -653,8 +653,8 @@ class WgradPlan:
     dy: torch.Tensor            # same shape/layout as the forward output base tensor
     dw: torch.Tensor            # fp32 [n_class, rows, K]
     n_total: int
-    group: int = 2
-    stages: int = 3
+    group: int = 4
+    stages: int = 2
     splits: int = 0
     name: str = ""
     dy_views: Optional[List[TView]] = None   # explicit per-class dY views (attention products)
