@@ -402,6 +402,52 @@ def run_train(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def run_vae(args, rank, world, local_rank):
+    """Secondary workload: VAE3D(4, 32, 3, latent 3) encode_to_latent of
+    4x160x192x160 volumes and decode_from_latent of 3x40x48x40 latents (BASELINE cfg4 shapes),
+    `--batch` volumes per call.  Prints volumes/s for the decode (the step after sampling)."""
+    import torch
+    from mri_image_generation_b200 import _lib
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.vae import VAE3D
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.require_device()
+    B, K, W = args.batch, args.steps, max(3, args.warmup)
+    torch.manual_seed(0)
+    vae = VAE3D(4, 32, 3, 3).to(dev).eval()
+    x = torch.randn(B, 4, 160, 192, 160, device=dev)
+    z = torch.randn(B, *LATENT, device=dev)
+    res = {}
+    with torch.no_grad():
+        for name, fn, inp in (("decode", vae.decode_from_latent, z), ("encode", vae.encode_to_latent, x)):
+            for _ in range(W):
+                fn(inp)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(K):
+                out = fn(inp)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            prog = vae._program(name, inp)
+            res[name] = {"ms": e0.elapsed_time(e1) / K, "executed_gemm_tflop": prog.gemm_flops / 1e12,
+                         "finite": bool(torch.isfinite(out).all().item())}
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    for r in res.values():
+        r["tflops_executed"] = r["executed_gemm_tflop"] / (r["ms"] * 1e-3)
+    line = {"metric": "volumes/sec (VAE3D decode_from_latent, 3x40x48x40 -> 4x160x192x160)",
+            "value": world * B / (res["decode"]["ms"] / 1e3), "unit": "volumes/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": res["decode"]["ms"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "vae3d_decode", "batch_per_gpu": B,
+                       "model": "VAE3D(4, base 32, num_down 3, latent 3)",
+                       "note": "executed FLOPs include the zero padding of 32-channel layers to 64"},
+            "decode": res["decode"], "encode": res["encode"], "peak_tflops": peaks["tflops"]}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -409,8 +455,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=4, help="volumes per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="sample", choices=["sample", "train"],
-                    help="sample = headline (cfg4); train = DDP training step (cfg5)")
+    ap.add_argument("--mode", default="sample", choices=["sample", "train", "vae"],
+                    help="sample = headline (cfg4); train = DDP training step (cfg5); vae = VAE3D "
+                         "encode / decode at the cfg4 volume size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-op", default="", help="write per-GEMM timings (CUDA events) to this file")
     args = ap.parse_args()
@@ -430,6 +477,8 @@ def main():
     try:
         if args.mode == "train":
             run_train(args, rank, world, local_rank)
+        elif args.mode == "vae":
+            run_vae(args, rank, world, local_rank)
         else:
             run_ours(args, rank, world, local_rank)
     finally:

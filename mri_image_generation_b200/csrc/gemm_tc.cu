@@ -697,8 +697,13 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
         } else {
           // ============ swap_ab: lane = channel, columns = positions of box 0 | box 1 ============
           const int ch = t.n0 + r;              // this thread's output channel
-          const float bias_c = bias != nullptr ? __ldg(bias + ch) : 0.f;
-          const int grp = p.stats != nullptr ? ch / cpg : 0;
+          // n_total % 64 == 0: a warp (32 channels) is entirely inside or outside the valid range;
+          // outside, the weight rows were zero-filled by TMA and nothing is added or stored
+          const bool ch_ok = ch < p.n_total;
+          const bool chunk1 = t.n0 + 64 < p.n_total;
+          const float bias_c = (bias != nullptr && ch_ok) ? __ldg(bias + ch) : 0.f;
+          const int grp = (p.stats != nullptr && ch_ok) ? ch / cpg : 0;
+          double* const stats_p = ch_ok ? p.stats : nullptr;
           const bool has_res = p.r_maps != nullptr;
           const bool per_pos_sample = !uniform_sample && (p.rowbias != nullptr || p.stats != nullptr);
           // staging: chunk buffer (q >> 1) holds channels [64*(q>>1), +64); 128B rows, swizzled.
@@ -739,14 +744,15 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
               // residual box -> the staging buffers (same layout as the output), by TMA
               if (epi_tid == 0) {
                 const CUtensorMap* r_map = reinterpret_cast<const CUtensorMap*>(p.r_maps) + t.cls;
-                mbar_arrive_expect_tx(resid_bar, (uint32_t)rows_in_box * 256u);
+                mbar_arrive_expect_tx(resid_bar, (uint32_t)rows_in_box * (chunk1 ? 256u : 128u));
                 tma_load_5d(stag, r_map, resid_bar, t.n0, oh[0], oh[1], oh[2], oh[3]);
-                tma_load_5d(stag + kChunkBytes, r_map, resid_bar, t.n0 + 64, oh[0], oh[1], oh[2], oh[3]);
+                if (chunk1)
+                  tma_load_5d(stag + kChunkBytes, r_map, resid_bar, t.n0 + 64, oh[0], oh[1], oh[2], oh[3]);
               }
               mbar_wait(resid_bar, resid_phase);
               resid_phase ^= 1u;
             }
-            const float add_c = bias_c + ((p.rowbias != nullptr && uniform_sample)
+            const float add_c = bias_c + ((p.rowbias != nullptr && uniform_sample && ch_ok)
                                               ? __ldg(p.rowbias + (size_t)tile_sample * p.rowbias_ld + ch)
                                               : 0.f);
             float s_sum = 0.f, s_sq = 0.f;
@@ -754,7 +760,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
             const bool pow2 = (cpg & (cpg - 1)) == 0 && cpg <= 32;
             const int span = pow2 ? cpg : (cpg % 32 == 0 ? 32 : 1);  // lanes sharing a stats group
             auto flush_pp = [&](float& a, float& b, int smp) {  // warp-uniform call
-              if (p.stats != nullptr && smp >= 0) {
+              if (stats_p != nullptr && smp >= 0) {
                 for (int o = span >> 1; o > 0; o >>= 1) {
                   a += __shfl_xor_sync(0xffffffffu, a, o);
                   b += __shfl_xor_sync(0xffffffffu, b, o);
@@ -806,7 +812,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
                     flush_pp(s_sum, s_sq, pp_sample);
                     pp_sample = smp;
                   }
-                  const float rbv = p.rowbias != nullptr
+                  const float rbv = (p.rowbias != nullptr && ch_ok)
                                         ? __ldg(p.rowbias + (size_t)smp * p.rowbias_ld + ch)
                                         : 0.f;
 #pragma unroll
@@ -820,8 +826,8 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
                   for (int i = 0; i < 16; ++i) {
                     const int info = s_pos_info[c0 + i];
                     if (info < 0) continue;
-                    if (p.rowbias != nullptr) f[i] += __ldg(p.rowbias + (size_t)info * p.rowbias_ld + ch);
-                    if (p.stats != nullptr) {
+                    if (p.rowbias != nullptr && ch_ok) f[i] += __ldg(p.rowbias + (size_t)info * p.rowbias_ld + ch);
+                    if (stats_p != nullptr) {
                       double* dstp = p.stats + ((size_t)info * p.stats_ld + grp) * 2;
                       atomicAdd(dstp, (double)f[i]);
                       atomicAdd(dstp + 1, (double)f[i] * (double)f[i]);
@@ -851,7 +857,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
               }
             }
             if (per_pos_sample) flush_pp(s_sum, s_sq, pp_sample);
-            if (p.stats != nullptr && uniform_sample) {
+            if (stats_p != nullptr && uniform_sample) {
               // reduce the lanes that share a statistics group, then one atomic per group
               for (int o = span >> 1; o > 0; o >>= 1) {
                 s_sum += __shfl_xor_sync(0xffffffffu, s_sum, o);
@@ -868,7 +874,8 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
             named_bar_sync(1, 128);
             if (epi_tid == 0) {
               tma_store_5d(o_map, stag, t.n0, oh[0], oh[1], oh[2], oh[3]);
-              tma_store_5d(o_map, stag + kChunkBytes, t.n0 + 64, oh[0], oh[1], oh[2], oh[3]);
+              if (chunk1)
+                tma_store_5d(o_map, stag + kChunkBytes, t.n0 + 64, oh[0], oh[1], oh[2], oh[3]);
               tma_store_commit();
             }
           }
@@ -939,9 +946,9 @@ extern "C" int mri_gemm_launch(const MriGemmArgs* a, void* stream) {
     boxes *= a->tiles[i];
   }
   const int swap = a->swap_ab != 0;
-  if (swap && (bn != 128 || a->n_total % 128 != 0 || a->out_f32 || a->bias_m != nullptr ||
+  if (swap && (bn != 128 || a->n_total % 64 != 0 || a->out_f32 || a->bias_m != nullptr ||
                a->bz_sel[0] > 1 || a->bz_sel[1] > 1))
-    return set_error(-2, "mri_gemm_launch: swap_ab needs block_n 128, n_total % 128 == 0, bf16 "
+    return set_error(-2, "mri_gemm_launch: swap_ab needs block_n 128, n_total % 64 == 0, bf16 "
                          "output, no bias_m and class-only weight selection");
   if (a->r_base != nullptr) {  // 16-byte residual loads / 8-element offset units
     bool ok = true;
@@ -953,8 +960,9 @@ extern "C" int mri_gemm_launch(const MriGemmArgs* a, void* stream) {
   if (rows > kBlockM) return set_error(-2, "mri_gemm_launch: box has more than 128 rows");
   if (tiles > 0x7fffffffLL / a->n_kb) return set_error(-2, "mri_gemm_launch: too many work units");
   if (a->n_total % 8 != 0) return set_error(-2, "mri_gemm_launch: n_total must be a multiple of 8");
-  if (a->stats != nullptr && (a->stats_cpg < 8 || a->stats_cpg % 8 != 0))
+  if (a->stats != nullptr && !a->swap_ab && (a->stats_cpg < 8 || a->stats_cpg % 8 != 0))
     return set_error(-2, "mri_gemm_launch: statistics need channel groups in multiples of 8");
+  if (a->stats != nullptr && a->stats_cpg < 1) return set_error(-2, "mri_gemm_launch: stats_cpg < 1");
   if (a->r_base != nullptr && a->out_f32)
     return set_error(-2, "mri_gemm_launch: residual input requires bf16 output");
   if (a->r_base != nullptr && a->n_class > 8)

@@ -49,7 +49,9 @@ gn_stats_kernel(const uint4* __restrict__ x, double* __restrict__ stats, int64_t
   const int rows_step = blockDim.x / vec_per_row;  // host guarantees blockDim % vec_per_row == 0
   const int cv = threadIdx.x % vec_per_row;
   const int rsub = threadIdx.x / vec_per_row;
-  float s = 0.f, ss = 0.f;
+  // two accumulators per thread: channels [0,4) and [4,8) of its vector may belong to different
+  // fine groups when stats_cpg == 4 (GroupNorm(8, 32) of the VAE, ddpm_3d_ldm/vae.py:8)
+  float s[2] = {0.f, 0.f}, ss[2] = {0.f, 0.f};
   const uint4* base = x + (size_t)sample * spatial * vec_per_row;
   for (int64_t r = r0 + rsub; r < r1; r += rows_step) {
     const uint4 v = __ldg(base + r * vec_per_row + cv);
@@ -57,13 +59,16 @@ gn_stats_kernel(const uint4* __restrict__ x, double* __restrict__ stats, int64_t
     unpack8(v, f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      s += f[i];
-      ss = fmaf(f[i], f[i], ss);
+      s[i >> 2] += f[i];
+      ss[i >> 2] = fmaf(f[i], f[i], ss[i >> 2]);
     }
   }
-  const int g = (cv * 8) / stats_cpg;
-  atomicAdd(&red[2 * g], (double)s);
-  atomicAdd(&red[2 * g + 1], (double)ss);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int g = (cv * 8 + 4 * h) / stats_cpg;
+    atomicAdd(&red[2 * g], (double)s[h]);
+    atomicAdd(&red[2 * g + 1], (double)ss[h]);
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < n_fine * 2; i += blockDim.x) {
     const int gi = i >> 1;
@@ -91,27 +96,29 @@ gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double
   const int rsub = threadIdx.x / vec_per_row;
   const int rows_step = blockDim.x / vec_per_row;
   const int c = cv * 8;
-  const int g = c / cpg;
-
-  const double* st = stats + ((size_t)sample * stats_ld + stats_g0 + g * comb) * 2;
-  double s = 0.0, ss = 0.0;
-  for (int j = 0; j < comb; ++j) {
-    s += __ldg(st + 2 * j);
-    ss += __ldg(st + 2 * j + 1);
-  }
-  const double inv_cnt = 1.0 / ((double)cpg * (double)spatial);
-  const double mean_d = s * inv_cnt;
-  double var_d = ss * inv_cnt - mean_d * mean_d;  // fp64: no cancellation problem
-  var_d = var_d < 0.0 ? 0.0 : var_d;
-  const float mean = (float)mean_d;
-  const float rstd = rsqrtf((float)var_d + eps);
   float sc[8], sh[8], rb[8];
+  const double inv_cnt = 1.0 / ((double)cpg * (double)spatial);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float gm = __ldg(gamma + c + k), bt = __ldg(beta + c + k);
-    sc[k] = rstd * gm;
-    sh[k] = bt - mean * rstd * gm;
-    rb[k] = rowbias != nullptr ? __ldg(rowbias + (size_t)sample * rowbias_ld + c + k) : 0.f;
+  for (int h = 0; h < 2; ++h) {  // the two halves of the vector may lie in different groups
+    const int g = (c + 4 * h) / cpg;
+    const double* st = stats + ((size_t)sample * stats_ld + stats_g0 + g * comb) * 2;
+    double s = 0.0, ss = 0.0;
+    for (int j = 0; j < comb; ++j) {
+      s += __ldg(st + 2 * j);
+      ss += __ldg(st + 2 * j + 1);
+    }
+    const double mean_d = s * inv_cnt;
+    double var_d = ss * inv_cnt - mean_d * mean_d;  // fp64: no cancellation problem
+    var_d = var_d < 0.0 ? 0.0 : var_d;
+    const float mean = (float)mean_d;
+    const float rstd = rsqrtf((float)var_d + eps);
+#pragma unroll
+    for (int k = 4 * h; k < 4 * h + 4; ++k) {
+      const float gm = __ldg(gamma + c + k), bt = __ldg(beta + c + k);
+      sc[k] = rstd * gm;
+      sh[k] = bt - mean * rstd * gm;
+      rb[k] = rowbias != nullptr ? __ldg(rowbias + (size_t)sample * rowbias_ld + c + k) : 0.f;
+    }
   }
 
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
@@ -159,8 +166,8 @@ using namespace mri;
 
 extern "C" int mri_gn_stats(const void* x, double* stats, int samples, int64_t spatial, int C,
                             int stats_ld, int stats_g0, int stats_cpg, void* stream) {
-  if (C % 8 != 0 || stats_cpg % 8 != 0 || C % stats_cpg != 0)
-    return set_error(-2, "mri_gn_stats: C and stats_cpg must be multiples of 8");
+  if (C % 8 != 0 || stats_cpg % 4 != 0 || C % stats_cpg != 0)
+    return set_error(-2, "mri_gn_stats: C must be a multiple of 8 and stats_cpg of 4");
   const int vec_per_row = C / 8;
   int threads = 256;
   if (vec_per_row > 256) return set_error(-2, "mri_gn_stats: C > 2048 unsupported");
@@ -183,7 +190,8 @@ extern "C" int mri_gn_apply(const void* x, void* y, const double* stats, const f
                             const void* residual, int samples, int64_t spatial, int C, int groups,
                             int stats_ld, int stats_g0, int stats_cpg, float eps, int silu,
                             void* stream) {
-  if (C % 8 != 0 || groups < 1 || C % groups != 0 || (C / groups) % stats_cpg != 0)
+  if (C % 8 != 0 || groups < 1 || C % groups != 0 || (C / groups) % stats_cpg != 0 ||
+      (C / groups) % 4 != 0)
     return set_error(-2, "mri_gn_apply: bad channel / group configuration");
   const int vec_per_row = C / 8;
   if (vec_per_row > 256) return set_error(-2, "mri_gn_apply: C > 2048 unsupported");

@@ -219,22 +219,34 @@ class UNetProgram(BackwardMixin):
                                      dgrad_dy=rec.get("dgrad_dy"), name=name))
         return y
 
-    def thin_out_conv(self, a: torch.Tensor, oc, name: str = "out_conv") -> None:
-        """Inference head for a k^d convolution with 1..4 output channels (out_conv): one GEMM
+    def thin_out_conv(self, a: torch.Tensor, oc, name: str = "out_conv", cin_pad: int = 0) -> None:
+        """Inference head for a k^d convolution with 1..8 output channels (out_conv): one GEMM
         computes every tap's product Y[q][tap*cout + co] = W[tap][co] . a[q] (K = Cin, the
         activation is read once instead of once per tap), mri_tap_gather sums the shifted taps.
-        Sets self.eps_nhwc / self.cout / self.cout_pad."""
+        `a`: [B, *sp, Cin(_pad)] bf16.  Sets self.eps_nhwc / self.cout / self.cout_pad."""
         cout = oc.weight.shape[0]
         ksize = oc.weight.shape[2]
-        taps = ksize ** self.ndim
-        n_y = _rup(taps * cout, 16) if taps * cout <= 64 else _rup(taps * cout, 128)
+        sp = tuple(a.shape[1:-1])
+        nd = len(sp)
+        taps = ksize ** nd
+        n_y = _rup(taps * cout, 16) if taps * cout <= 48 else _rup(taps * cout, 64)
+        cin_pad = cin_pad or oc.weight.shape[1]
         self.track(oc.weight, oc.bias)
-        w_exp = self.packed(lambda: P.pack_tap_weight(oc.weight.detach(), n_y))
+
+        def make():
+            w = oc.weight.detach()
+            if w.shape[1] != cin_pad:
+                wp = torch.zeros(w.shape[0], cin_pad, *w.shape[2:], dtype=w.dtype, device=w.device)
+                wp[:, :w.shape[1]] = w
+                w = wp
+            return P.pack_tap_weight(w, n_y)
+
+        w_exp = self.packed(make)
         y = self.conv([P.ConvSource(a)], w_exp, n_y, 1, None, with_stats=False, name=f"{name}.taps")
         ldo = _rup(cout, 4)
-        eps = self.pool.get((self.B, *self.sp, ldo))
-        sp3 = (1,) * (3 - self.ndim) + self.sp
-        B, nd, bias = self.B, self.ndim, oc.bias
+        eps = self.pool.get((self.B, *sp, ldo))
+        sp3 = (1,) * (3 - nd) + sp
+        B, bias = self.B, oc.bias
         self._add(f"{name}.gather",
                   lambda: ops.tap_gather(y.t, eps, bias, B, sp3[0], sp3[1], sp3[2], ksize, nd, cout,
                                          n_y, ldo), [eps])

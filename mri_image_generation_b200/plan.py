@@ -200,8 +200,8 @@ class GemmPlan:
             return self.swap_ab
         env = os.environ.get("MRI_GEMM_SWAP")  # tuning experiments only
         if env:
-            return bool(int(env)) and self.block_n == 128 and self.n_total % 128 == 0
-        return (self.block_n == 128 and self.n_total % 128 == 0 and not self.out_f32
+            return bool(int(env)) and self.block_n == 128 and self.n_total % 64 == 0
+        return (self.block_n == 128 and self.n_total % 64 == 0 and not self.out_f32
                 and self.bias_m is None and max(self.bz_sel) <= 1)
 
     def grid(self) -> int:
@@ -455,7 +455,9 @@ def _out_chunk(block_n: int, out_f32: bool) -> int:
 
 
 def pick_block_n(cout_pad: int) -> int:
-    for bn in (128, 64, 32, 16):
+    if cout_pad % 64 == 0:
+        return 128  # Cout = 64 rides in half of a 128-channel tile (zero-filled weight rows)
+    for bn in (32, 16):
         if cout_pad % bn == 0:
             return bn
     raise ValueError(f"Cout {cout_pad} must be a multiple of 16")

@@ -1,0 +1,242 @@
+"""Static-shape inference programs for the 3D VAE of the latent-diffusion package
+(ddpm_3d_ldm/vae.py): the step either side of the diffusion hot path -- `encode_to_latent`
+before every LDM training step (ddpm_3d_ldm/train.py:386-388) and `decode_from_latent` after
+sampling (ddpm_3d_ldm/show_model.py:255).
+
+Same kernels as the UNets (engine.py): tcgen05 implicit-GEMM convolutions with fused bias /
+residual / GroupNorm partial sums, one fused GroupNorm-apply + SiLU pass per norm, 1x1 skip
+convolutions folded into conv2's K loop, im2col'd thin input convolutions and the
+GEMM-over-taps + gather head for the thin output convolutions.
+
+Channel counts below 64 (the VAE's 32-channel full-resolution level) are zero-padded to 64 so
+that every K slab is 64 channels wide; the padding channels stay exactly zero through
+GroupNorm (gamma = beta = 0 there), SiLU and the convolutions (zero weight rows / columns), and
+GroupNorm(8, 32) runs as 16 groups of 4 channels over the padded tensor.
+
+Inference only: the reference trains the VAE in a separate first stage
+(ddpm_3d_ldm/train.py:258-300); that stage is not on the diffusion hot path and keeps using the
+reference implementation (the drop-in class raises if a gradient is required).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib, ops
+from . import plan as P
+from .engine import Act, UNetProgram, _pad_k, _pad_vec, _rup
+
+
+def _pad_cin(w: torch.Tensor, cin_pad: int) -> torch.Tensor:
+    """Zero-pad dim 1 (input channels of a Conv weight / output channels of a ConvTranspose)."""
+    if w.shape[1] == cin_pad:
+        return w
+    out = torch.zeros(w.shape[0], cin_pad, *w.shape[2:], dtype=w.dtype, device=w.device)
+    out[:, :w.shape[1]] = w
+    return out
+
+
+def _pad_c0(w: torch.Tensor, c0_pad: int) -> torch.Tensor:
+    if w.shape[0] == c0_pad:
+        return w
+    out = torch.zeros(c0_pad, *w.shape[1:], dtype=w.dtype, device=w.device)
+    out[:w.shape[0]] = w
+    return out
+
+
+class VAE3DProgram(UNetProgram):
+    """mode 'encode': x (B, Cin, D, H, W) fp32 -> [mu | logvar] (B, 2*latent, d, h, w) fp32
+    (Encoder3D.forward, vae.py:49-55);
+    mode 'decode': z (B, latent, d, h, w) fp32 -> reconstruction (B, Cout, D, H, W) fp32
+    (Decoder3D.forward, vae.py:82-87)."""
+
+    def __init__(self, vae, mode: str, batch: int, spatial: Sequence[int]):
+        dev = next(vae.parameters()).device
+        enc, dec = vae.encoder, vae.decoder
+        first_block = enc.downs[0] if mode == "encode" else dec.ups[0]
+        self.gn_groups = first_block.norm1.num_groups
+        super().__init__(dev, batch, spatial, groups=self.gn_groups, training=False)
+        self.mode = mode
+        if len(self.sp) != 3:
+            raise _lib.MriError("VAE3D expects 3 spatial dims")
+        self.eps_gn = first_block.norm1.eps
+        B = batch
+        if mode == "encode":
+            n_down = enc.num_down
+            for s in self.sp:
+                if s % (2 ** (n_down - 1)) != 0:
+                    raise _lib.MriError(f"volume size {self.sp} must be divisible by {2 ** (n_down - 1)}")
+            cin = enc.in_conv.weight.shape[1]
+            self.x_in = torch.zeros(B, cin, *self.sp, device=dev)
+            h = self.thin_in_conv(self.x_in, enc.in_conv, self.sp, "encoder.in_conv")
+            for i, layer in enumerate(enc.downs):
+                h = self.layer(h, layer, f"encoder.downs.{i}")
+            self.head(h, enc.to_mu_logvar, "encoder.to_mu_logvar")
+        elif mode == "decode":
+            lat = dec.from_latent.weight.shape[1]
+            self.x_in = torch.zeros(B, lat, *self.sp, device=dev)
+            h = self.thin_in_conv(self.x_in, dec.from_latent, self.sp, "decoder.from_latent")
+            for i, layer in enumerate(dec.ups):
+                h = self.layer(h, layer, f"decoder.ups.{i}")
+            self.head(h, dec.out_conv, "decoder.out_conv")
+        else:
+            raise ValueError(mode)
+        self.params_changed()
+
+    # ------------------------------------------------------------------ helpers
+    def cpad(self, c: int) -> int:
+        return _rup(c, 64)
+
+    def groups_of(self, c_real: int) -> int:
+        """Normalisation groups over the padded tensor (real groups + all-zero padding groups)."""
+        cpg = c_real // self.gn_groups
+        if c_real % self.gn_groups or cpg % 4:
+            raise _lib.MriError(f"GroupNorm({self.gn_groups}, {c_real}): channels per group must be a "
+                                "multiple of 4 on the B200 path")
+        return self.cpad(c_real) // cpg
+
+    def new_vact(self, sp: Sequence[int], c_real: int) -> Act:
+        """Activation [B, *sp, cpad(c)] whose producer convolution can emit GroupNorm partial
+        sums (swap-mode epilogue: any power-of-two group width)."""
+        cp = self.cpad(c_real)
+        t = self.pool.get((self.B, *sp, cp))
+        g = self.groups_of(c_real)
+        return Act(t, self.new_stats(g), cp // g)
+
+    def ensure_stats(self, x: Act, c_real: int, name: str) -> None:
+        if x.stats is not None:
+            return
+        g = self.groups_of(c_real)
+        x.stats = self.new_stats(g)
+        x.cpg = x.C // g
+        B, S, C, xs, st, cpg = self.B, x.spatial, x.C, x.t, x.stats, x.cpg
+        self._add(f"{name}.stats", lambda: ops.gn_stats(xs, st, B, S, C, cpg), [st])
+
+    def norm_silu(self, x: Act, norm, c_real: int, name: str) -> torch.Tensor:
+        self.ensure_stats(x, c_real, name)
+        cp = x.C
+        self.track(norm.weight, norm.bias)
+        gm = self.packed(lambda: _pad_vec(norm.weight.detach(), cp))
+        bt = self.packed(lambda: _pad_vec(norm.bias.detach(), cp))
+        return self.gn(x, gm, bt, self.groups_of(c_real), norm.eps, True, name=name)
+
+    def thin_in_conv(self, x_in: torch.Tensor, conv, sp, name: str) -> Act:
+        """Conv3d with 1..8 input channels: patch matrix + GEMM (vae.py:31,67)."""
+        B, S = self.B, sp[0] * sp[1] * sp[2]
+        cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+        kpad = _rup(27 * cin, 64)
+        col = torch.zeros(B * S, kpad, dtype=torch.bfloat16, device=self.device)
+        D, H, W = sp
+        self._add(f"{name}.im2col", lambda: ops.im2col(x_in, col, B, cin, D, H, W, 3, 3, kpad), [col])
+        self.track(conv.weight, conv.bias)
+        cp = self.cpad(cout)
+        w = self.packed(lambda: _pad_c0(_pad_k(P.pack_conv_weight(conv.weight.detach()), kpad), cp))
+        b = self.packed(lambda: _pad_vec(conv.bias.detach(), cp))
+        h = self.new_vact(sp, cout)
+        a = P.TView(col, (kpad, S, B, 1, 1), (1, kpad, S * kpad, B * S * kpad, B * S * kpad))
+        bv = P.TView(w, (kpad, cp, 1, 1), (1, kpad, kpad * cp, kpad * cp))
+        o = P.TView(h.t, (cp, S, B, 1, 1), (1, cp, S * cp, B * S * cp, B * S * cp))
+        pl = P.matrix_plan(a, (128, 1, 1, 1), bv, o, K=kpad, n_total=cp, block_n=P.pick_block_n(cp),
+                           ext=(S, B, 1, 1), tiles=(-(-S // 128), B, 1, 1), sample_dim=2, bias=b,
+                           stats=h.stats, stats_cpg=h.cpg, name=name, flops=2 * B * S * cp * kpad)
+        self.gemm(pl)
+        return h
+
+    def layer(self, h: Act, layer, name: str) -> Act:
+        if isinstance(layer, torch.nn.ConvTranspose3d):
+            return self.up(h, layer, name)
+        if isinstance(layer, torch.nn.Conv3d):
+            return self.down(h, layer, name)
+        return self.resblock(h, layer, name)
+
+    def resblock(self, x: Act, blk, name: str) -> Act:
+        """ResidualBlock3DNoTime.forward (vae.py:19-22): conv2(silu(gn2(conv1(silu(gn1(x)))))) + skip(x)."""
+        c1, c2 = blk.conv1, blk.conv2
+        cin, cout = c1.weight.shape[1], c1.weight.shape[0]
+        cip, cop = self.cpad(cin), self.cpad(cout)
+        sp = tuple(x.t.shape[1:-1])
+        self.track(c1.weight, c1.bias, c2.weight, c2.bias)
+        a1 = self.norm_silu(x, blk.norm1, cin, f"{name}.norm1")
+        w1 = self.packed(lambda: P.pack_conv_weight(_pad_cin(c1.weight.detach(), cip), cout_pad=cop))
+        b1 = self.packed(lambda: _pad_vec(c1.bias.detach(), cop))
+        h = self.new_vact(sp, cout)
+        pl = P.conv_plan([P.ConvSource(a1)], w1, h.t, 3, bias=b1, stats=h.stats, stats_cpg=h.cpg,
+                         name=f"{name}.conv1")
+        self._conv_or_stats(pl, h)
+        self.pool.release(a1)
+        a2 = self.norm_silu(h, blk.norm2, cout, f"{name}.norm2")
+        self.pool.release(h.t)
+        out = self.new_vact(sp, cout)
+        if isinstance(blk.skip, torch.nn.Identity):
+            w2 = self.packed(lambda: P.pack_conv_weight(_pad_cin(c2.weight.detach(), cop), cout_pad=cop))
+            b2 = self.packed(lambda: _pad_vec(c2.bias.detach(), cop))
+            pl = P.conv_plan([P.ConvSource(a2)], w2, out.t, 3, bias=b2, residual=x.t, stats=out.stats,
+                             stats_cpg=out.cpg, name=f"{name}.conv2")
+        else:
+            sk = blk.skip
+            self.track(sk.weight, sk.bias)
+            w2 = self.packed(lambda: P.pack_conv_weight(
+                _pad_cin(c2.weight.detach(), cop), cout_pad=cop,
+                extra=[_pad_cin(sk.weight.detach().reshape(cout, cin), cip)]))
+            b2 = self.packed(lambda: _pad_vec(c2.bias.detach() + sk.bias.detach(), cop))
+            pl = P.conv_plan([P.ConvSource(a2), P.ConvSource(x.t, taps=False)], w2, out.t, 3, bias=b2,
+                             stats=out.stats, stats_cpg=out.cpg, name=f"{name}.conv2+skip")
+        self._conv_or_stats(pl, out)
+        self.pool.release(a2)
+        self.pool.release(x.t)
+        return out
+
+    def _conv_or_stats(self, pl: P.GemmPlan, y: Act) -> None:
+        """Emit the convolution; if its epilogue cannot produce statistics at this group width
+        (normal mode needs groups of >= 8 channels) leave them to a standalone pass."""
+        if not pl.pick_swap() and y.cpg % 8 != 0:
+            pl.stats, pl.stats_ld, pl.stats_cpg = None, 0, 0
+            y.stats = None
+        self.gemm(pl)
+
+    def down(self, x: Act, conv, name: str) -> Act:
+        """Conv3d k=4 s=2 p=1 (vae.py:41-43)."""
+        c = conv.weight.shape[0]
+        cp = self.cpad(c)
+        self.track(conv.weight, conv.bias)
+        w = self.packed(lambda: P.pack_conv_weight(_pad_cin(conv.weight.detach(), cp), cout_pad=cp))
+        b = self.packed(lambda: _pad_vec(conv.bias.detach(), cp))
+        y = self.new_vact([s // 2 for s in x.t.shape[1:-1]], c)
+        pl = P.down_conv_plan(x.t, w, y.t, bias=b, stats=y.stats, stats_cpg=y.cpg, name=name)
+        self._conv_or_stats(pl, y)
+        self.pool.release(x.t)
+        return y
+
+    def up(self, x: Act, conv, name: str) -> Act:
+        """ConvTranspose3d k=4 s=2 p=1 (vae.py:75-79); weight layout [Cin, Cout, 4, 4, 4]."""
+        c = conv.weight.shape[1]
+        cp = self.cpad(c)
+        cip = self.cpad(conv.weight.shape[0])
+        self.track(conv.weight, conv.bias)
+        w = self.packed(lambda: P.pack_convT_weight(_pad_c0(_pad_cin(conv.weight.detach(), cp), cip),
+                                                    cout_pad=cp))
+        b = self.packed(lambda: _pad_vec(conv.bias.detach(), cp))
+        y = self.new_vact([s * 2 for s in x.t.shape[1:-1]], c)
+        pl = P.up_conv_plan(x.t, w, y.t, bias=b, stats=y.stats, stats_cpg=y.cpg, name=name)
+        self._conv_or_stats(pl, y)
+        self.pool.release(x.t)
+        return y
+
+    def head(self, h: Act, conv, name: str) -> None:
+        """Thin-Cout 3x3x3 convolution WITHOUT a preceding norm (to_mu_logvar vae.py:47,
+        out_conv vae.py:81): GEMM over taps + gather."""
+        self.thin_out_conv(h.t, conv, name=name, cin_pad=h.C)
+        self.sp_out = tuple(h.t.shape[1:-1])
+        self.out = torch.zeros(self.B, self.cout, *self.sp_out, device=self.device)
+
+    # ------------------------------------------------------------------ entry
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.params_changed():
+            for fn in self.refresh:
+                fn()
+        self.x_in.copy_(x)
+        self.run()
+        S = self.sp_out[0] * self.sp_out[1] * self.sp_out[2]
+        ops.nhwc_to_nchw(self.eps_nhwc, self.out, self.B, S, self.cout, self.cout_pad)
+        return self.out

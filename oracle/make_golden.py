@@ -47,8 +47,40 @@ def quiet(fn, *a, **k):
         return fn(*a, **k)
 
 
+def vae_cases():
+    """tests/golden/vae3d.pt: encode / decode of the unmodified reference VAE3D (vae.py)."""
+    from model_scripts.ddpm_3d_ldm.vae import VAE3D
+    cases = {}
+    for name, kw, vol, seed in [("vae_b32", dict(in_channels=4, base_channels=32, num_down=3, latent_channels=3), (16, 16, 16), 301),
+                                ("vae_b64_l8", dict(in_channels=4, base_channels=64, num_down=2, latent_channels=8), (8, 12, 8), 302)]:
+        m = VAE3D(**kw).eval()
+        shapes = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+        sd = synthetic_state_dict(shapes, seed)
+        m.load_state_dict(sd, strict=True)
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(2, kw["in_channels"], *vol, generator=g)
+        with torch.no_grad():
+            mu, logvar = m.encode(x)
+            rec = m.decode(mu)
+            lat = m.encode_to_latent(x)
+            mu_o, lv_o = O.vae3d_encode(sd, x)
+            rec_o = O.vae3d_decode(sd, mu)
+        assert torch.equal(mu, mu_o) and torch.equal(logvar, lv_o) and torch.equal(rec, rec_o), name
+        assert torch.equal(lat, mu)
+        cases[name] = {"kwargs": kw, "shapes": shapes, "seed": seed, "x": x, "mu": mu, "logvar": logvar,
+                       "recon_of_mu": rec}
+        print(f"{name}: {len(shapes)} keys, mu {tuple(mu.shape)} sha {sha(mu)}, recon {tuple(rec.shape)} "
+              f"sha {sha(rec)}  (oracle == reference)")
+    torch.save(cases, os.path.join(GOLD, "vae3d.pt"))
+
+
 def main():
     sys.path.insert(0, "/root/reference")
+    if "--only=vae" in sys.argv:
+        os.makedirs(GOLD, exist_ok=True)
+        torch.set_num_threads(4)
+        vae_cases()
+        return
     from model_scripts.ddpm_3d_ldm.diffusion import GaussianDiffusionLatent3D
     from model_scripts.ddpm_3d_ldm.unet import UNet3DModel
     from model_scripts.ddpm_3d_ldm.unet_attention import UNet3DModelWithAttention
@@ -175,6 +207,7 @@ def main():
     assert torch.equal(diff["p_sample_2d"], O.p_sample_update(buf2, x2d, t, Stub()(x2d, t), z2d))
     torch.save(diff, os.path.join(GOLD, "diffusion.pt"))
     print("diffusion arithmetic fixtures written (oracle == reference, bit-exact)")
+    vae_cases()
     for f in sorted(os.listdir(GOLD)):
         print(f"  {f}: {os.path.getsize(os.path.join(GOLD, f)) / 1024:.1f} KiB")
 

@@ -128,6 +128,48 @@ def unet3d_forward(sd: SD, x, t, heads: int = 4, groups: int = 8):
 
 
 # ------------------------------------------------------------------------------------------
+# 3D VAE (ddpm_3d_ldm/vae.py) -- the step either side of the diffusion path
+# ------------------------------------------------------------------------------------------
+def vae_resblock(sd: SD, p: str, x, groups=8):
+    """ResidualBlock3DNoTime.forward -- ddpm_3d_ldm/vae.py:19-22."""
+    h = _conv(sd, p + ".conv1", F.silu(_gn(sd, p + ".norm1", x, groups)), 3, padding=1)
+    h = _conv(sd, p + ".conv2", F.silu(_gn(sd, p + ".norm2", h, groups)), 3, padding=1)
+    if (p + ".skip.weight") in sd:
+        return h + _conv(sd, p + ".skip", x, 3)
+    return h + x
+
+
+def _vae_layers(sd: SD, prefix: str, h, groups, transposed: bool):
+    i = 0
+    while any(k.startswith(f"{prefix}.{i}.") for k in sd):
+        p = f"{prefix}.{i}"
+        if (p + ".norm1.weight") in sd:
+            h = vae_resblock(sd, p, h, groups)
+        elif transposed:   # nn.ConvTranspose3d(c, c, 4, stride=2, padding=1), vae.py:75-79
+            h = _convT(sd, p, h, 3, stride=2, padding=1)
+        else:              # nn.Conv3d(c, c, 4, stride=2, padding=1), vae.py:41-43
+            h = _conv(sd, p, h, 3, stride=2, padding=1)
+        i += 1
+    return h
+
+
+def vae3d_encode(sd: SD, x, groups: int = 8):
+    """VAE3D.encode -> Encoder3D.forward (vae.py:49-55, 102-104): returns (mu, logvar)."""
+    h = _conv(sd, "encoder.in_conv", x, 3, padding=1)
+    h = _vae_layers(sd, "encoder.downs", h, groups, transposed=False)
+    stats = _conv(sd, "encoder.to_mu_logvar", h, 3, padding=1)
+    mu, logvar = torch.chunk(stats, 2, dim=1)
+    return mu, logvar
+
+
+def vae3d_decode(sd: SD, z, groups: int = 8):
+    """VAE3D.decode -> Decoder3D.forward (vae.py:82-87, 111-112)."""
+    h = _conv(sd, "decoder.from_latent", z, 3, padding=1)
+    h = _vae_layers(sd, "decoder.ups", h, groups, transposed=True)
+    return _conv(sd, "decoder.out_conv", h, 3, padding=1)
+
+
+# ------------------------------------------------------------------------------------------
 # 2D / 2.5D UNet (slice_cond_2d_ddpm, ddpm_25d_all_modalities)
 # ------------------------------------------------------------------------------------------
 def resblock2d(sd: SD, p: str, x, cond):

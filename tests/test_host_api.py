@@ -107,3 +107,14 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert "reference_oracle" not in src and "import oracle" not in src and "from oracle" not in src, f
+
+
+@pytest.mark.parametrize("name", ["vae_b32", "vae_b64_l8"])
+def test_vae_state_dict_keys_and_shapes_match_reference(name):
+    """VAE3D drop-in (ddpm_3d_ldm/vae.py:90): same keys / shapes as the reference fixture; picklable."""
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.vae import VAE3D
+    g = load_gold("vae3d.pt")[name]
+    m = VAE3D(**g["kwargs"])
+    got = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    assert got == [(k, tuple(s)) for k, s in g["shapes"]]
+    pickle.loads(pickle.dumps(m))
