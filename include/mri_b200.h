@@ -156,6 +156,22 @@ int mri_linear(const float* x, const float* W, const float* bias, const float* a
  * ------------------------------------------------------------------------------------------ */
 int mri_im2col(const float* src, const float* src2, void* dst, int samples, int cin, int cin2,
                int D, int H, int W, int ksize, int ndim, int kpad, void* stream);
+/* Weight re-pack after a parameter update (torch.optim step, ddpm_3d_ldm/train.py:399): every
+ * packed buffer of a program is a gather of fp32 parameter elements.  One launch refreshes all
+ * segments: dst[i] = idx[i] < 0 ? 0 : src[idx[i] >> 28][idx[i] & 0x0fffffff], converted to bf16
+ * when dst_bf16.  block0 = index of the segment's first 2048-element block (prefix sum, the host
+ * passes the total).  segs_dev lives in device memory. */
+typedef struct MriGatherSeg {
+  void* dst;
+  const int32_t* idx;
+  const float* src[4];
+  int64_t n;
+  int64_t block0;
+  int32_t dst_bf16;
+  int32_t reserved;
+} MriGatherSeg;
+int mri_gather_pack(const MriGatherSeg* segs_dev, int n_segs, int64_t total_blocks, void* stream);
+
 /* Thin-Cout convolution (out_conv: 128 -> 3 / 64 -> 1 / 64 -> 4 channels,
  * slice_cond_2d_ddpm/unet.py:167, unet_attention.py:155) finished from the per-tap products
  * Y[q][tap*cout + co] = W[tap][co] . x[q] (one tensor-core GEMM, K = Cin):

@@ -73,6 +73,18 @@ class MriWgradArgs(C.Structure):
     ]
 
 
+class MriGatherSeg(C.Structure):
+    _fields_ = [
+        ("dst", C.c_void_p),
+        ("idx", C.c_void_p),
+        ("src", C.c_void_p * 4),
+        ("n", C.c_int64),
+        ("block0", C.c_int64),
+        ("dst_bf16", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/mri_b200.h one to one
 _vp, _i, _i64, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
 SIGNATURES = {
@@ -90,6 +102,7 @@ SIGNATURES = {
     "mri_sinusoidal": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "mri_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mri_im2col": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "mri_gather_pack": (_i, [_vp, _i, _i64, _vp]),
     "mri_tap_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mri_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i64, _i, _i, _vp]),
     "mri_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i64, _i, _i, _vp]),

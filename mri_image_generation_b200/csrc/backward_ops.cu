@@ -91,28 +91,43 @@ gn_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
   int64_t r1 = r0 + rows_per_block;
   if (r1 > spatial) r1 = spatial;
   const size_t base = (size_t)sample * spatial * vec_per_row + cv;
-  for (int64_t r = r0 + rsub; r < r1; r += rows_step) {
-    float d[8];
-    unpack8b(__ldg(dy + base + r * vec_per_row), d);
-    if (x == nullptr) {
+  constexpr int U = 4;  // independent 16-byte loads in flight per thread
+  for (int64_t r = r0 + rsub; r < r1; r += (int64_t)rows_step * U) {
+    uint4 dv[U], xv[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s0[j] += d[j];
-      continue;
-    }
-    float f[8];
-    unpack8b(__ldg(x + base + r * vec_per_row), f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (f[j] - mean) * rstd;
-      float du = d[j];
-      if (kSilu) {
-        const float u = fmaf(xh, sc[j], sh[j]);
-        const float sg = 1.0f / (1.0f + __expf(-u));
-        du *= sg * (1.0f + u * (1.0f - sg));
+    for (int u = 0; u < U; ++u) {
+      const int64_t ru = r + (int64_t)u * rows_step;
+      if (ru < r1) {
+        dv[u] = __ldg(dy + base + ru * vec_per_row);
+        if (x != nullptr) xv[u] = __ldg(x + base + ru * vec_per_row);
       }
-      s0[j] += d[j];
-      s1[j] += du;
-      s2[j] = fmaf(du, xh, s2[j]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t ru = r + (int64_t)u * rows_step;
+      if (ru >= r1) continue;
+      float d[8];
+      unpack8b(dv[u], d);
+      if (x == nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s0[j] += d[j];
+        continue;
+      }
+      float f[8];
+      unpack8b(xv[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (f[j] - mean) * rstd;
+        float du = d[j];
+        if (kSilu) {
+          const float uu = fmaf(xh, sc[j], sh[j]);
+          const float sg = __fdividef(1.0f, 1.0f + __expf(-uu));
+          du *= sg * (1.0f + uu * (1.0f - sg));
+        }
+        s0[j] += d[j];
+        s1[j] += du;
+        s2[j] = fmaf(du, xh, s2[j]);
+      }
     }
   }
 #pragma unroll
@@ -173,28 +188,44 @@ gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
   int64_t r1 = r0 + rows_per_block;
   if (r1 > spatial) r1 = spatial;
   const size_t base = (size_t)sample * spatial * vec_per_row + cv;
-  for (int64_t r = r0 + rsub; r < r1; r += rows_step) {
-    float f[8], d[8], o[8];
-    unpack8b(__ldg(x + base + r * vec_per_row), f);
-    unpack8b(__ldg(dy + base + r * vec_per_row), d);
+  constexpr int U = 4;  // independent 16-byte loads in flight per thread
+  for (int64_t r = r0 + rsub; r < r1; r += (int64_t)rows_step * U) {
+    uint4 xv[U], dv[U], av[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (f[j] - k.mean) * k.rstd;
-      float du = d[j];
-      if (kSilu) {
-        const float u = fmaf(xh, gmv[j], btv[j]);
-        const float sg = 1.0f / (1.0f + __expf(-u));
-        du *= sg * (1.0f + u * (1.0f - sg));
+    for (int u = 0; u < U; ++u) {
+      const int64_t ru = r + (int64_t)u * rows_step;
+      if (ru < r1) {
+        xv[u] = __ldg(x + base + ru * vec_per_row);
+        dv[u] = __ldg(dy + base + ru * vec_per_row);
+        if (add != nullptr) av[u] = __ldg(add + base + ru * vec_per_row);
       }
-      o[j] = k.rstd * (gmv[j] * du - m1 - xh * m2);
     }
-    if (add != nullptr) {
-      float a[8];
-      unpack8b(__ldg(add + base + r * vec_per_row), a);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += a[j];
+    for (int u = 0; u < U; ++u) {
+      const int64_t ru = r + (int64_t)u * rows_step;
+      if (ru >= r1) continue;
+      float f[8], d[8], o[8];
+      unpack8b(xv[u], f);
+      unpack8b(dv[u], d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (f[j] - k.mean) * k.rstd;
+        float du = d[j];
+        if (kSilu) {
+          const float uu = fmaf(xh, gmv[j], btv[j]);
+          const float sg = __fdividef(1.0f, 1.0f + __expf(-uu));
+          du *= sg * (1.0f + uu * (1.0f - sg));
+        }
+        o[j] = k.rstd * (gmv[j] * du - m1 - xh * m2);
+      }
+      if (add != nullptr) {
+        float a[8];
+        unpack8b(av[u], a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += a[j];
+      }
+      dx[base + ru * vec_per_row] = pack8b(o);
     }
-    dx[base + r * vec_per_row] = pack8b(o);
   }
 }
 

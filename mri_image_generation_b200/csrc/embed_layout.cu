@@ -235,6 +235,32 @@ softmax_rows_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P, 
   }
 }
 
+// Re-pack of derived weight buffers after an optimizer step: every packed buffer (K-major bf16
+// conv matrices, transposed / flipped dgrad matrices, concatenated projections ...) is a pure
+// gather of parameter elements, so ONE launch refreshes them all from a table of segments.
+// idx: (source slot << 28) | element offset inside that source, or -1 for a zero (padding).
+__global__ void __launch_bounds__(256)
+gather_pack_kernel(const MriGatherSeg* __restrict__ segs, int n_segs) {
+  // binary search: last segment whose first block <= blockIdx.x
+  int lo = 0, hi = n_segs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (segs[mid].block0 <= (int64_t)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const MriGatherSeg sg = segs[lo];
+  const int64_t i0 = ((int64_t)blockIdx.x - sg.block0) * 2048 + threadIdx.x;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int64_t i = i0 + (int64_t)u * 256;
+    if (i >= sg.n) break;
+    const int32_t e = __ldg(sg.idx + i);
+    float v = 0.f;
+    if (e >= 0) v = __ldg(sg.src[(e >> 28) & 3] + (e & 0x0fffffff));
+    if (sg.dst_bf16) reinterpret_cast<__nv_bfloat16*>(sg.dst)[i] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(sg.dst)[i] = v;
+  }
+}
+
 static inline unsigned grid_for(int64_t total) {
   int64_t b = (total + 255) / 256;
   const int64_t cap = 148 * 16;
@@ -283,6 +309,14 @@ extern "C" int mri_im2col(const float* src, const float* src2, void* dst, int sa
   im2col_kernel<<<grid_for(total), 256, kpad * sizeof(int), (cudaStream_t)stream>>>(
       src, src2, reinterpret_cast<uint4*>(dst), samples, cin, cin2, D, H, W, ksize, ndim, kpad);
   return check_launch("im2col_kernel");
+}
+
+extern "C" int mri_gather_pack(const MriGatherSeg* segs_dev, int n_segs, int64_t total_blocks,
+                               void* stream) {
+  if (n_segs < 1 || total_blocks < 1) return 0;
+  if (total_blocks > 0x7fffffffLL) return set_error(-2, "mri_gather_pack: too many blocks");
+  gather_pack_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>(segs_dev, n_segs);
+  return check_launch("gather_pack_kernel");
 }
 
 extern "C" int mri_tap_gather(const void* y, void* out, const float* bias, int samples, int D, int H,

@@ -145,7 +145,7 @@ gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           float t = fmaf(f[k], sc[k], sh[k]);
-          if (kSilu) t = t / (1.0f + __expf(-t));
+          if (kSilu) t = __fdividef(t, 1.0f + __expf(-t));
           f[k] = t + rb[k];
         }
         if (kResidual) {

@@ -122,8 +122,7 @@ class DiffusionBase(nn.Module):
         x_in is the sampler state).  mode: 'ddpm' | 'ddim'."""
         dev = img.device
         if prog.params_changed():
-            for fn in prog.refresh:
-                fn()
+            prog.do_refresh()
         B = prog.B
         per_sample = img[0].numel()
         noise = prog.__dict__.setdefault("_noise_buf", torch.empty_like(prog.x_in))

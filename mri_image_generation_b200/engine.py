@@ -98,6 +98,8 @@ class UNetProgram(BackwardMixin):
         self.op_outs: List[List[torch.Tensor]] = []
         self.plans: List[P.GemmPlan] = []
         self.refresh: List[Callable[[], None]] = []  # re-pack weights after a parameter update
+        self._packed: List[Tuple[torch.Tensor, Callable[[], torch.Tensor]]] = []
+        self._gather = None
         self._arena = torch.zeros(self.STATS_ARENA, dtype=torch.float64, device=device)
         self._arena_used = 0
         self.gemm_flops = 0
@@ -142,7 +144,128 @@ class UNetProgram(BackwardMixin):
         """A derived weight buffer that is re-computed in place when parameters change."""
         buf = make()
         self.refresh.append(lambda: buf.copy_(make()))
+        self._packed.append((buf, make))
         return buf
+
+    # ------------------------------------------------------------------ refresh after a param update
+    def do_refresh(self) -> None:
+        """Bring every packed buffer up to date.  Almost all of them are pure gathers of parameter
+        elements: those are refreshed by ONE mri_gather_pack launch driven by index maps that are
+        derived once (see _build_gather); the few arithmetic ones (summed biases) re-run their
+        torch expression."""
+        if self._gather is None:
+            self._gather = self._build_gather()
+        table, n_segs, blocks, fallback, _keep = self._gather
+        if n_segs:
+            _lib.check(_lib.load().mri_gather_pack(table.data_ptr(), n_segs, blocks,
+                                                   _lib.current_stream_ptr()), "mri_gather_pack")
+        for i in fallback:
+            self.refresh[i]()
+
+    def _build_gather(self):
+        """Derive, for each packed buffer, the index of the parameter element every output element
+        copies.  The `make` closures are opaque torch expressions over the module parameters, so
+        the map is found by probing: the parameters' data is temporarily replaced by base-128
+        digits of each element's global address (+1; values 1..128 are exact in bf16 and fp32,
+        0 stays reserved for padding), `make` is evaluated once per digit, and the digits read off
+        the results.  A buffer whose map does not reproduce `make` on the real parameters
+        (an arithmetic expression, not a gather) keeps its torch refresh."""
+        import ctypes as C
+        params, seen = [], set()
+        for p_ in self._params:
+            if id(p_) not in seen and p_.dtype == torch.float32:
+                seen.add(id(p_))
+                params.append(p_)
+        offs, tot = [], 0
+        for p_ in params:
+            offs.append(tot)
+            tot += p_.numel()
+        n_dig = 1
+        while (1 << (7 * n_dig)) <= tot + 1:
+            n_dig += 1
+        saved = [p_.data for p_ in params]
+        addr = [None] * len(self._packed)
+        try:
+            with torch.no_grad():
+                for k in range(n_dig):
+                    for p_, off in zip(params, offs):
+                        a = torch.arange(off + 1, off + 1 + p_.numel(), device=p_.device, dtype=torch.int64)
+                        p_.data = ((((a >> (7 * k)) & 127) + 1).to(torch.float32)).view(p_.shape)
+                    for i, (buf, make) in enumerate(self._packed):
+                        if addr[i] is False:
+                            continue
+                        try:
+                            d = make().reshape(-1).to(torch.float32)
+                        except Exception:  # noqa: BLE001  (expression not defined on probe values)
+                            addr[i] = False
+                            continue
+                        dl = d.round().to(torch.int64)
+                        ok = bool(((d == dl.to(torch.float32)) & (dl >= 0) & (dl <= 128)).all().item())
+                        if not ok or dl.numel() != buf.numel():
+                            addr[i] = False
+                            continue
+                        if k == 0:
+                            addr[i] = {"zero": dl == 0, "a": (dl - 1).clamp_min(0)}
+                        else:
+                            if not bool(((dl == 0) == addr[i]["zero"]).all().item()):
+                                addr[i] = False
+                                continue
+                            addr[i]["a"] += (dl - 1).clamp_min(0) << (7 * k)
+        finally:
+            for p_, d in zip(params, saved):
+                p_.data = d
+        offs_t = torch.tensor(offs, device=self.device, dtype=torch.int64)
+        segs, keep, fallback, blocks = [], [], [], 0
+        flat = None
+        for i, (buf, make) in enumerate(self._packed):
+            info = addr[i]
+            if not info or buf.dtype not in (torch.bfloat16, torch.float32) or not buf.is_contiguous():
+                fallback.append(i)
+                continue
+            a = info["a"] - 1          # global element address, -1 for padding (a stored +1)
+            a = torch.where(info["zero"], torch.full_like(a, -1), a)
+            valid = a >= 0
+            which = torch.searchsorted(offs_t, a.clamp_min(0), right=True) - 1
+            used = torch.unique(which[valid]).tolist() if bool(valid.any().item()) else []
+            if len(used) > 4 or bool((a >= tot).any().item()):
+                fallback.append(i)
+                continue
+            slot_of = {pi: s_ for s_, pi in enumerate(used)}
+            slot = torch.zeros_like(a)
+            local = torch.zeros_like(a)
+            for pi in used:
+                m = valid & (which == pi)
+                slot[m] = slot_of[pi]
+                local[m] = a[m] - offs[pi]
+            if bool((local >= (1 << 28)).any().item()):
+                fallback.append(i)
+                continue
+            idx = torch.where(valid, (slot << 28) | local, torch.full_like(a, -1)).to(torch.int32)
+            # verify against the real expression before trusting the map
+            flat_srcs = [params[pi].detach().reshape(-1) for pi in used]
+            got = torch.zeros(buf.numel(), dtype=torch.float32, device=self.device)
+            for s_, src in enumerate(flat_srcs):
+                m = valid & (slot == s_)
+                got[m] = src[local[m]]
+            if not torch.equal(got.to(buf.dtype), make().reshape(-1)):
+                fallback.append(i)
+                continue
+            sg = _lib.MriGatherSeg()
+            sg.dst, sg.idx, sg.n = buf.data_ptr(), idx.data_ptr(), buf.numel()
+            for s_, pi in enumerate(used):
+                sg.src[s_] = params[pi].data_ptr()
+            sg.block0 = blocks
+            sg.dst_bf16 = 1 if buf.dtype == torch.bfloat16 else 0
+            blocks += -(-buf.numel() // 2048)
+            segs.append(sg)
+            keep.append(idx)
+        table = None
+        if segs:
+            arr = (_lib.MriGatherSeg * len(segs))(*segs)
+            raw = bytes(memoryview(arr))
+            table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
+        self.gather_info = {"segments": len(segs), "fallback": len(fallback), "elements": sum(s_.n for s_ in segs)}
+        return table, len(segs), blocks, fallback, keep
 
     def params_changed(self) -> bool:
         v = tuple(p._version for p in self._params)
@@ -568,8 +691,7 @@ class UNet3DProgram(UNetProgram):
     def forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
         """Eager entry: copy inputs into the static buffers, run, return fp32 NCDHW eps."""
         if self.params_changed():
-            for fn in self.refresh:
-                fn()
+            self.do_refresh()
         self.x_in.copy_(x)
         self.t_in.copy_(t)
         self.run()
@@ -782,8 +904,7 @@ class UNet2DProgram(UNetProgram):
 
     def _load_inputs(self, x, t, z_pos, context):
         if self.params_changed():
-            for fn in self.refresh:
-                fn()
+            self.do_refresh()
         self.x_in.copy_(x)
         self.t_in.copy_(t)
         self.z_in.copy_(z_pos.reshape(-1, 1))

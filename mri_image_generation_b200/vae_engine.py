@@ -233,8 +233,7 @@ class VAE3DProgram(UNetProgram):
     # ------------------------------------------------------------------ entry
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.params_changed():
-            for fn in self.refresh:
-                fn()
+            self.do_refresh()
         self.x_in.copy_(x)
         self.run()
         S = self.sp_out[0] * self.sp_out[1] * self.sp_out[2]
