@@ -352,7 +352,11 @@ def run_train(args, rank, world, local_rank):
     model = UNet3DModelWithAttention(**MODEL_KW).to(dev).train()
     net = wrap_ddp(model, dev) if world > 1 else model
     diff = quiet(GaussianDiffusionLatent3D, net, LATENT[0], timesteps=T_STEPS).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=2e-4)
+    if args.torch_adam:
+        opt = torch.optim.Adam(model.parameters(), lr=2e-4)
+    else:  # one-launch Adam (mri_adam_step), same update rule and state layout
+        from mri_image_generation_b200.optim import Adam
+        opt = Adam(model.parameters(), lr=2e-4)
     torch.manual_seed(1234 + rank)
     z = torch.randn(B, *LATENT, device=dev)
 
@@ -392,6 +396,7 @@ def run_train(args, rank, world, local_rank):
         "config": {"workload": "ddpm_3d_ldm_train_step", "latent": list(LATENT), "batch_per_gpu": B,
                    "model": "UNet3DModelWithAttention(base 128, mults 1-2-4, 136.4M params)",
                    "step": "q_sample + fwd + min-SNR loss + bwd + DDP all-reduce + Adam",
+                   "optimizer": "torch.optim.Adam" if args.torch_adam else "mri_b200 fused Adam",
                    "loss": float(loss.item())},
         "roofline": {"bound": "tensor", "achieved": flops / (ms_per_step * 1e-3) / 1e12,
                      "peak": peaks["tflops"], "unit": "TFLOP/s",
@@ -459,6 +464,8 @@ def main():
                     help="sample = headline (cfg4); train = DDP training step (cfg5); vae = VAE3D "
                          "encode / decode at the cfg4 volume size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-adam", action="store_true", help="train mode: torch.optim.Adam instead of "
+                    "mri_image_generation_b200.optim.Adam")
     ap.add_argument("--per-op", default="", help="write per-GEMM timings (CUDA events) to this file")
     args = ap.parse_args()
 

@@ -282,6 +282,27 @@ int mri_minsnr_loss_bwd(const float* pred, const float* noise, const int64_t* t,
                         float gamma, const float* upstream, float* dpred, int samples,
                         int64_t per_sample, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Optimizer step (torch.optim.Adam as used by ddpm_3d_ldm/train.py:243,399 and
+ * slice_cond_2d_ddpm/model.py:126,167): one launch updates every parameter (fp32 p, g, exp_avg m,
+ * exp_avg_sq v).  step_dev: device float holding the number of updates applied so far; the kernel
+ * uses step + 1 for the bias corrections and advances it.  grad_scale / found_inf (device
+ * scalars, may be NULL) implement torch.amp.GradScaler's fused protocol: g /= grad_scale, and
+ * the whole update (and the step counter) is skipped when *found_inf != 0.
+ * block0 = index of the segment's first 1024-element block; segs_dev lives in device memory.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MriAdamSeg {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int64_t n;
+  int64_t block0;
+} MriAdamSeg;
+int mri_adam_step(const MriAdamSeg* segs_dev, int n_segs, int64_t total_blocks, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, float* step_dev, const float* grad_scale,
+                  const float* found_inf, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,6 +85,11 @@ class MriGatherSeg(C.Structure):
     ]
 
 
+class MriAdamSeg(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
+                ("n", C.c_int64), ("block0", C.c_int64)]
+
+
 # name -> (restype, argtypes); mirrors include/mri_b200.h one to one
 _vp, _i, _i64, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
 SIGNATURES = {
@@ -102,6 +107,7 @@ SIGNATURES = {
     "mri_sinusoidal": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "mri_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mri_im2col": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "mri_adam_step": (_i, [_vp, _i, _i64, _f, _f, _f, _f, _f, _vp, _vp, _vp, _vp]),
     "mri_gather_pack": (_i, [_vp, _i, _i64, _vp]),
     "mri_tap_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mri_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i64, _i, _i, _vp]),

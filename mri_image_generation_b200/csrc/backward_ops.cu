@@ -4,6 +4,7 @@
 // fp32 accumulation.  Reference semantics: autograd of the modules cited in include/mri_b200.h.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <math.h>
 
 #include "../../include/mri_b200.h"
 #include "common.h"
@@ -338,6 +339,49 @@ loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ noise,
     dpred[base + j] = coef * (pred[base + j] - noise[base + j]);
 }
 
+// Multi-tensor Adam (torch.optim.Adam semantics: L2 weight decay added to the gradient, bias
+// corrections, eps outside the square root of the corrected second moment), one launch for all
+// parameters.  grad_scale / found_inf follow torch.amp.GradScaler's fused-optimizer protocol.
+__global__ void __launch_bounds__(256)
+adam_kernel(const MriAdamSeg* __restrict__ segs, int n_segs, float lr, float beta1, float beta2,
+            float omb1, float omb2, float eps, float weight_decay, const float* __restrict__ step_dev,
+            const float* __restrict__ grad_scale, const float* __restrict__ found_inf) {
+  if (found_inf != nullptr && *found_inf != 0.f) return;  // skipped step (inf / nan gradients)
+  // the step counter lives on the device (it must not advance on a skipped step, and the host
+  // never learns about skips): bias corrections for step + 1
+  const double stp = (double)*step_dev + 1.0;
+  const float bc1 = (float)(1.0 - pow((double)beta1, stp));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, stp));
+  int lo = 0, hi = n_segs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (segs[mid].block0 <= (int64_t)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const MriAdamSeg sg = segs[lo];
+  const float inv_scale = grad_scale != nullptr ? 1.0f / *grad_scale : 1.0f;
+  const int64_t i0 = ((int64_t)blockIdx.x - sg.block0) * 1024 + threadIdx.x;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int64_t i = i0 + (int64_t)u * 256;
+    if (i >= sg.n) break;
+    float p = sg.p[i];
+    float g = sg.g[i] * inv_scale;
+    if (weight_decay != 0.f) g = fmaf(weight_decay, p, g);
+    float m = sg.m[i], v = sg.v[i];
+    m = m + omb1 * (g - m);               // exp_avg.lerp_(grad, 1 - beta1)
+    v = fmaf(omb2 * g, g, beta2 * v);      // exp_avg_sq.mul_(beta2).addcmul_(g, g, value = 1 - beta2)
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    p -= (lr / bc1) * (m / denom);
+    sg.p[i] = p;
+    sg.m[i] = m;
+    sg.v[i] = v;
+  }
+}
+
+__global__ void adam_advance_kernel(float* step_dev, const float* found_inf) {
+  if (found_inf == nullptr || *found_inf == 0.f) *step_dev += 1.f;
+}
+
 static inline int rows_per_block_for(int samples, int64_t spatial, int rows_step, dim3* grid) {
   int64_t want_blocks = (148 * 8 + samples - 1) / samples;
   int64_t rows_per = (spatial + want_blocks - 1) / want_blocks;
@@ -350,6 +394,21 @@ static inline int rows_per_block_for(int samples, int64_t spatial, int rows_step
 }  // namespace mri
 
 using namespace mri;
+
+extern "C" int mri_adam_step(const MriAdamSeg* segs_dev, int n_segs, int64_t total_blocks, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, float* step_dev,
+                             const float* grad_scale, const float* found_inf, void* stream) {
+  if (n_segs < 1 || total_blocks < 1) return 0;
+  if (step_dev == nullptr) return set_error(-2, "mri_adam_step: step counter missing");
+  if (total_blocks > 0x7fffffffLL) return set_error(-2, "mri_adam_step: too many blocks");
+  adam_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>(
+      segs_dev, n_segs, lr, beta1, beta2, (float)(1.0 - (double)beta1), (float)(1.0 - (double)beta2), eps,
+      weight_decay, step_dev, grad_scale, found_inf);
+  int rc = check_launch("adam_kernel");
+  if (rc != 0) return rc;
+  adam_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, found_inf);
+  return check_launch("adam_advance_kernel");
+}
 
 extern "C" int mri_gn_bwd_reduce(const void* x, const void* dy, const double* stats,
                                  const float* gamma, const float* beta, double* sums, int samples,

@@ -1,0 +1,68 @@
+"""mri_image_generation_b200.optim.Adam (one-launch mri_adam_step) vs torch.optim.Adam on the same
+parameters / gradients: fp32 arithmetic in a different association order -> rtol 2e-6 per step."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def make_params(seed):
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(128, 64, 3, 3, 3), (128,), (7, 5), (1,), (300, 33)]
+    return [torch.nn.Parameter(torch.randn(*s, generator=g).cuda()) for s in shapes]
+
+
+@pytest.mark.parametrize("wd", [0.0, 0.01])
+def test_adam_matches_torch(wd):
+    from mri_image_generation_b200.optim import Adam
+    pa, pb = make_params(1), make_params(1)
+    oa = Adam(pa, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+    ob = torch.optim.Adam(pb, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+    g = torch.Generator().manual_seed(2)
+    for step in range(5):
+        v0 = [p._version for p in pa]
+        for x, y in zip(pa, pb):
+            gr = torch.randn(*x.shape, generator=g).cuda()
+            x.grad, y.grad = gr.clone(), gr.clone()
+        oa.step()
+        ob.step()
+        assert all(p._version > v for p, v in zip(pa, v0)), "parameter versions must advance"
+        for x, y in zip(pa, pb):
+            assert torch.allclose(x, y, rtol=2e-6, atol=1e-7), (step, (x - y).abs().max().item())
+    sa, sb = oa.state_dict(), ob.state_dict()
+    assert sa["state"].keys() == sb["state"].keys()
+    for k in sa["state"]:
+        assert set(sa["state"][k]) == {"step", "exp_avg", "exp_avg_sq"}
+        for key in ("exp_avg", "exp_avg_sq"):
+            a, b = sa["state"][k][key], sb["state"][k][key]
+            assert torch.allclose(a, b, rtol=1e-4, atol=1e-6), (k, key, (a - b).abs().max().item())
+        assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"]) == 5.0
+
+
+def test_adam_with_grad_scaler_skips_on_inf_and_unscales():
+    from mri_image_generation_b200.optim import Adam
+    pa, pb = make_params(3), make_params(3)
+    oa = Adam(pa, lr=1e-3)
+    ob = torch.optim.Adam(pb, lr=1e-3)
+    sa = torch.amp.GradScaler("cuda", init_scale=1024.0)
+    sb = torch.amp.GradScaler("cuda", init_scale=1024.0)
+    for it in range(3):
+        la = sum((p * p).sum() for p in pa)
+        lb = sum((p * p).sum() for p in pb)
+        oa.zero_grad(set_to_none=True)
+        ob.zero_grad(set_to_none=True)
+        sa.scale(la).backward()
+        sb.scale(lb).backward()
+        if it == 1:  # poison one gradient: both scalers must skip the step
+            pa[0].grad[0, 0, 0, 0, 0] = float("inf")
+            pb[0].grad[0, 0, 0, 0, 0] = float("inf")
+        before = [p.detach().clone() for p in pa]
+        sa.step(oa)
+        sb.step(ob)
+        sa.update()
+        sb.update()
+        if it == 1:
+            assert all(torch.equal(a, b) for a, b in zip(before, pa))
+        for x, y in zip(pa, pb):
+            assert torch.allclose(x, y, rtol=5e-6, atol=1e-7), it
+    assert sa.get_scale() == sb.get_scale()
