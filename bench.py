@@ -458,7 +458,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=4, help="volumes per GPU")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="volumes per GPU (default: 16 for sampling -- measured sweep in "
+                         "profiles/README.md: 2 -> 0.59, 4 -> 0.67, 8 -> 0.74, 16 -> 0.76 volumes/s --, "
+                         "8 for the training step (BASELINE cfg5), 1 for the VAE)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="sample", choices=["sample", "train", "vae"],
                     help="sample = headline (cfg4); train = DDP training step (cfg5); vae = VAE3D "
@@ -469,6 +472,8 @@ def main():
     ap.add_argument("--per-op", default="", help="write per-GEMM timings (CUDA events) to this file")
     args = ap.parse_args()
 
+    if args.batch <= 0:
+        args.batch = {"sample": 16, "train": 8, "vae": 1}[args.mode]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -82,7 +82,7 @@ def full(src, dst):
         if h2:
             isrc, isamp = h2.index("Source"), h2.index("# Samples")
             stall = [i for i, h in enumerate(h2) if h.startswith("stall_") and "Not Issued" not in h]
-            body = [r for r in rows[rows.index(h2) + 1:] if len(r) == len(h2)]
+            body = [r for r in rows[rows.index(h2) + 1:] if len(r) == len(h2) and r[isamp].isdigit()]
             tot = sum(int(r[isamp] or 0) for r in body) or 1
             f.write(f"\n# top sampled SASS instructions of launch 1 ({tot} samples)\n")
             for r in sorted(body, key=lambda r: -int(r[isamp] or 0))[:12]:
