@@ -116,8 +116,44 @@ class DiffusionBase(nn.Module):
             m = inner
         return m if isinstance(m, EngineModule) else None
 
+    def _step_graph(self, prog, mode: str, one_step, tprev):
+        """The CUDA graph of one reverse step on `prog` (captured once per program and mode)."""
+        dev = prog.x_in.device
+        key = (id(prog), mode)
+        graphs = self._graphs()
+        graph = graphs.get(key)
+        if graph is None:
+            # warm-up + capture must not disturb the caller's RNG stream
+            rng = torch.cuda.get_rng_state(dev)
+            prog.x_in.zero_()
+            prog.t_in.fill_(1)
+            tprev.fill_(0)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                one_step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            prog.t_in.fill_(1)
+            with torch.cuda.graph(graph):
+                one_step()
+            torch.cuda.synchronize(dev)
+            torch.cuda.set_rng_state(rng, dev)
+            graphs[key] = graph
+        return graph
+
+    def _p_sample_on(self, prog, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """One ancestral step x_t -> x_{t-1} on `prog` (whose conditioning inputs the caller has
+        set): eager the first time a program is used, a replay of the captured step afterwards
+        (the same launches, so the same values and the same draws from torch's Philox stream)."""
+        calls = prog.__dict__.get("_p_sample_calls", 0)
+        prog.__dict__["_p_sample_calls"] = calls + 1
+        out = self._reverse_loop(prog, x.float(), 0, 1, "ddpm", use_graph=calls >= 1, t_vec=t)
+        return out
+
     def _reverse_loop(self, prog, img: torch.Tensor, start_t: int, n_steps: int, mode: str,
-                      use_graph: bool = True) -> torch.Tensor:
+                      use_graph: bool = True, t_vec: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Run n_steps reverse steps (i = start_t, start_t-1, ...) on `prog` (a UNetProgram whose
         x_in is the sampler state).  mode: 'ddpm' | 'ddim'."""
         dev = img.device
@@ -143,31 +179,13 @@ class DiffusionBase(nn.Module):
             ops.add_i64(prog.t_in, -1)
 
         graph = None
-        if use_graph and n_steps >= 3:
-            key = (id(prog), mode)
-            graphs = self._graphs()
-            graph = graphs.get(key)
-            if graph is None:
-                # warm-up + capture must not disturb the caller's RNG stream
-                rng = torch.cuda.get_rng_state(dev)
-                prog.x_in.zero_()
-                prog.t_in.fill_(1)
-                tprev.fill_(0)
-                side = torch.cuda.Stream(device=dev)
-                side.wait_stream(torch.cuda.current_stream(dev))
-                with torch.cuda.stream(side):
-                    one_step()
-                torch.cuda.current_stream(dev).wait_stream(side)
-                torch.cuda.synchronize(dev)
-                graph = torch.cuda.CUDAGraph()
-                prog.t_in.fill_(1)
-                with torch.cuda.graph(graph):
-                    one_step()
-                torch.cuda.synchronize(dev)
-                torch.cuda.set_rng_state(rng, dev)
-                graphs[key] = graph
+        if use_graph and (n_steps >= 3 or t_vec is not None):
+            graph = self._step_graph(prog, mode, one_step, tprev)
         prog.x_in.copy_(img)
-        prog.t_in.fill_(start_t)
+        if t_vec is not None:  # per-sample timesteps (p_sample called directly)
+            prog.t_in.copy_(t_vec.to(dev).long())
+        else:
+            prog.t_in.fill_(start_t)
         tprev.fill_(start_t - 1)
         for _ in range(n_steps):
             if graph is not None:

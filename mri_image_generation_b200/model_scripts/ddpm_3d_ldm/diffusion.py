@@ -51,6 +51,9 @@ class GaussianDiffusionLatent3D(DiffusionBase):
         """ddpm_3d_ldm/diffusion.py:103-126: eps = model(x, t); z = randn_like(x) is drawn for
         every t (masked at t == 0)."""
         _require_cuda(x, "p_sample")
+        eng = self._engine_model()
+        if eng is not None and cond is None:
+            return self._p_sample_on(eng.program(x.shape[0], x.shape[2:]), x, t)
         eps_theta = self.model(x, t) if cond is None else self.model(x, t, cond)
         noise = torch.randn_like(x)
         return self._p_update(x, t, eps_theta, noise)

@@ -49,6 +49,11 @@ class GaussianDiffusion(DiffusionBase):
     def p_sample(self, x, t, z_pos):
         """diffusion.py:110-132."""
         _require_cuda(x, "p_sample")
+        eng = self._engine_model()
+        if eng is not None:
+            prog = eng.program(x.shape[0], x.shape[2:], x.shape[1], 0)
+            prog.z_in.copy_(self._z_tensor(z_pos, x.shape[0], x.device).reshape(-1, 1))
+            return self._p_sample_on(prog, x, t)
         eps_theta = self.model(x, t, z_pos)
         noise = torch.randn_like(x)
         return self._p_update(x, t, eps_theta, noise)
