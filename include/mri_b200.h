@@ -102,7 +102,7 @@ typedef struct MriGemmArgs {
   int32_t sk_ctas;
   int32_t swap_ab;        /* 1: weights are the M = 128 MMA operand, two boxes of positions the N = 256
                              operand (needs block_n 128, n_total % 128 == 0, bf16 output) */
-  int32_t reserved;
+  int32_t staging2;       /* set by the library (short K loops: second set of staging buffers) */
   uint64_t* trace;        /* profiling only (normally NULL): [grid][8] per-CTA timestamps, see gemm_tc.cu */
 } MriGemmArgs;
 

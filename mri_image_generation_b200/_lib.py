@@ -47,7 +47,7 @@ class MriGemmArgs(C.Structure):
         ("sk_flags", C.c_void_p),
         ("sk_ctas", C.c_int32),
         ("swap_ab", C.c_int32),
-        ("reserved", C.c_int32),
+        ("staging2", C.c_int32),
         ("trace", C.c_void_p),
     ]
 

@@ -430,6 +430,21 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
       }
     }
 
+    // swap_ab: position `epi_tid` of a box -> box-local coordinates (fixed for the whole kernel)
+    int pl[4];
+    {
+      int rr = epi_tid;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        pl[i] = rr % p.box[i];
+        rr /= p.box[i];
+      }
+    }
+    // swap_ab with short K loops: two sets of staging buffers so that box h+1 is written while
+    // the TMA store of box h still reads its set (host picks 3 pipeline stages to make room)
+    const bool staging2 = p.staging2 != 0;
+    uint32_t box_ctr = 0;
+
     auto flush_smem_stats = [&]() {  // all 128 epilogue threads
       named_bar_sync(1, 128);
       if (cur_sample >= 0 && epi_tid < 2 * p.stats_ld) {
@@ -708,25 +723,21 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
           const bool per_pos_sample = !uniform_sample && (p.rowbias != nullptr || p.stats != nullptr);
           // staging: chunk buffer (q >> 1) holds channels [64*(q>>1), +64); 128B rows, swizzled.
           // Position c0 + i (c0 % 16 == 0) lives in row c0 + i, 16-byte unit (cunit ^ (i & 7)).
-          const uint32_t sbuf = stag + (uint32_t)(q >> 1) * kChunkBytes;
           const uint32_t cbyte = (uint32_t)(((q & 1) * 32 + lane) * 2);
-          uint32_t swz8[8];
+          for (int h = 0; h < t.nbox; ++h, ++box_ctr) {
+            const uint32_t sset = stag + ((staging2 && (box_ctr & 1u)) ? (uint32_t)kStagingBytes : 0u);
+            const uint32_t sbuf = sset + (uint32_t)(q >> 1) * kChunkBytes;
+            uint32_t swz8[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) swz8[j] = sbuf + ((((cbyte >> 4) ^ (uint32_t)j) << 4) | (cbyte & 15u));
-          for (int h = 0; h < t.nbox; ++h) {
+            for (int j = 0; j < 8; ++j) swz8[j] = sbuf + ((((cbyte >> 4) ^ (uint32_t)j) << 4) | (cbyte & 15u));
             int oh[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) oh[i] = h ? t.org[1][i] : t.org[0][i];
             // per-position tables of this box (thread epi_tid describes position epi_tid)
             {
-              int pl[4], rr = epi_tid;
               bool ok = epi_tid < rows_in_box;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                pl[i] = rr % p.box[i];
-                rr /= p.box[i];
-                ok = ok && (oh[i] + pl[i] < p.ext[i]);
-              }
+              for (int i = 0; i < 4; ++i) ok = ok && (oh[i] + pl[i] < p.ext[i]);
               const int smp = sd > 0 ? oh[sd - 1] + pl[sd - 1] : 0;
               s_pos_info[epi_tid] = ok ? smp : -1;
               const uint32_t bal = __ballot_sync(0xffffffffu, ok);
@@ -737,17 +748,19 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
               flush_smem_stats();
               cur_sample = tile_sample;
             }
-            // both staging buffers must have been read out by the previous box's stores
-            if (epi_tid == 0) tma_store_wait_read0();
+            // this set of staging buffers must have been read out by the store that last used it
+            if (epi_tid == 0) {
+              if (staging2) tma_store_wait_read1(); else tma_store_wait_read0();
+            }
             named_bar_sync(1, 128);  // also publishes the position tables
             if (has_res) {
               // residual box -> the staging buffers (same layout as the output), by TMA
               if (epi_tid == 0) {
                 const CUtensorMap* r_map = reinterpret_cast<const CUtensorMap*>(p.r_maps) + t.cls;
                 mbar_arrive_expect_tx(resid_bar, (uint32_t)rows_in_box * (chunk1 ? 256u : 128u));
-                tma_load_5d(stag, r_map, resid_bar, t.n0, oh[0], oh[1], oh[2], oh[3]);
+                tma_load_5d(sset, r_map, resid_bar, t.n0, oh[0], oh[1], oh[2], oh[3]);
                 if (chunk1)
-                  tma_load_5d(stag + kChunkBytes, r_map, resid_bar, t.n0 + 64, oh[0], oh[1], oh[2], oh[3]);
+                  tma_load_5d(sset + kChunkBytes, r_map, resid_bar, t.n0 + 64, oh[0], oh[1], oh[2], oh[3]);
               }
               mbar_wait(resid_bar, resid_phase);
               resid_phase ^= 1u;
@@ -873,9 +886,9 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
             fence_proxy_async_smem();
             named_bar_sync(1, 128);
             if (epi_tid == 0) {
-              tma_store_5d(o_map, stag, t.n0, oh[0], oh[1], oh[2], oh[3]);
+              tma_store_5d(o_map, sset, t.n0, oh[0], oh[1], oh[2], oh[3]);
               if (chunk1)
-                tma_store_5d(o_map, stag + kChunkBytes, t.n0 + 64, oh[0], oh[1], oh[2], oh[3]);
+                tma_store_5d(o_map, sset + kChunkBytes, t.n0 + 64, oh[0], oh[1], oh[2], oh[3]);
               tma_store_commit();
             }
           }
@@ -909,8 +922,8 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
 // =============================== host side =============================================
 using namespace mri;
 
-static int pick_stages(int block_n, int swap_ab, int requested) {
-  const int budget = kSmemLimit - 1024 - kStagingBytes;
+static int pick_stages(int block_n, int swap_ab, int requested, int staging2 = 0) {
+  const int budget = kSmemLimit - 1024 - kStagingBytes * (staging2 ? 2 : 1);
   int s = budget / stage_bytes(block_n, swap_ab);
   if (s > kMaxStages) s = kMaxStages;
   if (requested >= 2 && requested < s) s = requested;
@@ -979,8 +992,11 @@ extern "C" int mri_gemm_launch(const MriGemmArgs* a, void* stream) {
     if (e != cudaSuccess) return set_cuda_error(e, "cudaDeviceGetAttribute(SM count)");
   }
   MriGemmArgs k = *a;
-  k.stages = pick_stages(bn, swap, a->stages);
-  const int smem = k.stages * stage_bytes(bn, swap) + kStagingBytes + 1024;
+  // short K loops (2D convolutions: 9 taps): the epilogue, not the main loop, paces the CTA ->
+  // trade one pipeline stage for a second set of staging buffers
+  k.staging2 = (swap && a->n_kb <= 40) ? 1 : 0;
+  k.stages = pick_stages(bn, swap, a->stages, k.staging2);
+  const int smem = k.stages * stage_bytes(bn, swap) + kStagingBytes * (k.staging2 ? 2 : 1) + 1024;
   long long grid = tiles < n_sms ? tiles : n_sms;
   if (k.sched != 0) {
     if (k.sk_partials == nullptr || k.sk_flags == nullptr)

@@ -144,7 +144,14 @@ def choose_box(ext: Sequence[int], prefer_unit: Sequence[int] = ()) -> Tuple[int
             tiles *= -(-e // bb)
         eff = total / (tiles * BLOCK_M)
         unit_pen = sum(1 for i in prefer_unit if b[i] != 1)
-        key = (round(eff, 6), -unit_pen, b[0], b[1], b[2])
+        # a box that spans several samples is only cheap for the statistics epilogue when every
+        # 16-position chunk of it lies inside one sample (positions of a sample are contiguous
+        # in the box): otherwise demand a clear efficiency advantage
+        score = eff
+        for i in prefer_unit:
+            if b[i] != 1 and (rows // b[i]) % 16 != 0:
+                score = eff * 0.75
+        key = (round(score, 6), -unit_pen, b[0], b[1], b[2])
         if best_key is None or key > best_key:
             best, best_key = b, key
     return best
