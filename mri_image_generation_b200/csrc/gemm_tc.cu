@@ -787,14 +787,15 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
               a = 0.f;
               b = 0.f;
             };
-            for (int c0 = 0; c0 < kBlockM; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tacc + (uint32_t)(h * 128), v);  // software pipeline: next chunk's TMEM load
+            for (int c0 = 0; c0 < kBlockM; c0 += 16) { // is in flight while this one is processed
               if (c0 >= rows_in_box) break;
-              uint32_t v[16];
-              tmem_ld16(tacc + (uint32_t)(h * 128 + c0), v);
               tmem_ld_wait();
               float f[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + add_c;
+              if (c0 + 16 < rows_in_box) tmem_ld16(tacc + (uint32_t)(h * 128 + c0 + 16), v);
               const uint32_t vm = (s_vmask[c0 >> 5] >> (c0 & 31)) & 0xffffu;  // valid positions
               const uint32_t rowb = (uint32_t)c0 * 128u;
               if (has_res) {  // TMA zero-filled the positions outside the tensor
@@ -848,11 +849,14 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
                   }
                 }
               } else if (vm == 0xffffu) {
+                float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};  // short dependency chains
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                  s_sum += f[i];
-                  s_sq = fmaf(f[i], f[i], s_sq);
+                  ps[i & 3] += f[i];
+                  pq[i & 3] = fmaf(f[i], f[i], pq[i & 3]);
                 }
+                s_sum += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+                s_sq += (pq[0] + pq[1]) + (pq[2] + pq[3]);
               } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
