@@ -103,6 +103,11 @@ typedef struct MriGemmArgs {
   int32_t swap_ab;        /* 1: weights are the M = 128 MMA operand, two boxes of positions the N = 256
                              operand (needs block_n 128, n_total % 128 == 0, bf16 output) */
   int32_t staging2;       /* set by the library (short K loops: second set of staging buffers) */
+  int32_t xreuse;         /* swap_ab only, box[0] == 8 and 16 groups per box: the a_maps boxes are 10
+                             positions wide along x1 (x - 1 .. x + 8) and k-table entries form groups
+                             (entry[7] = 1 marks a group leader) that share one activation tile; each
+                             entry's o1 in {-1, 0, 1} selects the view of that tile (3 taps per load) */
+  int32_t reserved2;
   uint64_t* trace;        /* profiling only (normally NULL): [grid][8] per-CTA timestamps, see gemm_tc.cu */
 } MriGemmArgs;
 

@@ -48,6 +48,8 @@ class MriGemmArgs(C.Structure):
         ("sk_ctas", C.c_int32),
         ("swap_ab", C.c_int32),
         ("staging2", C.c_int32),
+        ("xreuse", C.c_int32),
+        ("reserved2", C.c_int32),
         ("trace", C.c_void_p),
     ]
 

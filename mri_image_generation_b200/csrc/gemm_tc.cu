@@ -52,6 +52,8 @@ constexpr int kStagingBytes = 2 * kChunkBytes;
 constexpr int kPartialLd = 256;                  // floats per row of a stream-K partial tile
 constexpr int kMaxStatGroups = 32;
 constexpr int kSmemLimit = 227 * 1024;
+constexpr int kXTileBytes = 2 * 160 * 128;       // xreuse: two boxes of (8+2) x 16 positions x 64 channels
+constexpr int kXStages = 2;
 
 __host__ __device__ inline int stage_bytes(int block_n, int swap_ab) {
   return swap_ab ? 3 * kSlabBytes : kSlabBytes + block_n * 128;
@@ -233,11 +235,12 @@ __device__ __forceinline__ float4* partial_ptr(const MriGemmArgs& p, int cta, in
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 5];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 5 + kXStages];
   __shared__ uint32_t tmem_holder;
   __shared__ double s_stats[kMaxStatGroups * 2];
   __shared__ int s_pos_info[kBlockM];       // swap_ab: sample index, or -1 for an invalid position
   __shared__ uint32_t s_vmask[4];           // swap_ab: validity bits of the box's 128 positions
+  __shared__ uint32_t s_winfo[kMaxStages];  // xreuse: per weight stage, (dx + 1) | next-needs-tile << 8
 
   const int warp = uniform((int)(threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
@@ -247,13 +250,17 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
   const int block_n = p.block_n;
   const bool swap = p.swap_ab != 0;
   const int sbytes = stage_bytes(block_n, p.swap_ab);
-  const uint32_t stag = smem_base + (uint32_t)(S * sbytes);  // staging follows the ring
+  const uint32_t stag = smem_base + (uint32_t)(p.xreuse ? S * kSlabBytes + kXStages * kXTileBytes
+                                                        : S * sbytes);  // staging follows the ring(s)
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
   auto tmem_full_bar = [&](int b) { return bar0 + 8u * (2 * kMaxStages + b); };
   auto tmem_empty_bar = [&](int b) { return bar0 + 8u * (2 * kMaxStages + 2 + b); };
   const uint32_t resid_bar = bar0 + 8u * (2 * kMaxStages + 4);
+  auto xempty_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + 5 + s); };
+  const bool xreuse = p.xreuse != 0;
+  const uint32_t x_ring = smem_base + (uint32_t)(S * kSlabBytes);  // xreuse: after the weight ring
 
   const int n_kb = p.n_kb;
   const int G = (int)gridDim.x;
@@ -275,6 +282,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
       mbar_init(tmem_empty_bar(b), 4);  // one arrive per epilogue warp
     }
     mbar_init(resid_bar, 1);
+    for (int xs = 0; xs < kXStages; ++xs) mbar_init(xempty_bar(xs), 1);
     mbar_fence_init();
     tma_prefetch_desc(p.b_map);
     tma_prefetch_desc(p.a_maps);
@@ -303,7 +311,69 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
   if (warp == 0) {
     // ================================ TMA producer ==================================
     // The whole warp walks the loop (converged, warp-uniform values); one elected lane issues.
-    {
+    if (xreuse) {
+      // k-table entries come in groups that share ONE activation tile: the group leader (entry[7]
+      // = 1, or the first entry of a segment) loads both boxes 10 positions wide (x - 1 .. x + 8),
+      // every entry loads its own 64-channel weight slab; the MMA reads the tap dx as the view that
+      // starts dx + 1 rows into the tile (group stride 10 rows)
+      int ws = 0, xs = 0;
+      uint32_t wphase = 0, xphase = 0;
+      SegIter it;
+      it.init(p, sch, my_r);
+      int tile, kb0, len;
+      long long seg_end;
+      while (it.next(tile, kb0, len, seg_end)) {
+        Work t;
+        decode_tile(p, geom, tile, t);
+        const int bz1 = p.bz_sel[0] == 1 ? t.cls : 0;
+        const int bz2 = p.bz_sel[1] == 1 ? t.cls : 0;
+        const int4* kt = reinterpret_cast<const int4*>(p.ktable) + ((size_t)t.cls * n_kb + kb0) * 2;
+        int4 e0 = __ldg(kt), e1 = __ldg(kt + 1);
+        for (int i = 0; i < len; ++i) {
+          int4 f0 = e0, f1 = e1;
+          if (i + 1 < len) {
+            f0 = __ldg(kt + 2 * (i + 1));
+            f1 = __ldg(kt + 2 * (i + 1) + 1);
+          }
+          const int am = uniform(e0.x), c0 = uniform(e0.y), o2 = uniform(e0.w);
+          const int o3 = uniform(e1.x), o4 = uniform(e1.y), bk = uniform(e1.z);
+          const bool need_x = (uniform(e1.w) != 0) || i == 0;
+          const int o1 = uniform(e0.z);
+          // the tile stays current until the next leader (or the end of the segment)
+          const bool next_needs_x = (i + 1 < len) ? (uniform(f1.w) != 0) : true;
+          mbar_wait(empty_bar(ws), wphase ^ 1u);
+          if (need_x) mbar_wait(xempty_bar(xs), xphase ^ 1u);
+          const uint32_t w_dst = smem_base + ws * kSlabBytes;
+          const uint32_t x_dst = x_ring + xs * kXTileBytes;
+          if (elect_one_sync()) {
+            const uint32_t tx = (uint32_t)block_n * 128u + (need_x ? (uint32_t)(160 * t.nbox) * 128u : 0u);
+            s_winfo[ws] = (uint32_t)(o1 + 1) | (next_needs_x ? 256u : 0u);  // read by the MMA warp
+            mbar_arrive_expect_tx(full_bar(ws), tx);
+            if (need_x) {
+              tma_load_5d(x_dst, a_maps + am, full_bar(ws), c0, t.org[0][0] - 1, t.org[0][1] + o2,
+                          t.org[0][2] + o3, t.org[0][3] + o4);
+              if (t.nbox == 2)
+                tma_load_5d(x_dst + kXTileBytes / 2, a_maps + am, full_bar(ws), c0, t.org[1][0] - 1,
+                            t.org[1][1] + o2, t.org[1][2] + o3, t.org[1][3] + o4);
+            }
+            tma_load_4d(w_dst, b_map, full_bar(ws), bk, t.n0, bz1, bz2);
+          }
+          __syncwarp();
+          e0 = f0;
+          e1 = f1;
+          if (++ws == S) {
+            ws = 0;
+            wphase ^= 1u;
+          }
+          if (next_needs_x) {
+            if (++xs == kXStages) {
+              xs = 0;
+              xphase ^= 1u;
+            }
+          }
+        }
+      }
+    } else {
       int stage = 0;
       uint32_t phase = 0;
       SegIter it;
@@ -355,7 +425,51 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ====================================
-    {
+    if (xreuse) {
+      const uint32_t idesc = umma_idesc_bf16(kBlockM, 256u);
+      int ws = 0, xs = 0;
+      uint32_t wphase = 0;
+      int seg = 0;
+      SegIter it;
+      it.init(p, sch, my_r);
+      int tile, kb0, len;
+      long long seg_end;
+      while (it.next(tile, kb0, len, seg_end)) {
+        const int buf = seg & 1;
+        mbar_wait(tmem_empty_bar(buf), (((uint32_t)seg >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(buf * 256);
+        for (int i = 0; i < len; ++i) {
+          mbar_wait(full_bar(ws), wphase);
+          tc_fence_after();
+          const uint32_t info = (uint32_t)uniform((int)s_winfo[ws]);  // written before the arrive
+          const bool next_needs_x = (info & 256u) != 0u;
+          const uint32_t w_addr = smem_base + ws * kSlabBytes;
+          // view of the activation tile for tap dx: rows shifted by dx + 1, groups 10 rows apart
+          const uint32_t x_addr = x_ring + xs * kXTileBytes + (info & 255u) * 128u;
+          const uint64_t a_desc = umma_desc_k_sw128(w_addr, 1024);
+          const uint64_t b_desc = umma_desc_k_sw128(x_addr, 1280);
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_bf16(d0, a_desc + 2u * k, b_desc + 2u * k, idesc, (k != 0 || i != 0) ? 1u : 0u);
+            umma_commit(empty_bar(ws));                        // weight slab free
+            if (next_needs_x) umma_commit(xempty_bar(xs));     // activation tile free
+            if (i == len - 1) umma_commit(tmem_full_bar(buf));
+          }
+          __syncwarp();
+          if (++ws == S) {
+            ws = 0;
+            wphase ^= 1u;
+          }
+          if (next_needs_x) {
+            if (++xs == kXStages) xs = 0;
+          }
+        }
+        ++seg;
+      }
+      if (trace != nullptr && lane == 0) trace[3] = (uint64_t)clock64();
+    } else {
       const uint32_t idesc = umma_idesc_bf16(kBlockM, swap ? 256u : (uint32_t)block_n);
       int stage = 0;
       uint32_t phase = 0;
@@ -1000,7 +1114,13 @@ extern "C" int mri_gemm_launch(const MriGemmArgs* a, void* stream) {
   // trade one pipeline stage for a second set of staging buffers
   k.staging2 = (swap && a->n_kb <= 40) ? 1 : 0;
   k.stages = pick_stages(bn, swap, a->stages, k.staging2);
-  const int smem = k.stages * stage_bytes(bn, swap) + kStagingBytes * (k.staging2 ? 2 : 1) + 1024;
+  int smem = k.stages * stage_bytes(bn, swap) + kStagingBytes * (k.staging2 ? 2 : 1) + 1024;
+  if (a->xreuse) {
+    if (!swap || a->box[0] != 8 || rows != kBlockM || a->bz_sel[0] > 1 || a->bz_sel[1] > 1)
+      return set_error(-2, "mri_gemm_launch: xreuse needs swap_ab and boxes of 8 x 16 positions");
+    k.stages = k.staging2 ? 4 : 6;  // weight ring; the activation ring has kXStages tiles
+    smem = k.stages * kSlabBytes + kXStages * kXTileBytes + kStagingBytes * (k.staging2 ? 2 : 1) + 1024;
+  }
   long long grid = tiles < n_sms ? tiles : n_sms;
   if (k.sched != 0) {
     if (k.sk_partials == nullptr || k.sk_flags == nullptr)

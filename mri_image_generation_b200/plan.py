@@ -151,7 +151,7 @@ def choose_box(ext: Sequence[int], prefer_unit: Sequence[int] = ()) -> Tuple[int
         for i in prefer_unit:
             if b[i] != 1 and (rows // b[i]) % 16 != 0:
                 score = eff * 0.75
-        key = (round(score, 6), -unit_pen, b[0], b[1], b[2])
+        key = (round(score, 6), -unit_pen, b[0] == 8, b[0], b[1], b[2])
         if best_key is None or key > best_key:
             best, best_key = b, key
     return best
@@ -182,6 +182,8 @@ class GemmPlan:
     stages: int = 0
     sched: Optional[int] = None
     swap_ab: Optional[bool] = None
+    xreuse: bool = False                       # k-table groups share one 10-wide activation tile
+    a_maps_std: Optional[List[MapSpec]] = None  # xreuse: the same inputs with the standard boxes
     trace: Optional[torch.Tensor] = None     # int64 [grid, 8]: per-CTA timestamps (profiling only)
     name: str = ""
     flops: int = 0
@@ -286,6 +288,9 @@ class GemmPlan:
         a.sk_partials, a.sk_flags, a.sk_ctas = ws.partials_ptr, ws.flags_ptr, ws.n_ctas
         a.sched = self.pick_sched(ws.n_ctas)
         a.swap_ab = 1 if self.pick_swap() else 0
+        a.xreuse = 1 if self.xreuse else 0
+        if self.xreuse and not a.swap_ab:
+            raise _lib.MriError("xreuse plans need the swap_ab tile shape")
         a.trace = self.trace.data_ptr() if self.trace is not None else None
         self._args = a
 
@@ -321,7 +326,7 @@ class GemmPlan:
                         e = self.ktable[cls, kb]
                         am = self.a_maps[int(e[0])]
                         coords = [int(e[1])] + [org[i] + int(e[2 + i]) for i in range(4)]
-                        a = _load_box(am.view, coords, am.box).reshape(rows_in_box, BLOCK_K)
+                        a = _load_box(am.view, coords, (BLOCK_K,) + tuple(self.box)).reshape(rows_in_box, BLOCK_K)
                         b = _load_box(self.b_map.view, [int(e[6]), n0, bz[0], bz[1]],
                                       self.b_map.box).reshape(self.block_n, BLOCK_K)
                         acc += a @ b.t()
@@ -489,7 +494,8 @@ def _spatial_ext(y: torch.Tensor, ndim: int):
 
 def conv_plan(sources: Sequence[ConvSource], wmat: torch.Tensor, y: torch.Tensor, ksize: int,
               *, bias=None, rowbias=None, rowbias_ld=0, residual: Optional[torch.Tensor] = None,
-              stats=None, stats_cpg=0, block_n: Optional[int] = None, stages=0, name="") -> GemmPlan:
+              stats=None, stats_cpg=0, block_n: Optional[int] = None, stages=0, name="",
+              xreuse: Optional[bool] = None) -> GemmPlan:
     """Stride-1, pad k//2 convolution over the channel-concatenation of `sources`.
 
     wmat: packed weights [Cout_pad, K] bf16, K = sum over sources of (taps * C_i), see
@@ -500,23 +506,43 @@ def conv_plan(sources: Sequence[ConvSource], wmat: torch.Tensor, y: torch.Tensor
     cout_pad = y.shape[-1]
     bn = block_n or pick_block_n(cout_pad)
     p = ksize // 2
-    a_maps, rows = [], []
+    # "xreuse": with boxes of 8 x 16 positions the three kw taps of a (kd, kh, channel slab) read
+    # ONE activation tile loaded 10 positions wide -> a third of the activation traffic from L2
+    env_x = os.environ.get("MRI_GEMM_XREUSE")
+    want_x = xreuse if xreuse is not None else (env_x != "0")
+    use_x = bool(want_x and ksize == 3 and bn == 128 and cout_pad % 64 == 0 and box[0] == 8
+                 and int(np.prod(box)) == BLOCK_M and os.environ.get("MRI_GEMM_SWAP", "1") != "0")
+    a_maps, a_std, rows = [], [], []
     bk = 0
     for si, src in enumerate(sources):
         Ci = src.x.shape[-1]
         assert Ci % BLOCK_K == 0, f"source channels {Ci} must be a multiple of 64"
         assert list(src.x.shape[:-1]) == list(y.shape[:-1])
-        a_maps.append(MapSpec(_act_view(src.x, ndim), (BLOCK_K,) + box, 3))
-        tap_list = list(itertools.product(range(ksize), repeat=ndim)) if src.taps else [None]
-        for tap in tap_list:
-            if tap is None:
-                offs = [0, 0, 0, 0]
-            else:
+        a_std.append(MapSpec(_act_view(src.x, ndim), (BLOCK_K,) + box, 3))
+        a_maps.append(MapSpec(_act_view(src.x, ndim), (BLOCK_K, 10) + tuple(box[1:]), 3) if use_x
+                      else a_std[-1])
+        if not src.taps:  # centre tap only (folded 1x1 skip): its own group
+            for c0 in range(0, Ci, BLOCK_K):
+                rows.append([si, c0, 0, 0, 0, 0, bk, 1])
+                bk += BLOCK_K
+        elif use_x:
+            for ot in itertools.product(range(ksize), repeat=ndim - 1):  # (kd, kh) / (kh,)
+                for c0 in range(0, Ci, BLOCK_K):
+                    for kw in range(ksize):
+                        tap = tuple(ot) + (kw,)
+                        tap_index = 0
+                        for t_ in tap:
+                            tap_index = tap_index * ksize + t_
+                        offs = [k - p for k in reversed(tap)] + [0] * (4 - ndim)
+                        rows.append([si, c0] + offs + [bk + tap_index * Ci + c0, 1 if kw == 0 else 0])
+            bk += (ksize ** ndim) * Ci
+        else:
+            for tap in itertools.product(range(ksize), repeat=ndim):
                 # tap = (kd, kh, kw) / (kh, kw); x1 = w
                 offs = [k - p for k in reversed(tap)] + [0] * (4 - ndim)
-            for c0 in range(0, Ci, BLOCK_K):
-                rows.append([si, c0] + offs + [bk, 0])
-                bk += BLOCK_K
+                for c0 in range(0, Ci, BLOCK_K):
+                    rows.append([si, c0] + offs + [bk, 0])
+                    bk += BLOCK_K
     assert wmat.shape == (cout_pad, bk), (wmat.shape, cout_pad, bk)
     kt = np.asarray(rows, dtype=np.int32)[None]
     bview = TView(wmat, (bk, cout_pad, 1, 1), (1, bk, _rup8(bk * cout_pad), _rup8(bk * cout_pad)))
@@ -532,7 +558,8 @@ def conv_plan(sources: Sequence[ConvSource], wmat: torch.Tensor, y: torch.Tensor
                     r_maps=rmaps, ktable=kt, tiles=tiles, box=box, ext=ext, block_n=bn,
                     n_total=cout_pad, sample_dim=sample_dim, bias=bias, rowbias=rowbias,
                     rowbias_ld=rowbias_ld, stats=stats, stats_ld=(stats.shape[1] if stats is not None else 0),
-                    stats_cpg=stats_cpg, stages=stages, name=name, flops=2 * m_rows * cout_pad * bk)
+                    stats_cpg=stats_cpg, stages=stages, name=name, flops=2 * m_rows * cout_pad * bk,
+                    xreuse=use_x, a_maps_std=a_std if use_x else None)
 
 
 def _rup8(n: int) -> int:
@@ -692,7 +719,7 @@ class WgradPlan:
 
     def materialize(self, device) -> None:
         f = self.fwd
-        maps = list(f.a_maps) + self.dy_specs()
+        maps = list(f.a_maps_std or f.a_maps) + self.dy_specs()
         blob = encode_maps(maps, device)
         kt = torch.from_numpy(np.ascontiguousarray(f.ktable, dtype=np.int32)).to(device)
         self._keep = [blob, kt]
@@ -734,7 +761,7 @@ class WgradPlan:
                     e = f.ktable[cls, kb]
                     am = f.a_maps[int(e[0])]
                     coords = [int(e[1])] + [org[i] + int(e[2 + i]) for i in range(4)]
-                    a = _load_box(am.view, coords, am.box).reshape(rows, BLOCK_K)
+                    a = _load_box(am.view, coords, (BLOCK_K,) + tuple(f.box)).reshape(rows, BLOCK_K)
                     bk = int(e[6])
                     self.dw[cls, :self.n_total, bk:bk + BLOCK_K] += (dyt.t() @ a)[:self.n_total]
 

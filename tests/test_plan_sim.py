@@ -24,7 +24,7 @@ def rel(a, b):
     return ((a - b).norm() / b.norm()).item()
 
 
-@pytest.mark.parametrize("nd,sp", [(3, (6, 8, 10)), (2, (12, 20)), (3, (4, 4, 6))])
+@pytest.mark.parametrize("nd,sp", [(3, (6, 8, 10)), (2, (12, 20)), (3, (4, 4, 6)), (3, (2, 16, 8)), (2, (16, 8))])
 def test_conv_concat_skipfold_residual(nd, sp):
     torch.manual_seed(0)
     N, C1, C2, Co = 2, 64, 128, 64
@@ -42,6 +42,10 @@ def test_conv_concat_skipfold_residual(nd, sp):
     stats = torch.zeros(N, 8, 2, dtype=torch.float64)
     pl = P.conv_plan([P.ConvSource(a1), P.ConvSource(a2), P.ConvSource(a1, taps=False)], wm, y, 3,
                      bias=b, rowbias=rb, rowbias_ld=Co + 5, residual=res, stats=stats, stats_cpg=8)
+    if sp[-1] == 8:  # boxes of 8 x 16 positions: the kw taps share one 10-wide activation tile
+        assert pl.xreuse and pl.box[0] == 8 and pl.a_maps[0].box[1] == 10 and pl.a_maps_std[0].box[1] == 8
+        lead = pl.ktable[0, :, 7]
+        assert lead.sum() == pl.n_kb - 2 * (pl.n_kb - 1) // 3  # one leader per (kd, kh, slab) + the 1x1 slab
     pl.simulate()
     assert rel(nchw(y), ref) < TOL
     r = ref.reshape(N, 8, -1)

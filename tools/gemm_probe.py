@@ -39,7 +39,8 @@ def build(B, sp, cins, cout, k, var):
     stats = torch.zeros(B, 8, 2, device=dev, dtype=torch.float64) if var.get("stats", 1) else None
     pl = P.conv_plan([P.ConvSource(a) for a in acts], wm, y, k, bias=bias, stats=stats,
                      stats_cpg=cout // 8 if stats is not None else 0,
-                     block_n=var.get("bn") or None, stages=var.get("stages", 0))
+                     block_n=var.get("bn") or None, stages=var.get("stages", 0),
+                     xreuse=bool(var["xr"]) if "xr" in var else None)
     if "sched" in var:
         pl.sched = var["sched"]
     if "swap" in var:
