@@ -113,3 +113,38 @@ def test_optimizer_step_changes_output_and_repacks_weights():
     got_train = diff.p_losses(x0, t, noise=noise).item()
     assert abs(got_eval - want) <= 1e-2 * abs(want), (got_eval, want)
     assert abs(got_train - want) <= 1e-2 * abs(want), (got_train, want)
+
+
+def test_graph_replayed_training_step_equals_eager(monkeypatch):
+    """From the third step on the forward / backward launch lists run as replayed CUDA graphs
+    (engine.UNetProgram._replay): gradients must equal those of the eager launch lists."""
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.unet_attention import UNet3DModelWithAttention
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.diffusion import GaussianDiffusionLatent3D
+
+    def grads(no_graph: bool):
+        monkeypatch.setenv("MRI_NO_GRAPH", "1" if no_graph else "0")
+        torch.manual_seed(0)
+        m = UNet3DModelWithAttention(3, base_channels=64, time_emb_dim=64).cuda().train()
+        diff = quiet(GaussianDiffusionLatent3D, m, 3, timesteps=50).cuda()
+        g = torch.Generator(device="cuda").manual_seed(5)
+        out = None
+        for it in range(4):
+            x0 = torch.randn(2, 3, 8, 8, 8, device="cuda", generator=g)
+            noise = torch.randn(2, 3, 8, 8, 8, device="cuda", generator=g)
+            t = torch.tensor([3 + it, 40 - it], device="cuda")
+            for p in m.parameters():
+                p.grad = None
+            diff.p_losses(x0, t, noise=noise).backward()
+            out = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+        prog = m.program(2, (8, 8, 8), training=True)
+        return out, prog
+
+    ge, pe = grads(True)
+    gg, pg = grads(False)
+    assert pe._rt_graphs.get("bwd", [0, None])[1] is None
+    assert pg._rt_graphs["fwd"][1] is not None and pg._rt_graphs["bwd"][1] is not None
+    # wgrad accumulates with fp32 red.global.add (arrival order varies run to run): equality up to
+    # that summation noise, far below any addressing / ordering mistake a broken capture would show
+    worst = max(rel_l2(gg[n], ge[n]) for n in ge)
+    print(f"graph vs eager: worst gradient rel-L2 {worst:.2e}")
+    assert worst < 1e-4, worst
