@@ -184,6 +184,12 @@ int mri_gather_pack(const MriGatherSeg* segs_dev, int n_segs, int64_t total_bloc
  * y: [samples][D][H][W][ldy] bf16, out: [samples][D][H][W][ldo] bf16 (channels >= cout written 0). */
 int mri_tap_gather(const void* y, void* out, const float* bias, int samples, int D, int H, int W,
                    int ksize, int ndim, int cout, int ldy, int ldo, void* stream);
+/* mri_im2col4: the same patch matrix from a channels-last bf16 copy of the input, src
+ * [samples][D*H*W][cp] with cp = channels padded to a multiple of 4 (mri_nchw_to_nhwc writes it):
+ * dst[m][tap*cp + c], zero padded to kpad.  The packed weights use the same (tap, padded channel)
+ * column order. */
+int mri_im2col4(const void* src, void* dst, int samples, int cp, int D, int H, int W, int ksize,
+                int ndim, int kpad, void* stream);
 int mri_nhwc_to_nchw(const void* src, float* dst, int samples, int64_t spatial, int C, int ldc,
                      void* stream);
 int mri_nchw_to_nhwc(const float* src, void* dst, int samples, int64_t spatial, int C, int ldc,

@@ -125,6 +125,59 @@ im2col_kernel(const float* __restrict__ src, const float* __restrict__ src2,
   }
 }
 
+// Patch matrix from a channels-last bf16 copy of the thin input ([n][pos][cp], cp = channels padded
+// to a multiple of 4): column (tap * cp + c).  One thread per 16-byte destination vector = two
+// "quads" (4 channels of one tap): two 8-byte loads, bounds checks from a shared-memory table,
+// no divisions in the loop.  ~5x fewer instructions per byte than im2col_kernel.
+__global__ void __launch_bounds__(256)
+im2col4_kernel(const uint2* __restrict__ src, uint4* __restrict__ dst, int samples, int cp, int D,
+               int H, int W, int k, int ndim, int kpad) {
+  extern __shared__ int quad_tab[];  // per quad: (dd+8) | (dh+8)<<4 | (dw+8)<<8 | cq<<12, or -1
+  const int taps = ndim == 3 ? k * k * k : k * k;
+  const int qpt = cp >> 2;           // quads per tap
+  const int nquad = kpad >> 2;
+  const int pad = k / 2;
+  for (int q = threadIdx.x; q < nquad; q += blockDim.x) {
+    int e = -1;
+    const int tap = q / qpt;
+    if (tap < taps) {
+      const int kw = tap % k, kh = (tap / k) % k, kd = ndim == 3 ? tap / (k * k) : pad;
+      e = (kd - pad + 8) | ((kh - pad + 8) << 4) | ((kw - pad + 8) << 8) | ((q - tap * qpt) << 12);
+    }
+    quad_tab[q] = e;
+  }
+  __syncthreads();
+  const int64_t spatial = (int64_t)D * H * W;
+  const int64_t M = (int64_t)samples * spatial;
+  const int vec_per_row = kpad >> 3;
+  const int64_t total = M * vec_per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / vec_per_row;
+    const int v = (int)(i - m * vec_per_row);
+    const int n = (int)(m / spatial);
+    int s = (int)(m - (int64_t)n * spatial);
+    const int w0 = s % W;
+    s /= W;
+    const int h0 = s % H;
+    const int d0 = s / H;
+    const uint2* sn = src + (size_t)n * spatial * qpt;
+    uint2 r[2];
+#pragma unroll
+    for (int hq = 0; hq < 2; ++hq) {
+      const int e = quad_tab[2 * v + hq];
+      uint2 val = make_uint2(0u, 0u);
+      if (e >= 0) {
+        const int d = d0 + (e & 15) - 8, h = h0 + ((e >> 4) & 15) - 8, w = w0 + ((e >> 8) & 15) - 8;
+        if ((unsigned)w < (unsigned)W && (unsigned)h < (unsigned)H && (unsigned)d < (unsigned)D)
+          val = __ldg(sn + (((size_t)d * H + h) * W + w) * qpt + (e >> 12));
+      }
+      r[hq] = val;
+    }
+    dst[i] = make_uint4(r[0].x, r[0].y, r[1].x, r[1].y);
+  }
+}
+
 // Thin-Cout convolution as "GEMM over taps, then gather": Y[q][tap*cout + co] = W[tap][co] . x[q]
 // was computed for every position q by the tensor-core kernel; the convolution output is
 //   out[o][co] = bias[co] + sum_tap Y[o + tap - pad][tap*cout + co]      (zero outside the volume)
@@ -309,6 +362,19 @@ extern "C" int mri_im2col(const float* src, const float* src2, void* dst, int sa
   im2col_kernel<<<grid_for(total), 256, kpad * sizeof(int), (cudaStream_t)stream>>>(
       src, src2, reinterpret_cast<uint4*>(dst), samples, cin, cin2, D, H, W, ksize, ndim, kpad);
   return check_launch("im2col_kernel");
+}
+
+extern "C" int mri_im2col4(const void* src, void* dst, int samples, int cp, int D, int H, int W, int ksize,
+                           int ndim, int kpad, void* stream) {
+  if (ndim != 2 && ndim != 3) return set_error(-2, "mri_im2col4: ndim must be 2 or 3");
+  const int taps = ndim == 3 ? ksize * ksize * ksize : ksize * ksize;
+  if (cp < 4 || cp % 4 != 0 || kpad % 8 != 0 || taps * cp > kpad || ksize > 15)
+    return set_error(-2, "mri_im2col4: channels must be padded to a multiple of 4 and fit kpad");
+  const int64_t total = (int64_t)samples * D * H * W * (kpad / 8);
+  im2col4_kernel<<<grid_for(total), 256, (kpad / 4) * sizeof(int), (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint2*>(src), reinterpret_cast<uint4*>(dst), samples, cp, D, H, W, ksize,
+      ndim, kpad);
+  return check_launch("im2col4_kernel");
 }
 
 extern "C" int mri_gather_pack(const MriGatherSeg* segs_dev, int n_segs, int64_t total_blocks,

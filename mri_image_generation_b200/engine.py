@@ -370,6 +370,36 @@ class UNetProgram(BackwardMixin):
                                      dgrad_dy=rec.get("dgrad_dy"), name=name))
         return y
 
+    def thin_patch_matrix(self, x_in: torch.Tensor, conv, sp: Sequence[int], name: str):
+        """Inference: patch matrix of a thin-channel input convolution through a channels-last
+        bf16 copy padded to a multiple of 4 channels (mri_nchw_to_nhwc + mri_im2col4: 8-byte
+        gathers instead of per-element ones).  Returns (col [B*S, kpad], packed weights
+        [Cout, kpad] with column order (tap, padded channel), kpad)."""
+        B = self.B
+        nd = len(sp)
+        cin, ksize = conv.weight.shape[1], conv.weight.shape[2]
+        cp = _rup(cin, 4)
+        S = 1
+        for e in sp:
+            S *= e
+        kpad = _rup((ksize ** nd) * cp, 64)
+        x4 = torch.zeros(B, S, cp, dtype=torch.bfloat16, device=self.device)
+        col = torch.zeros(B * S, kpad, dtype=torch.bfloat16, device=self.device)
+        sp3 = (1,) * (3 - nd) + tuple(sp)
+        self._add(f"{name}.nhwc", lambda: ops.nchw_to_nhwc(x_in, x4, B, S, cin, cp), [x4])
+        self._add(f"{name}.im2col",
+                  lambda: ops.im2col4(x4, col, B, cp, sp3[0], sp3[1], sp3[2], ksize, nd, kpad), [col])
+
+        def make():
+            w = conv.weight.detach()
+            if cp != cin:
+                wp = torch.zeros(w.shape[0], cp, *w.shape[2:], dtype=w.dtype, device=w.device)
+                wp[:, :cin] = w
+                w = wp
+            return _pad_k(P.pack_conv_weight(w), kpad)
+
+        return col, self.packed(make), kpad
+
     def thin_out_conv(self, a: torch.Tensor, oc, name: str = "out_conv", cin_pad: int = 0) -> None:
         """Inference head for a k^d convolution with 1..8 output channels (out_conv): one GEMM
         computes every tap's product Y[q][tap*cout + co] = W[tap][co] . a[q] (K = Cin, the
@@ -489,13 +519,16 @@ class UNet3DProgram(UNetProgram):
 
         # ---- in_conv: thin Cin -> explicit patch matrix + GEMM ------------------------------
         S = D * H * W
-        kpad = _rup(27 * cin, 64)
-        col = torch.zeros(B * S, kpad, dtype=torch.bfloat16, device=dev)
-        x_in = self.x_in
-        self._add("im2col", lambda: ops.im2col(x_in, col, B, cin, D, H, W, 3, 3, kpad), [col])
         ic = model.in_conv
         self.track(ic.weight, ic.bias)
-        w_in = self.packed(lambda: _pad_k(P.pack_conv_weight(ic.weight.detach()), kpad))
+        if training:
+            kpad = _rup(27 * cin, 64)
+            col = torch.zeros(B * S, kpad, dtype=torch.bfloat16, device=dev)
+            x_in = self.x_in
+            self._add("im2col", lambda: ops.im2col(x_in, col, B, cin, D, H, W, 3, 3, kpad), [col])
+            w_in = self.packed(lambda: _pad_k(P.pack_conv_weight(ic.weight.detach()), kpad))
+        else:
+            col, w_in, kpad = self.thin_patch_matrix(self.x_in, ic, self.sp, "in_conv")
         h = self.new_act(self.sp, chs[0])
         pl = self._matrix_conv(col, w_in, h, S, kpad, ic.bias, "in_conv")
         self.gemm(pl)
@@ -808,14 +841,17 @@ class UNet2DProgram(UNetProgram):
 
         # ---- init_conv: thin Cin -> patch matrix + GEMM --------------------------------------------
         S = H * W
-        kpad = _rup(9 * cin, 64)
-        col = torch.zeros(B * S, kpad, dtype=torch.bfloat16, device=dev)
-        x_in, ctx_in = self.x_in, self.ctx_in
-        self._add("im2col", lambda: ops.im2col(x_in, col, B, x_channels, 1, H, W, 3, 2, kpad,
-                                               src2=ctx_in, cin2=ctx_channels), [col])
         ic = model.init_conv
         self.track(ic.weight, ic.bias)
-        w_in = self.packed(lambda: _pad_k(P.pack_conv_weight(ic.weight.detach()), kpad))
+        if training or ctx_channels:
+            kpad = _rup(9 * cin, 64)
+            col = torch.zeros(B * S, kpad, dtype=torch.bfloat16, device=dev)
+            x_in, ctx_in = self.x_in, self.ctx_in
+            self._add("im2col", lambda: ops.im2col(x_in, col, B, x_channels, 1, H, W, 3, 2, kpad,
+                                                   src2=ctx_in, cin2=ctx_channels), [col])
+            w_in = self.packed(lambda: _pad_k(P.pack_conv_weight(ic.weight.detach()), kpad))
+        else:
+            col, w_in, kpad = self.thin_patch_matrix(self.x_in, ic, self.sp, "init_conv")
         h = self.new_act(self.sp, chs[0], with_stats=False)
         pl = self._matrix_conv2d(col, w_in, h, S, kpad, ic.bias, "init_conv")
         self.gemm(pl)

@@ -76,6 +76,12 @@ def im2col(src, dst, samples, cin, D, H, W, ksize, ndim, kpad, src2=None, cin2: 
                                       ksize, ndim, kpad, _s()), "mri_im2col")
 
 
+def im2col4(src, dst, samples, cp, D, H, W, ksize, ndim, kpad) -> None:
+    _chk_contig(src, dst)
+    _lib.check(_lib.load().mri_im2col4(_p(src), _p(dst), samples, cp, D, H, W, ksize, ndim, kpad, _s()),
+               "mri_im2col4")
+
+
 def tap_gather(y, out, bias, samples, D, H, W, ksize, ndim, cout, ldy, ldo) -> None:
     _chk_contig(y, out, bias)
     _lib.check(_lib.load().mri_tap_gather(_p(y), _p(out), _p(bias), samples, D, H, W, ksize, ndim,

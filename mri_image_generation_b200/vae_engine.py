@@ -125,13 +125,10 @@ class VAE3DProgram(UNetProgram):
         """Conv3d with 1..8 input channels: patch matrix + GEMM (vae.py:31,67)."""
         B, S = self.B, sp[0] * sp[1] * sp[2]
         cout, cin = conv.weight.shape[0], conv.weight.shape[1]
-        kpad = _rup(27 * cin, 64)
-        col = torch.zeros(B * S, kpad, dtype=torch.bfloat16, device=self.device)
-        D, H, W = sp
-        self._add(f"{name}.im2col", lambda: ops.im2col(x_in, col, B, cin, D, H, W, 3, 3, kpad), [col])
         self.track(conv.weight, conv.bias)
         cp = self.cpad(cout)
-        w = self.packed(lambda: _pad_c0(_pad_k(P.pack_conv_weight(conv.weight.detach()), kpad), cp))
+        col, w0, kpad = self.thin_patch_matrix(x_in, conv, sp, name)
+        w = w0 if cp == cout else self.packed(lambda: _pad_c0(w0, cp))
         b = self.packed(lambda: _pad_vec(conv.bias.detach(), cp))
         h = self.new_vact(sp, cout)
         a = P.TView(col, (kpad, S, B, 1, 1), (1, kpad, S * kpad, B * S * kpad, B * S * kpad))
