@@ -33,16 +33,20 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Upper bound (ns) the hardware may keep a waiting thread suspended before try_wait returns false;
+// it wakes as soon as the phase completes, so a long hint costs no latency and keeps the polling
+// warps (producer / MMA / epilogue roles wait most of the time) off the issue ports.
+constexpr uint32_t kMbarSuspendNs = 20000;
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(kMbarSuspendNs)
       : "memory");
   return ok != 0;
 }
