@@ -276,15 +276,22 @@ softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P, const float* __restrict_
 }
 
 // ---- tiny fp32 linear layers ------------------------------------------------------------
-// dX[b, i] = sum_o dZ[b, o] W[o, i]     (one thread per (b, i))
-__global__ void linear_bwd_input_kernel(const float* __restrict__ dZ, const float* __restrict__ W,
-                                        float* __restrict__ dX, int batch, int in_f, int out_f) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= batch * in_f) return;
-  const int b = idx / in_f, i = idx % in_f;
+// dX[b, i] = sum_o dZ[b, o] W[o, i].  grid (i tiles, o chunks of 64, b): every block adds its
+// partial sum with one fp32 atomic per element (dX is zeroed first) -- the concatenated block
+// projections have out_f ~ 3.5-5 k, which one thread per (b, i) would walk serially.
+__global__ void __launch_bounds__(256)
+linear_bwd_input_kernel(const float* __restrict__ dZ, const float* __restrict__ W,
+                        float* __restrict__ dX, int batch, int in_f, int out_f) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.z;
+  const int o0 = blockIdx.y * 64;
+  const int o1 = o0 + 64 < out_f ? o0 + 64 : out_f;
+  if (i >= in_f) return;
   float acc = 0.f;
-  for (int o = 0; o < out_f; ++o) acc = fmaf(__ldg(dZ + (size_t)b * out_f + o), __ldg(W + (size_t)o * in_f + i), acc);
-  dX[idx] = acc;
+#pragma unroll 4
+  for (int o = o0; o < o1; ++o)
+    acc = fmaf(__ldg(dZ + (size_t)b * out_f + o), __ldg(W + (size_t)o * in_f + i), acc);
+  atomicAdd(dX + (size_t)b * in_f + i, acc);
 }
 // dW[o, i] = sum_b dZ[b, o] X[b, i];  db[o] = sum_b dZ[b, o]   (overwrite)
 __global__ void linear_bwd_weight_kernel(const float* __restrict__ dZ, const float* __restrict__ X,
@@ -490,8 +497,10 @@ extern "C" int mri_linear_bwd(const float* dZ, const float* X, const float* W, f
   if (batch < 1 || in_f < 1 || out_f < 1) return set_error(-2, "mri_linear_bwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   if (dX != nullptr) {
-    const int n = batch * in_f;
-    linear_bwd_input_kernel<<<(n + 127) / 128, 128, 0, st>>>(dZ, W, dX, batch, in_f, out_f);
+    cudaError_t e = cudaMemsetAsync(dX, 0, (size_t)batch * in_f * sizeof(float), st);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(dX)");
+    const dim3 grid((in_f + 255) / 256, (out_f + 63) / 64, batch);
+    linear_bwd_input_kernel<<<grid, 256, 0, st>>>(dZ, W, dX, batch, in_f, out_f);
     int rc = check_launch("linear_bwd_input_kernel");
     if (rc) return rc;
   }
