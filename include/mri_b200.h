@@ -270,14 +270,16 @@ int mri_wgrad_launch(const MriWgradArgs* args_host, void* stream);
  *   [0] = sum_s dy, [1] = sum_s du, [2] = sum_s du*xhat  (du = dy*act'(u)); x == NULL: only [0]
  *   (plain per-(sample, channel) column sum: bias and time-embedding-projection gradients).
  *   dgamma = sum_n sums[2], dbeta = sum_n sums[1].
- * mri_gn_bwd_apply: dx = rstd*(gamma*du - mean_g(gamma*du) - xhat*mean_g(gamma*du*xhat)) (+ add). */
+ * mri_gn_bwd_apply: dx = rstd*(gamma*du - mean_g(gamma*du) - xhat*mean_g(gamma*du*xhat)) (+ add);
+ *   colsum (fp64 [samples][C], may be NULL, zero it first) += sum_s dx: the bias / time-projection
+ *   gradient of the convolution that produced x, for free while dx is in registers. */
 int mri_gn_bwd_reduce(const void* x, const void* dy, const double* stats, const float* gamma,
                       const float* beta, double* sums, int samples, int64_t spatial, int C,
                       int groups, int stats_ld, int stats_cpg, float eps, int silu, void* stream);
 int mri_gn_bwd_apply(const void* x, const void* dy, const void* add, void* dx, const double* stats,
                      const float* gamma, const float* beta, const double* sums, int samples,
                      int64_t spatial, int C, int groups, int stats_ld, int stats_cpg, float eps,
-                     int silu, void* stream);
+                     int silu, double* colsum, void* stream);
 /* out = a + b, bf16, n elements (multiple of 8) */
 int mri_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
 /* attention: dS = scale * P * (dP - rowsum(dP * P)); P, dS bf16 [rows][ld_p], dP fp32 [rows][ld_dp] */

@@ -124,7 +124,7 @@ SIGNATURES = {
     "mri_wgrad_launch": (_i, [C.POINTER(MriWgradArgs), _vp]),
     "mri_gn_bwd_reduce": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _i, _f, _i, _vp]),
     "mri_gn_bwd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _i, _f,
-                              _i, _vp]),
+                              _i, _vp, _vp]),
     "mri_add_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "mri_softmax_bwd": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _f, _vp]),
     "mri_linear_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -13,6 +13,7 @@ the reference parameter layout (what `.grad` must hold).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -108,6 +109,9 @@ class BackwardMixin:
         self._zero_each_bwd: List[torch.Tensor] = []
         self.dtproj: Optional[torch.Tensor] = None
         self.bwd_flops = 0
+        # id(gradient tensor) -> [colsum buffer or None] when its LAST writer is a gn_bwd_apply
+        # launch (which can then emit the tensor's per-(sample, channel) sums for free)
+        self._gn_writer: Dict[int, Optional[list]] = {}
 
     def badd(self, name: str, fn: Callable[[], None]) -> None:
         self.bwd_names.append(name)
@@ -139,6 +143,7 @@ class BackwardMixin:
             produce(g, None)
         else:
             produce(g, g)
+        self._gn_writer[id(g)] = None
 
     def pass_grad(self, t: torch.Tensor, dy: torch.Tensor) -> None:
         """grad[t] += dy for an identity edge (residual); aliases dy when it is the first."""
@@ -147,6 +152,7 @@ class BackwardMixin:
             self.grads[id(t)] = dy
         else:
             self.badd("add", lambda: ops.add_bf16(g, dy, g))
+            self._gn_writer[id(g)] = None
 
     # ------------------------------------------------------------------ per-op backward
     def _bwd_bias_and_tproj(self, dy: torch.Tensor, C: int, bias_params, tproj_off, name):
@@ -155,7 +161,11 @@ class BackwardMixin:
         B = self.B
         S = dy.numel() // (B * C)
         cs = self.zeros_each_bwd(1, B, C, dtype=torch.float64)
-        self.badd(f"colsum:{name}", lambda: ops.colsum(dy, cs, B, S, C))
+        holder = self._gn_writer.get(id(dy))
+        if holder is not None and holder[0] is None and os.environ.get("MRI_NO_COLSUM_FUSION") != "1":
+            holder[0] = cs[0]  # the gn_bwd_apply launch that writes dy also accumulates its column sums
+        else:
+            self.badd(f"colsum:{name}", lambda: ops.colsum(dy, cs, B, S, C))
         for bp in bias_params:
             g = self.pg(bp)
             n = bp.numel()
@@ -289,8 +299,11 @@ class BackwardMixin:
         if r.tproj_off is not None:
             dst = self.dtproj[:, r.tproj_off:r.tproj_off + C]
             self.badd("dtproj", lambda: dst.copy_(sums[0]))
+        holder = [None]
         self.emit_grad(xs, lambda out, add: self.badd(f"gn_bwd_apply:{r.name}", lambda: ops.gn_bwd_apply(
-            xs, dy, add, out, st, gamma, beta, sums, B, S, C, r.groups, cpg, r.eps, r.silu)))
+            xs, dy, add, out, st, gamma, beta, sums, B, S, C, r.groups, cpg, r.eps, r.silu,
+            colsum=holder[0])))
+        self._gn_writer[id(self.grads[id(xs)])] = holder
 
     def bwd_attention(self, r: AttnRec) -> None:
         dev, B = self.device, self.B

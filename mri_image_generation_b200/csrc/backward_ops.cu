@@ -158,7 +158,8 @@ gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
                     const double* __restrict__ stats, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const double* __restrict__ sums, int samples,
                     int64_t spatial, int C, int groups, int stats_ld, int stats_cpg, float eps,
-                    int rows_per_block) {
+                    int rows_per_block, double* __restrict__ colsum) {
+  extern __shared__ double cred[];  // [C], only when colsum != nullptr
   const int vec_per_row = C >> 3;
   const int sample = blockIdx.y;
   const int cv = threadIdx.x % vec_per_row;
@@ -167,6 +168,13 @@ gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
   const int c = cv * 8;
   const int cpg = C / groups;
   const int g = c / cpg;
+  if (colsum != nullptr) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) cred[i] = 0.0;
+    __syncthreads();
+  }
+  float csum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) csum[j] = 0.f;
   const GnCoef k = gn_coef(stats, sample, stats_ld, g, cpg / stats_cpg, cpg, spatial, eps);
   const double* S1 = sums + ((size_t)1 * samples + sample) * C;
   const double* S2 = sums + ((size_t)2 * samples + sample) * C;
@@ -225,8 +233,22 @@ gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] += a[j];
       }
-      dx[base + ru * vec_per_row] = pack8b(o);
+      const uint4 packed = pack8b(o);
+      dx[base + ru * vec_per_row] = packed;
+      if (colsum != nullptr) {  // column sums of the bf16 values a later pass would read
+        float q[8];
+        unpack8b(packed, q);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) csum[j] += q[j];
+      }
     }
+  }
+  if (colsum != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&cred[c + j], (double)csum[j]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x)
+      atomicAdd(colsum + (size_t)sample * C + i, cred[i]);
   }
 }
 
@@ -443,7 +465,8 @@ extern "C" int mri_gn_bwd_reduce(const void* x, const void* dy, const double* st
 extern "C" int mri_gn_bwd_apply(const void* x, const void* dy, const void* add, void* dx,
                                 const double* stats, const float* gamma, const float* beta,
                                 const double* sums, int samples, int64_t spatial, int C, int groups,
-                                int stats_ld, int stats_cpg, float eps, int silu, void* stream) {
+                                int stats_ld, int stats_cpg, float eps, int silu, double* colsum,
+                                void* stream) {
   if (C % 8 != 0 || C / 8 > 256 || groups < 1 || C % groups != 0 || (C / groups) % stats_cpg != 0)
     return set_error(-2, "mri_gn_bwd_apply: bad channel / group configuration");
   const int vpr = C / 8;
@@ -454,14 +477,15 @@ extern "C" int mri_gn_bwd_apply(const void* x, const void* dy, const void* add, 
   const uint4* dp = reinterpret_cast<const uint4*>(dy);
   const uint4* ap = reinterpret_cast<const uint4*>(add);
   uint4* op = reinterpret_cast<uint4*>(dx);
+  const size_t csm = colsum != nullptr ? (size_t)C * sizeof(double) : 0;
   if (silu)
-    gn_bwd_apply_kernel<true><<<grid, threads, 0, (cudaStream_t)stream>>>(
+    gn_bwd_apply_kernel<true><<<grid, threads, csm, (cudaStream_t)stream>>>(
         xp, dp, ap, op, stats, gamma, beta, sums, samples, spatial, C, groups, stats_ld, stats_cpg,
-        eps, rpb);
+        eps, rpb, colsum);
   else
-    gn_bwd_apply_kernel<false><<<grid, threads, 0, (cudaStream_t)stream>>>(
+    gn_bwd_apply_kernel<false><<<grid, threads, csm, (cudaStream_t)stream>>>(
         xp, dp, ap, op, stats, gamma, beta, sums, samples, spatial, C, groups, stats_ld, stats_cpg,
-        eps, rpb);
+        eps, rpb, colsum);
   return check_launch("gn_bwd_apply_kernel");
 }
 

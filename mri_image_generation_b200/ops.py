@@ -161,11 +161,12 @@ def colsum(dy, sums, samples, spatial, C) -> None:
 
 
 def gn_bwd_apply(x, dy, add, dx, stats, gamma, beta, sums, samples, spatial, C, groups, stats_cpg,
-                 eps, silu: bool) -> None:
-    _chk_contig(x, dy, add, dx, sums)
+                 eps, silu: bool, colsum=None) -> None:
+    _chk_contig(x, dy, add, dx, sums, colsum)
     _lib.check(_lib.load().mri_gn_bwd_apply(_p(x), _p(dy), _p(add), _p(dx), _p(stats), _p(gamma),
                                             _p(beta), _p(sums), samples, spatial, C, groups,
-                                            stats.shape[1], stats_cpg, eps, 1 if silu else 0, _s()),
+                                            stats.shape[1], stats_cpg, eps, 1 if silu else 0,
+                                            _p(colsum), _s()),
                "mri_gn_bwd_apply")
 
 
