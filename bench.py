@@ -350,7 +350,7 @@ def run_train(args, rank, world, local_rank):
     B, K, W = args.batch, args.steps, max(3, args.warmup)
     torch.manual_seed(0)
     model = UNet3DModelWithAttention(**MODEL_KW).to(dev).train()
-    net = wrap_ddp(model, dev) if world > 1 else model
+    net = wrap_ddp(model, dev, overlap=not args.torch_ddp) if world > 1 else model
     diff = quiet(GaussianDiffusionLatent3D, net, LATENT[0], timesteps=T_STEPS).to(dev)
     if args.torch_adam:
         opt = torch.optim.Adam(model.parameters(), lr=2e-4)
@@ -396,6 +396,9 @@ def run_train(args, rank, world, local_rank):
         "config": {"workload": "ddpm_3d_ldm_train_step", "latent": list(LATENT), "batch_per_gpu": B,
                    "model": "UNet3DModelWithAttention(base 128, mults 1-2-4, 136.4M params)",
                    "step": "q_sample + fwd + min-SNR loss + bwd + DDP all-reduce + Adam",
+                   "ddp": ("none (1 GPU)" if world == 1 else "torch DDP (reducer after backward)" if args.torch_ddp
+                           else "bucketed NCCL all-reduce overlapped with the backward launch list: buckets "
+                           + str(len(net.grad_sync.buckets_last_step))),
                    "optimizer": "torch.optim.Adam" if args.torch_adam else "mri_b200 fused Adam",
                    "loss": float(loss.item())},
         "roofline": {"bound": "tensor", "achieved": flops / (ms_per_step * 1e-3) / 1e12,
@@ -469,6 +472,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--torch-adam", action="store_true", help="train mode: torch.optim.Adam instead of "
                     "mri_image_generation_b200.optim.Adam")
+    ap.add_argument("--torch-ddp", action="store_true", help="train mode, N > 1: torch DDP instead of the "
+                    "overlapped bucketed all-reduce (parallel.DistributedDataParallel)")
     ap.add_argument("--per-op", default="", help="write per-GEMM timings (CUDA events) to this file")
     args = ap.parse_args()
 

@@ -112,6 +112,15 @@ class BackwardMixin:
         # id(gradient tensor) -> [colsum buffer or None] when its LAST writer is a gn_bwd_apply
         # launch (which can then emit the tensor's per-(sample, channel) sums for free)
         self._gn_writer: Dict[int, Optional[list]] = {}
+        # parameter gradients live in ONE flat fp32 arena, allocated in the order the backward
+        # pass first touches them, so that "everything ready after op k" is a prefix of the
+        # arena: DDP buckets are contiguous slices (parallel.GradSync)
+        self.garena: Optional[torch.Tensor] = None
+        self._garena_used = 0
+        self._g_off: Dict[int, Tuple[int, int]] = {}      # id(param) -> (offset, numel)
+        self._g_last_op: Dict[int, int] = {}              # id(param) -> index of the last op of
+        self._g_touched: List[int] = []                   # ... the last tape record touching it
+        self.bwd_segments: List[Tuple[int, int, int, int]] = []  # (op_lo, op_hi, arena_lo, arena_hi)
 
     def badd(self, name: str, fn: Callable[[], None]) -> None:
         self.bwd_names.append(name)
@@ -127,12 +136,44 @@ class BackwardMixin:
         self._zero_each_bwd.append(t)
         return t
 
+    def _galloc(self, n: int) -> Tuple[int, torch.Tensor]:
+        if self.garena is None:
+            seen, total = set(), 0
+            for p_ in self._params:
+                if id(p_) not in seen:
+                    seen.add(id(p_))
+                    total += -(-p_.numel() // 64) * 64
+            self.garena = torch.zeros(total + 4096, dtype=torch.float32, device=self.device)
+        off = self._garena_used
+        if off + n > self.garena.numel():
+            raise _lib.MriError("backward: gradient arena overflow (untracked parameter?)")
+        self._garena_used = off + -(-n // 64) * 64   # 256-byte aligned slices
+        return off, self.garena[off:off + n]
+
     def pg(self, p: torch.Tensor) -> torch.Tensor:
+        """fp32 gradient buffer of parameter p (reference layout), a view of the arena."""
         g = self.pgrad.get(id(p))
         if g is None:
-            g = torch.zeros(p.shape, dtype=torch.float32, device=self.device)
+            off, flat = self._galloc(p.numel())
+            g = flat.view(p.shape)
             self.pgrad[id(p)] = g
+            self._g_off[id(p)] = (off, p.numel())
+        self._g_touched.append(id(p))
         return g
+
+    def pg_block(self, params: Sequence[torch.Tensor], width: int) -> torch.Tensor:
+        """One contiguous [sum rows, width] gradient block for parameters that are row-slices of
+        a concatenated matrix (the per-block time projections); registers every slice."""
+        rows = [p.shape[0] for p in params]
+        off, flat = self._galloc(sum(rows) * width)
+        blk = flat.view(sum(rows), width) if width > 1 else flat
+        o = 0
+        for p, n in zip(params, rows):
+            self.pgrad[id(p)] = blk[o:o + n]
+            self._g_off[id(p)] = (off + o * width, n * width)
+            self._g_touched.append(id(p))
+            o += n
+        return blk
 
     def emit_grad(self, t: torch.Tensor, produce: Callable[[torch.Tensor, Optional[torch.Tensor]], None]):
         """grad[t] (+)= contribution; produce(out, add) must emit ops writing contribution + add."""
@@ -415,14 +456,15 @@ class BackwardMixin:
             self.badd("silu_bwd:tproj", lambda: ops.silu_bwd(r.zproj, self.dtproj, dzz))
             dz = dzz
         total, tdim = r.W_all.shape
-        dW_all = torch.zeros(total, tdim, device=dev)
-        db_all = torch.zeros(total, device=dev)
+        o_chk = 0
+        for blk, o in zip(r.blocks, r.offs):   # W_all is the row-wise concatenation, in order
+            assert o == o_chk, "block projections are not contiguous"
+            o_chk += blk.time_mlp.weight.shape[0]
+        assert o_chk == total
+        dW_all = self.pg_block([blk.time_mlp.weight for blk in r.blocks], tdim)
+        db_all = self.pg_block([blk.time_mlp.bias for blk in r.blocks], 1)
         dcond = torch.zeros(B, tdim, device=dev)
         self.badd("linear_bwd:tproj", lambda: ops.linear_bwd(dz, r.cond, r.W_all, dcond, dW_all, db_all))
-        for blk, o in zip(r.blocks, r.offs):
-            n = blk.time_mlp.weight.shape[0]
-            self.pgrad[id(blk.time_mlp.weight)] = dW_all[o:o + n]
-            self.pgrad[id(blk.time_mlp.bias)] = db_all[o:o + n]
 
         def mlp_bwd(dout, lin_a, lin_b, x_in, z_mid, h_mid, tag):
             """out = lin_b(silu(lin_a(x_in)))"""
@@ -444,6 +486,7 @@ class BackwardMixin:
         """dy_seed: id(forward tensor) -> gradient buffer filled before the backward ops run."""
         self.grads.update(dy_seed)
         for rec in reversed(self.tape):
+            self._g_touched = []
             if isinstance(rec, ConvRec):
                 self.bwd_conv(rec)
             elif isinstance(rec, GnRec):
@@ -454,9 +497,69 @@ class BackwardMixin:
                 self.bwd_time(rec)
             else:  # pragma: no cover
                 raise _lib.MriError(f"unknown tape record {type(rec)}")
+            self._close_record()
+        self.bwd_segments = []
 
-    def run_backward(self) -> None:
-        if self._zero_each_bwd:
+    def _close_record(self) -> None:
+        """Gradients touched by the record just emitted are final once all its ops have run."""
+        for pid in self._g_touched:
+            self._g_last_op[pid] = len(self.bwd_ops)
+        self._g_touched = []
+
+    def plan_segments(self, bucket_bytes: int) -> List[Tuple[int, int, int, int]]:
+        """Cut the backward launch list into segments (op_lo, op_hi, arena_lo, arena_hi): after
+        ops[:op_hi] have run, arena[:arena_hi] holds final parameter gradients.  Cuts are placed
+        where at least `bucket_bytes` of new gradients became final; the last segment takes the
+        rest.  The gradient all-reduce of segment i overlaps the launches of segment i + 1."""
+        order = sorted(self._g_off.items(), key=lambda kv: kv[1][0])   # by arena offset
+        segs, op_lo, a_lo, i = [], 0, 0, 0
+        n_ops = len(self.bwd_ops)
+        ready_at = 0   # ops needed for arena[:a_hi]
+        a_hi = 0
+        while i < len(order):
+            pid, (off, n) = order[i]
+            ready_at = max(ready_at, self._g_last_op[pid])
+            a_hi = -(-(off + n) // 64) * 64
+            i += 1
+            # the prefix is final only if no later-placed parameter finishes earlier... it is a
+            # prefix property: ready_at is the max over the prefix, which is what we need
+            if (a_hi - a_lo) * 4 >= bucket_bytes and ready_at < n_ops and ready_at > op_lo:
+                segs.append((op_lo, ready_at, a_lo, a_hi))
+                op_lo, a_lo = ready_at, a_hi
+        segs.append((op_lo, n_ops, a_lo, self._garena_used))
+        self.bwd_segments = segs
+        return segs
+
+    def run_backward(self, lo: int = 0, hi: Optional[int] = None) -> None:
+        """Enqueue backward ops [lo, hi) (all by default)."""
+        if lo == 0 and self._zero_each_bwd:
             torch._foreach_zero_(self._zero_each_bwd)
-        for fn in self.bwd_ops:
+        for fn in self.bwd_ops[lo:hi]:
             fn()
+
+    def _bwd_head(self, S: int) -> None:
+        """fp32 NC[D]HW loss gradient -> the bf16 channels-last seeds of the backward list."""
+        ops.nchw_to_nhwc(self.dout_in, self.deps16, self.B, S, self.cout, self.cout_pad)
+        ops.nchw_to_nhwc(self.dout_in, self.deps64, self.B, S, self.cout, 64)
+
+    def _backward(self, dout: torch.Tensor, S: int, sync) -> None:
+        self.dout_in.copy_(dout)
+        if sync is None or not sync.active():
+            def body():
+                self._bwd_head(S)
+                self.run_backward()
+            self._replay("bwd", body)
+            return
+        # segmented: one replayed graph per segment; after each, its (contiguous) slice of the
+        # gradient arena is handed to the all-reduce, which runs on the communication stream
+        # while the next segment's launches execute
+        segs = self.bwd_segments or self.plan_segments(sync.bucket_bytes)
+        sync.begin(self.garena)
+        for i, (lo, hi, a_lo, a_hi) in enumerate(segs):
+            def body(lo=lo, hi=hi):
+                if lo == 0:
+                    self._bwd_head(S)
+                self.run_backward(lo, hi)
+            self._replay(f"bwd_seg{i}/{len(segs)}", body)
+            sync.bucket_ready(a_lo, a_hi)
+        sync.finish()

@@ -306,7 +306,9 @@ class UNetProgram(BackwardMixin):
                 return
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread_local: the NCCL watchdog thread of an overlapped DDP step may query events
+            # while this thread captures
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 body()
             st[1] = g
         st[1].replay()
@@ -760,18 +762,11 @@ class UNet3DProgram(UNetProgram):
         ops.nhwc_to_nchw(self.eps_nhwc, self.out, self.B, S, self.cout, self.cout_pad)
         return self.out
 
-    def backward(self, dout: torch.Tensor) -> None:
+    def backward(self, dout: torch.Tensor, sync=None) -> None:
         """Training: gradient of the loss w.r.t. the fp32 NCDHW output -> parameter gradients in
-        self.pgrad (fp32, reference layouts)."""
-        S = self.sp[0] * self.sp[1] * self.sp[2]
-        self.dout_in.copy_(dout)
-
-        def body():
-            ops.nchw_to_nhwc(self.dout_in, self.deps16, self.B, S, self.cout, self.cout_pad)
-            ops.nchw_to_nhwc(self.dout_in, self.deps64, self.B, S, self.cout, 64)
-            self.run_backward()
-
-        self._replay("bwd", body)
+        self.pgrad (fp32, reference layouts).  `sync` (parallel.GradSync): all-reduce finished
+        gradient buckets while the rest of the backward launch list runs."""
+        self._backward(dout, self.sp[0] * self.sp[1] * self.sp[2], sync)
 
 
 def _pad_k(w: torch.Tensor, kpad: int) -> torch.Tensor:
@@ -986,13 +981,5 @@ class UNet2DProgram(UNetProgram):
                          self.cout_pad)
         return self.out
 
-    def backward(self, dout: torch.Tensor) -> None:
-        S = self.sp[0] * self.sp[1]
-        self.dout_in.copy_(dout)
-
-        def body():
-            ops.nchw_to_nhwc(self.dout_in, self.deps16, self.B, S, self.cout, self.cout_pad)
-            ops.nchw_to_nhwc(self.dout_in, self.deps64, self.B, S, self.cout, 64)
-            self.run_backward()
-
-        self._replay("bwd", body)
+    def backward(self, dout: torch.Tensor, sync=None) -> None:
+        self._backward(dout, self.sp[0] * self.sp[1], sync)

@@ -106,6 +106,8 @@ class _UNet3DBase(EngineModule):
             # training: forward + backward launch lists behind one autograd node
             prog = self.program(x.shape[0], x.shape[2:], training=True)
             prog.param_list = list(self.parameters())
+            sync = self.__dict__.get("_mri_grad_sync")  # set by parallel.DistributedDataParallel
+            prog.grad_sync = sync.take() if sync is not None else None
             return UNetFunction.apply(prog, lambda: prog.forward(xf, tl), len(prog.param_list),
                                       *prog.param_list)
         prog = self.program(x.shape[0], x.shape[2:])

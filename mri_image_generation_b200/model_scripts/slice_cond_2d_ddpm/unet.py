@@ -97,6 +97,8 @@ class _UNet2DBase(EngineModule):
         if self._needs_grad():
             prog = self.program(x.shape[0], x.shape[2:], x.shape[1], cc, training=True)
             prog.param_list = list(self.parameters())
+            sync = self.__dict__.get("_mri_grad_sync")  # set by parallel.DistributedDataParallel
+            prog.grad_sync = sync.take() if sync is not None else None
             return UNetFunction.apply(prog, lambda: prog.forward(xf, t, z_pos, ctx),
                                       len(prog.param_list), *prog.param_list)
         prog = self.program(x.shape[0], x.shape[2:], x.shape[1], cc)

@@ -43,6 +43,7 @@ class EngineModule(nn.Module):
         # slice_cond_2d_ddpm/model.py:320, pickles the module)
         state = self.__dict__.copy()
         state.pop("_mri_programs", None)
+        state.pop("_mri_grad_sync", None)   # process-group handle of parallel.DistributedDataParallel
         return state
 
     def _apply(self, fn, *args, **kwargs):
@@ -88,10 +89,16 @@ class UNetFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         prog = ctx.prog
-        prog.backward(dout.contiguous().float())
+        prog.backward(dout.contiguous().float(), sync=getattr(prog, "grad_sync", None))
+        # one copy of the whole gradient arena (the program overwrites it next step); every
+        # parameter's gradient is a view of that copy
+        flat = prog.garena[:prog._garena_used].clone()
         grads = []
         for p in prog.param_list:
-            g = prog.pgrad.get(id(p))
-            grads.append(g.clone() if (g is not None and p.requires_grad) else None)
+            loc = prog._g_off.get(id(p))
+            if loc is None or not p.requires_grad:
+                grads.append(None)
+            else:
+                grads.append(flat[loc[0]:loc[0] + loc[1]].view(p.shape))
         extra = len(ctx.needs_input_grad) - 3 - len(grads)
         return (None, None, None, *grads, *([None] * extra))

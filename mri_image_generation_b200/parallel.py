@@ -5,9 +5,12 @@ torch.distributed (NCCL over NVLink 5 / NVSwitch) for the plumbing only.
   collective: every sample's trajectory depends only on its own noise stream (per-sample
   GroupNorm, per-sample attention).  Rank r draws from seed `base_seed + r`; an optional final
   gather brings the volumes to rank 0 for saving (ddpm_3d_ldm/show_model.py:254-255).
-* DDP training is pure data parallelism: the drop-in UNets are ordinary nn.Modules whose
+* DDP training is pure data parallelism.  The drop-in UNets are ordinary nn.Modules whose
   gradients arrive through one autograd node, so torch's DistributedDataParallel (the wrapper
-  the reference uses, ddpm_3d_ldm/train.py:232-233) reduces them with NCCL unchanged.
+  the reference uses, ddpm_3d_ldm/train.py:232-233) works unchanged but can only reduce after
+  the whole backward.  `DistributedDataParallel` here has the same constructor and `.module`,
+  and all-reduces contiguous buckets of the gradient arena on a communication stream while the
+  rest of the backward launch list executes (GradSync).
 """
 from __future__ import annotations
 
@@ -75,11 +78,138 @@ def gather_to_rank0(local: Optional[torch.Tensor], total: int) -> Optional[torch
     return out
 
 
-def wrap_ddp(module: torch.nn.Module, device: torch.device, **kw) -> torch.nn.Module:
-    """DistributedDataParallel over the drop-in UNet (train.py:232-233).  All parameters receive
-    their gradients from one autograd node, so the reducer's buckets fire back to back at the
-    end of the backward launch list; the all-reduce of 545.6 MB (136.4 M fp32 grads) is ~1 ms over
-    NVSwitch against a ~100 ms step."""
+class GradSync:
+    """Bucketed gradient all-reduce (mean) that overlaps the backward launch list.
+
+    The UNet programs keep all parameter gradients in one flat fp32 arena ordered by the time
+    the backward pass finishes them (backward.py: plan_segments), so a bucket is a contiguous
+    slice.  `bucket_ready(lo, hi)` is called right after the launches that complete
+    arena[lo:hi] were enqueued: an event on the compute stream gates the communication stream,
+    where NCCL reduces the slice in place over NVLink / NVSwitch while the compute stream keeps
+    executing the next segment.  `finish()` makes the compute stream wait for every bucket.
+    Works on CPU tensors / gloo as well (host-logic tests): there the reduction is synchronous.
+
+    Reference: torch DDP's reducer as used by ddpm_3d_ldm/train.py:232-233 (bucketed mean
+    all-reduce of all UNet gradients, issued in reverse order, overlapped with backward)."""
+
+    def __init__(self, process_group=None, bucket_cap_mb: float = 48.0):
+        self.group = process_group
+        self.bucket_bytes = int(bucket_cap_mb * (1 << 20))
+        self.enabled = True                 # False inside DistributedDataParallel.no_sync()
+        self._armed = False                 # set by the wrapper's forward, consumed by the UNet's
+        self._arena: Optional[torch.Tensor] = None
+        self._works: list = []
+        self._comm_stream = None
+        self.buckets_last_step: List[Tuple[int, int]] = []
+
+    def take(self) -> Optional["GradSync"]:
+        """Called by the UNet's forward: the next backward synchronises only if the call came
+        through the DistributedDataParallel wrapper (calling `.module` directly stays local,
+        as with torch DDP)."""
+        armed, self._armed = self._armed, False
+        return self if armed else None
+
+    def world(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def active(self) -> bool:
+        return self.enabled and self.world() > 1
+
+    def begin(self, arena: torch.Tensor) -> None:
+        self._arena = arena
+        self._works = []
+        self.buckets_last_step = []
+        if arena.is_cuda and self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(arena.device)
+
+    def bucket_ready(self, lo: int, hi: int) -> None:
+        if hi <= lo:
+            return
+        self.buckets_last_step.append((lo, hi))
+        buf = self._arena[lo:hi]
+        backend = dist.get_backend(self.group)
+        if not buf.is_cuda:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+            buf.mul_(1.0 / self.world())
+            return
+        cur = torch.cuda.current_stream(buf.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        with torch.cuda.stream(self._comm_stream):
+            self._comm_stream.wait_event(ev)
+            if backend == "nccl":
+                w = dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+            else:
+                w = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._works.append((w, buf, backend))
+
+    def finish(self) -> None:
+        """Compute stream waits for all buckets (no host synchronisation with NCCL)."""
+        for w, buf, backend in self._works:
+            w.wait()
+            if backend != "nccl":
+                buf.mul_(1.0 / self.world())
+        self._works = []
+
+
+class DistributedDataParallel(torch.nn.Module):
+    """Drop-in for `torch.nn.parallel.DistributedDataParallel` around the drop-in UNets
+    (`DDP(model, device_ids=[local_rank])`, ddpm_3d_ldm/train.py:232-233; `.module` unwrap,
+    train.py:607): parameters and buffers are broadcast from rank 0 at construction, and every
+    backward pass mean-all-reduces the gradients in buckets that overlap the remaining backward
+    launches (GradSync).  torch's own DDP also works on these modules, but their gradients come
+    out of ONE autograd node, so its reducer can only start after the whole backward."""
+
+    def __init__(self, module: torch.nn.Module, device_ids=None, output_device=None, dim=0,
+                 broadcast_buffers=True, process_group=None, bucket_cap_mb: float = 48.0,
+                 find_unused_parameters=False, gradient_as_bucket_view=False, static_graph=False,
+                 **_ignored):
+        super().__init__()
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("DistributedDataParallel needs an initialised process group")
+        from .modules import EngineModule
+        if not isinstance(module, EngineModule):
+            raise TypeError("mri_image_generation_b200.parallel.DistributedDataParallel wraps the "
+                            "drop-in UNet classes; use torch's DDP for other modules")
+        self.module = module
+        self.process_group = process_group
+        self.device_ids = device_ids
+        self.broadcast_buffers = broadcast_buffers
+        with torch.no_grad():
+            for t in list(module.parameters()) + list(module.buffers()):
+                dist.broadcast(t, src=dist.get_global_rank(process_group, 0) if process_group else 0,
+                               group=process_group)
+        self.grad_sync = GradSync(process_group, bucket_cap_mb)
+        module.__dict__["_mri_grad_sync"] = self.grad_sync
+
+    def forward(self, *args, **kwargs):
+        self.grad_sync._armed = True
+        try:
+            return self.module(*args, **kwargs)
+        finally:
+            self.grad_sync._armed = False
+
+    def no_sync(self):
+        """Context manager: gradients are accumulated locally (no all-reduce) inside it."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            old = self.grad_sync.enabled
+            self.grad_sync.enabled = False
+            try:
+                yield
+            finally:
+                self.grad_sync.enabled = old
+        return ctx()
+
+
+def wrap_ddp(module: torch.nn.Module, device: torch.device, overlap: bool = True, **kw) -> torch.nn.Module:
+    """Data-parallel wrapper of a drop-in UNet (train.py:232-233).  overlap=True: the bucketed
+    all-reduce of this package, running under the backward launch list; overlap=False: torch's
+    DistributedDataParallel, whose reducer fires after the (single-node) backward."""
+    if overlap:
+        return DistributedDataParallel(module, device_ids=[device.index], **kw)
     from torch.nn.parallel import DistributedDataParallel as DDP
     return DDP(module, device_ids=[device.index], output_device=device.index,
                find_unused_parameters=False, **kw)

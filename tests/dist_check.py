@@ -65,7 +65,7 @@ def main():
     x0 = torch.randn(b * world, 3, 8, 8, 8, generator=g)
     noise = torch.randn(b * world, 3, 8, 8, 8, generator=g)
     t = torch.randint(1, 6, (b * world,), generator=g)
-    ddp = wrap_ddp(model, dev)
+    ddp = wrap_ddp(model, dev, overlap=False)   # torch DDP: the reference wrapper
     diff_ddp = quiet(GaussianDiffusionLatent3D, ddp, 3, timesteps=6).to(dev)
     sl = slice(rank * b, (rank + 1) * b)
     loss = diff_ddp.p_losses(x0[sl].to(dev), t[sl].to(dev), noise=noise[sl].to(dev))
@@ -92,6 +92,38 @@ def main():
               f"mean loss {lt.item() / world:.6f} vs {loss_full.item():.6f}")
     assert median < 3e-2, median
     assert worst < 8e-2, errs[:3]
+    # ---- 3. overlapped bucketed all-reduce == torch DDP ---------------------------------------
+    # same inputs through parallel.DistributedDataParallel: eager steps, the graph-capturing step
+    # and replayed steps must all reproduce torch DDP's averaged gradients
+    del ddp, diff_ddp
+    ours = wrap_ddp(model, dev, overlap=True, bucket_cap_mb=8)
+    diff_o = quiet(GaussianDiffusionLatent3D, ours, 3, timesteps=6).to(dev)
+    for step in range(6):
+        for p in model.parameters():
+            p.grad = None
+        loss_o = diff_o.p_losses(x0[sl].to(dev), t[sl].to(dev), noise=noise[sl].to(dev))
+        loss_o.backward()
+        bad = []
+        for n, p in model.named_parameters():
+            same = torch.equal(p.grad, grads_ddp[n]) if world == 2 else rel(p.grad, grads_ddp[n]) < 1e-5
+            if not same:
+                bad.append((n, rel(p.grad, grads_ddp[n])))
+        assert not bad, (step, bad[:4])
+    nb = len(ours.grad_sync.buckets_last_step)
+    assert nb >= 4, nb
+    # no_sync(): local gradients only
+    with ours.no_sync():
+        for p in model.parameters():
+            p.grad = None
+        diff_o.p_losses(x0[sl].to(dev), t[sl].to(dev), noise=noise[sl].to(dev)).backward()
+    g_local = model.mid_attn.qkv.weight.grad.clone()
+    gathered = [torch.empty_like(g_local) for _ in range(world)]
+    dist.all_gather(gathered, g_local)
+    assert rel(sum(gathered) / world, grads_ddp["mid_attn.qkv.weight"]) < 1e-5
+    assert world == 1 or not torch.equal(gathered[0], gathered[1])
+    if rank == 0:
+        print(f"[dist_check] overlapped all-reduce ({nb} buckets, eager + captured + replayed steps) == "
+              f"torch DDP gradients ({'bit-exact' if world == 2 else 'rel < 1e-5'}); no_sync() keeps local gradients")
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

@@ -69,3 +69,127 @@ def test_sample_sharded_gloo_world2(tmp_path):
         parts.append(torch.randn(hi - lo, 1, 4, 4) + z[lo:hi].view(-1, 1, 1, 1))
     assert torch.equal(r0["local"], parts[0]) and torch.equal(r1["local"], parts[1])
     assert torch.equal(r0["gathered"], torch.cat(parts, 0))
+
+
+# ------------------------------------------------------------------ overlapped gradient all-reduce
+class _FakeProgram:
+    """The bookkeeping half of backward.BackwardMixin over CPU tensors: 'records' whose ops write
+    rank-dependent values into parameter gradients, one of them touching a parameter that an
+    earlier record already touched (as the three q/k/v slices of mid_attn.qkv.weight do)."""
+
+    def __new__(cls, rank):
+        from mri_image_generation_b200.backward import BackwardMixin
+
+        class Prog(BackwardMixin):
+            def _replay(self, key, body):
+                self.replayed.append(key)
+                body()
+
+            def _bwd_head(self, S):
+                self.head_calls += 1
+
+        pr = Prog()
+        pr._binit()
+        pr.device = "cpu"
+        pr.replayed, pr.head_calls = [], 0
+        pr.dout_in = torch.zeros(1)
+        g = torch.Generator().manual_seed(5)
+        pr.shapes = [(3, 5), (70,), (128, 9), (1,), (64, 64), (200,), (33, 3), (512,)]
+        pr._params = [torch.zeros(s) for s in pr.shapes]
+        pr.values = {}
+
+        def record(idxs, scale):
+            for i in idxs:
+                p = pr._params[i]
+                gbuf = pr.pg(p)
+                val = torch.randn(p.shape, generator=g)
+                pr.values[i] = val * scale
+
+                def op(gbuf=gbuf, val=val, scale=scale):
+                    gbuf.copy_(val * scale * (rank + 1))   # rank r contributes (r + 1) * value
+                pr.badd(f"w{i}", op)
+            pr.badd("filler", lambda: None)
+            pr._close_record()
+
+        record([0, 1], 1.0)
+        record([2], 1.0)
+        record([3, 4], 1.0)
+        record([2], 2.0)          # parameter 2 is written again: its first value must not be reduced
+        record([5], 1.0)
+        record([6, 7], 1.0)
+        blk = pr.pg_block([torch.zeros(4, 6), torch.zeros(2, 6)], 6)   # untracked -> arena slack
+        pr.values["blk"] = torch.arange(36, dtype=torch.float32).view(6, 6)
+        pr.badd("blk", lambda: blk.copy_(pr.values["blk"] * (rank + 1)))
+        pr._close_record()
+        return pr
+
+
+def test_plan_segments_prefix_property():
+    pr = _FakeProgram(0)
+    segs = pr.plan_segments(bucket_bytes=256)
+    assert segs[0][0] == 0 and segs[-1][1] == len(pr.bwd_ops)
+    assert segs[0][2] == 0 and segs[-1][3] == pr._garena_used
+    for (lo, hi, a, b), (lo2, hi2, a2, b2) in zip(segs, segs[1:]):
+        assert hi == lo2 and b == a2 and lo < hi and a < b
+    assert len(segs) >= 3
+    # every parameter inside a segment's arena slice is final once the segment's ops have run
+    for (lo, hi, a, b) in segs:
+        for pid, (off, n) in pr._g_off.items():
+            if off < b:
+                assert pr._g_last_op[pid] <= hi
+    # parameter 2 (re-written by a later record) delays the cut that contains it
+    off2 = pr._g_off[id(pr._params[2])][0]
+    seg2 = next(s for s in segs if s[2] <= off2 < s[3])
+    assert seg2[1] >= pr._g_last_op[id(pr._params[2])]
+    # one huge bucket -> a single segment
+    assert len(pr.plan_segments(bucket_bytes=1 << 30)) == 1
+
+
+def _sync_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mri_image_generation_b200.parallel import GradSync
+    pr = _FakeProgram(rank)
+    sync = GradSync(bucket_cap_mb=256 / (1 << 20))
+    out = {}
+    for step in range(2):
+        pr._backward(torch.zeros(1), 1, sync)
+        out[f"arena{step}"] = pr.garena[:pr._garena_used].clone()
+    out["buckets"] = list(sync.buckets_last_step)
+    out["replayed"] = list(pr.replayed)
+    out["off"] = {i: pr._g_off[id(p)] for i, p in enumerate(pr._params)}
+    out["values"] = {k: v for k, v in pr.values.items()}
+    out["blk_off"] = min(o for pid, (o, n) in pr._g_off.items() if pid not in {id(p) for p in pr._params})
+    sync.enabled = False      # no_sync(): plain local backward, one un-segmented launch list
+    pr._backward(torch.zeros(1), 1, sync)
+    out["local"] = pr.garena[:pr._garena_used].clone()
+    torch.save(out, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_sync_gloo_world2(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_sync_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(tmp_path / "r0.pt")
+    r1 = torch.load(tmp_path / "r1.pt")
+    assert torch.equal(r0["arena0"], r1["arena0"]) and torch.equal(r0["arena1"], r0["arena0"])
+    # mean over ranks of (r + 1) * value = 1.5 * value, for the LAST value written to each parameter
+    for i, (off, n) in r0["off"].items():
+        want = (1.5 * r0["values"][i]).reshape(-1)
+        assert torch.allclose(r0["arena0"][off:off + n], want, rtol=0, atol=1e-6), i
+    bo = r0["blk_off"]
+    assert torch.allclose(r0["arena0"][bo:bo + 36], 1.5 * r0["values"]["blk"].reshape(-1))
+    # buckets tile the arena in order and there are several of them
+    b = r0["buckets"]
+    assert len(b) >= 3 and b[0][0] == 0 and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+    assert b[-1][1] == r0["arena0"].numel()
+    assert any(k.startswith("bwd_seg") for k in r0["replayed"])
+    # no_sync: rank-local gradients, whole-list launch
+    for i, (off, n) in r1["off"].items():
+        assert torch.allclose(r1["local"][off:off + n], (2.0 * r1["values"][i]).reshape(-1))
