@@ -63,15 +63,13 @@ gn_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
                      const float* __restrict__ beta, double* __restrict__ sums, int samples,
                      int64_t spatial, int C, int groups, int stats_ld, int stats_cpg, float eps,
                      int rows_per_block) {
-  extern __shared__ double red[];  // [3][C]
+  extern __shared__ float part[];  // [rows_step][3][C]
   const int vec_per_row = C >> 3;
   const int sample = blockIdx.y;
   const int cv = threadIdx.x % vec_per_row;
   const int rsub = threadIdx.x / vec_per_row;
   const int rows_step = blockDim.x / vec_per_row;
   const int c = cv * 8;
-  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.0;
-  __syncthreads();
 
   float sc[8], sh[8], mean = 0.f, rstd = 1.f;
   if (x != nullptr) {
@@ -131,19 +129,24 @@ gn_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
       }
     }
   }
+  // block reduction without shared-memory atomics: every thread parks its 24 fp32 partial sums,
+  // then one thread per (quantity, channel) folds the rows_step partials in fp64 and issues the
+  // block's single fp64 atomic for that address
+  const int nq = x != nullptr ? 3 : 1;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    atomicAdd(&red[c + j], (double)s0[j]);
+    part[(size_t)(rsub * 3 + 0) * C + c + j] = s0[j];
     if (x != nullptr) {
-      atomicAdd(&red[C + c + j], (double)s1[j]);
-      atomicAdd(&red[2 * C + c + j], (double)s2[j]);
+      part[(size_t)(rsub * 3 + 1) * C + c + j] = s1[j];
+      part[(size_t)(rsub * 3 + 2) * C + c + j] = s2[j];
     }
   }
   __syncthreads();
-  const int nq = x != nullptr ? 3 : 1;
   for (int i = threadIdx.x; i < nq * C; i += blockDim.x) {
-    const int qi = i / C, ci = i % C;
-    atomicAdd(sums + ((size_t)qi * samples + sample) * C + ci, red[i]);
+    const int qi = i / C, ci = i - qi * C;
+    double acc = 0.0;
+    for (int r = 0; r < rows_step; ++r) acc += (double)part[(size_t)(r * 3 + qi) * C + ci];
+    atomicAdd(sums + ((size_t)qi * samples + sample) * C + ci, acc);
   }
 }
 
@@ -159,7 +162,8 @@ gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
                     const float* __restrict__ beta, const double* __restrict__ sums, int samples,
                     int64_t spatial, int C, int groups, int stats_ld, int stats_cpg, float eps,
                     int rows_per_block, double* __restrict__ colsum) {
-  extern __shared__ double cred[];  // [C], only when colsum != nullptr
+  extern __shared__ float cpart[];  // [rows_step][C], only when colsum != nullptr
+  __shared__ double gmean[2][64];   // per group: mean(gamma*du), mean(gamma*du*xhat)
   const int vec_per_row = C >> 3;
   const int sample = blockIdx.y;
   const int cv = threadIdx.x % vec_per_row;
@@ -168,25 +172,39 @@ gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
   const int c = cv * 8;
   const int cpg = C / groups;
   const int g = c / cpg;
-  if (colsum != nullptr) {
-    for (int i = threadIdx.x; i < C; i += blockDim.x) cred[i] = 0.0;
-    __syncthreads();
-  }
   float csum[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) csum[j] = 0.f;
   const GnCoef k = gn_coef(stats, sample, stats_ld, g, cpg / stats_cpg, cpg, spatial, eps);
-  const double* S1 = sums + ((size_t)1 * samples + sample) * C;
-  const double* S2 = sums + ((size_t)2 * samples + sample) * C;
-  double m1d = 0.0, m2d = 0.0;
-  for (int j = g * cpg; j < (g + 1) * cpg; ++j) {
-    const double gm = (double)__ldg(gamma + j);
-    m1d += gm * __ldg(S1 + j);
-    m2d += gm * __ldg(S2 + j);
+  {  // one warp per group folds the pass-A sums (every thread used to walk cpg channels itself)
+    const double* S1 = sums + ((size_t)1 * samples + sample) * C;
+    const double* S2 = sums + ((size_t)2 * samples + sample) * C;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    const bool full = (blockDim.x & 31) == 0 || warp < nwarps - 1;  // partial last warp sits out
+    if (full) {
+      for (int gg = warp; gg < groups; gg += ((blockDim.x & 31) == 0 ? nwarps : nwarps - 1)) {
+        double a1 = 0.0, a2 = 0.0;
+        for (int j = gg * cpg + lane; j < (gg + 1) * cpg; j += 32) {
+          const double gm = (double)__ldg(gamma + j);
+          a1 += gm * __ldg(S1 + j);
+          a2 += gm * __ldg(S2 + j);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+          a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+        if (lane == 0) {
+          const double inv_cnt = 1.0 / ((double)cpg * (double)spatial);
+          gmean[0][gg] = a1 * inv_cnt;
+          gmean[1][gg] = a2 * inv_cnt;
+        }
+      }
+    }
+    __syncthreads();
   }
-  const double inv_cnt = 1.0 / ((double)cpg * (double)spatial);
-  const float m1 = (float)(m1d * inv_cnt);
-  const float m2 = (float)(m2d * inv_cnt);
+  const float m1 = (float)gmean[0][g];
+  const float m2 = (float)gmean[1][g];
   float gmv[8], btv[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -245,10 +263,13 @@ gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
   }
   if (colsum != nullptr) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&cred[c + j], (double)csum[j]);
+    for (int j = 0; j < 8; ++j) cpart[(size_t)rsub * C + c + j] = csum[j];
     __syncthreads();
-    for (int i = threadIdx.x; i < C; i += blockDim.x)
-      atomicAdd(colsum + (size_t)sample * C + i, cred[i]);
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      double acc = 0.0;
+      for (int r = 0; r < rows_step; ++r) acc += (double)cpart[(size_t)r * C + i];
+      atomicAdd(colsum + (size_t)sample * C + i, acc);
+    }
   }
 }
 
@@ -450,7 +471,7 @@ extern "C" int mri_gn_bwd_reduce(const void* x, const void* dy, const double* st
   const int threads = (256 / vpr) * vpr;
   dim3 grid;
   const int rpb = rows_per_block_for(samples, spatial, threads / vpr, &grid);
-  const size_t smem = 3 * C * sizeof(double);
+  const size_t smem = (size_t)threads * 24 * sizeof(float);  // [rows_step][3][C]
   const uint4* xp = reinterpret_cast<const uint4*>(x);
   const uint4* dp = reinterpret_cast<const uint4*>(dy);
   if (silu)
@@ -477,7 +498,8 @@ extern "C" int mri_gn_bwd_apply(const void* x, const void* dy, const void* add, 
   const uint4* dp = reinterpret_cast<const uint4*>(dy);
   const uint4* ap = reinterpret_cast<const uint4*>(add);
   uint4* op = reinterpret_cast<uint4*>(dx);
-  const size_t csm = colsum != nullptr ? (size_t)C * sizeof(double) : 0;
+  if (groups > 64) return set_error(-2, "mri_gn_bwd_apply: more than 64 groups");
+  const size_t csm = colsum != nullptr ? (size_t)threads * 8 * sizeof(float) : 0;
   if (silu)
     gn_bwd_apply_kernel<true><<<grid, threads, csm, (cudaStream_t)stream>>>(
         xp, dp, ap, op, stats, gamma, beta, sums, samples, spatial, C, groups, stats_ld, stats_cpg,
