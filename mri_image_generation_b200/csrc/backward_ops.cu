@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/mri_b200.h"
 #include "common.h"
@@ -27,6 +28,34 @@ __device__ __forceinline__ uint4 pack8b(const float (&f)[8]) {
     w[j] = *reinterpret_cast<uint32_t*>(&h2);
   }
   return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2 issue two fp32 lanes per
+// instruction).  The GroupNorm backward passes are co-limited by instruction issue (SiLU' costs
+// ~20 scalar instructions per element against 4-6 bytes of HBM traffic), so the per-element
+// math runs on channel PAIRS, and the sigmoid is 0.5 * tanh.approx(u / 2) + 0.5 (one MUFU
+// instead of ex2 + rcp; relative error 2^-11, below the bf16 resolution of everything stored).
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t f2_to_bf2(float2 v) {
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(v.x, v.y);
+  return *reinterpret_cast<uint32_t*>(&h2);
+}
+// du = d * silu'(u), u = xh * sc + sh
+__device__ __forceinline__ float2 silu_bwd2(float2 d, float2 xh, float2 sc, float2 sh) {
+  const float2 u = __ffma2_rn(xh, sc, sh);
+  const float2 hu = __fmul2_rn(u, make_float2(0.5f, 0.5f));
+  const float2 th = make_float2(tanh_approx(hu.x), tanh_approx(hu.y));
+  const float2 sg = __ffma2_rn(th, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+  const float2 t = __ffma2_rn(th, make_float2(-0.5f, -0.5f), make_float2(0.5f, 0.5f));  // 1 - sg
+  const float2 w = __ffma2_rn(u, t, make_float2(1.0f, 1.0f));
+  return __fmul2_rn(d, __fmul2_rn(sg, w));
 }
 
 struct GnCoef {
@@ -56,7 +85,7 @@ __device__ __forceinline__ GnCoef gn_coef(const double* stats, int sample, int s
 // produced (plain column sum).  grid (chunks, samples); thread = fixed 8-channel vector.
 // sums: fp64 [3][samples][C] (fp64 atomics: the result does not depend on arrival order)
 // ---------------------------------------------------------------------------------------
-template <bool kSilu>
+template <bool kSilu, bool kHasX>
 __global__ void __launch_bounds__(256)
 gn_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
                      const double* __restrict__ stats, const float* __restrict__ gamma,
@@ -71,72 +100,76 @@ gn_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
   const int rows_step = blockDim.x / vec_per_row;
   const int c = cv * 8;
 
-  float sc[8], sh[8], mean = 0.f, rstd = 1.f;
-  if (x != nullptr) {
+  float2 sc[4], sh[4];
+  float2 rs2 = make_float2(1.f, 1.f), nmr2 = make_float2(0.f, 0.f);  // xh = x * rstd - mean * rstd
+  if (kHasX) {
     const int cpg = C / groups;
     const GnCoef k = gn_coef(stats, sample, stats_ld, c / cpg, cpg / stats_cpg, cpg, spatial, eps);
-    mean = k.mean;
-    rstd = k.rstd;
+    rs2 = make_float2(k.rstd, k.rstd);
+    nmr2 = make_float2(-k.mean * k.rstd, -k.mean * k.rstd);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sc[j] = __ldg(gamma + c + j);
-      sh[j] = __ldg(beta + c + j);
+    for (int j = 0; j < 4; ++j) {
+      sc[j] = make_float2(__ldg(gamma + c + 2 * j), __ldg(gamma + c + 2 * j + 1));
+      sh[j] = make_float2(__ldg(beta + c + 2 * j), __ldg(beta + c + 2 * j + 1));
     }
+  }
+  float2 a0[4], a1[4], a2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a0[j] = a1[j] = a2[j] = make_float2(0.f, 0.f);
+  auto accum = [&](const uint4& dq, const uint4& xq) {
+    const uint32_t dw[4] = {dq.x, dq.y, dq.z, dq.w};
+    const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 d = bf2_to_f2(dw[j]);
+      a0[j] = __fadd2_rn(a0[j], d);
+      if (kHasX) {
+        const float2 xh = __ffma2_rn(bf2_to_f2(xw[j]), rs2, nmr2);
+        const float2 du = kSilu ? silu_bwd2(d, xh, sc[j], sh[j]) : d;
+        a1[j] = __fadd2_rn(a1[j], du);
+        a2[j] = __ffma2_rn(du, xh, a2[j]);
+      }
+    }
+  };
+  // this block's rows [r0, r1) of the sample; thread rows r0 + rsub + k * rows_step
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = (int64_t)r0 + rows_per_block > spatial ? (int)spatial : r0 + rows_per_block;
+  const uint4* dp = dy + (size_t)sample * spatial * vec_per_row + cv;
+  const uint4* xp = kHasX ? x + (size_t)sample * spatial * vec_per_row + cv : dp;
+  constexpr int U = 4;  // independent 16-byte loads in flight per thread and tensor
+  const int stepv = rows_step * vec_per_row;
+  int r = r0 + rsub;
+  for (; r + (U - 1) * rows_step < r1; r += U * rows_step) {  // whole batches: no predicates
+    uint4 dv[U], xv[U];
+    const int o = r * vec_per_row;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      dv[u] = __ldg(dp + o + u * stepv);
+      if (kHasX) xv[u] = __ldg(xp + o + u * stepv);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) accum(dv[u], kHasX ? xv[u] : dv[u]);
+  }
+  for (; r < r1; r += rows_step) {  // ragged end of the sample's last block
+    const uint4 dq = __ldg(dp + r * vec_per_row);
+    const uint4 xq = kHasX ? __ldg(xp + r * vec_per_row) : dq;
+    accum(dq, xq);
   }
   float s0[8], s1[8], s2[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s0[j] = s1[j] = s2[j] = 0.f;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  int64_t r1 = r0 + rows_per_block;
-  if (r1 > spatial) r1 = spatial;
-  const size_t base = (size_t)sample * spatial * vec_per_row + cv;
-  constexpr int U = 4;  // independent 16-byte loads in flight per thread
-  for (int64_t r = r0 + rsub; r < r1; r += (int64_t)rows_step * U) {
-    uint4 dv[U], xv[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t ru = r + (int64_t)u * rows_step;
-      if (ru < r1) {
-        dv[u] = __ldg(dy + base + ru * vec_per_row);
-        if (x != nullptr) xv[u] = __ldg(x + base + ru * vec_per_row);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t ru = r + (int64_t)u * rows_step;
-      if (ru >= r1) continue;
-      float d[8];
-      unpack8b(dv[u], d);
-      if (x == nullptr) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s0[j] += d[j];
-        continue;
-      }
-      float f[8];
-      unpack8b(xv[u], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (f[j] - mean) * rstd;
-        float du = d[j];
-        if (kSilu) {
-          const float uu = fmaf(xh, sc[j], sh[j]);
-          const float sg = __fdividef(1.0f, 1.0f + __expf(-uu));
-          du *= sg * (1.0f + uu * (1.0f - sg));
-        }
-        s0[j] += d[j];
-        s1[j] += du;
-        s2[j] = fmaf(du, xh, s2[j]);
-      }
-    }
+  for (int j = 0; j < 4; ++j) {
+    s0[2 * j] = a0[j].x; s0[2 * j + 1] = a0[j].y;
+    s1[2 * j] = a1[j].x; s1[2 * j + 1] = a1[j].y;
+    s2[2 * j] = a2[j].x; s2[2 * j + 1] = a2[j].y;
   }
   // block reduction without shared-memory atomics: every thread parks its 24 fp32 partial sums,
   // then one thread per (quantity, channel) folds the rows_step partials in fp64 and issues the
   // block's single fp64 atomic for that address
-  const int nq = x != nullptr ? 3 : 1;
+  const int nq = kHasX ? 3 : 1;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     part[(size_t)(rsub * 3 + 0) * C + c + j] = s0[j];
-    if (x != nullptr) {
+    if (kHasX) {
       part[(size_t)(rsub * 3 + 1) * C + c + j] = s1[j];
       part[(size_t)(rsub * 3 + 2) * C + c + j] = s2[j];
     }
@@ -205,12 +238,21 @@ gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
   }
   const float m1 = (float)gmean[0][g];
   const float m2 = (float)gmean[1][g];
-  float gmv[8], btv[8];
+  // dx = (gamma * rstd) * du - rstd * m1 - (rstd * m2) * xh, on channel pairs
+  float2 sc[4], sh[4], grs[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    gmv[j] = __ldg(gamma + c + j);
-    btv[j] = __ldg(beta + c + j);
+  for (int j = 0; j < 4; ++j) {
+    sc[j] = make_float2(__ldg(gamma + c + 2 * j), __ldg(gamma + c + 2 * j + 1));
+    sh[j] = make_float2(__ldg(beta + c + 2 * j), __ldg(beta + c + 2 * j + 1));
+    grs[j] = make_float2(sc[j].x * k.rstd, sc[j].y * k.rstd);
   }
+  const float2 rs2 = make_float2(k.rstd, k.rstd);
+  const float2 nmr2 = make_float2(-k.mean * k.rstd, -k.mean * k.rstd);
+  const float2 nrm1 = make_float2(-k.rstd * m1, -k.rstd * m1);
+  const float2 nrm2 = make_float2(-k.rstd * m2, -k.rstd * m2);
+  float2 cs2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) cs2[j] = make_float2(0.f, 0.f);
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   int64_t r1 = r0 + rows_per_block;
   if (r1 > spatial) r1 = spatial;
@@ -231,35 +273,29 @@ gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
     for (int u = 0; u < U; ++u) {
       const int64_t ru = r + (int64_t)u * rows_step;
       if (ru >= r1) continue;
-      float f[8], d[8], o[8];
-      unpack8b(xv[u], f);
-      unpack8b(dv[u], d);
+      const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+      const uint32_t dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+      const uint32_t aw[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
+      uint32_t ow[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (f[j] - k.mean) * k.rstd;
-        float du = d[j];
-        if (kSilu) {
-          const float uu = fmaf(xh, gmv[j], btv[j]);
-          const float sg = __fdividef(1.0f, 1.0f + __expf(-uu));
-          du *= sg * (1.0f + uu * (1.0f - sg));
-        }
-        o[j] = k.rstd * (gmv[j] * du - m1 - xh * m2);
+      for (int j = 0; j < 4; ++j) {
+        const float2 d = bf2_to_f2(dw[j]);
+        const float2 xh = __ffma2_rn(bf2_to_f2(xw[j]), rs2, nmr2);
+        const float2 du = kSilu ? silu_bwd2(d, xh, sc[j], sh[j]) : d;
+        float2 o = __ffma2_rn(du, grs[j], nrm1);
+        o = __ffma2_rn(xh, nrm2, o);
+        if (add != nullptr) o = __fadd2_rn(o, bf2_to_f2(aw[j]));
+        ow[j] = f2_to_bf2(o);
+        if (colsum != nullptr)  // column sums of the bf16 values a later pass would read
+          cs2[j] = __fadd2_rn(cs2[j], bf2_to_f2(ow[j]));
       }
-      if (add != nullptr) {
-        float a[8];
-        unpack8b(av[u], a);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += a[j];
-      }
-      const uint4 packed = pack8b(o);
-      dx[base + ru * vec_per_row] = packed;
-      if (colsum != nullptr) {  // column sums of the bf16 values a later pass would read
-        float q[8];
-        unpack8b(packed, q);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) csum[j] += q[j];
-      }
+      dx[base + ru * vec_per_row] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    csum[2 * j] = cs2[j].x;
+    csum[2 * j + 1] = cs2[j].y;
   }
   if (colsum != nullptr) {
 #pragma unroll
@@ -432,8 +468,14 @@ __global__ void adam_advance_kernel(float* step_dev, const float* found_inf) {
   if (found_inf == nullptr || *found_inf == 0.f) *step_dev += 1.f;
 }
 
-static inline int rows_per_block_for(int samples, int64_t spatial, int rows_step, dim3* grid) {
-  int64_t want_blocks = (148 * 8 + samples - 1) / samples;
+static inline int rows_per_block_for(int samples, int64_t spatial, int rows_step, dim3* grid,
+                                     int blocks_per_sm = 2) {
+  static const int env_bps = [] {
+    const char* e = getenv("MRI_GN_BLOCKS_PER_SM");  // tuning probe (tools/gn_probe.py)
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  if (env_bps > 0) blocks_per_sm = env_bps;
+  int64_t want_blocks = (148 * blocks_per_sm + samples - 1) / samples;
   int64_t rows_per = (spatial + want_blocks - 1) / want_blocks;
   const int64_t quantum = (int64_t)rows_step * 4;
   rows_per = (rows_per + quantum - 1) / quantum * quantum;
@@ -474,12 +516,16 @@ extern "C" int mri_gn_bwd_reduce(const void* x, const void* dy, const double* st
   const size_t smem = (size_t)threads * 24 * sizeof(float);  // [rows_step][3][C]
   const uint4* xp = reinterpret_cast<const uint4*>(x);
   const uint4* dp = reinterpret_cast<const uint4*>(dy);
-  if (silu)
-    gn_bwd_reduce_kernel<true><<<grid, threads, smem, (cudaStream_t)stream>>>(
-        xp, dp, stats, gamma, beta, sums, samples, spatial, C, groups, stats_ld, stats_cpg, eps, rpb);
-  else
-    gn_bwd_reduce_kernel<false><<<grid, threads, smem, (cudaStream_t)stream>>>(
-        xp, dp, stats, gamma, beta, sums, samples, spatial, C, groups, stats_ld, stats_cpg, eps, rpb);
+  if (spatial * vpr > 0x7fffffffLL) return set_error(-2, "mri_gn_bwd_reduce: sample too large");
+  cudaStream_t st = (cudaStream_t)stream;
+#define MRI_GN_RED(S, X)                                                                        \
+  gn_bwd_reduce_kernel<S, X><<<grid, threads, smem, st>>>(xp, dp, stats, gamma, beta, sums,     \
+                                                          samples, spatial, C, groups, stats_ld, \
+                                                          stats_cpg, eps, rpb)
+  if (x == nullptr) MRI_GN_RED(false, false);
+  else if (silu) MRI_GN_RED(true, true);
+  else MRI_GN_RED(false, true);
+#undef MRI_GN_RED
   return check_launch("gn_bwd_reduce_kernel");
 }
 
