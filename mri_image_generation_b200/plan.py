@@ -681,6 +681,26 @@ def matrix_plan(a: TView, a_box_rows: Tuple[int, int, int, int], b: TView, o: TV
                     stages=stages, name=name, flops=flops)
 
 
+def pick_wgrad_splits(base: int, total_mt: int, sms: int = 148, max_waves: int = 4) -> int:
+    """Split count for the wgrad grid (grid = base * splits CTAs, ONE resident CTA per SM, all of
+    about equal duration): the grid must FILL whole waves -- 300 CTAs on 148 SMs run as three
+    waves, the last one with 4 CTAs.  Take the wave count (<= max_waves) whose grid uses the
+    largest fraction of its SM-waves; ties go to fewer waves (fewer partial-sum reductions).
+    Every CTA's share of the M tiles is rounded up, which is part of the cost."""
+    best, best_cost = 1, None
+    for waves in range(1, max_waves + 1):
+        splits = min(total_mt, (waves * sms) // base)
+        if splits < 1:
+            continue
+        w_real = -(-(base * splits) // sms)
+        cost = w_real * -(-total_mt // splits)      # waves x tiles per CTA
+        if best_cost is None or cost < best_cost * 0.97:
+            best, best_cost = splits, cost
+    if best_cost is None:                            # base > max_waves * sms: no split at all
+        return 1
+    return best
+
+
 @dataclass
 class WgradPlan:
     """dW[class][co][b_k + c] += sum_m dY[m, co] * A_kb[m, c] over the forward plan's k-table
@@ -715,7 +735,7 @@ class WgradPlan:
         co_blocks = -(-self.n_total // 128)
         base = f.n_class * co_blocks * (-(-f.n_kb // self.group))
         total_mt = int(np.prod(f.tiles))
-        return max(1, min(total_mt, -(-2 * 148 // base)))
+        return pick_wgrad_splits(base, total_mt)
 
     def materialize(self, device) -> None:
         f = self.fwd
