@@ -316,6 +316,29 @@ int mri_adam_step(const MriAdamSeg* segs_dev, int n_segs, int64_t total_blocks, 
                   float beta2, float eps, float weight_decay, float* step_dev, const float* grad_scale,
                   const float* found_inf, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Parameter-gradient finalisation: ONE launch per backward segment turns the raw products of the
+ * backward kernels into `.grad` tensors in the reference layouts (what autograd leaves in
+ * `param.grad` for nn.ConvNd / nn.ConvTransposeNd / nn.GroupNorm, e.g.
+ * ddpm_3d_ldm/unet_attention.py:62-74).  Two segment kinds:
+ *   idx != NULL: dst[i] = ((const float*)src)[idx[i]] (0 where idx[i] < 0) -- the wgrad matrix
+ *                [class][Cout][source, tap, channel] re-ordered to [Cout][Cin][taps] /
+ *                [Cin][Cout][taps];
+ *   idx == NULL: dst[i] = (float) sum_{b < batch} ((const double*)src)[b * ld + i] -- bias and
+ *                GroupNorm gamma / beta gradients from the per-(sample, channel) fp64 sums.
+ * block0 = index of the segment's first 2048-element block; segs_dev lives in device memory.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MriFinalSeg {
+  float* dst;
+  const void* src;
+  const int32_t* idx;
+  int64_t n;
+  int64_t block0;
+  int32_t batch;
+  int32_t ld;
+} MriFinalSeg;
+int mri_grad_finalize(const MriFinalSeg* segs_dev, int n_segs, int64_t total_blocks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

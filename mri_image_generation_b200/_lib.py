@@ -92,6 +92,11 @@ class MriAdamSeg(C.Structure):
                 ("n", C.c_int64), ("block0", C.c_int64)]
 
 
+class MriFinalSeg(C.Structure):
+    _fields_ = [("dst", C.c_void_p), ("src", C.c_void_p), ("idx", C.c_void_p), ("n", C.c_int64),
+                ("block0", C.c_int64), ("batch", C.c_int32), ("ld", C.c_int32)]
+
+
 # name -> (restype, argtypes); mirrors include/mri_b200.h one to one
 _vp, _i, _i64, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
 SIGNATURES = {
@@ -111,6 +116,7 @@ SIGNATURES = {
     "mri_im2col": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mri_adam_step": (_i, [_vp, _i, _i64, _f, _f, _f, _f, _f, _vp, _vp, _vp, _vp]),
     "mri_gather_pack": (_i, [_vp, _i, _i64, _vp]),
+    "mri_grad_finalize": (_i, [_vp, _i, _i64, _vp]),
     "mri_im2col4": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mri_tap_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mri_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i64, _i, _i, _vp]),

@@ -96,6 +96,10 @@ class TimeRec:
     slice: Optional[dict] = None   # 2D: {"z_in", "zz", "zh", "s0", "s2"}
 
 
+def _noop() -> None:
+    return None
+
+
 class BackwardMixin:
     """Mixed into engine.UNetProgram."""
 
@@ -121,10 +125,62 @@ class BackwardMixin:
         self._g_last_op: Dict[int, int] = {}              # id(param) -> index of the last op of
         self._g_touched: List[int] = []                   # ... the last tape record touching it
         self.bwd_segments: List[Tuple[int, int, int, int]] = []  # (op_lo, op_hi, arena_lo, arena_hi)
+        # deferred parameter-gradient finalisers: (op index, dst, src, idx or None, batch, ld);
+        # all finalisers of a launch range run as ONE mri_grad_finalize launch at its end
+        self._final: List[Tuple[int, torch.Tensor, torch.Tensor, Optional[torch.Tensor], int, int]] = []
+        self._final_tables: Dict[Tuple[int, int], Optional[tuple]] = {}
+        self._fuse_final = os.environ.get("MRI_NO_FINAL_FUSION") != "1"
 
     def badd(self, name: str, fn: Callable[[], None]) -> None:
         self.bwd_names.append(name)
         self.bwd_ops.append(fn)
+
+    def bfinal_gather(self, dst: torch.Tensor, src: torch.Tensor, fn: Callable[[torch.Tensor], torch.Tensor],
+                      name: str = "unpack") -> None:
+        """dst <- fn(src) where fn only re-orders elements (reshape / permute / cat / slicing).
+        The element map is read off by running fn on element indices once; at run time it is a
+        segment of the range's single mri_grad_finalize launch."""
+        assert dst.is_contiguous() and src.is_contiguous() and dst.dtype == src.dtype == torch.float32
+        if not self._fuse_final:
+            self.badd(name, lambda: dst.copy_(fn(src).reshape(dst.shape)))
+            return
+        probe = torch.arange(1, src.numel() + 1, dtype=torch.int32, device=src.device).view(src.shape)
+        idx = (fn(probe).reshape(-1) - 1).to(torch.int32).contiguous()
+        assert idx.numel() == dst.numel(), (name, idx.numel(), dst.numel())
+        self._final.append((len(self.bwd_ops), dst, src, idx, 0, 0))
+        self.badd(name, _noop)
+
+    def bfinal_bsum(self, dst: torch.Tensor, src: torch.Tensor, name: str) -> None:
+        """dst[i] <- sum_b src[b, i] (src fp64 [batch, ld], dst fp32 [n <= ld])."""
+        assert dst.is_contiguous() and src.is_contiguous() and src.dim() == 2
+        assert dst.dtype == torch.float32 and src.dtype == torch.float64 and dst.numel() <= src.shape[1]
+        if not self._fuse_final:
+            n = dst.numel()
+            self.badd(name, lambda: dst.copy_(src.sum(0)[:n]))
+            return
+        self._final.append((len(self.bwd_ops), dst, src, None, src.shape[0], src.shape[1]))
+        self.badd(name, _noop)
+
+    def _final_table(self, lo: int, hi: int):
+        key = (lo, hi)
+        if key not in self._final_tables:
+            import ctypes as C
+            segs, blocks = [], 0
+            for (k, dst, src, idx, batch, ld) in self._final:
+                if lo <= k < hi:
+                    sg = _lib.MriFinalSeg()
+                    sg.dst, sg.src = dst.data_ptr(), src.data_ptr()
+                    sg.idx = idx.data_ptr() if idx is not None else None
+                    sg.n, sg.block0, sg.batch, sg.ld = dst.numel(), blocks, batch, ld
+                    blocks += -(-dst.numel() // 2048)
+                    segs.append(sg)
+            if not segs:
+                self._final_tables[key] = None
+            else:
+                arr = (_lib.MriFinalSeg * len(segs))(*segs)
+                table = torch.frombuffer(bytearray(bytes(memoryview(arr))), dtype=torch.uint8).to(self.device)
+                self._final_tables[key] = (table, len(segs), blocks)
+        return self._final_tables[key]
 
     def bgemm(self, pl, name=None) -> None:
         pl.materialize(self.device)
@@ -210,7 +266,7 @@ class BackwardMixin:
         for bp in bias_params:
             g = self.pg(bp)
             n = bp.numel()
-            self.badd("bias_grad", lambda g=g, n=n: g.copy_(cs[0].sum(0)[:n]))
+            self.bfinal_bsum(g.view(-1)[:n], cs[0], "bias_grad")
         if tproj_off is not None:
             dst = self.dtproj[:, tproj_off:tproj_off + C]
             self.badd("dtproj", lambda: dst.copy_(cs[0]))
@@ -234,37 +290,30 @@ class BackwardMixin:
             self.bwd_flops += pl.flops
             self.badd(f"wgrad:{r.name}", wg.launch)
             gw = self.pg(r.weight)
+            wshape = tuple(r.weight.shape)
             if r.kind == "up":
-                self.badd("unpack", lambda: gw.copy_(P.unpack_convT_wgrad(dw, tuple(r.weight.shape))))
+                self.bfinal_gather(gw, dw, lambda d: P.unpack_convT_wgrad(d, wshape))
             else:
                 taps_splits = r.splits
                 extra_shapes = []
                 if r.extra_weight is not None:
                     cin_e = r.extra_weight.shape[1]
-                    c0 = 0
                     for (t, has_taps) in r.sources:
                         if not has_taps:
                             extra_shapes.append((r.cout, t.shape[-1]))
                     assert sum(s[1] for s in extra_shapes) == cin_e
                 ge = self.pg(r.extra_weight) if r.extra_weight is not None else None
-                wshape = tuple(r.weight.shape)
                 rows = r.w_rows
+                shp = wshape if rows is None else (rows[1] - rows[0],) + wshape[1:]
 
-                def unpack():
-                    shp = wshape if rows is None else (rows[1] - rows[0],) + wshape[1:]
+                def unpack(d):
                     if r.kind == "matrix":
-                        g, _ = P.unpack_conv_wgrad(dw[0][:, :int(np.prod(shp[1:]))], shp)
-                        ex = []
-                    else:
-                        g, ex = P.unpack_conv_wgrad(dw[0], shp, taps_splits, extra_shapes)
-                    if rows is None:
-                        gw.copy_(g)
-                    else:
-                        gw[rows[0]:rows[1]].copy_(g)
-                    if ge is not None:
-                        ge.copy_(torch.cat(ex, dim=1).reshape(ge.shape))
+                        return P.unpack_conv_wgrad(d[0][:, :int(np.prod(shp[1:]))], shp)[0], []
+                    return P.unpack_conv_wgrad(d[0], shp, taps_splits, extra_shapes)
 
-                self.badd("unpack", unpack)
+                self.bfinal_gather(gw if rows is None else gw[rows[0]:rows[1]], dw, lambda d: unpack(d)[0])
+                if ge is not None:
+                    self.bfinal_gather(ge, dw, lambda d: torch.cat(unpack(d)[1], dim=1))
         # ---- data gradients through the adjoint plans ---------------------------------------
         if not r.need_dgrad:
             return
@@ -336,7 +385,8 @@ class BackwardMixin:
             xs, dy, st, gamma, beta, sums, B, S, C, r.groups, cpg, r.eps, r.silu))
         gg = self.pg(r.gamma)[r.c_off:r.c_off + C]
         gb = self.pg(r.beta)[r.c_off:r.c_off + C]
-        self.badd("gn_param_grad", lambda: (gg.copy_(sums[2].sum(0)), gb.copy_(sums[1].sum(0))))
+        self.bfinal_bsum(gg, sums[2], "gn_param_grad")
+        self.bfinal_bsum(gb, sums[1], "gn_param_grad")
         if r.tproj_off is not None:
             dst = self.dtproj[:, r.tproj_off:r.tproj_off + C]
             self.badd("dtproj", lambda: dst.copy_(sums[0]))
@@ -365,7 +415,7 @@ class BackwardMixin:
         wg.materialize(dev)
         self.badd(f"wgrad:{r.name}.proj", wg.launch)
         gwp = self.pg(blk.proj.weight)
-        self.badd("unpack", lambda: gwp.copy_(dwp[0].reshape(gwp.shape)))
+        self.bfinal_gather(gwp, dwp, lambda d: d[0])
         dO = torch.zeros(B, *sp, C, dtype=bf, device=dev)
         wpT = self.packed(lambda: P.pack_conv_weight(
             blk.proj.weight.detach().reshape(C, C).t().reshape(C, C, *([1] * self.ndim))))
@@ -440,7 +490,7 @@ class BackwardMixin:
         wg2.materialize(dev)
         self.badd(f"wgrad:{r.name}.qkv", wg2.launch)
         gwq = self.pg(blk.qkv.weight)
-        self.badd("unpack", lambda: gwq.copy_(dwq[0].reshape(gwq.shape)))
+        self.bfinal_gather(gwq, dwq, lambda d: d[0])
         wqT = self.packed(lambda: P.pack_conv_weight(
             blk.qkv.weight.detach().reshape(C3, C).t().reshape(C, C3, *([1] * self.ndim))))
         hn = r.hn
@@ -534,8 +584,14 @@ class BackwardMixin:
         """Enqueue backward ops [lo, hi) (all by default)."""
         if lo == 0 and self._zero_each_bwd:
             torch._foreach_zero_(self._zero_each_bwd)
+        hi = len(self.bwd_ops) if hi is None else hi
         for fn in self.bwd_ops[lo:hi]:
             fn()
+        if self._final:
+            tab = self._final_table(lo, hi)
+            if tab is not None:
+                _lib.check(_lib.load().mri_grad_finalize(tab[0].data_ptr(), tab[1], tab[2],
+                                                         _lib.current_stream_ptr()), "mri_grad_finalize")
 
     def _bwd_head(self, S: int) -> None:
         """fp32 NC[D]HW loss gradient -> the bf16 channels-last seeds of the backward list."""

@@ -468,6 +468,45 @@ __global__ void adam_advance_kernel(float* step_dev, const float* found_inf) {
   if (found_inf == nullptr || *found_inf == 0.f) *step_dev += 1.f;
 }
 
+// One launch finalises every parameter gradient of a backward segment (see MriFinalSeg).
+__global__ void __launch_bounds__(256)
+grad_finalize_kernel(const MriFinalSeg* __restrict__ segs, int n_segs) {
+  int lo = 0, hi = n_segs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (segs[mid].block0 <= (int64_t)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const MriFinalSeg sg = segs[lo];
+  const int64_t i0 = ((int64_t)blockIdx.x - sg.block0) * 2048 + threadIdx.x;
+  if (sg.idx != nullptr) {
+    const float* src = reinterpret_cast<const float*>(sg.src);
+    int32_t e[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int64_t i = i0 + (int64_t)u * 256;
+      e[u] = i < sg.n ? __ldg(sg.idx + i) : -1;
+    }
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = e[u] >= 0 ? __ldg(src + e[u]) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int64_t i = i0 + (int64_t)u * 256;
+      if (i < sg.n) sg.dst[i] = v[u];
+    }
+  } else {
+    const double* src = reinterpret_cast<const double*>(sg.src);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int64_t i = i0 + (int64_t)u * 256;
+      if (i >= sg.n) break;
+      double acc = 0.0;
+      for (int b = 0; b < sg.batch; ++b) acc += __ldg(src + (size_t)b * sg.ld + i);
+      sg.dst[i] = (float)acc;
+    }
+  }
+}
+
 static inline int rows_per_block_for(int samples, int64_t spatial, int rows_step, dim3* grid,
                                      int blocks_per_sm = 2) {
   static const int env_bps = [] {
@@ -500,6 +539,14 @@ extern "C" int mri_adam_step(const MriAdamSeg* segs_dev, int n_segs, int64_t tot
   if (rc != 0) return rc;
   adam_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, found_inf);
   return check_launch("adam_advance_kernel");
+}
+
+extern "C" int mri_grad_finalize(const MriFinalSeg* segs_dev, int n_segs, int64_t total_blocks,
+                                 void* stream) {
+  if (n_segs < 1 || total_blocks < 1) return 0;
+  if (total_blocks > 0x7fffffffLL) return set_error(-2, "mri_grad_finalize: too many blocks");
+  grad_finalize_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>(segs_dev, n_segs);
+  return check_launch("grad_finalize_kernel");
 }
 
 extern "C" int mri_gn_bwd_reduce(const void* x, const void* dy, const double* stats,

@@ -35,6 +35,13 @@ def bwd():
     for n, fn in zip(prog.bwd_names, prog.bwd_ops):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); ev.append((n, a, b))
+    if prog._final:   # deferred parameter-gradient finalisers: one launch for the whole list
+        from mri_image_generation_b200 import _lib
+        tab = prog._final_table(0, len(prog.bwd_ops))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.check(_lib.load().mri_grad_finalize(tab[0].data_ptr(), tab[1], tab[2], _lib.current_stream_ptr()), "fin")
+        b.record(); ev.append(("grad_finalize", a, b))
     torch.cuda.synchronize()
     return [(n, a.elapsed_time(b)) for n, a, b in ev]
 for _ in range(2): fwd(); bwd()
