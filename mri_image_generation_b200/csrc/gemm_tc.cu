@@ -310,8 +310,14 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
 
   if (warp == 0) {
     // ================================ TMA producer ==================================
-    // The whole warp walks the loop (converged, warp-uniform values); one elected lane issues.
-    if (xreuse) {
+    // ONE elected thread owns the whole loop (barrier waits, table reads, TMA issue).  Measured
+    // with tools/feed_probe.cu: keeping the warp converged around a per-step elect.sync costs
+    // ~130 cycles per k-step on the issue path (644 -> 512 cycles per 128x256x64 k-step once both
+    // the producer and the MMA loop are single-thread loops); the elect tells the compiler the
+    // region has exactly one thread, so TMA operands still move through uniform registers.
+    if (!elect_one_sync()) {
+      // the other 31 lanes have nothing to do until the teardown barrier
+    } else if (xreuse) {
       // k-table entries come in groups that share ONE activation tile: the group leader (entry[7]
       // = 1, or the first entry of a segment) loads both boxes 10 positions wide (x - 1 .. x + 8),
       // every entry loads its own 64-channel weight slab; the MMA reads the tap dx as the view that
@@ -335,17 +341,17 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
             f0 = __ldg(kt + 2 * (i + 1));
             f1 = __ldg(kt + 2 * (i + 1) + 1);
           }
-          const int am = uniform(e0.x), c0 = uniform(e0.y), o2 = uniform(e0.w);
-          const int o3 = uniform(e1.x), o4 = uniform(e1.y), bk = uniform(e1.z);
-          const bool need_x = (uniform(e1.w) != 0) || i == 0;
-          const int o1 = uniform(e0.z);
+          const int am = e0.x, c0 = e0.y, o2 = e0.w;
+          const int o3 = e1.x, o4 = e1.y, bk = e1.z;
+          const bool need_x = (e1.w != 0) || i == 0;
+          const int o1 = e0.z;
           // the tile stays current until the next leader (or the end of the segment)
-          const bool next_needs_x = (i + 1 < len) ? (uniform(f1.w) != 0) : true;
+          const bool next_needs_x = (i + 1 < len) ? (f1.w != 0) : true;
           mbar_wait(empty_bar(ws), wphase ^ 1u);
           if (need_x) mbar_wait(xempty_bar(xs), xphase ^ 1u);
           const uint32_t w_dst = smem_base + ws * kSlabBytes;
           const uint32_t x_dst = x_ring + xs * kXTileBytes;
-          if (elect_one_sync()) {
+          {
             const uint32_t tx = (uint32_t)block_n * 128u + (need_x ? (uint32_t)(160 * t.nbox) * 128u : 0u);
             s_winfo[ws] = (uint32_t)(o1 + 1) | (next_needs_x ? 256u : 0u);  // read by the MMA warp
             mbar_arrive_expect_tx(full_bar(ws), tx);
@@ -358,7 +364,6 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
             }
             tma_load_4d(w_dst, b_map, full_bar(ws), bk, t.n0, bz1, bz2);
           }
-          __syncwarp();
           e0 = f0;
           e1 = f1;
           if (++ws == S) {
@@ -395,16 +400,15 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
             f0 = __ldg(kt + 2 * (i + 1));
             f1 = __ldg(kt + 2 * (i + 1) + 1);
           }
-          // every lane loaded the same entry; tell the compiler so
-          const int am = uniform(e0.x), c0 = uniform(e0.y), o1 = uniform(e0.z), o2 = uniform(e0.w);
-          const int o3 = uniform(e1.x), o4 = uniform(e1.y), bk = uniform(e1.z);
+          const int am = e0.x, c0 = e0.y, o1 = e0.z, o2 = e0.w;
+          const int o3 = e1.x, o4 = e1.y, bk = e1.z;
           mbar_wait(empty_bar(stage), phase ^ 1u);
           // stage layout: normal [positions 16K][weights block_n x 128B];
           //               swap_ab [weights 16K][positions box0 16K][positions box1 16K]
           const uint32_t s0 = smem_base + stage * sbytes;
           const uint32_t x_dst = swap ? s0 + kSlabBytes : s0;
           const uint32_t w_dst = swap ? s0 : s0 + kSlabBytes;
-          if (elect_one_sync()) {
+          {
             mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
             tma_load_5d(x_dst, a_maps + am, full_bar(stage), c0, t.org[0][0] + o1, t.org[0][1] + o2,
                         t.org[0][2] + o3, t.org[0][3] + o4);
@@ -413,7 +417,6 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
                           t.org[1][1] + o2, t.org[1][2] + o3, t.org[1][3] + o4);
             tma_load_4d(w_dst, b_map, full_bar(stage), bk, t.n0, bz1, bz2);
           }
-          __syncwarp();
           e0 = f0;
           e1 = f1;
           if (++stage == S) {
@@ -425,7 +428,9 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ====================================
-    if (xreuse) {
+    // one elected thread owns the loop as well (see the producer): waits, tcgen05.mma, commits
+    if (!elect_one_sync()) {
+    } else if (xreuse) {
       const uint32_t idesc = umma_idesc_bf16(kBlockM, 256u);
       int ws = 0, xs = 0;
       uint32_t wphase = 0;
@@ -442,14 +447,14 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
         for (int i = 0; i < len; ++i) {
           mbar_wait(full_bar(ws), wphase);
           tc_fence_after();
-          const uint32_t info = (uint32_t)uniform((int)s_winfo[ws]);  // written before the arrive
+          const uint32_t info = *reinterpret_cast<volatile uint32_t*>(&s_winfo[ws]);  // written before the arrive
           const bool next_needs_x = (info & 256u) != 0u;
           const uint32_t w_addr = smem_base + ws * kSlabBytes;
           // view of the activation tile for tap dx: rows shifted by dx + 1, groups 10 rows apart
           const uint32_t x_addr = x_ring + xs * kXTileBytes + (info & 255u) * 128u;
           const uint64_t a_desc = umma_desc_k_sw128(w_addr, 1024);
           const uint64_t b_desc = umma_desc_k_sw128(x_addr, 1280);
-          if (elect_one_sync()) {
+          {
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
               umma_bf16(d0, a_desc + 2u * k, b_desc + 2u * k, idesc, (k != 0 || i != 0) ? 1u : 0u);
@@ -457,7 +462,6 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
             if (next_needs_x) umma_commit(xempty_bar(xs));     // activation tile free
             if (i == len - 1) umma_commit(tmem_full_bar(buf));
           }
-          __syncwarp();
           if (++ws == S) {
             ws = 0;
             wphase ^= 1u;
@@ -468,7 +472,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
         }
         ++seg;
       }
-      if (trace != nullptr && lane == 0) trace[3] = (uint64_t)clock64();
+      if (trace != nullptr) trace[3] = (uint64_t)clock64();
     } else {
       const uint32_t idesc = umma_idesc_bf16(kBlockM, swap ? 256u : (uint32_t)block_n);
       int stage = 0;
@@ -485,7 +489,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
         const uint32_t d0 = tmem_base + (uint32_t)(buf * 256);
         for (int i = 0; i < len; ++i) {
           mbar_wait(full_bar(stage), phase);
-          if (trace != nullptr && lane == 0 && seg == 0 && i == 0) trace[2] = (uint64_t)clock64();
+          if (trace != nullptr && seg == 0 && i == 0) trace[2] = (uint64_t)clock64();
           tc_fence_after();
           // the M = 128 operand is always the first slab of the stage
           const uint32_t m_addr = smem_base + stage * sbytes;
@@ -494,7 +498,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
           const uint64_t b_desc = umma_desc_k_sw128(n_addr, 1024);
           const uint32_t d = d0 + ((dual && (i & 1)) ? 128u : 0u);
           const uint32_t acc_first = (dual ? (i >= 2) : (i >= 1)) ? 1u : 0u;
-          if (elect_one_sync()) {
+          {
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
               // advance 16 bf16 = 32 bytes inside the 128B swizzle span: +2 in 16-byte units
@@ -503,7 +507,6 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
             umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs have read it
             if (i == len - 1) umma_commit(tmem_full_bar(buf));  // segment complete -> epilogue
           }
-          __syncwarp();
           if (++stage == S) {
             stage = 0;
             phase ^= 1u;
@@ -511,7 +514,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
         }
         ++seg;
       }
-      if (trace != nullptr && lane == 0) trace[3] = (uint64_t)clock64();
+      if (trace != nullptr) trace[3] = (uint64_t)clock64();
     }
   } else {
     // ================================ epilogue ======================================
