@@ -112,8 +112,8 @@ gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
   const CUtensorMap* dy_map = reinterpret_cast<const CUtensorMap*>(p.dy_maps) + cls;
 
   if (warp == 0) {
-    // whole warp converged, one elected lane issues (operands stay in uniform registers)
-    if (my_tiles > 0) {
+    // one elected thread owns the producer loop (see gemm_tc.cu / tools/feed_probe.cu)
+    if (my_tiles > 0 && elect_one_sync()) {
       // k-table entries of this group (registers; every lane loads the same values)
       int em[kWgMaxGroup], ec[kWgMaxGroup], eo[kWgMaxGroup][4];
       const int4* kt = reinterpret_cast<const int4*>(p.ktable) + ((size_t)cls * p.n_kb + kb0) * 2;
@@ -121,12 +121,12 @@ gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
       for (int g = 0; g < kWgMaxGroup; ++g) {
         if (g < gact) {
           const int4 e0 = __ldg(kt + 2 * g), e1 = __ldg(kt + 2 * g + 1);
-          em[g] = uniform(e0.x);
-          ec[g] = uniform(e0.y);
-          eo[g][0] = uniform(e0.z);
-          eo[g][1] = uniform(e0.w);
-          eo[g][2] = uniform(e1.x);
-          eo[g][3] = uniform(e1.y);
+          em[g] = e0.x;
+          ec[g] = e0.y;
+          eo[g][0] = e0.z;
+          eo[g][1] = e0.w;
+          eo[g][2] = e1.x;
+          eo[g][3] = e1.y;
         }
       }
       const uint32_t tx = (uint32_t)rows_in_box * 128u * (2u + (uint32_t)gact);
@@ -142,7 +142,7 @@ gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
         }
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t base = smem_base + stage * stage_bytes;
-        if (elect_one_sync()) {
+        {
           mbar_arrive_expect_tx(full_bar(stage), tx);
           tma_load_5d(base, dy_map, full_bar(stage), co0, org[0], org[1], org[2], org[3]);
           tma_load_5d(base + kTileBytes, dy_map, full_bar(stage), co0 + 64, org[0], org[1], org[2],
@@ -154,7 +154,6 @@ gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
                           org[0] + eo[g][0], org[1] + eo[g][1], org[2] + eo[g][2], org[3] + eo[g][3]);
           }
         }
-        __syncwarp();
         if (++stage == S) {
           stage = 0;
           phase ^= 1u;
@@ -162,7 +161,7 @@ gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
       }
     }
   } else if (warp == 1) {
-    if (my_tiles > 0) {
+    if (my_tiles > 0 && elect_one_sync()) {
       // D = f32, A = B = bf16, both MN-major (bits 15, 16), M = 128 (co), N = 64 * gact (channels)
       const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)(64 * gact)) | (1u << 15) | (1u << 16);
       int stage = 0;
@@ -172,7 +171,7 @@ gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
         tc_fence_after();
         const uint32_t base = smem_base + stage * stage_bytes;
         const uint32_t b_addr = base + 2 * kTileBytes;
-        if (elect_one_sync()) {
+        {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {  // 16 rows (K) per MMA = 2 swizzle atoms = 2048 B
             const uint64_t a_desc = umma_desc_mn_sw128(base + ks * 2048, kTileBytes, 1024);
@@ -182,7 +181,6 @@ gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
           umma_commit(empty_bar(stage));
           if (it == my_tiles - 1) umma_commit(tmem_full_bar);
         }
-        __syncwarp();
         if (++stage == S) {
           stage = 0;
           phase ^= 1u;
