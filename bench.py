@@ -248,22 +248,25 @@ def run_ours(args, rank, world, local_rank):
 
         # ---- per-kernel timing of the dominant kernel (tcgen05 implicit GEMM), CUDA events ---
         gemm_idx = [i for i, n in enumerate(prog.op_names) if n.startswith("gemm:")]
-        evs = []
+        gn_idx = {i for i, _ in prog.gn_ops}   # GroupNorm-apply launches: the HBM-bound family
+        evs, gn_evs = [], []
         reps = 3
         stream = torch.cuda.current_stream(dev)
         for r in range(reps + 1):
             prog._arena[:max(prog._arena_used, 4)].zero_()
             for i, fn in enumerate(prog.ops):
-                if i in gemm_idx and r > 0:
+                if (i in gemm_idx or i in gn_idx) and r > 0:
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     a.record(stream)
                     fn()
                     b.record(stream)
-                    evs.append((a, b))
+                    (evs if i in gemm_idx else gn_evs).append((a, b))
                 else:
                     fn()
         torch.cuda.synchronize(dev)
         gemm_ms = sum(a.elapsed_time(b) for a, b in evs) / reps
+        gn_ms = sum(a.elapsed_time(b) for a, b in gn_evs) / reps
+        gn_bytes = sum(nb for _, nb in prog.gn_ops)
         if args.per_op and rank == 0:
             per = {}
             for j, (a, b) in enumerate(evs):
@@ -327,6 +330,13 @@ def run_ours(args, rank, world, local_rank):
                      "flops_per_step": conv_flops, "executed_flops_per_step": executed_flops,
                      "kernel_ms_per_step": gemm_ms,
                      "share_of_step": gemm_ms / ms_per_step},
+        # second kernel family of the step: GroupNorm-apply (+SiLU, + time-embedding add, + residual),
+        # HBM-bound; algorithmic bytes = 2 B read + 2 B written per element (+2 B with a residual)
+        "roofline_hbm": {"bound": "hbm", "kernel": "gn_apply_kernel (all GroupNorm+SiLU launches of the step)",
+                         "achieved": gn_bytes / (gn_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                         "frac": gn_bytes / (gn_ms * 1e-3) / 1e9 / peaks["hbm"], "traffic": None,
+                         "bytes_per_step": gn_bytes, "kernel_ms_per_step": gn_ms,
+                         "share_of_step": gn_ms / ms_per_step, "launches_per_step": len(prog.gn_ops)},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

@@ -3,6 +3,7 @@
 // Reference call sites: see include/mri_b200.h (mri_gn_stats / mri_gn_apply).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "../../include/mri_b200.h"
 #include "common.h"
@@ -121,42 +122,64 @@ gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double
     }
   }
 
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  int64_t r1 = r0 + rows_per_block;
-  if (r1 > spatial) r1 = spatial;
+  // channel PAIRS on the packed fp32x2 pipe (FFMA2 / FMUL2 / FADD2): the pass is co-limited by
+  // instruction issue, not only by HBM; SiLU's sigmoid is 0.5 * tanh.approx(t / 2) + 0.5 (one
+  // MUFU per element, relative error 2^-11: below the bf16 resolution of the stored result)
+  float2 sc2[4], sh2[4], rb2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sc2[j] = make_float2(sc[2 * j], sc[2 * j + 1]);
+    sh2[j] = make_float2(sh[2 * j], sh[2 * j + 1]);
+    rb2[j] = make_float2(rb[2 * j], rb[2 * j + 1]);
+  }
+  auto apply = [&](const uint4& xq, const uint4& rq) -> uint4 {
+    const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w};
+    const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = make_float2(__uint_as_float(xw[j] << 16), __uint_as_float(xw[j] & 0xffff0000u));
+      float2 t = __ffma2_rn(f, sc2[j], sh2[j]);
+      if (kSilu) {
+        const float2 h = __fmul2_rn(t, make_float2(0.5f, 0.5f));
+        float2 th;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(h.x));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(h.y));
+        t = __fmul2_rn(t, __ffma2_rn(th, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f)));
+      }
+      t = __fadd2_rn(t, rb2[j]);
+      if (kResidual)
+        t = __fadd2_rn(t, make_float2(__uint_as_float(rw[j] << 16), __uint_as_float(rw[j] & 0xffff0000u)));
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(t.x, t.y);
+      ow[j] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    return make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  };
+  // rows [r0, r1) of the sample; whole batches of U rows without predicates, then the ragged end
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = (int64_t)r0 + rows_per_block > spatial ? (int)spatial : r0 + rows_per_block;
   const size_t base = (size_t)sample * spatial * vec_per_row + cv;
+  const uint4* xp = x + base;
+  const uint4* rp = kResidual ? residual + base : xp;
+  uint4* yp = y + base;
   constexpr int U = 4;
-  for (int64_t r = r0 + rsub; r < r1; r += (int64_t)rows_step * U) {
+  const int stepv = rows_step * vec_per_row;
+  int r = r0 + rsub;
+  for (; r + (U - 1) * rows_step < r1; r += U * rows_step) {
     uint4 v[U], rr[U];
+    const int o = r * vec_per_row;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t ru = r + (int64_t)u * rows_step;
-      if (ru < r1) {
-        v[u] = __ldg(x + base + ru * vec_per_row);
-        if (kResidual) rr[u] = __ldg(residual + base + ru * vec_per_row);
-      }
+      v[u] = __ldg(xp + o + u * stepv);
+      if (kResidual) rr[u] = __ldg(rp + o + u * stepv);
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t ru = r + (int64_t)u * rows_step;
-      if (ru < r1) {
-        float f[8];
-        unpack8(v[u], f);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float t = fmaf(f[k], sc[k], sh[k]);
-          if (kSilu) t = __fdividef(t, 1.0f + __expf(-t));
-          f[k] = t + rb[k];
-        }
-        if (kResidual) {
-          float q[8];
-          unpack8(rr[u], q);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) f[k] += q[k];
-        }
-        y[base + ru * vec_per_row] = pack8(f);
-      }
-    }
+    for (int u = 0; u < U; ++u) yp[o + u * stepv] = apply(v[u], kResidual ? rr[u] : v[u]);
+  }
+  for (; r < r1; r += rows_step) {
+    const uint4 v = __ldg(xp + r * vec_per_row);
+    const uint4 q = kResidual ? __ldg(rp + r * vec_per_row) : v;
+    yp[r * vec_per_row] = apply(v, q);
   }
 }
 
@@ -197,8 +220,14 @@ extern "C" int mri_gn_apply(const void* x, void* y, const double* stats, const f
   if (vec_per_row > 256) return set_error(-2, "mri_gn_apply: C > 2048 unsupported");
   const int threads = (256 / vec_per_row) * vec_per_row;
   const int rows_step = threads / vec_per_row;
-  // ~8 blocks per SM over the whole grid, each covering a multiple of 4*rows_step rows
-  int64_t want_blocks = (148 * 8 + samples - 1) / samples;
+  // ~4 blocks of 256 threads per SM (3 resident; measured best of 2/3/4/6), each covering a
+  // multiple of 4*rows_step rows
+  if (spatial * vec_per_row > 0x7fffffffLL) return set_error(-2, "mri_gn_apply: sample too large");
+  static const int env_bps = [] {
+    const char* e = getenv("MRI_GN_BLOCKS_PER_SM");  // tuning probe (tools/gn_probe.py)
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  int64_t want_blocks = (148 * (env_bps > 0 ? env_bps : 4) + samples - 1) / samples;
   int64_t rows_per = (spatial + want_blocks - 1) / want_blocks;
   const int64_t quantum = (int64_t)rows_step * 4;
   rows_per = (rows_per + quantum - 1) / quantum * quantum;

@@ -106,6 +106,7 @@ class UNetProgram(BackwardMixin):
         self._arena_used = 0
         self.gemm_flops = 0
         self.hbm_bytes_elementwise = 0
+        self.gn_ops: List[Tuple[int, int]] = []
         self._param_versions: Optional[Tuple] = None
         self._params: List[torch.Tensor] = []
 
@@ -331,7 +332,9 @@ class UNetProgram(BackwardMixin):
         B, S, C = self.B, x.spatial, x.C
         xs, st, cpg = x.t, x.stats, x.cpg
         gm, bt = gamma[c_off:c_off + C], beta[c_off:c_off + C]
-        self.hbm_bytes_elementwise += 2 * xs.numel() * 2 + (residual.numel() * 2 if residual is not None else 0)
+        nbytes = 2 * xs.numel() * 2 + (residual.numel() * 2 if residual is not None else 0)
+        self.hbm_bytes_elementwise += nbytes
+        self.gn_ops.append((len(self.ops), nbytes))   # (op index, algorithmic HBM bytes) for bench.py
 
         def fn():
             ops.gn_apply(xs, y, st, gm, bt, B, S, C, groups, cpg, eps, silu, rowbias=rowbias,
