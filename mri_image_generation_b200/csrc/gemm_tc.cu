@@ -33,6 +33,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/mri_b200.h"
@@ -52,8 +53,9 @@ constexpr int kStagingBytes = 2 * kChunkBytes;
 constexpr int kPartialLd = 256;                  // floats per row of a stream-K partial tile
 constexpr int kMaxStatGroups = 32;
 constexpr int kSmemLimit = 227 * 1024;
-constexpr int kXTileBytes = 2 * 160 * 128;       // xreuse: two boxes of (8+2) x 16 positions x 64 channels
-constexpr int kXStages = 2;
+constexpr int kXTileBytes = 2 * 160 * 128;       // xreuse 1: two boxes of (8+2) x 16 positions x 64 channels
+constexpr int kXYTileBytes = 2 * 180 * 128;      // xreuse 2: two boxes of (8+2) x (16+2) positions
+constexpr int kXStages = 3;                       // activation-tile ring (2 when a second staging set is in use)
 
 __host__ __device__ inline int stage_bytes(int block_n, int swap_ab) {
   return swap_ab ? 3 * kSlabBytes : kSlabBytes + block_n * 128;
@@ -250,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
   const int block_n = p.block_n;
   const bool swap = p.swap_ab != 0;
   const int sbytes = stage_bytes(block_n, p.swap_ab);
-  const uint32_t stag = smem_base + (uint32_t)(p.xreuse ? S * kSlabBytes + kXStages * kXTileBytes
+  const uint32_t stag = smem_base + (uint32_t)(p.xreuse ? S * kSlabBytes + (p.xreuse == 2 ? 2 * kXYTileBytes : ((p.staging2 || p.stages > 4) ? 2 : kXStages) * kXTileBytes)
                                                         : S * sbytes);  // staging follows the ring(s)
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -260,6 +262,13 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
   const uint32_t resid_bar = bar0 + 8u * (2 * kMaxStages + 4);
   auto xempty_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + 5 + s); };
   const bool xreuse = p.xreuse != 0;
+  // xreuse 1: the three kw taps of a (kd, kh, slab) group share a 10-wide tile (ring of 3 tiles,
+  // 2 beside a second staging set); xreuse 2: the nine (kh, kw) taps of a (kd, slab) group share
+  // a 10 x 18 tile (ring of 2 tiles = 18 k-steps of lookahead)
+  const bool xy = p.xreuse == 2;
+  const int XS = (xy || p.staging2 || p.stages > 4) ? 2 : kXStages;  // weight ring of 6 leaves room for 2 tiles
+  const uint32_t x_tile_bytes = xy ? (uint32_t)kXYTileBytes : (uint32_t)kXTileBytes;
+  const int x_box_rows = xy ? 180 : 160;
   const uint32_t x_ring = smem_base + (uint32_t)(S * kSlabBytes);  // xreuse: after the weight ring
 
   const int n_kb = p.n_kb;
@@ -298,8 +307,11 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_holder;
   // profiling: [0] kernel entry (globaltimer ns), [1] setup done, [2] first stage landed,
-  // [3] last MMA issued, [4] last accumulator complete, [5] epilogue done (clock64 cycles)
-  uint64_t* trace = p.trace != nullptr ? p.trace + (size_t)blockIdx.x * 8 : nullptr;
+  // [3] last MMA issued, [4] last accumulator complete, [5] epilogue done (clock64 cycles),
+  // [6] exit (ns); cycles spent waiting: [7] MMA thread on full barriers (operand starvation),
+  // [8] MMA thread on tmem_empty (epilogue back-pressure), [9] producer on empty barriers
+  // (ring full: healthy), [10] producer on the activation ring, [11] segments run by the CTA
+  uint64_t* trace = p.trace != nullptr ? p.trace + (size_t)blockIdx.x * 16 : nullptr;
   if (trace != nullptr && threadIdx.x == 0) {
     trace[0] = globaltimer_ns();
     trace[1] = (uint64_t)clock64();
@@ -307,6 +319,16 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
 
   const CUtensorMap* a_maps = reinterpret_cast<const CUtensorMap*>(p.a_maps);
   const CUtensorMap* b_map = reinterpret_cast<const CUtensorMap*>(p.b_map);
+  // barrier wait that charges its duration to a trace slot (profiling runs only)
+  auto wait_t = [&](uint32_t bar, uint32_t parity, int slot) {
+    if (trace == nullptr) {
+      mbar_wait(bar, parity);
+    } else {
+      const long long t0 = clock64();
+      mbar_wait(bar, parity);
+      trace[slot] += (uint64_t)(clock64() - t0);
+    }
+  };
 
   if (warp == 0) {
     // ================================ TMA producer ==================================
@@ -347,20 +369,24 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
           const int o1 = e0.z;
           // the tile stays current until the next leader (or the end of the segment)
           const bool next_needs_x = (i + 1 < len) ? (f1.w != 0) : true;
-          mbar_wait(empty_bar(ws), wphase ^ 1u);
-          if (need_x) mbar_wait(xempty_bar(xs), xphase ^ 1u);
+          wait_t(empty_bar(ws), wphase ^ 1u, 9);
+          if (need_x) wait_t(xempty_bar(xs), xphase ^ 1u, 10);
           const uint32_t w_dst = smem_base + ws * kSlabBytes;
-          const uint32_t x_dst = x_ring + xs * kXTileBytes;
+          const uint32_t x_dst = x_ring + xs * x_tile_bytes;
           {
-            const uint32_t tx = (uint32_t)block_n * 128u + (need_x ? (uint32_t)(160 * t.nbox) * 128u : 0u);
-            s_winfo[ws] = (uint32_t)(o1 + 1) | (next_needs_x ? 256u : 0u);  // read by the MMA warp
+            const uint32_t tx =
+                (uint32_t)block_n * 128u + (need_x ? (uint32_t)(x_box_rows * t.nbox) * 128u : 0u);
+            // row offset of this tap's view inside the tile (read by the MMA thread)
+            const uint32_t row_off = xy ? (uint32_t)((o2 + 1) * 10 + o1 + 1) : (uint32_t)(o1 + 1);
+            s_winfo[ws] = row_off | (next_needs_x ? 256u : 0u);
             mbar_arrive_expect_tx(full_bar(ws), tx);
             if (need_x) {
-              tma_load_5d(x_dst, a_maps + am, full_bar(ws), c0, t.org[0][0] - 1, t.org[0][1] + o2,
+              const int y0 = xy ? -1 : o2;  // the 18-line tile starts one line above the box
+              tma_load_5d(x_dst, a_maps + am, full_bar(ws), c0, t.org[0][0] - 1, t.org[0][1] + y0,
                           t.org[0][2] + o3, t.org[0][3] + o4);
               if (t.nbox == 2)
-                tma_load_5d(x_dst + kXTileBytes / 2, a_maps + am, full_bar(ws), c0, t.org[1][0] - 1,
-                            t.org[1][1] + o2, t.org[1][2] + o3, t.org[1][3] + o4);
+                tma_load_5d(x_dst + x_tile_bytes / 2, a_maps + am, full_bar(ws), c0, t.org[1][0] - 1,
+                            t.org[1][1] + y0, t.org[1][2] + o3, t.org[1][3] + o4);
             }
             tma_load_4d(w_dst, b_map, full_bar(ws), bk, t.n0, bz1, bz2);
           }
@@ -371,7 +397,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
             wphase ^= 1u;
           }
           if (next_needs_x) {
-            if (++xs == kXStages) {
+            if (++xs == XS) {
               xs = 0;
               xphase ^= 1u;
             }
@@ -402,7 +428,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
           }
           const int am = e0.x, c0 = e0.y, o1 = e0.z, o2 = e0.w;
           const int o3 = e1.x, o4 = e1.y, bk = e1.z;
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+          wait_t(empty_bar(stage), phase ^ 1u, 9);
           // stage layout: normal [positions 16K][weights block_n x 128B];
           //               swap_ab [weights 16K][positions box0 16K][positions box1 16K]
           const uint32_t s0 = smem_base + stage * sbytes;
@@ -432,6 +458,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
     if (!elect_one_sync()) {
     } else if (xreuse) {
       const uint32_t idesc = umma_idesc_bf16(kBlockM, 256u);
+      const uint32_t idesc128 = umma_idesc_bf16(kBlockM, 128u);
       int ws = 0, xs = 0;
       uint32_t wphase = 0;
       int seg = 0;
@@ -441,23 +468,34 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
       long long seg_end;
       while (it.next(tile, kb0, len, seg_end)) {
         const int buf = seg & 1;
-        mbar_wait(tmem_empty_bar(buf), (((uint32_t)seg >> 1) & 1u) ^ 1u);
+        wait_t(tmem_empty_bar(buf), (((uint32_t)seg >> 1) & 1u) ^ 1u, 8);
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(buf * 256);
         for (int i = 0; i < len; ++i) {
-          mbar_wait(full_bar(ws), wphase);
+          wait_t(full_bar(ws), wphase, 7);
           tc_fence_after();
           const uint32_t info = *reinterpret_cast<volatile uint32_t*>(&s_winfo[ws]);  // written before the arrive
           const bool next_needs_x = (info & 256u) != 0u;
           const uint32_t w_addr = smem_base + ws * kSlabBytes;
           // view of the activation tile for tap dx: rows shifted by dx + 1, groups 10 rows apart
-          const uint32_t x_addr = x_ring + xs * kXTileBytes + (info & 255u) * 128u;
+          const uint32_t x_addr = x_ring + xs * x_tile_bytes + (info & 255u) * 128u;
           const uint64_t a_desc = umma_desc_k_sw128(w_addr, 1024);
           const uint64_t b_desc = umma_desc_k_sw128(x_addr, 1280);
-          {
+          if (xy) {
+            // 18-line tiles: the second box starts 180 rows in, which breaks the uniform group
+            // stride of a 256-row operand -> one N = 128 instruction per box (same pipe rate)
+            const uint64_t b_desc1 = umma_desc_k_sw128(x_addr + (uint32_t)kXYTileBytes / 2u, 1280);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              umma_bf16(d0, a_desc + 2u * k, b_desc + 2u * k, idesc128, (k != 0 || i != 0) ? 1u : 0u);
+              umma_bf16(d0 + 128u, a_desc + 2u * k, b_desc1 + 2u * k, idesc128, (k != 0 || i != 0) ? 1u : 0u);
+            }
+          } else {
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
               umma_bf16(d0, a_desc + 2u * k, b_desc + 2u * k, idesc, (k != 0 || i != 0) ? 1u : 0u);
+          }
+          {
             umma_commit(empty_bar(ws));                        // weight slab free
             if (next_needs_x) umma_commit(xempty_bar(xs));     // activation tile free
             if (i == len - 1) umma_commit(tmem_full_bar(buf));
@@ -467,12 +505,15 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
             wphase ^= 1u;
           }
           if (next_needs_x) {
-            if (++xs == kXStages) xs = 0;
+            if (++xs == XS) xs = 0;
           }
         }
         ++seg;
       }
-      if (trace != nullptr) trace[3] = (uint64_t)clock64();
+      if (trace != nullptr) {
+        trace[3] = (uint64_t)clock64();
+        trace[11] = (uint64_t)seg;
+      }
     } else {
       const uint32_t idesc = umma_idesc_bf16(kBlockM, swap ? 256u : (uint32_t)block_n);
       int stage = 0;
@@ -484,11 +525,11 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
       long long seg_end;
       while (it.next(tile, kb0, len, seg_end)) {
         const int buf = seg & 1;
-        mbar_wait(tmem_empty_bar(buf), (((uint32_t)seg >> 1) & 1u) ^ 1u);
+        wait_t(tmem_empty_bar(buf), (((uint32_t)seg >> 1) & 1u) ^ 1u, 8);
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(buf * 256);
         for (int i = 0; i < len; ++i) {
-          mbar_wait(full_bar(stage), phase);
+          wait_t(full_bar(stage), phase, 7);
           if (trace != nullptr && seg == 0 && i == 0) trace[2] = (uint64_t)clock64();
           tc_fence_after();
           // the M = 128 operand is always the first slab of the stage
@@ -514,7 +555,10 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
         }
         ++seg;
       }
-      if (trace != nullptr) trace[3] = (uint64_t)clock64();
+      if (trace != nullptr) {
+        trace[3] = (uint64_t)clock64();
+        trace[11] = (uint64_t)seg;
+      }
     }
   } else {
     // ================================ epilogue ======================================
@@ -1121,8 +1165,23 @@ extern "C" int mri_gemm_launch(const MriGemmArgs* a, void* stream) {
   if (a->xreuse) {
     if (!swap || a->box[0] != 8 || rows != kBlockM || a->bz_sel[0] > 1 || a->bz_sel[1] > 1)
       return set_error(-2, "mri_gemm_launch: xreuse needs swap_ab and boxes of 8 x 16 positions");
-    k.stages = k.staging2 ? 4 : 6;  // weight ring; the activation ring has kXStages tiles
-    smem = k.stages * kSlabBytes + kXStages * kXTileBytes + kStagingBytes * (k.staging2 ? 2 : 1) + 1024;
+    // per-CTA wait trace (tools/gemm_probe.py trace=1): the MMA thread waits for operands ~24 %
+    // of the time with either ring split -- TMA latency under load is ~2 k cycles and the rings
+    // hold ~3 k cycles of work
+    static const int env_xring = [] {
+      const char* e = getenv("MRI_GEMM_XRING");  // tuning probe: 3 = weight ring 4 + 3 tiles
+      return e != nullptr ? atoi(e) : 0;
+    }();
+    // weight ring 6 + 2 activation tiles vs 4 + 3: within 1 % of each other on the same GPU
+    // (the step is power-bound, not latency-bound); 6 + 2 is the default
+    k.stages = (env_xring == 3 || k.staging2) ? 4 : 6;
+    smem = k.stages * kSlabBytes + ((k.staging2 || k.stages > 4) ? 2 : kXStages) * kXTileBytes +
+           kStagingBytes * (k.staging2 ? 2 : 1) + 1024;
+    if (a->xreuse == 2) {  // 10 x 18 tiles shared by nine taps: 2 tiles, weight ring of 6 (4)
+      if (a->box[1] != 16) return set_error(-2, "mri_gemm_launch: xreuse 2 needs boxes of 8 x 16 positions");
+      k.stages = k.staging2 ? 4 : 6;
+      smem = k.stages * kSlabBytes + 2 * kXYTileBytes + kStagingBytes * (k.staging2 ? 2 : 1) + 1024;
+    }
   }
   long long grid = tiles < n_sms ? tiles : n_sms;
   if (k.sched != 0) {

@@ -182,7 +182,7 @@ class GemmPlan:
     stages: int = 0
     sched: Optional[int] = None
     swap_ab: Optional[bool] = None
-    xreuse: bool = False                       # k-table groups share one 10-wide activation tile
+    xreuse: int = 0                            # 1: three kw taps share a 10-wide tile; 2: nine (kh, kw) taps share a 10 x 18 tile
     a_maps_std: Optional[List[MapSpec]] = None  # xreuse: the same inputs with the standard boxes
     trace: Optional[torch.Tensor] = None     # int64 [grid, 8]: per-CTA timestamps (profiling only)
     name: str = ""
@@ -288,7 +288,7 @@ class GemmPlan:
         a.sk_partials, a.sk_flags, a.sk_ctas = ws.partials_ptr, ws.flags_ptr, ws.n_ctas
         a.sched = self.pick_sched(ws.n_ctas)
         a.swap_ab = 1 if self.pick_swap() else 0
-        a.xreuse = 1 if self.xreuse else 0
+        a.xreuse = int(self.xreuse)
         if self.xreuse and not a.swap_ab:
             raise _lib.MriError("xreuse plans need the swap_ab tile shape")
         a.trace = self.trace.data_ptr() if self.trace is not None else None
@@ -495,7 +495,7 @@ def _spatial_ext(y: torch.Tensor, ndim: int):
 def conv_plan(sources: Sequence[ConvSource], wmat: torch.Tensor, y: torch.Tensor, ksize: int,
               *, bias=None, rowbias=None, rowbias_ld=0, residual: Optional[torch.Tensor] = None,
               stats=None, stats_cpg=0, block_n: Optional[int] = None, stages=0, name="",
-              xreuse: Optional[bool] = None) -> GemmPlan:
+              xreuse=None) -> GemmPlan:
     """Stride-1, pad k//2 convolution over the channel-concatenation of `sources`.
 
     wmat: packed weights [Cout_pad, K] bf16, K = sum over sources of (taps * C_i), see
@@ -508,10 +508,22 @@ def conv_plan(sources: Sequence[ConvSource], wmat: torch.Tensor, y: torch.Tensor
     p = ksize // 2
     # "xreuse": with boxes of 8 x 16 positions the three kw taps of a (kd, kh, channel slab) read
     # ONE activation tile loaded 10 positions wide -> a third of the activation traffic from L2
-    env_x = os.environ.get("MRI_GEMM_XREUSE")
-    want_x = xreuse if xreuse is not None else (env_x != "0")
-    use_x = bool(want_x and ksize == 3 and bn == 128 and cout_pad % 64 == 0 and box[0] == 8
+    env_x = os.environ.get("MRI_GEMM_XREUSE")   # tuning experiments: 0 / 1 / 2
+    # default 1.  Level 2 (10 x 18 tile, nine taps) is correct but SLOWER on B200 (1165 vs 1206
+    # TFLOP/s at the cfg4 top level): the second box of an 18-line tile breaks the uniform group
+    # stride of a 256-row operand, so every k-step needs two N = 128 instructions, which read the
+    # weight operand twice -- 128 B/clk of shared-memory operand traffic, the whole budget.
+    if xreuse is None:
+        level = int(env_x) if env_x in ("0", "1", "2") else 1
+    elif isinstance(xreuse, bool):
+        level = 1 if xreuse else 0
+    else:
+        level = int(xreuse)
+    use_x = bool(level >= 1 and ksize == 3 and bn == 128 and cout_pad % 64 == 0 and box[0] == 8
                  and int(np.prod(box)) == BLOCK_M and os.environ.get("MRI_GEMM_SWAP", "1") != "0")
+    # level 2: boxes of exactly 8 x 16 x 1 x 1 positions load a 10 x 18 tile once per (kd, channel
+    # slab) and all nine (kh, kw) taps read shifted views of it
+    use_xy = bool(use_x and level >= 2 and box[1] == 16)
     a_maps, a_std, rows = [], [], []
     bk = 0
     for si, src in enumerate(sources):
@@ -519,12 +531,25 @@ def conv_plan(sources: Sequence[ConvSource], wmat: torch.Tensor, y: torch.Tensor
         assert Ci % BLOCK_K == 0, f"source channels {Ci} must be a multiple of 64"
         assert list(src.x.shape[:-1]) == list(y.shape[:-1])
         a_std.append(MapSpec(_act_view(src.x, ndim), (BLOCK_K,) + box, 3))
-        a_maps.append(MapSpec(_act_view(src.x, ndim), (BLOCK_K, 10) + tuple(box[1:]), 3) if use_x
-                      else a_std[-1])
+        xbox = (BLOCK_K, 10, 18) + tuple(box[2:]) if use_xy else (BLOCK_K, 10) + tuple(box[1:])
+        a_maps.append(MapSpec(_act_view(src.x, ndim), xbox, 3) if use_x else a_std[-1])
         if not src.taps:  # centre tap only (folded 1x1 skip): its own group
             for c0 in range(0, Ci, BLOCK_K):
                 rows.append([si, c0, 0, 0, 0, 0, bk, 1])
                 bk += BLOCK_K
+        elif use_xy:
+            for ot in itertools.product(range(ksize), repeat=ndim - 2):  # (kd,) / ()
+                for c0 in range(0, Ci, BLOCK_K):
+                    for kh in range(ksize):
+                        for kw in range(ksize):
+                            tap = tuple(ot) + (kh, kw)
+                            tap_index = 0
+                            for t_ in tap:
+                                tap_index = tap_index * ksize + t_
+                            offs = [k - p for k in reversed(tap)] + [0] * (4 - ndim)
+                            rows.append([si, c0] + offs + [bk + tap_index * Ci + c0,
+                                                           1 if (kh == 0 and kw == 0) else 0])
+            bk += (ksize ** ndim) * Ci
         elif use_x:
             for ot in itertools.product(range(ksize), repeat=ndim - 1):  # (kd, kh) / (kh,)
                 for c0 in range(0, Ci, BLOCK_K):
@@ -559,7 +584,7 @@ def conv_plan(sources: Sequence[ConvSource], wmat: torch.Tensor, y: torch.Tensor
                     n_total=cout_pad, sample_dim=sample_dim, bias=bias, rowbias=rowbias,
                     rowbias_ld=rowbias_ld, stats=stats, stats_ld=(stats.shape[1] if stats is not None else 0),
                     stats_cpg=stats_cpg, stages=stages, name=name, flops=2 * m_rows * cout_pad * bk,
-                    xreuse=use_x, a_maps_std=a_std if use_x else None)
+                    xreuse=(2 if use_xy else 1) if use_x else 0, a_maps_std=a_std if use_x else None)
 
 
 def _rup8(n: int) -> int:

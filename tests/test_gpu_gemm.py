@@ -53,8 +53,12 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("nd,sp,N,cins,cout,k", CASES)
-def test_conv_stride1(P, nd, sp, N, cins, cout, k):
+@pytest.mark.parametrize("nd,sp,N,cins,cout,k,xr", [c + (None,) for c in CASES] + [
+    (3, (12, 32, 16), 2, [128], 128, 3, 2),   # 10 x 18 halo tiles shared by the nine (kh, kw) taps
+    (2, (48, 24), 3, [64, 64], 128, 3, 2),
+    (3, (12, 32, 16), 2, [128], 128, 3, 0),   # no tap sharing at all
+])
+def test_conv_stride1(P, nd, sp, N, cins, cout, k, xr):
     torch.manual_seed(1)
     dev = "cuda"
     xs = [torch.randn(N, c, *sp, device=dev) for c in cins]
@@ -72,7 +76,9 @@ def test_conv_stride1(P, nd, sp, N, cins, cout, k):
     groups = 8 if cout % 64 == 0 else 2
     stats = torch.zeros(N, groups, 2, device=dev, dtype=torch.float64)
     pl = P.conv_plan([P.ConvSource(a) for a in acts], wm, y, k, bias=bias, rowbias=rb,
-                     rowbias_ld=cout + 8, residual=res, stats=stats, stats_cpg=cout // groups)
+                     rowbias_ld=cout + 8, residual=res, stats=stats, stats_cpg=cout // groups, xreuse=xr)
+    if xr is not None:
+        assert pl.xreuse == xr, (pl.xreuse, pl.box)
     pl.materialize(dev)
     pl.launch()
     torch.cuda.synchronize()

@@ -45,7 +45,11 @@ def test_conv_concat_skipfold_residual(nd, sp):
     if sp[-1] == 8:  # boxes of 8 x 16 positions: the kw taps share one 10-wide activation tile
         assert pl.xreuse and pl.box[0] == 8 and pl.a_maps[0].box[1] == 10 and pl.a_maps_std[0].box[1] == 8
         lead = pl.ktable[0, :, 7]
-        assert lead.sum() == pl.n_kb - 2 * (pl.n_kb - 1) // 3  # one leader per (kd, kh, slab) + the 1x1 slab
+        if pl.xreuse == 2:  # 8 x 16 boxes: the nine (kh, kw) taps share one 10 x 18 tile
+            assert pl.a_maps[0].box[2] == 18
+            assert lead.sum() == (pl.n_kb - 1) // 9 + 1     # one leader per (kd, slab) + the 1x1 slab
+        else:
+            assert lead.sum() == pl.n_kb - 2 * (pl.n_kb - 1) // 3  # one leader per (kd, kh, slab) + the 1x1 slab
     pl.simulate()
     assert rel(nchw(y), ref) < TOL
     r = ref.reshape(N, 8, -1)

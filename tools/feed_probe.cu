@@ -31,13 +31,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* map, uint3
       : "memory");
 }
 
-__global__ void __launch_bounds__(64, 1)
+__global__ void __launch_bounds__(192, 1)
 feed_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant__ CUtensorMap x_map,
             int steps, int reuse, int n_per_mma, int rows_per_cta, long long* cycles, int kWStages,
             int no_tma, int ksteps_per_slot, int flags) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxWStages + kXStages + 1];
   __shared__ uint32_t tmem_holder;
+  __shared__ uint32_t done_flag;
+  __shared__ float scratch[192];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t x_ring = base + kWStages * kWBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -47,6 +49,7 @@ feed_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant__ C
   auto xempty_bar = [&](int s) { return bar0 + 8u * (2 * kMaxWStages + s); };
   const uint32_t done_bar = bar0 + 8u * (2 * kMaxWStages + kXStages);
   if (threadIdx.x == 0) {
+    done_flag = 0u;
     for (int s = 0; s < kWStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -111,6 +114,20 @@ feed_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant__ C
       __syncwarp();
       if (++ws == kWStages) { ws = 0; wphase ^= 1u; }
       if (next_needs_x && ++xs == kXStages) { xs = 0; xphase ^= 1u; }
+    }
+  } else if (warp >= 2) {
+    // "epilogue-like" co-resident warps (flags bit 6): dependent FMA / shared-memory work on all
+    // four SM sub-partitions until the MMA warp is done -- do they slow the issue threads down?
+    if (flags & 64) {
+      float acc = (float)threadIdx.x;
+      volatile uint32_t* flag = &done_flag;
+      uint32_t it = 0;
+      while (*flag == 0u) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc = fmaf(acc, 1.0001f, 0.5f);
+        scratch[threadIdx.x] = acc + (float)(it++);
+      }
+      if (acc == 1.2345f) cycles[0] = 0;
     }
   } else if (flags & 8) {
     // variant: ONE elected thread runs the whole issue loop (waits, MMAs, commits); the ring
@@ -182,7 +199,10 @@ feed_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant__ C
   }
   if (warp == 1) {
     mbar_wait(done_bar, 0);
-    if (lane == 0) cycles[blockIdx.x] = clock64() - t0;
+    if (lane == 0) {
+      cycles[blockIdx.x] = clock64() - t0;
+      *reinterpret_cast<volatile uint32_t*>(&done_flag) = 1u;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -228,26 +248,24 @@ int main() {
   const int steps = 50000;
   struct Case { int n, reuse, stages, no_tma, kps, flags; const char* what; };
   const Case cases[] = {
-      {256, 0, 10, 1, 1, 16, "warp-converged loops (kernel as is), barriers only"},
-      {256, 0, 10, 1, 1, 8, "single-thread MMA loop, barriers only"},
+      {256, 0, 10, 1, 1, 16, "warp-converged loops (revisions B/C), barriers only"},
       {256, 0, 10, 1, 1, 8 | 32, "single-thread MMA + producer loops, barriers only"},
-      {256, 0, 10, 0, 1, 8, "single-thread MMA loop, weight TMA"},
-      {256, 0, 10, 0, 1, 8 | 32, "single-thread MMA + producer loops, weight TMA"},
-      {256, 0, 4, 0, 1, 8 | 32, "  ... ring of 4"},
+      {256, 0, 10, 0, 1, 8 | 32, "  ... + weight TMA"},
       {256, 27, 10, 0, 1, 8 | 32, "  ... + activation tile every 27 k-steps"},
       {256, 9, 10, 0, 1, 8 | 32, "  ... + activation tile every 9 k-steps"},
       {256, 3, 10, 0, 1, 8 | 32, "  ... + activation tile every 3 k-steps"},
-      {256, 3, 4, 0, 1, 8 | 32, "  ... + activation tile every 3 k-steps, ring of 4"},
+      {256, 3, 6, 0, 1, 8 | 32, "  ... + activation tile every 3 k-steps, ring of 6"},
+      {256, 3, 6, 0, 1, 8 | 32 | 64, "  ... ring of 6, four busy co-resident warps"},
+      {256, 3, 10, 0, 1, 8 | 32 | 64, "  ... ring of 10, four busy co-resident warps"},
       {256, 1, 10, 0, 1, 8 | 32, "  ... + activation tile every k-step"},
-      {256, 1, 4, 0, 1, 8 | 32, "  ... + activation tile every k-step, ring of 4"},
-      {256, 3, 4, 0, 1, 16, "kernel as is: activation tile every 3 k-steps, ring of 4"},
-      {256, 1, 4, 0, 1, 16, "kernel as is: activation tile every k-step, ring of 4"},
+      {256, 3, 4, 0, 1, 16, "revisions B/C: activation tile every 3 k-steps, ring of 4"},
+      {256, 1, 4, 0, 1, 16, "revisions B/C: activation tile every k-step, ring of 4"},
   };
   for (const Case& cs : cases) {
     float ms = 0;
     for (int rep = 0; rep < 2; ++rep) {
       cudaEventRecord(e0);
-      feed_kernel<<<148, 64, smem>>>(wm, xm, steps, cs.reuse, cs.n, rows_per_cta, d_cycles, cs.stages, cs.no_tma,
+      feed_kernel<<<148, 192, smem>>>(wm, xm, steps, cs.reuse, cs.n, rows_per_cta, d_cycles, cs.stages, cs.no_tma,
                                      cs.kps, cs.flags);
       cudaEventRecord(e1);
       cudaError_t e = cudaDeviceSynchronize();

@@ -40,7 +40,7 @@ def build(B, sp, cins, cout, k, var):
     pl = P.conv_plan([P.ConvSource(a) for a in acts], wm, y, k, bias=bias, stats=stats,
                      stats_cpg=cout // 8 if stats is not None else 0,
                      block_n=var.get("bn") or None, stages=var.get("stages", 0),
-                     xreuse=bool(var["xr"]) if "xr" in var else None)
+                     xreuse=int(var["xr"]) if "xr" in var else None)
     if "sched" in var:
         pl.sched = var["sched"]
     if "swap" in var:
@@ -52,7 +52,7 @@ def build(B, sp, cins, cout, k, var):
         if key in var and hasattr(pl, key):
             setattr(pl, key, var[key])
     if var.get("trace"):
-        pl.trace = torch.zeros(148, 8, dtype=torch.int64, device=dev)
+        pl.trace = torch.zeros(148, 16, dtype=torch.int64, device=dev)
     pl.materialize(dev)
     return pl, (acts, wm, y, bias, stats)
 
@@ -133,6 +133,10 @@ def main():
                                 ("epilogue done", 5)):
                     d = tr[:, col] - tr[:, 1]
                     print(f"    {nm:22s} min {int(d.min()):8d}  median {int(np.median(d)):8d}  max {int(d.max()):8d} cycles")
+                for nm, col in (("MMA waits for operands", 7), ("MMA waits for epilogue", 8),
+                                ("producer waits (ring full)", 9), ("producer waits (x ring)", 10), ("segments", 11)):
+                    d = tr[:, col]
+                    print(f"    {nm:26s} min {int(d.min()):8d}  median {int(np.median(d)):8d}  max {int(d.max()):8d}")
             del pl, keep
 
 
