@@ -54,6 +54,23 @@ def load_peaks():
     return {"tflops": 1590.0, "hbm": 6650.0, "source": "fallback"}
 
 
+def load_traffic(batch: int):
+    """DRAM bytes per step of the two kernel families, from the committed `ncu` capture of this very
+    command (profiles/*_step_dram_traffic.json; the capture's command line is in its "source").
+    None when no capture matches the batch size -- a number measured under a profiler is never
+    produced at bench time."""
+    import glob
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_step_dram_traffic.json")), reverse=True):
+        try:
+            d = json.load(open(f))
+        except Exception:  # noqa: BLE001
+            continue
+        if d.get("batch_per_gpu") == batch:
+            d["file"] = os.path.relpath(f, ROOT)
+            return d
+    return None
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled through NVML DURING the timed region."""
 
@@ -307,6 +324,8 @@ def run_ours(args, rank, world, local_rank):
             cpu = {"value": 1.0 / (T_STEPS * sec), "unit": "volumes/s", "cores": threads,
                    "kind": "port",
                    "sample": f"{nfw} reverse steps at batch 1 ({sec:.2f} s each) x {T_STEPS} per volume"}
+    traffic = load_traffic(B) or {}
+    tr_gemm, tr_gn = traffic.get("gemm_tc", {}), traffic.get("gn_apply", {})
     line = {
         "metric": "volumes/sec (3D LDM DDPM sampling)", "value": value, "unit": "volumes/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
@@ -325,7 +344,9 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM, all convs + attention GEMMs)",
                      "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["tflops"], "traffic": None,
+                     "frac": achieved / peaks["tflops"], "traffic": tr_gemm.get("dram_bytes"),
+                     "traffic_note": ("DRAM bytes read + written by the %d GEMM launches of one step, ncu capture %s"
+                                      % (tr_gemm.get("launches_per_step", 0), traffic.get("file"))) if tr_gemm else None,
                      "peak_source": peaks["source"] + " (bf16_tflops_sustained)",
                      "flops_per_step": conv_flops, "executed_flops_per_step": executed_flops,
                      "kernel_ms_per_step": gemm_ms,
@@ -334,7 +355,8 @@ def run_ours(args, rank, world, local_rank):
         # HBM-bound; algorithmic bytes = 2 B read + 2 B written per element (+2 B with a residual)
         "roofline_hbm": {"bound": "hbm", "kernel": "gn_apply_kernel (all GroupNorm+SiLU launches of the step)",
                          "achieved": gn_bytes / (gn_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                         "frac": gn_bytes / (gn_ms * 1e-3) / 1e9 / peaks["hbm"], "traffic": None,
+                         "frac": gn_bytes / (gn_ms * 1e-3) / 1e9 / peaks["hbm"],
+                         "traffic": tr_gn.get("dram_bytes"),
                          "bytes_per_step": gn_bytes, "kernel_ms_per_step": gn_ms,
                          "share_of_step": gn_ms / ms_per_step, "launches_per_step": len(prog.gn_ops)},
         "cpu_baseline": cpu,

@@ -106,9 +106,15 @@ typedef struct MriGemmArgs {
   int32_t xreuse;         /* swap_ab only, box[0] == 8 and 16 groups per box: the a_maps boxes are 10
                              positions wide along x1 (x - 1 .. x + 8) and k-table entries form groups
                              (entry[7] = 1 marks a group leader) that share one activation tile; each
-                             entry's o1 in {-1, 0, 1} selects the view of that tile (3 taps per load) */
-  int32_t reserved2;
-  uint64_t* trace;        /* profiling only (normally NULL): [grid][8] per-CTA timestamps, see gemm_tc.cu */
+                             entry's o1 in {-1, 0, 1} selects the view of that tile (3 taps per load).
+                             2: box[1] == 16 as well, tiles are 10 x 18 and the nine (o2, o1) taps
+                             share one (correct, but slower on B200: see plan.conv_plan) */
+  int32_t tile_fast_dim;  /* 0..3: the x dim along which consecutive boxes (and the two boxes of a
+                             swap_ab tile) advance first.  0 = x1.  3-D stride-1 convolutions use 2
+                             (depth): a CTA then walks a column of boxes plane by plane, so the input
+                             planes shared by the kd = -1, 0, +1 taps of neighbouring tiles are still
+                             in L2 (measured: DRAM reads of a top-level cfg4 conv 3.1x -> ~1x input) */
+  uint64_t* trace;        /* profiling only (normally NULL): [grid][16] per-CTA timestamps / wait cycles, see gemm_tc.cu */
 } MriGemmArgs;
 
 /* dynamic shared memory one CTA uses for (block_n, swap_ab, requested stages; 0 = maximum) */

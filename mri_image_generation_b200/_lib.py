@@ -49,7 +49,7 @@ class MriGemmArgs(C.Structure):
         ("swap_ab", C.c_int32),
         ("staging2", C.c_int32),
         ("xreuse", C.c_int32),
-        ("reserved2", C.c_int32),
+        ("tile_fast_dim", C.c_int32),
         ("trace", C.c_void_p),
     ]
 

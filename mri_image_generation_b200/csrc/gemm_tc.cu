@@ -93,15 +93,23 @@ __device__ __forceinline__ void decode_tile(const MriGemmArgs& p, const Geom& g,
     b0 = 2 * pr;
     w.nbox = (b0 + 1 < g.boxes_per_class) ? 2 : 1;
   }
+  const int f = p.tile_fast_dim;  // boxes advance along this dim first, then x1..x4 in order
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     int b = b0 + h;
+    if (f != 0) {
+      w.tix[h][f] = b % p.tiles[f];
+      b /= p.tiles[f];
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      w.tix[h][i] = b % p.tiles[i];
-      b /= p.tiles[i];
-      w.org[h][i] = w.tix[h][i] * p.box[i];
+      if (i != f || f == 0) {
+        w.tix[h][i] = b % p.tiles[i];
+        b /= p.tiles[i];
+      }
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w.org[h][i] = w.tix[h][i] * p.box[i];
   }
 }
 
@@ -1162,6 +1170,7 @@ extern "C" int mri_gemm_launch(const MriGemmArgs* a, void* stream) {
   k.staging2 = (swap && a->n_kb <= 40) ? 1 : 0;
   k.stages = pick_stages(bn, swap, a->stages, k.staging2);
   int smem = k.stages * stage_bytes(bn, swap) + kStagingBytes * (k.staging2 ? 2 : 1) + 1024;
+  if (a->tile_fast_dim < 0 || a->tile_fast_dim > 3) return set_error(-2, "mri_gemm_launch: tile_fast_dim must be 0..3");
   if (a->xreuse) {
     if (!swap || a->box[0] != 8 || rows != kBlockM || a->bz_sel[0] > 1 || a->bz_sel[1] > 1)
       return set_error(-2, "mri_gemm_launch: xreuse needs swap_ab and boxes of 8 x 16 positions");

@@ -182,6 +182,7 @@ class GemmPlan:
     stages: int = 0
     sched: Optional[int] = None
     swap_ab: Optional[bool] = None
+    tile_fast_dim: int = 0                     # boxes are enumerated along this x dim first (see mri_b200.h)
     xreuse: int = 0                            # 1: three kw taps share a 10-wide tile; 2: nine (kh, kw) taps share a 10 x 18 tile
     a_maps_std: Optional[List[MapSpec]] = None  # xreuse: the same inputs with the standard boxes
     trace: Optional[torch.Tensor] = None     # int64 [grid, 8]: per-CTA timestamps (profiling only)
@@ -289,6 +290,7 @@ class GemmPlan:
         a.sched = self.pick_sched(ws.n_ctas)
         a.swap_ab = 1 if self.pick_swap() else 0
         a.xreuse = int(self.xreuse)
+        a.tile_fast_dim = int(self.tile_fast_dim)
         if self.xreuse and not a.swap_ab:
             raise _lib.MriError("xreuse plans need the swap_ab tile shape")
         a.trace = self.trace.data_ptr() if self.trace is not None else None
@@ -584,7 +586,16 @@ def conv_plan(sources: Sequence[ConvSource], wmat: torch.Tensor, y: torch.Tensor
                     n_total=cout_pad, sample_dim=sample_dim, bias=bias, rowbias=rowbias,
                     rowbias_ld=rowbias_ld, stats=stats, stats_ld=(stats.shape[1] if stats is not None else 0),
                     stats_cpg=stats_cpg, stages=stages, name=name, flops=2 * m_rows * cout_pad * bk,
-                    xreuse=(2 if use_xy else 1) if use_x else 0, a_maps_std=a_std if use_x else None)
+                    xreuse=(2 if use_xy else 1) if use_x else 0, a_maps_std=a_std if use_x else None,
+                    tile_fast_dim=_depth_first(ndim, ksize, tiles))
+
+
+def _depth_first(ndim: int, ksize: int, tiles) -> int:
+    """3-D convolutions with a depth extent in their filter walk the boxes depth-first (x3)."""
+    env = os.environ.get("MRI_GEMM_TILE_ORDER")  # tuning experiments: force a dim
+    if env is not None:
+        return int(env)
+    return 2 if (ndim == 3 and ksize > 1 and tiles[2] > 1) else 0
 
 
 def _rup8(n: int) -> int:
