@@ -266,7 +266,10 @@ typedef struct MriWgradArgs {
   int32_t dw_rows;
   int32_t dw_ld;
   int32_t stages;         /* 2..6 */
-  int32_t reserved;
+  int32_t xgroup;         /* 1: the k-table consists of kw triples (xreuse forward plans, boxes of 8 x 16
+                             positions, one class); a_maps are the 10-wide maps; group = 3 or 6: each triple
+                             reads ONE activation tile through an MN-major operand whose three 64-channel
+                             blocks are one row apart (see gemm_wgrad.cu) */
 } MriWgradArgs;
 int mri_wgrad_launch(const MriWgradArgs* args_host, void* stream);
 

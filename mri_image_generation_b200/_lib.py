@@ -71,7 +71,7 @@ class MriWgradArgs(C.Structure):
         ("dw_rows", C.c_int32),
         ("dw_ld", C.c_int32),
         ("stages", C.c_int32),
-        ("reserved", C.c_int32),
+        ("xgroup", C.c_int32),
     ]
 
 

@@ -16,6 +16,15 @@
 // vectorised reductions (red.global.add.v4.f32).  Replaces autograd's conv weight gradients for every
 // nn.Conv*/ConvTranspose* of the UNets (reference sites: include/mri_b200.h, MriGemmArgs) and,
 // with per-class maps, the dV / dK products of the attention backward.
+//
+// xgroup mode (stride-1 3x3(x3) convolutions whose forward plan shares activation tiles, boxes
+// of 8 x 16 positions): the k-table comes in triples (kw = 0, 1, 2 of one (kd, kh, channel slab)).
+// One box loaded 10 positions wide serves all three taps: the three 64-channel blocks of the
+// MN-major B operand are the SAME rows shifted by one position each, i.e. the descriptor's
+// leading-dimension offset is 128 B (one row) and its stride offset 1280 B (one 10-position
+// line) -- tools/umma_mn_probe.cu verifies that tcgen05 accepts this.  A CTA owns two triples:
+// per 128 positions it loads 32 KB of dY + 2 x 20 KB of activations for SIX taps (12 KB per tap
+// instead of 24 KB) and issues two 128 x 192 x 16 MMAs per 16 positions.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -30,6 +39,8 @@ constexpr int kWgThreads = 192;
 constexpr int kWgMaxStages = 6;
 constexpr int kTileBytes = 128 * 128;  // one [128 rows x 64 ch] bf16 box
 constexpr int kWgMaxGroup = 4;
+constexpr int kWgXTileBytes = 160 * 128;  // xgroup: one box loaded 10 positions wide (x - 1 .. x + 8) x 16 lines
+constexpr int kWgMaxTriples = 2;
 
 // MN-major operand, 128B swizzle: 64 MN elements contiguous (128 B) per K row, 8 K rows per
 // 1024-byte atom; lbo = distance between 64-element MN blocks, sbo = distance between atoms.
@@ -55,7 +66,8 @@ gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int S = p.stages;
   const int G = p.group;
-  const int stage_bytes = (2 + G) * kTileBytes;
+  const bool xg = p.xgroup != 0;                       // G = 3 * triples (3 or 6)
+  const int stage_bytes = xg ? 2 * kTileBytes + kWgMaxTriples * kWgXTileBytes : (2 + G) * kTileBytes;
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kWgMaxStages + s); };
@@ -78,7 +90,8 @@ gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
   const int my_tiles = split < total_mt ? (total_mt - split + p.splits - 1) / p.splits : 0;
 
   uint32_t tmem_cols = 64;
-  while ((int)tmem_cols < 64 * G) tmem_cols <<= 1;
+  while ((int)tmem_cols < 64 * G) tmem_cols <<= 1;  // 6 entries -> 384 columns -> 512
+  const int ntri = gact / 3;                          // xgroup: triples this CTA owns (1 or 2)
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < S; ++s) {
@@ -117,10 +130,12 @@ gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
       // k-table entries of this group (registers; every lane loads the same values)
       int em[kWgMaxGroup], ec[kWgMaxGroup], eo[kWgMaxGroup][4];
       const int4* kt = reinterpret_cast<const int4*>(p.ktable) + ((size_t)cls * p.n_kb + kb0) * 2;
+      const int n_src = xg ? ntri : gact;   // xgroup: one load per triple, at its first entry (kw = 0, o1 = -1)
+      const int e_step = xg ? 3 : 1;
 #pragma unroll
       for (int g = 0; g < kWgMaxGroup; ++g) {
-        if (g < gact) {
-          const int4 e0 = __ldg(kt + 2 * g), e1 = __ldg(kt + 2 * g + 1);
+        if (g < n_src) {
+          const int4 e0 = __ldg(kt + 2 * g * e_step), e1 = __ldg(kt + 2 * g * e_step + 1);
           em[g] = e0.x;
           ec[g] = e0.y;
           eo[g][0] = e0.z;
@@ -129,7 +144,9 @@ gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
           eo[g][3] = e1.y;
         }
       }
-      const uint32_t tx = (uint32_t)rows_in_box * 128u * (2u + (uint32_t)gact);
+      const uint32_t tx = xg ? (uint32_t)(2 * kTileBytes + ntri * kWgXTileBytes)
+                             : (uint32_t)rows_in_box * 128u * (2u + (uint32_t)gact);
+      const uint32_t x_bytes = xg ? (uint32_t)kWgXTileBytes : (uint32_t)kTileBytes;
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < my_tiles; ++it) {
@@ -149,8 +166,8 @@ gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
                       org[3]);
 #pragma unroll
           for (int g = 0; g < kWgMaxGroup; ++g) {
-            if (g < gact)
-              tma_load_5d(base + (2 + g) * kTileBytes, a_maps + em[g], full_bar(stage), ec[g],
+            if (g < n_src)
+              tma_load_5d(base + 2 * kTileBytes + g * x_bytes, a_maps + em[g], full_bar(stage), ec[g],
                           org[0] + eo[g][0], org[1] + eo[g][1], org[2] + eo[g][2], org[3] + eo[g][3]);
           }
         }
@@ -163,7 +180,8 @@ gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
   } else if (warp == 1) {
     if (my_tiles > 0 && elect_one_sync()) {
       // D = f32, A = B = bf16, both MN-major (bits 15, 16), M = 128 (co), N = 64 * gact (channels)
-      const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)(64 * gact)) | (1u << 15) | (1u << 16);
+      const uint32_t idesc =
+          umma_idesc_bf16(128, xg ? 192u : (uint32_t)(64 * gact)) | (1u << 15) | (1u << 16);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < my_tiles; ++it) {
@@ -175,8 +193,17 @@ gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {  // 16 rows (K) per MMA = 2 swizzle atoms = 2048 B
             const uint64_t a_desc = umma_desc_mn_sw128(base + ks * 2048, kTileBytes, 1024);
-            const uint64_t b_desc = umma_desc_mn_sw128(b_addr + ks * 2048, kTileBytes, 1024);
-            umma_bf16(tmem_base, a_desc, b_desc, idesc, (it | ks) != 0 ? 1u : 0u);
+            if (xg) {
+              // 16 positions = two 10-row lines of the tile; blocks of N = the taps, one row apart
+              for (int t = 0; t < ntri; ++t) {
+                const uint64_t b_desc =
+                    umma_desc_mn_sw128(b_addr + t * kWgXTileBytes + ks * 2560, 128, 1280);
+                umma_bf16(tmem_base + (uint32_t)(t * 192), a_desc, b_desc, idesc, (it | ks) != 0 ? 1u : 0u);
+              }
+            } else {
+              const uint64_t b_desc = umma_desc_mn_sw128(b_addr + ks * 2048, kTileBytes, 1024);
+              umma_bf16(tmem_base, a_desc, b_desc, idesc, (it | ks) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(empty_bar(stage));
           if (it == my_tiles - 1) umma_commit(tmem_full_bar);
@@ -200,7 +227,7 @@ gemm_wgrad_kernel(const __grid_constant__ MriWgradArgs p) {
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 16) {
         uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64 + c0), v);
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64 + c0), v);  // triples sit 192 apart: 3 * 64
         tmem_ld_wait();
         if (co < p.n_total) {
           float* dst = dw_row + bk + c0;
@@ -226,7 +253,14 @@ using namespace mri;
 
 extern "C" int mri_wgrad_launch(const MriWgradArgs* a, void* stream) {
   if (a == nullptr) return set_error(-1, "mri_wgrad_launch: null args");
-  if (a->group < 1 || a->group > kWgMaxGroup) return set_error(-2, "mri_wgrad_launch: group must be 1..4");
+  if (a->xgroup) {
+    if (a->group != 3 && a->group != 6) return set_error(-2, "mri_wgrad_launch: xgroup needs group 3 or 6");
+    if (a->n_kb % 3 != 0 || a->n_class != 1 || a->box[0] != 8 || a->box[1] != 16 ||
+        a->box[0] * a->box[1] * a->box[2] * a->box[3] != 128)
+      return set_error(-2, "mri_wgrad_launch: xgroup needs whole kw triples, one class and boxes of 8 x 16 positions");
+  } else if (a->group < 1 || a->group > kWgMaxGroup) {
+    return set_error(-2, "mri_wgrad_launch: group must be 1..4");
+  }
   if (a->stages < 2 || a->stages > kWgMaxStages) return set_error(-2, "mri_wgrad_launch: stages must be 2..6");
   if (a->n_kb < 1 || a->n_class < 1 || a->splits < 1 || a->co_blocks < 1)
     return set_error(-2, "mri_wgrad_launch: empty problem");
@@ -237,7 +271,8 @@ extern "C" int mri_wgrad_launch(const MriWgradArgs* a, void* stream) {
   }
   if (rows > 128) return set_error(-2, "mri_wgrad_launch: box has more than 128 rows");
   if (a->dw_ld % 4 != 0) return set_error(-2, "mri_wgrad_launch: dw_ld must be a multiple of 4");
-  const int smem = a->stages * (2 + a->group) * kTileBytes + 1024;
+  const int smem = a->stages * (a->xgroup ? 2 * kTileBytes + kWgMaxTriples * kWgXTileBytes
+                                            : (2 + a->group) * kTileBytes) + 1024;
   if (smem > 227 * 1024) return set_error(-2, "mri_wgrad_launch: shared memory over 227 KB");
   static int configured = 0;
   if (smem > configured) {

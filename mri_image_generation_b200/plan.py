@@ -751,6 +751,7 @@ class WgradPlan:
     name: str = ""
     dy_views: Optional[List[TView]] = None   # explicit per-class dY views (attention products)
     _args: Optional[_lib.MriWgradArgs] = field(default=None, repr=False)
+    _launches: list = field(default_factory=list, repr=False)
     _keep: list = field(default_factory=list, repr=False)
 
     def dy_specs(self) -> List[MapSpec]:
@@ -764,43 +765,87 @@ class WgradPlan:
                                (BLOCK_K,) + tuple(self.fwd.box), 3))
         return out
 
-    def pick_splits(self) -> int:
+    def pick_splits(self, n_kb: Optional[int] = None, group: Optional[int] = None) -> int:
         if self.splits:
             return self.splits
         f = self.fwd
         co_blocks = -(-self.n_total // 128)
-        base = f.n_class * co_blocks * (-(-f.n_kb // self.group))
+        n_kb = f.n_kb if n_kb is None else n_kb
+        group = self.group if group is None else group
+        base = f.n_class * co_blocks * (-(-n_kb // group))
         total_mt = int(np.prod(f.tiles))
         return pick_wgrad_splits(base, total_mt)
 
+    def runs(self) -> List[Tuple[int, int, bool]]:
+        """Cut the k-table into launches: (first entry, entries, xgroup).  Forward plans that share
+        activation tiles (xreuse 1, one class, boxes of 8 x 16 positions) list their taps as kw
+        triples; runs of whole triples go to the kernel's xgroup mode (one 10-wide tile per
+        triple), everything else (folded 1x1 slabs, other plans) to the plain mode."""
+        f = self.fwd
+        use = (f.xreuse == 1 and f.n_class == 1 and self.dy_views is None and f.a_maps_std is not None
+               and int(np.prod(f.box)) == BLOCK_M and f.box[0] == 8 and f.box[1] == 16
+               and os.environ.get("MRI_WGRAD_XGROUP", "1") != "0")
+        if not use:
+            return [(0, f.n_kb, False)]
+        kt = f.ktable[0]
+
+        def is_triple(i):
+            if i + 2 > f.n_kb - 1:
+                return False
+            r0, r1, r2 = kt[i], kt[i + 1], kt[i + 2]
+            same = all(r0[c] == r1[c] == r2[c] for c in (0, 1, 3, 4, 5))
+            return bool(same and r0[2] == -1 and r1[2] == 0 and r2[2] == 1
+                        and r0[7] == 1 and r1[7] == 0 and r2[7] == 0)
+
+        out, i = [], 0
+        while i < f.n_kb:
+            j = i
+            if is_triple(i):
+                while j < f.n_kb and is_triple(j):
+                    j += 3
+                out.append((i, j - i, True))
+            else:
+                while j < f.n_kb and not is_triple(j):
+                    j += 1
+                out.append((i, j - i, False))
+            i = j
+        return out
+
     def materialize(self, device) -> None:
         f = self.fwd
-        maps = list(f.a_maps_std or f.a_maps) + self.dy_specs()
+        std = list(f.a_maps_std or f.a_maps)
+        maps = std + list(f.a_maps) + self.dy_specs()
         blob = encode_maps(maps, device)
         kt = torch.from_numpy(np.ascontiguousarray(f.ktable, dtype=np.int32)).to(device)
         self._keep = [blob, kt]
-        a = _lib.MriWgradArgs()
-        a.a_maps = blob.data_ptr()
-        a.dy_maps = blob.data_ptr() + 128 * len(f.a_maps)
-        a.ktable = kt.data_ptr()
-        a.n_kb, a.n_class = f.n_kb, f.n_class
-        for i in range(4):
-            a.tiles[i], a.box[i] = f.tiles[i], f.box[i]
-        a.n_total = self.n_total
-        a.co_blocks = -(-self.n_total // 128)
-        a.splits = self.pick_splits()
-        a.group = self.group
         assert self.dw.dtype == torch.float32 and self.dw.is_contiguous() and self.dw.dim() == 3
         assert self.dw.shape[0] == f.n_class and self.dw.shape[1] >= self.n_total
-        a.dw = self.dw.data_ptr()
-        a.dw_rows, a.dw_ld = self.dw.shape[1], self.dw.shape[2]
-        a.stages = self.stages
-        self._args = a
+        self._launches = []
+        for (k0, nk, xg) in self.runs():
+            a = _lib.MriWgradArgs()
+            a.a_maps = blob.data_ptr() + (128 * len(std) if xg else 0)
+            a.dy_maps = blob.data_ptr() + 128 * (len(std) + len(f.a_maps))
+            # sub-ranges of the table are only formed for single-class plans (runs())
+            a.ktable = kt.data_ptr() + k0 * 8 * 4
+            a.n_kb, a.n_class = nk, f.n_class
+            for i in range(4):
+                a.tiles[i], a.box[i] = f.tiles[i], f.box[i]
+            a.n_total = self.n_total
+            a.co_blocks = -(-self.n_total // 128)
+            a.group = 6 if xg else self.group
+            a.splits = self.pick_splits(nk, a.group)
+            a.dw = self.dw.data_ptr()
+            a.dw_rows, a.dw_ld = self.dw.shape[1], self.dw.shape[2]
+            a.stages = 3 if xg else self.stages
+            a.xgroup = 1 if xg else 0
+            self._launches.append(a)
+        self._args = self._launches[0]
 
     def launch(self, stream: Optional[int] = None) -> None:
-        rc = _lib.load().mri_wgrad_launch(C.byref(self._args),
-                                          stream if stream is not None else _lib.current_stream_ptr())
-        _lib.check(rc, f"mri_wgrad_launch[{self.name}]")
+        st = stream if stream is not None else _lib.current_stream_ptr()
+        for a in self._launches:
+            rc = _lib.load().mri_wgrad_launch(C.byref(a), st)
+            _lib.check(rc, f"mri_wgrad_launch[{self.name}]")
 
     def simulate(self) -> None:
         """CPU emulation (tests): same tables, TMA zero fill."""

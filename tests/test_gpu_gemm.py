@@ -155,7 +155,9 @@ def test_matrix_fp32_out(P):
 # backward: weight gradients (MN-major tcgen05 GEMM) and data gradients (fprop kernel on the
 # adjoint plan) vs torch autograd on the same bf16-rounded operands
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("nd,sp,N", [(3, (8, 12, 10), 2), (2, (30, 30), 3), (3, (10, 12, 10), 1)])
+@pytest.mark.parametrize("nd,sp,N", [(3, (8, 12, 10), 2), (2, (30, 30), 3), (3, (10, 12, 10), 1),
+                                     (3, (12, 32, 16), 2), (2, (48, 24), 3),   # 8 x 16 boxes: wgrad xgroup mode
+                                     (3, (5, 16, 8), 1)])                        # ... with an odd number of boxes
 def test_wgrad_and_dgrad_stride1_concat_skipfold(P, nd, sp, N):
     torch.manual_seed(5)
     dev = "cuda"
