@@ -1,5 +1,6 @@
-// Implicit-GEMM convolution / GEMM on Blackwell tensor cores (tcgen05 + TMEM + TMA), revision B:
-// persistent CTAs, stream-K work split, epilogue overlapped with the next tile's main loop.
+// Implicit-GEMM convolution / GEMM on Blackwell tensor cores (tcgen05 + TMEM + TMA), revision D:
+// persistent CTAs, stream-K work split, epilogue overlapped with the next tile's main loop,
+// single-thread producer / MMA-issue loops.
 //
 //   D[m, n] = sum_k A[m, k] * B[n, k]      A, B bf16 (K-major, 128B swizzle), D fp32 in TMEM
 //   m = output position (a box of up to 128 positions), n = output channel, k = (tap, channel)
@@ -8,19 +9,21 @@
 // whole tiles, plus -- for the tiles that would leave the last wave under-filled -- an equal
 // share of their K loops ("stream-K").
 //
-// Two tile shapes (measured on B200: one tcgen05.mma with M = 128 occupies the tensor pipe for
-// ~137 cycles whatever N <= 128 is, and ~150 cycles at N = 256, so only N = 256 instructions
-// come near the pipe's peak):
+// Two tile shapes (the M = 128 operand is read from shared memory once per instruction, so N = 256
+// halves that operand's traffic per FLOP; tools/umma_rate_probe.cu: the pipe itself runs N = 128
+// and N = 256 instructions at full rate):
 //   swap_ab = 1  (convolutions with Cout % 128 == 0): the WEIGHTS are the M = 128 operand and
 //                two boxes of positions are the N = 256 operand; the accumulator holds D^T
 //                (lane = channel, column = position) and the epilogue transposes on its way
 //                to the channels-last output;
 //   swap_ab = 0  (thin / odd shapes, fp32 outputs): positions are M, block_n channels are N.
 // Warp roles (192 threads):
-//   warp 0     TMA producer: walks the k-table, one stage = activation slab(s) + weight slab
-//   warp 1     TMEM allocator + tcgen05.mma issuer (whole warp walks the loop converged, one
-//              elected lane issues: operands stay in uniform registers).  TMEM holds two tile
-//              buffers of 256 columns, so tile i+1 accumulates while tile i drains
+//   warp 0     TMA producer: walks the k-table, one stage = activation slab(s) + weight slab;
+//              ONE elected thread owns the whole loop (tools/feed_probe.cu: a warp kept converged
+//              around a per-step elect.sync costs ~130 cycles per k-step on the issue path)
+//   warp 1     TMEM allocator + tcgen05.mma issuer, also a single elected thread (waits, MMAs,
+//              commits).  TMEM holds two tile buffers of 256 columns, so tile i+1 accumulates
+//              while tile i drains
 //   warps 2-5  epilogue: tcgen05.ld -> (+ partial sums of the CTAs that share the tile) ->
 //              bias / time-embedding / residual / GroupNorm partial sums -> bf16|fp32 ->
 //              swizzled staging (2 x 16 KB) -> TMA store

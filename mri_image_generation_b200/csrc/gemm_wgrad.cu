@@ -10,9 +10,10 @@
 // One CTA owns (class, 128-wide co block, group of `group` <= 4 k-table entries) and a strided
 // share (`splits`) of the M tiles.  The `group` activation boxes of a stage sit back to back in
 // shared memory and form ONE MN-major B operand of N = 64 * group columns, so every 16 positions
-// cost a single tcgen05.mma of shape 128 x (64*group) x 16 (measured: an M = 128 instruction
-// occupies the tensor pipe ~137 cycles for any N <= 128 and ~150 cycles at N = 256, so N = 256
-// is the only shape near the pipe's peak).  Partial sums are added to the fp32 dW matrix with
+// cost a single tcgen05.mma of shape 128 x (64*group) x 16 (the M = 128 weight-gradient operand
+// is read from shared memory once per instruction, so wide N halves the operand traffic per
+// FLOP; tools/umma_rate_probe.cu: the pipe itself runs N = 128 and N = 256 at full rate).
+// Partial sums are added to the fp32 dW matrix with
 // vectorised reductions (red.global.add.v4.f32).  Replaces autograd's conv weight gradients for every
 // nn.Conv*/ConvTranspose* of the UNets (reference sites: include/mri_b200.h, MriGemmArgs) and,
 // with per-class maps, the dV / dK products of the attention backward.

@@ -106,3 +106,30 @@ def test_schedule_choice_and_smem_budget():
         assert lib.mri_gemm_smem_bytes(bn, 0, 0) <= 227 * 1024
         assert lib.mri_gemm_smem_bytes(bn, 0, 2) == 2 * (128 * 128 + bn * 128) + 2 * 16384 + 1024
     assert lib.mri_gemm_smem_bytes(128, 1, 0) == 4 * 3 * 16384 + 2 * 16384 + 1024
+
+
+def test_wgrad_runs_split_the_ktable_into_triples_and_singles():
+    """WgradPlan.runs(): forward plans that share activation tiles list their taps as kw triples;
+    whole runs of triples go to the kernel's xgroup mode, folded 1x1 slabs to the plain mode."""
+    a1, a2 = torch.zeros(2, 16, 32, 8, 128, dtype=torch.bfloat16), torch.zeros(2, 16, 32, 8, 64, dtype=torch.bfloat16)
+    wm = P.pack_conv_weight(torch.zeros(128, 192, 3, 3, 3), splits=[128, 64], extra=[torch.zeros(128, 64, 1, 1, 1)])
+    y = torch.zeros(2, 16, 32, 8, 128, dtype=torch.bfloat16)
+    pl = P.conv_plan([P.ConvSource(a1), P.ConvSource(a2), P.ConvSource(a2, taps=False)], wm, y, 3)
+    assert pl.xreuse == 1 and tuple(pl.box) == (8, 16, 1, 1) and pl.tile_fast_dim == 2
+    wg = P.WgradPlan(pl, torch.zeros_like(y), torch.zeros(1, 128, pl.n_kb * 64), 128)
+    runs = wg.runs()
+    assert runs == [(0, 27 * 3, True), (81, 1, False)]
+    kt = pl.ktable[0]
+    for i in range(0, 81, 3):   # a triple: same source / slab / (kd, kh), kw = -1, 0, +1, one leader
+        assert list(kt[i:i + 3, 2]) == [-1, 0, 1] and list(kt[i:i + 3, 7]) == [1, 0, 0]
+        assert (kt[i:i + 3, [0, 1, 3, 4]] == kt[i, [0, 1, 3, 4]]).all()
+    # boxes that are not 8 x 16 positions, or plans without tile sharing: one plain launch
+    y2 = torch.zeros(2, 10, 12, 10, 128, dtype=torch.bfloat16)
+    a3 = torch.zeros(2, 10, 12, 10, 128, dtype=torch.bfloat16)
+    pl2 = P.conv_plan([P.ConvSource(a3)], P.pack_conv_weight(torch.zeros(128, 128, 3, 3, 3)), y2, 3)
+    wg2 = P.WgradPlan(pl2, torch.zeros_like(y2), torch.zeros(1, 128, pl2.n_kb * 64), 128)
+    assert wg2.runs() == [(0, pl2.n_kb, False)]
+    # the grid of every launch fills whole waves of the 148 SMs
+    for base, mt in ((14, 4800), (9, 4800), (54, 600), (216, 75)):
+        s = P.pick_wgrad_splits(base, mt)
+        assert 1 <= s <= mt and (base * s) % 148 <= 148 and -(-(base * s) // 148) * 148 - base * s < 0.1 * base * s + 148
