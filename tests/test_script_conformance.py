@@ -120,3 +120,23 @@ def test_attributes_read_by_the_scripts_exist():
     assert d3.model is u3 and d3.timesteps == 20 and d3.channels == 3
     assert d2.betas.numel() == 20 and d3.betas.device.type == "cpu"
     assert u3.in_channels == 3 and list(u3.chs) == [16, 32]
+
+
+def test_ddp_calls_of_the_training_script_bind_to_the_overlapped_wrapper():
+    """ddpm_3d_ldm/train.py wraps the UNet as `DDP(unet, device_ids=[local_rank],
+    output_device=local_rank, find_unused_parameters=False)` and later unwraps `.module`: every such
+    call must bind to mri_image_generation_b200.parallel.DistributedDataParallel (the drop-in whose
+    all-reduce overlaps the backward launch list), so that switching is a one-line import change."""
+    from mri_image_generation_b200.parallel import DistributedDataParallel
+    tree = parse("ddpm_3d_ldm", "train.py")
+    sig = inspect.signature(DistributedDataParallel.__init__)
+    calls = [n for n in ast.walk(tree) if isinstance(n, ast.Call) and isinstance(n.func, ast.Name) and n.func.id == "DDP"]
+    assert len(calls) >= 2
+    for c in calls:
+        args = [object()] * (1 + len(c.args))                  # self + positional
+        kwargs = {k.arg: object() for k in c.keywords}
+        sig.bind(*args, **kwargs)                               # raises TypeError if it does not fit
+    src = open(os.path.join(REF, "ddpm_3d_ldm", "train.py")).read()
+    assert ".module" in src
+    assert "module" in inspect.getsource(DistributedDataParallel.__init__)
+    assert hasattr(DistributedDataParallel, "no_sync") and hasattr(DistributedDataParallel, "forward")
