@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdint.h>
 #include <stdlib.h>
 
 #include "../../include/mri_b200.h"
@@ -445,19 +446,40 @@ adam_kernel(const MriAdamSeg* __restrict__ segs, int n_segs, float lr, float bet
   }
   const MriAdamSeg sg = segs[lo];
   const float inv_scale = grad_scale != nullptr ? 1.0f / *grad_scale : 1.0f;
-  const int64_t i0 = ((int64_t)blockIdx.x - sg.block0) * 1024 + threadIdx.x;
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int64_t i = i0 + (int64_t)u * 256;
-    if (i >= sg.n) break;
-    float p = sg.p[i];
-    float g = sg.g[i] * inv_scale;
+  const float step_size = lr / bc1;
+  auto update = [&](float& p, float g, float& m, float& v) {
+    g *= inv_scale;
     if (weight_decay != 0.f) g = fmaf(weight_decay, p, g);
-    float m = sg.m[i], v = sg.v[i];
     m = m + omb1 * (g - m);               // exp_avg.lerp_(grad, 1 - beta1)
     v = fmaf(omb2 * g, g, beta2 * v);      // exp_avg_sq.mul_(beta2).addcmul_(g, g, value = 1 - beta2)
     const float denom = sqrtf(v) / bc2_sqrt + eps;
-    p -= (lr / bc1) * (m / denom);
+    p -= step_size * (m / denom);
+  };
+  const int64_t b0 = ((int64_t)blockIdx.x - sg.block0) * 1024;
+  const bool vec = ((reinterpret_cast<uintptr_t>(sg.p) | reinterpret_cast<uintptr_t>(sg.g) |
+                     reinterpret_cast<uintptr_t>(sg.m) | reinterpret_cast<uintptr_t>(sg.v)) & 15u) == 0 &&
+                   b0 + 1024 <= sg.n;
+  if (vec) {  // whole 1024-element block, 16-byte aligned streams: one float4 per thread and stream
+    const int64_t i = b0 + (int64_t)threadIdx.x * 4;
+    float4 p4 = *reinterpret_cast<const float4*>(sg.p + i);
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(sg.g + i));
+    float4 m4 = *reinterpret_cast<const float4*>(sg.m + i);
+    float4 v4 = *reinterpret_cast<const float4*>(sg.v + i);
+    update(p4.x, g4.x, m4.x, v4.x);
+    update(p4.y, g4.y, m4.y, v4.y);
+    update(p4.z, g4.z, m4.z, v4.z);
+    update(p4.w, g4.w, m4.w, v4.w);
+    *reinterpret_cast<float4*>(sg.p + i) = p4;
+    *reinterpret_cast<float4*>(sg.m + i) = m4;
+    *reinterpret_cast<float4*>(sg.v + i) = v4;
+    return;
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int64_t i = b0 + threadIdx.x + (int64_t)u * 256;
+    if (i >= sg.n) break;
+    float p = sg.p[i], m = sg.m[i], v = sg.v[i];
+    update(p, sg.g[i], m, v);
     sg.p[i] = p;
     sg.m[i] = m;
     sg.v[i] = v;
