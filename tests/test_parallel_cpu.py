@@ -193,3 +193,45 @@ def test_grad_sync_gloo_world2(tmp_path):
     # no_sync: rank-local gradients, whole-list launch
     for i, (off, n) in r1["off"].items():
         assert torch.allclose(r1["local"][off:off + n], (2.0 * r1["values"][i]).reshape(-1))
+
+
+def test_plan_segments_prefix_property_random_programs():
+    """Random backward programs (random parameter sizes, records that touch several parameters,
+    parameters re-touched by later records): the buckets always tile the arena in order, and every
+    gradient inside a bucket is final when the bucket's last op has run."""
+    import random
+    from mri_image_generation_b200.backward import BackwardMixin
+
+    class Prog(BackwardMixin):
+        pass
+
+    rng = random.Random(7)
+    for trial in range(40):
+        pr = Prog()
+        pr._binit()
+        pr.device = "cpu"
+        n_params = rng.randint(1, 14)
+        pr._params = [torch.zeros(rng.choice([1, 3, 64, 65, 700, 4096])) for _ in range(n_params)]
+        touched = set()
+        for _rec in range(rng.randint(1, 20)):
+            for i in rng.sample(range(n_params), rng.randint(1, min(3, n_params))):
+                pr.pg(pr._params[i])
+                touched.add(i)
+                for _ in range(rng.randint(1, 3)):
+                    pr.badd("op", lambda: None)
+            pr._close_record()
+        bucket = rng.choice([1, 256, 4096, 1 << 20])
+        segs = pr.plan_segments(bucket)
+        assert segs[0][0] == 0 and segs[0][2] == 0
+        assert segs[-1][1] == len(pr.bwd_ops) and segs[-1][3] == pr._garena_used
+        for (lo, hi, a, b), (lo2, hi2, a2, b2) in zip(segs, segs[1:]):
+            assert hi == lo2 and b == a2 and lo < hi and a < b
+        for (lo, hi, a, b) in segs:
+            for pid, (off, n) in pr._g_off.items():
+                if off < b:
+                    assert pr._g_last_op[pid] <= hi, (trial, off, b, hi)
+        # arena slices are disjoint, 256-byte aligned and cover exactly the touched parameters
+        spans = sorted(pr._g_off.values())
+        assert len(spans) == len(touched)
+        for (o1, n1), (o2, _) in zip(spans, spans[1:]):
+            assert o1 % 64 == 0 and o1 + n1 <= o2
