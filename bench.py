@@ -436,18 +436,37 @@ def run_train(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):
         loss = step()
     e1.record()
     torch.cuda.synchronize(dev)
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    clocks = sampler.stop() if sampler else None
+    ms_dev = e0.elapsed_time(e1)
+    # end to end: every step's latents come from pinned host memory and every step's loss is read
+    # back to the host (a 4-byte D2H that also synchronises the step)
+    z_host = z.cpu().pin_memory()
+    Ke = min(K, 10)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(Ke):
+        z.copy_(z_host, non_blocking=True)
+        loss_host = step().item()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([ms_dev, e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     if rank != 0:
         return
-    ms_per_step = ms.item() / K
+    ms_per_step = ms[0].item() / K
+    ms_e2e_step = ms[1].item() / Ke
     prog = model.program(B, LATENT[1:], training=True)
     flops = B * 3 * 1276.4e9  # fwd + bwd = 3 x fwd (30.62 TFLOP per 8-sample step)
     peaks = load_peaks()
@@ -464,6 +483,14 @@ def run_train(args, rank, world, local_rank):
                            + str(len(net.grad_sync.buckets_last_step))),
                    "optimizer": "torch.optim.Adam" if args.torch_adam else "mri_b200 fused Adam",
                    "loss": float(loss.item())},
+        "e2e": {"value": world * B / (ms_e2e_step / 1e3), "unit": "samples/s",
+                "h2d_bytes_per_step": z_host.numel() * 4, "d2h_bytes_per_step": 4, "steps": Ke,
+                "path": "pinned host latents -> p_losses -> backward -> Adam -> loss.item() on the host, every step",
+                "last_loss": loss_host},
+        # launches of this library per step: forward + backward launch lists (replayed as CUDA
+        # graphs), q_sample, loss forward / backward, weight re-pack, gradient finalisation, Adam (2)
+        "gpu_launches": (len(prog.ops) + len(prog.bwd_ops) + 8) * K,
+        "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": flops / (ms_per_step * 1e-3) / 1e12,
                      "peak": peaks["tflops"], "unit": "TFLOP/s",
                      "frac": flops / (ms_per_step * 1e-3) / 1e12 / peaks["tflops"],
