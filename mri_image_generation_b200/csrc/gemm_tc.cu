@@ -245,6 +245,35 @@ __device__ __forceinline__ float4* partial_ptr(const MriGemmArgs& p, int cta, in
          ((size_t)cta * (kPartialLd / 4) + (size_t)(col >> 2)) * kBlockM + lane128;
 }
 
+// swap_ab epilogue through accumulator FRAGMENTS: experimental, OFF unless MRI_GEMM_FRAG_EPI=1.
+// tools/tmem_frag_probe.cu establishes the two layouts used here; the path is parity-tested
+// (tests/test_gpu_gemm.py::test_fragment_epilogue_in_a_subprocess) but measured 4.5 % SLOWER
+// than the element-wise stores on the cfg2 forward (29.6 vs 28.3 ms, same GPU, back to back), so
+// the staging stores are not what paces the epilogue -- see profiles/README.md item 8.
+__constant__ int g_frag_epilogue = 0;
+
+// 16 TMEM lanes x 16 columns: thread T gets rows T/4 and T/4 + 8, columns 2(T%4) + {0, 1} (+8):
+// r0 r1 = (row, c) (row, c+1), r2 r3 = (row+8, ..), r4..r7 = the same for columns + 8
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+// four 8x8 b16 matrices, transposed on the way: register i of thread T holds (rows 2(T%4) + {0, 1},
+// column T/4) of matrix i; lanes 8i .. 8i+7 give the addresses of that matrix's eight 16-byte rows
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t addr, const uint32_t (&m)[4]) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+               "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3])
+               : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&m)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(m[3])
+               : "r"(addr)
+               : "memory");
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -940,6 +969,108 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
             const float add_c = bias_c + ((p.rowbias != nullptr && uniform_sample && ch_ok)
                                               ? __ldg(p.rowbias + (size_t)tile_sample * p.rowbias_ld + ch)
                                               : 0.f);
+            // ---- fragment path: boxes inside one sample, statistics groups of whole 8-channel blocks.
+            // Per 16 positions a warp issues 2 TMEM loads (16 lanes x 16 columns each) and 2
+            // stmatrix.x4.trans instead of 16 16-bit shared-memory stores per thread: the fragment
+            // of thread T is (channels T/4 + 8k, positions 2(T%4) + {0, 1} (+8)), which stmatrix
+            // writes as 16-byte units of 8 channels into the position rows of the staging tile.
+            const bool frag = g_frag_epilogue != 0 && !per_pos_sample &&
+                              (p.stats == nullptr || (cpg & 7) == 0);
+            if (frag) {
+              float add4[4], fs[4], fq[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int chk = t.n0 + q * 32 + (lane >> 2) + 8 * k;
+                float a = 0.f;
+                if (chk < p.n_total) {
+                  if (bias != nullptr) a += __ldg(bias + chk);
+                  if (p.rowbias != nullptr) a += __ldg(p.rowbias + (size_t)tile_sample * p.rowbias_ld + chk);
+                }
+                add4[k] = a;
+                fs[k] = 0.f;
+                fq[k] = 0.f;
+              }
+              const int tp = (lane & 3) * 2;           // first position of my pairs in an 8-group
+              const int mi = lane >> 3, mr = lane & 7;  // stmatrix: my matrix and row
+              uint32_t ra[2][8];
+              tmem_ld_16x256b_x2(tacc + (uint32_t)(h * 128), ra[0]);   // software pipeline: the next
+              tmem_ld_16x256b_x2(tacc + (16u << 16) + (uint32_t)(h * 128), ra[1]);  // chunk is in flight
+              for (int c0 = 0; c0 < rows_in_box; c0 += 16) {
+                tmem_ld_wait();
+                float xa[2][8];
+#pragma unroll
+                for (int L = 0; L < 2; ++L) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) xa[L][e] = __uint_as_float(ra[L][e]);
+                }
+                if (c0 + 16 < rows_in_box) {
+                  tmem_ld_16x256b_x2(tacc + (uint32_t)(h * 128 + c0 + 16), ra[0]);
+                  tmem_ld_16x256b_x2(tacc + (16u << 16) + (uint32_t)(h * 128 + c0 + 16), ra[1]);
+                }
+                const uint32_t vm = (s_vmask[c0 >> 5] >> (c0 & 31)) & 0xffffu;
+                const uint32_t pos = (uint32_t)(c0 + 8 * (mi >> 1) + mr);
+#pragma unroll
+                for (int L = 0; L < 2; ++L) {
+                  const uint32_t unit = (uint32_t)((q & 1) * 4 + 2 * L + (mi & 1));
+                  const uint32_t addr = sbuf + pos * 128u + ((unit ^ (pos & 7u)) << 4);
+                  uint32_t rm[4] = {0u, 0u, 0u, 0u};
+                  if (has_res) ldmatrix_x4_trans(addr, rm);
+                  uint32_t m[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {   // i: (half = i & 1 -> channel slot 2L + half, j = i >> 1)
+                    const int k = 2 * L + (i & 1);
+                    float x0 = xa[L][2 * i] + add4[k];
+                    float x1 = xa[L][2 * i + 1] + add4[k];
+                    if (has_res) {
+                      x0 += __uint_as_float(rm[i] << 16);
+                      x1 += __uint_as_float(rm[i] & 0xffff0000u);
+                    }
+                    const int b = 8 * (i >> 1) + tp;
+                    const float v0 = ((vm >> b) & 1u) ? x0 : 0.f;
+                    const float v1 = ((vm >> (b + 1)) & 1u) ? x1 : 0.f;
+                    fs[k] += v0 + v1;
+                    fq[k] = fmaf(v0, v0, fmaf(v1, v1, fq[k]));
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+                    m[i] = *reinterpret_cast<uint32_t*>(&h2);
+                  }
+                  stmatrix_x4_trans(addr, m);
+                }
+              }
+              if (stats_p != nullptr) {
+                // my 4 slots are 4 blocks of 8 channels (lanes T/4 = 0..7): fold the 4 lanes of a
+                // channel and the 8 channels of a block; lane 0 adds one pair per statistics group
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                  for (int o = 1; o < 32; o <<= 1) {
+                    fs[k] += __shfl_xor_sync(0xffffffffu, fs[k], o);
+                    fq[k] += __shfl_xor_sync(0xffffffffu, fq[k], o);
+                  }
+                }
+                if (lane == 0) {
+                  double a = 0.0, b = 0.0;
+                  int g_prev = (t.n0 + q * 32) / cpg;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const int g = (t.n0 + q * 32 + 8 * k) / cpg;
+                    if (g != g_prev) {
+                      double* dstp = smem_stats ? &s_stats[g_prev * 2]
+                                                : p.stats + ((size_t)tile_sample * p.stats_ld + g_prev) * 2;
+                      atomicAdd(dstp, a);
+                      atomicAdd(dstp + 1, b);
+                      a = b = 0.0;
+                      g_prev = g;
+                    }
+                    a += (double)fs[k];
+                    b += (double)fq[k];
+                  }
+                  double* dstp = smem_stats ? &s_stats[g_prev * 2]
+                                            : p.stats + ((size_t)tile_sample * p.stats_ld + g_prev) * 2;
+                  atomicAdd(dstp, a);
+                  atomicAdd(dstp + 1, b);
+                }
+              }
+            }
             float s_sum = 0.f, s_sq = 0.f;
             int pp_sample = -1;  // per_pos_sample: sample the register sums belong to
             const bool pow2 = (cpg & (cpg - 1)) == 0 && cpg <= 32;
@@ -960,9 +1091,9 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
               b = 0.f;
             };
             uint32_t v[16];
-            tmem_ld16(tacc + (uint32_t)(h * 128), v);  // software pipeline: next chunk's TMEM load
+            if (!frag) tmem_ld16(tacc + (uint32_t)(h * 128), v);  // software pipeline: next chunk's TMEM load
             for (int c0 = 0; c0 < kBlockM; c0 += 16) { // is in flight while this one is processed
-              if (c0 >= rows_in_box) break;
+              if (frag || c0 >= rows_in_box) break;
               tmem_ld_wait();
               float f[16];
 #pragma unroll
@@ -1046,7 +1177,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
               }
             }
             if (per_pos_sample) flush_pp(s_sum, s_sq, pp_sample);
-            if (stats_p != nullptr && uniform_sample) {
+            if (stats_p != nullptr && uniform_sample && !frag) {
               // reduce the lanes that share a statistics group, then one atomic per group
               for (int o = span >> 1; o > 0; o >>= 1) {
                 s_sum += __shfl_xor_sync(0xffffffffu, s_sum, o);
@@ -1166,6 +1297,14 @@ extern "C" int mri_gemm_launch(const MriGemmArgs* a, void* stream) {
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaDeviceGetAttribute(SM count)");
+  }
+  static int frag_configured = 0;
+  if (!frag_configured) {
+    const char* e = getenv("MRI_GEMM_FRAG_EPI");
+    const int v = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+    cudaError_t ce = cudaMemcpyToSymbol(g_frag_epilogue, &v, sizeof(int));
+    if (ce != cudaSuccess) return set_cuda_error(ce, "cudaMemcpyToSymbol(g_frag_epilogue)");
+    frag_configured = 1;
   }
   MriGemmArgs k = *a;
   // short K loops (2D convolutions: 9 taps): the epilogue, not the main loop, paces the CTA ->
