@@ -190,7 +190,12 @@ class DistributedDataParallel(torch.nn.Module):
             self.grad_sync._armed = False
 
     def no_sync(self):
-        """Context manager: gradients are accumulated locally (no all-reduce) inside it."""
+        """Context manager: backward passes inside it skip the all-reduce (local gradients).
+
+        Difference from torch DDP: a later synchronised backward reduces only ITS OWN gradients
+        (the arena of that step), not what earlier no_sync() steps left in `.grad`.  For gradient
+        accumulation across ranks, all-reduce `.grad` yourself after the last micro-step, or use
+        torch's DDP (`wrap_ddp(overlap=False)`).  The reference scripts never use no_sync()."""
         import contextlib
 
         @contextlib.contextmanager
