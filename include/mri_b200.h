@@ -201,6 +201,16 @@ int mri_nhwc_to_nchw(const void* src, float* dst, int samples, int64_t spatial, 
 int mri_nchw_to_nhwc(const float* src, void* dst, int samples, int64_t spatial, int C, int ldc,
                      void* stream);
 
+/* Strided 4-D copy with dtype conversion, dst[i0,i1,i2,i3] = (dst_dtype) src[i0,i1,i2,i3] with
+ * element strides src_strides / dst_strides (host int64[4]) and `shape` (host int64[4]); dtypes
+ * 0 = bf16, 1 = f32, 2 = f64 (source only).  Used for the few layout shuffles of the backward
+ * launch list that torch's autograd does with copy_/permute (e.g. the per-head attention
+ * gradients back into the qkv layout, unet_attention.py:44-47), so that no ATen kernel runs
+ * inside a replayed step.  mri_memset_zero: cudaMemsetAsync(ptr, 0, bytes) on `stream`. */
+int mri_copy_cast(const void* src, int src_dtype, const int64_t* src_strides, void* dst,
+                  int dst_dtype, const int64_t* dst_strides, const int64_t* shape, void* stream);
+int mri_memset_zero(void* ptr, int64_t bytes, void* stream);
+
 /* Row softmax for the bottleneck attention (unet_attention.py:50): P = softmax(S * scale),
  * S fp32 [rows][ld_s], P bf16 [rows][ld_p], `cols` valid columns (padding columns written 0). */
 int mri_softmax_rows(const float* S, void* P, int64_t rows, int cols, int ld_s, int ld_p,
@@ -237,6 +247,35 @@ int mri_minsnr_loss(const float* pred, const float* noise, const int64_t* t, con
                     int64_t per_sample, void* stream);
 /* t[i] += delta for i < n (advances the device-resident timestep inside a CUDA graph) */
 int mri_add_i64(int64_t* t, int n, int64_t delta, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * In-kernel Philox4x32-10 + Box-Muller noise, bit-identical to torch.randn / torch.randn_like on
+ * the same device for the same generator state -- the draws the reference makes at
+ * ddpm_3d_ldm/diffusion.py:75,86,122,131 and slice_cond_2d_ddpm/diffusion.py:67,93,129,140
+ * (ATen mapping: element e of a tensor of `numel` elements is component (e % (4 Tt)) / Tt of the
+ * curand_normal4 call number e / (4 Tt) of subsequence e % Tt, Tt = 256 * min(#SM *
+ * (maxThreadsPerSM / 256), ceil(numel / 256)); ATen/native/cuda/DistributionTemplates.h).
+ * `rng`: device uint64[2] = {seed, philox offset} -- what torch.cuda's generator reports through
+ * initial_seed() / get_offset(); the offset must be a multiple of 4.  One draw of `numel` normals
+ * advances the offset by mri_randn_offset_increment(numel) (host helper, no launch).
+ *   mri_randn:          out[e] = z[e]
+ *   mri_q_sample_rng:   out = sqrt_ac[t]*x0 + sqrt_1mac[t]*z, noise_out = z (nullable)
+ *   mri_ddpm_step_rng:  mri_ddpm_step with z drawn in the kernel (x and out may alias)
+ *   mri_step_advance:   t[i] += delta (and t_prev[i] = max(t_prev[i] + delta, 0), nullable) for
+ *                       i < n; rng[1] += rng_increment
+ *                       (rng nullable) -- the bookkeeping between two replays of a captured step
+ * ------------------------------------------------------------------------------------------ */
+int mri_randn_offset_increment(int64_t numel, uint64_t* increment_out);
+int mri_randn(float* out, int64_t numel, const uint64_t* rng, void* stream);
+int mri_q_sample_rng(const float* x0, const uint64_t* rng, const int64_t* t, const float* sqrt_ac,
+                     const float* sqrt_1mac, float* out, float* noise_out, int samples,
+                     int64_t per_sample, void* stream);
+int mri_ddpm_step_rng(const float* x, const void* eps, int eps_nhwc_ldc, int channels,
+                      const uint64_t* rng, const int64_t* t, const float* betas,
+                      const float* sqrt_1mac, const float* sqrt_recip_alphas, const float* post_var,
+                      float* out, int samples, int64_t per_sample, void* stream);
+int mri_step_advance(int64_t* t, int64_t* t_prev, int n, int64_t delta, uint64_t* rng,
+                     uint64_t rng_increment, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Backward pass (training): what autograd computes for the modules above.

@@ -122,11 +122,19 @@ SIGNATURES = {
     "mri_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i64, _i, _i, _vp]),
     "mri_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i64, _i, _i, _vp]),
     "mri_softmax_rows": (_i, [_vp, _vp, _i64, _i, _i, _i, _f, _vp]),
+    "mri_copy_cast": (_i, [_vp, _i, C.POINTER(C.c_int64), _vp, _i, C.POINTER(C.c_int64),
+                           C.POINTER(C.c_int64), _vp]),
+    "mri_memset_zero": (_i, [_vp, _i64, _vp]),
     "mri_q_sample": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "mri_ddpm_step": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "mri_ddim_step": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "mri_minsnr_loss": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i64, _vp]),
     "mri_add_i64": (_i, [_vp, _i, _i64, _vp]),
+    "mri_randn_offset_increment": (_i, [_i64, C.POINTER(C.c_uint64)]),
+    "mri_randn": (_i, [_vp, _i64, _vp, _vp]),
+    "mri_q_sample_rng": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
+    "mri_ddpm_step_rng": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
+    "mri_step_advance": (_i, [_vp, _vp, _i, _i64, _vp, _u64, _vp]),
     "mri_wgrad_launch": (_i, [C.POINTER(MriWgradArgs), _vp]),
     "mri_gn_bwd_reduce": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _i, _f, _i, _vp]),
     "mri_gn_bwd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _i, _f,

@@ -110,7 +110,7 @@ class BackwardMixin:
         self.pgrad: Dict[int, torch.Tensor] = {}
         self.bwd_ops: List[Callable[[], None]] = []
         self.bwd_names: List[str] = []
-        self._zero_each_bwd: List[torch.Tensor] = []
+        self._zero_each_bwd: List[list] = []   # [uint8 chunk, bytes used]
         self.dtproj: Optional[torch.Tensor] = None
         self.bwd_flops = 0
         # id(gradient tensor) -> [colsum buffer or None] when its LAST writer is a gn_bwd_apply
@@ -187,10 +187,21 @@ class BackwardMixin:
         self.bwd_flops += pl.flops
         self.badd(f"gemm:{name or pl.name}", pl.launch)
 
+    ZERO_CHUNK = 256 << 20
+
     def zeros_each_bwd(self, *shape, dtype=torch.float32) -> torch.Tensor:
-        t = torch.zeros(*shape, dtype=dtype, device=self.device)
-        self._zero_each_bwd.append(t)
-        return t
+        """A buffer that is zero at the start of every backward pass.  All of them are carved out
+        of a few large chunks, so that zeroing is one cudaMemsetAsync per chunk."""
+        n = 1
+        for e in shape:
+            n *= int(e)
+        nbytes = -(-n * torch.empty((), dtype=dtype).element_size() // 256) * 256
+        if not self._zero_each_bwd or self._zero_each_bwd[-1][1] + nbytes > self._zero_each_bwd[-1][0].numel():
+            chunk = torch.zeros(max(nbytes, self.ZERO_CHUNK), dtype=torch.uint8, device=self.device)
+            self._zero_each_bwd.append([chunk, 0])
+        chunk, used = self._zero_each_bwd[-1]
+        self._zero_each_bwd[-1][1] = used + nbytes
+        return chunk[used:used + n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
 
     def _galloc(self, n: int) -> Tuple[int, torch.Tensor]:
         if self.garena is None:
@@ -269,7 +280,7 @@ class BackwardMixin:
             self.bfinal_bsum(g.view(-1)[:n], cs[0], "bias_grad")
         if tproj_off is not None:
             dst = self.dtproj[:, tproj_off:tproj_off + C]
-            self.badd("dtproj", lambda: dst.copy_(cs[0]))
+            self.badd("dtproj", lambda: ops.copy_cast(cs[0], dst))
 
     def bwd_conv(self, r: ConvRec) -> None:
         dy = self.grads.get(id(r.y))
@@ -389,7 +400,7 @@ class BackwardMixin:
         self.bfinal_bsum(gb, sums[1], "gn_param_grad")
         if r.tproj_off is not None:
             dst = self.dtproj[:, r.tproj_off:r.tproj_off + C]
-            self.badd("dtproj", lambda: dst.copy_(sums[0]))
+            self.badd("dtproj", lambda: ops.copy_cast(sums[0], dst))
         holder = [None]
         self.emit_grad(xs, lambda out, add: self.badd(f"gn_bwd_apply:{r.name}", lambda: ops.gn_bwd_apply(
             xs, dy, add, out, st, gamma, beta, sums, B, S, C, r.groups, cpg, r.eps, r.silu,
@@ -476,8 +487,10 @@ class BackwardMixin:
             self.badd(f"wgrad:{nm}", wgp.launch)
             dst = dqkv.view(B, n, 3, heads, d)[:, :, dst_slot]
 
+            src = dwb.view(B, heads, mpad, d)[:, :, :n].permute(0, 2, 1, 3)
+
             def scatter():
-                dst.copy_(dwb.view(B, heads, mpad, d)[:, :, :n].permute(0, 2, 1, 3))
+                ops.copy_cast(src, dst)
 
             self.badd(f"scatter:{nm}", scatter)
 
@@ -582,8 +595,9 @@ class BackwardMixin:
 
     def run_backward(self, lo: int = 0, hi: Optional[int] = None) -> None:
         """Enqueue backward ops [lo, hi) (all by default)."""
-        if lo == 0 and self._zero_each_bwd:
-            torch._foreach_zero_(self._zero_each_bwd)
+        if lo == 0:
+            for chunk, used in self._zero_each_bwd:
+                ops.memset_zero(chunk, used)
         hi = len(self.bwd_ops) if hi is None else hi
         for fn in self.bwd_ops[lo:hi]:
             fn()
@@ -601,6 +615,9 @@ class BackwardMixin:
     def _backward(self, dout: torch.Tensor, S: int, sync) -> None:
         self.dout_in.copy_(dout)
         if sync is None or not sync.active():
+            if sync is not None and not sync.enabled:
+                sync.note_local_backward()
+
             def body():
                 self._bwd_head(S)
                 self.run_backward()

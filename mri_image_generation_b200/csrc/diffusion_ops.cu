@@ -10,72 +10,321 @@
 
 namespace mri {
 
-__device__ __forceinline__ float load_eps(const void* eps, int ldc, int channels, int64_t per_sample,
-                                          int sample, int64_t j) {
-  if (ldc == 0) return __ldg(reinterpret_cast<const float*>(eps) + (size_t)sample * per_sample + j);
-  // channels-last bf16 UNet output: element (c, s) of NC[D]HW index j = c*spatial + s
-  const int64_t spatial = per_sample / channels;
-  const int c = (int)(j / spatial);
-  const int64_t s = j - (int64_t)c * spatial;
-  const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(eps);
-  return __bfloat162float(e[((size_t)sample * spatial + s) * ldc + c]);
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller with ATen's element mapping, so that the draws are bit-identical to
+// torch.randn / randn_like on the same device for the same (seed, offset):
+//   ATen launches G = min(#SM * (maxThreadsPerSM / 256), ceil(numel / 256)) blocks of 256 threads;
+//   thread j (subsequence j) makes one curand_normal4 call per grid-stride iteration `it`
+//   (Philox counter offset / 4 + it) and component ii of that call goes to element
+//   e = it * 4 * Tt + ii * Tt + j with Tt = 256 * G; the generator offset advances by
+//   4 * ceil(numel / (4 * Tt))  (ATen/native/cuda/DistributionTemplates.h: calc_execution_policy,
+//   distribution_elementwise_grid_stride_kernel, normal_and_transform; curand_normal.h:
+//   _curand_box_muller).  Here one thread owns FOUR consecutive subsequences, so that for each
+//   component it holds four consecutive elements: 16-byte loads and stores.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    if (i < 9) {
+      k.x += 0x9E3779B9u;
+      k.y += 0xBB67AE85u;
+    }
+  }
+  return c;
 }
 
-__global__ void __launch_bounds__(256)
-q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
-                const int64_t* __restrict__ t, const float* __restrict__ sqrt_ac,
-                const float* __restrict__ sqrt_1mac, float* __restrict__ out, int64_t per_sample) {
-  const int sample = blockIdx.y;
-  const int64_t ts = t[sample];
-  const float a = __ldg(sqrt_ac + ts), b = __ldg(sqrt_1mac + ts);
-  const size_t base = (size_t)sample * per_sample;
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < per_sample;
-       j += (int64_t)gridDim.x * blockDim.x) {
-    out[base + j] = __fadd_rn(__fmul_rn(a, x0[base + j]), __fmul_rn(b, noise[base + j]));
+// two standard normals from two 32-bit draws: the operations (and their roundings) of
+// _curand_box_muller followed by ATen's `rand * std + mean` with std = 1, mean = 0
+__device__ __forceinline__ float2 box_muller(uint32_t x, uint32_t y) {
+  const float kInv = 2.3283064e-10f;
+  const float kInv2Pi = 2.3283064e-10f * 6.2831855f;
+  const float u = fmaf((float)x, kInv, kInv / 2);
+  const float v = fmaf((float)y, kInv2Pi, kInv2Pi / 2);
+  const float s = sqrtf(-2.0f * logf(u));
+  float sn, cs;
+  __sincosf(v, &sn, &cs);
+  return make_float2(fmaf(sn * s, 1.0f, 0.0f), fmaf(cs * s, 1.0f, 0.0f));
+}
+
+struct AtenGrid {
+  long long Tt;     // threads of ATen's launch
+  int n_iter;       // grid-stride iterations = curand_normal4 calls per thread
+};
+
+static int g_sm_count = 0, g_threads_per_sm = 0;
+static int device_props() {
+  if (g_sm_count != 0) return 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (e == cudaSuccess)
+    e = cudaDeviceGetAttribute(&g_threads_per_sm, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+  if (e != cudaSuccess) {
+    g_sm_count = 0;
+    return set_cuda_error(e, "cudaDeviceGetAttribute(SM count / threads per SM)");
+  }
+  return 0;
+}
+
+static AtenGrid aten_grid(long long numel) {
+  long long grid = (numel + 255) / 256;
+  const long long cap = (long long)g_sm_count * (g_threads_per_sm / 256);
+  if (grid > cap) grid = cap;
+  AtenGrid g;
+  g.Tt = grid * 256;
+  g.n_iter = (int)((numel - 1) / (g.Tt * 4) + 1);
+  return g;
+}
+
+// z[m][ii]: component ii of subsequence j0 + m at counter c
+__device__ __forceinline__ void draw16(uint64_t seed, uint64_t c, uint64_t j0, float (&z)[4][4]) {
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const uint64_t sub = j0 + (uint64_t)m;
+    const uint4 r = philox4x32_10(
+        make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)sub, (uint32_t)(sub >> 32)), key);
+    const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+    z[m][0] = a.x;
+    z[m][1] = a.y;
+    z[m][2] = b.x;
+    z[m][3] = b.y;
   }
 }
 
-__global__ void __launch_bounds__(256)
-ddpm_step_kernel(const float* __restrict__ x, const void* __restrict__ eps, int ldc, int channels,
-                 const float* __restrict__ noise, const int64_t* __restrict__ t,
-                 const float* __restrict__ betas, const float* __restrict__ sqrt_1mac,
-                 const float* __restrict__ sqrt_recip_alphas, const float* __restrict__ post_var,
-                 float* __restrict__ out, int64_t per_sample) {
-  const int sample = blockIdx.y;
-  const int64_t ts = t[sample];
-  // q = beta/s ; sd = sqrt(pv) ; w = mask*sd   (per-sample scalars, same ops as the reference)
-  const float q = __fdiv_rn(__ldg(betas + ts), __ldg(sqrt_1mac + ts));
-  const float c1 = __ldg(sqrt_recip_alphas + ts);
-  const float mask = ts != 0 ? 1.0f : 0.0f;
-  const float w = __fmul_rn(mask, __fsqrt_rn(__ldg(post_var + ts)));
-  const size_t base = (size_t)sample * per_sample;
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < per_sample;
-       j += (int64_t)gridDim.x * blockDim.x) {
-    const float e = load_eps(eps, ldc, channels, per_sample, sample, j);
-    const float mean = __fmul_rn(c1, __fsub_rn(x[base + j], __fmul_rn(q, e)));
-    out[base + j] = __fadd_rn(mean, __fmul_rn(w, noise[base + j]));
+// per-sample coefficients of one reverse step; the same fp32 operations as the reference:
+// q = beta / s ; c1 = sqrt_recip_alphas ; w = mask * sqrt(pv)
+struct StepCoef {
+  float q, c1, w;
+};
+struct StepTables {
+  const int64_t* t;
+  const float *betas, *sqrt_1mac, *sqrt_recip_alphas, *post_var;
+};
+__device__ __forceinline__ StepCoef step_coef(const StepTables& T, long long n) {
+  const int64_t ts = T.t[n];
+  StepCoef c;
+  c.q = __fdiv_rn(__ldg(T.betas + ts), __ldg(T.sqrt_1mac + ts));
+  c.c1 = __ldg(T.sqrt_recip_alphas + ts);
+  c.w = __fmul_rn(ts != 0 ? 1.0f : 0.0f, __fsqrt_rn(__ldg(T.post_var + ts)));
+  return c;
+}
+
+// eps of NC[D]HW element (sample n, in-sample index j): fp32 in x's layout (ldc = 0) or the bf16
+// channels-last UNet output [n][spatial][ldc]
+__device__ __forceinline__ float load_eps(const void* eps, int ldc, long long spatial,
+                                          long long per_sample, long long n, long long j) {
+  if (ldc == 0) return reinterpret_cast<const float*>(eps)[n * per_sample + j];
+  const long long c = j / spatial;
+  const long long s = j - c * spatial;
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(eps)[(n * spatial + s) * ldc + c]);
+}
+
+// The element loop shared by the kernels below.  MODE_RNG: z comes from Philox (ATen mapping);
+// otherwise from `noise` (may be null when F ignores z).  F(e, z) handles ONE element; the
+// loop hands it four consecutive elements at a time, so the compiler keeps 16-byte accesses where
+// F's loads / stores are expressed through the Vec4 helpers.
+template <bool RNG, class F4, class F1>
+__device__ __forceinline__ void element_loop(long long numel, long long Tt, int n_iter,
+                                             const uint64_t* rng, const float* noise, F4 f4, F1 f1) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long j0 = 4 * k;
+  if (j0 >= Tt) return;
+  uint64_t seed = 0, ctr0 = 0;
+  if (RNG) {
+    seed = rng[0];
+    ctr0 = rng[1] >> 2;
+  }
+  const bool n_al = (reinterpret_cast<uintptr_t>(noise) & 15) == 0;
+  for (int it = 0; it < n_iter; ++it) {
+    const long long base = (long long)it * 4 * Tt + j0;
+    if (base >= numel) break;
+    float z[4][4];
+    if (RNG) draw16(seed, ctr0 + (uint64_t)it, (uint64_t)j0, z);
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const long long e0 = base + (long long)ii * Tt;
+      if (e0 >= numel) break;
+      float zz[4] = {0.f, 0.f, 0.f, 0.f};
+      const bool full = e0 + 3 < numel;
+      if (RNG) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) zz[m] = z[m][ii];
+      } else if (noise != nullptr) {
+        if (full && n_al) {
+          const float4 v = *reinterpret_cast<const float4*>(noise + e0);
+          zz[0] = v.x; zz[1] = v.y; zz[2] = v.z; zz[3] = v.w;
+        } else {
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+            if (e0 + m < numel) zz[m] = noise[e0 + m];
+        }
+      }
+      if (full) {
+        f4(e0, zz);
+      } else {
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          if (e0 + m < numel) f1(e0 + m, zz[m]);
+      }
+    }
   }
 }
 
-__global__ void __launch_bounds__(256)
-ddim_step_kernel(const float* __restrict__ x, const void* __restrict__ eps, int ldc, int channels,
-                 const int64_t* __restrict__ t, const int64_t* __restrict__ t_prev,
-                 const float* __restrict__ ac, float* __restrict__ out, int64_t per_sample) {
-  const int sample = blockIdx.y;
-  const float a_t = __ldg(ac + t[sample]);
-  const float a_p = __ldg(ac + t_prev[sample]);
-  const float sqrt_a_t = __fsqrt_rn(a_t);
-  const float s1m_t = __fsqrt_rn(__fsub_rn(1.0f, a_t));
-  const float denom = fmaxf(sqrt_a_t, 1e-8f);
-  const float sqrt_a_p = __fsqrt_rn(a_p);
-  const float s1m_p = __fsqrt_rn(__fsub_rn(1.0f, a_p));
-  const size_t base = (size_t)sample * per_sample;
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < per_sample;
-       j += (int64_t)gridDim.x * blockDim.x) {
-    const float e = load_eps(eps, ldc, channels, per_sample, sample, j);
-    const float x0 = __fdiv_rn(__fsub_rn(x[base + j], __fmul_rn(s1m_t, e)), denom);
-    out[base + j] = __fadd_rn(__fmul_rn(sqrt_a_p, x0), __fmul_rn(s1m_p, e));
+__device__ __forceinline__ bool aligned16(const void* p) {
+  return (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+}
+__device__ __forceinline__ void load4(const float* p, bool al, float (&v)[4]) {
+  if (al) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int m = 0; m < 4; ++m) v[m] = p[m];
   }
+}
+__device__ __forceinline__ void store4(float* p, bool al, const float (&v)[4]) {
+  if (al) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int m = 0; m < 4; ++m) p[m] = v[m];
+  }
+}
+
+template <bool RNG>
+__global__ void __launch_bounds__(256)
+randn_kernel(float* out, long long numel, long long Tt, int n_iter, const uint64_t* rng) {
+  const bool al = aligned16(out);
+  element_loop<RNG>(numel, Tt, n_iter, rng, nullptr,
+      [&](long long e0, const float (&z)[4]) { store4(out + e0, al, z); },
+      [&](long long e, float z) { out[e] = z; });
+}
+
+// x_t = sqrt_ac[t] * x0 + sqrt_1mac[t] * z ; z optionally written out (the loss needs it).
+// x0 / out may alias (no __restrict__).
+template <bool RNG>
+__global__ void __launch_bounds__(256)
+q_sample_kernel(const float* x0, const float* noise, const uint64_t* rng, const int64_t* t,
+                const float* sqrt_ac, const float* sqrt_1mac, float* out, float* noise_out,
+                long long per_sample, long long numel, long long Tt, int n_iter) {
+  const bool al = aligned16(x0) && aligned16(out) && (noise_out == nullptr || aligned16(noise_out));
+  auto one = [&](long long e, float z) {
+    const int64_t ts = t[e / per_sample];
+    out[e] = __fadd_rn(__fmul_rn(__ldg(sqrt_ac + ts), x0[e]), __fmul_rn(__ldg(sqrt_1mac + ts), z));
+    if (noise_out != nullptr) noise_out[e] = z;
+  };
+  element_loop<RNG>(numel, Tt, n_iter, rng, noise,
+      [&](long long e0, const float (&z)[4]) {
+        const long long n = e0 / per_sample;
+        if ((e0 + 3) / per_sample != n) {
+#pragma unroll
+          for (int m = 0; m < 4; ++m) one(e0 + m, z[m]);
+          return;
+        }
+        const int64_t ts = t[n];
+        const float a = __ldg(sqrt_ac + ts), b = __ldg(sqrt_1mac + ts);
+        float xv[4], o[4];
+        load4(x0 + e0, al, xv);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) o[m] = __fadd_rn(__fmul_rn(a, xv[m]), __fmul_rn(b, z[m]));
+        store4(out + e0, al, o);
+        if (noise_out != nullptr) store4(noise_out + e0, al, z);
+      },
+      one);
+}
+
+// x_{t-1} = c1 * (x - q * eps) + w * z.  x / out may alias (the sampler updates its state in place).
+template <bool RNG>
+__global__ void __launch_bounds__(256)
+ddpm_step_kernel(const float* x, const void* eps, int ldc, int channels, const float* noise,
+                 const uint64_t* rng, StepTables T, float* out, long long per_sample,
+                 long long numel, long long Tt, int n_iter) {
+  const long long spatial = per_sample / (channels > 0 ? channels : 1);
+  const bool al = aligned16(x) && aligned16(out);
+  const bool eps_al = ldc == 0 && aligned16(eps);
+  auto one = [&](long long e, float z) {
+    const long long n = e / per_sample;
+    const StepCoef c = step_coef(T, n);
+    const float ev = load_eps(eps, ldc, spatial, per_sample, n, e - n * per_sample);
+    out[e] = __fadd_rn(__fmul_rn(c.c1, __fsub_rn(x[e], __fmul_rn(c.q, ev))), __fmul_rn(c.w, z));
+  };
+  element_loop<RNG>(numel, Tt, n_iter, rng, noise,
+      [&](long long e0, const float (&z)[4]) {
+        const long long n = e0 / per_sample;
+        const long long j = e0 - n * per_sample;
+        // four elements inside one sample and, for the channels-last eps, inside one channel
+        const bool same = (j + 3 < per_sample) && (ldc == 0 || (j % spatial) + 3 < spatial);
+        if (!same) {
+#pragma unroll
+          for (int m = 0; m < 4; ++m) one(e0 + m, z[m]);
+          return;
+        }
+        const StepCoef c = step_coef(T, n);
+        float xv[4], ev[4], o[4];
+        load4(x + e0, al, xv);
+        if (ldc == 0) {
+          load4(reinterpret_cast<const float*>(eps) + e0, eps_al, ev);
+        } else {
+          const long long ch = j / spatial;
+          const long long s = j - ch * spatial;
+          const __nv_bfloat16* ep =
+              reinterpret_cast<const __nv_bfloat16*>(eps) + (n * spatial + s) * ldc + ch;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) ev[m] = __bfloat162float(ep[(long long)m * ldc]);
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          o[m] = __fadd_rn(__fmul_rn(c.c1, __fsub_rn(xv[m], __fmul_rn(c.q, ev[m]))),
+                           __fmul_rn(c.w, z[m]));
+        store4(out + e0, al, o);
+      },
+      one);
+}
+
+// deterministic DDIM step (eta = 0); x / out may alias
+__global__ void __launch_bounds__(256)
+ddim_step_kernel(const float* x, const void* eps, int ldc, int channels, const int64_t* t,
+                 const int64_t* t_prev, const float* ac, float* out, long long per_sample,
+                 long long numel, long long Tt, int n_iter) {
+  const long long spatial = per_sample / (channels > 0 ? channels : 1);
+  auto one = [&](long long e, float) {
+    const long long n = e / per_sample;
+    const float a_t = __ldg(ac + t[n]);
+    const float a_p = __ldg(ac + t_prev[n]);
+    const float sqrt_a_t = __fsqrt_rn(a_t);
+    const float s1m_t = __fsqrt_rn(__fsub_rn(1.0f, a_t));
+    const float denom = fmaxf(sqrt_a_t, 1e-8f);
+    const float sqrt_a_p = __fsqrt_rn(a_p);
+    const float s1m_p = __fsqrt_rn(__fsub_rn(1.0f, a_p));
+    const float ev = load_eps(eps, ldc, spatial, per_sample, n, e - n * per_sample);
+    const float x0 = __fdiv_rn(__fsub_rn(x[e], __fmul_rn(s1m_t, ev)), denom);
+    out[e] = __fadd_rn(__fmul_rn(sqrt_a_p, x0), __fmul_rn(s1m_p, ev));
+  };
+  element_loop<false>(numel, Tt, n_iter, nullptr, nullptr,
+      [&](long long e0, const float (&z)[4]) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) one(e0 + m, z[m]);
+      },
+      one);
+}
+
+// one thread: t -= 1 for every sample (and t_prev), generator offset += rng_inc -- the bookkeeping
+// between two replays of the captured reverse step
+__global__ void step_advance_kernel(int64_t* t, int64_t* t_prev, int n, int64_t delta,
+                                    uint64_t* rng, uint64_t rng_inc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    t[i] += delta;
+    if (t_prev != nullptr) {  // strided DDIM: the last step lands on t_prev = 0
+      const int64_t v = t_prev[i] + delta;
+      t_prev[i] = v < 0 ? 0 : v;
+    }
+  }
+  if (i == 0 && rng != nullptr) rng[1] += rng_inc;
 }
 
 // per-sample sum of squared differences; grid (blocks, samples)
@@ -138,13 +387,84 @@ static inline dim3 ew_grid(int samples, int64_t per_sample) {
 
 using namespace mri;
 
+static inline unsigned my_blocks(const AtenGrid& g) { return (unsigned)((g.Tt / 4 + 255) / 256); }
+
+static int check_rng_args(const char* who, long long numel) {
+  if (numel < 1) return set_error(-2, who);
+  return device_props();
+}
+
+extern "C" int mri_randn_offset_increment(int64_t numel, uint64_t* increment_out) {
+  if (numel < 1 || increment_out == nullptr)
+    return set_error(-2, "mri_randn_offset_increment: empty tensor / null output");
+  int rc = device_props();
+  if (rc) return rc;
+  *increment_out = 4ull * (uint64_t)aten_grid(numel).n_iter;
+  return 0;
+}
+
+extern "C" int mri_randn(float* out, int64_t numel, const uint64_t* rng, void* stream) {
+  int rc = check_rng_args("mri_randn: empty tensor", numel);
+  if (rc) return rc;
+  if (rng == nullptr) return set_error(-2, "mri_randn: null generator state");
+  const AtenGrid g = aten_grid(numel);
+  randn_kernel<true><<<my_blocks(g), 256, 0, (cudaStream_t)stream>>>(out, numel, g.Tt, g.n_iter, rng);
+  return check_launch("randn_kernel");
+}
+
+static int q_sample_impl(const float* x0, const float* noise, const uint64_t* rng, const int64_t* t,
+                         const float* sqrt_ac, const float* sqrt_1mac, float* out, float* noise_out,
+                         int samples, int64_t per_sample, void* stream) {
+  if (samples < 1 || per_sample < 1) return set_error(-2, "mri_q_sample: empty input");
+  const long long numel = (long long)samples * per_sample;
+  int rc = device_props();
+  if (rc) return rc;
+  const AtenGrid g = aten_grid(numel);
+  if (rng != nullptr)
+    q_sample_kernel<true><<<my_blocks(g), 256, 0, (cudaStream_t)stream>>>(
+        x0, nullptr, rng, t, sqrt_ac, sqrt_1mac, out, noise_out, per_sample, numel, g.Tt, g.n_iter);
+  else
+    q_sample_kernel<false><<<my_blocks(g), 256, 0, (cudaStream_t)stream>>>(
+        x0, noise, nullptr, t, sqrt_ac, sqrt_1mac, out, noise_out, per_sample, numel, g.Tt, g.n_iter);
+  return check_launch("q_sample_kernel");
+}
+
 extern "C" int mri_q_sample(const float* x0, const float* noise, const int64_t* t,
                             const float* sqrt_ac, const float* sqrt_1mac, float* out, int samples,
                             int64_t per_sample, void* stream) {
-  if (samples < 1 || per_sample < 1) return set_error(-2, "mri_q_sample: empty input");
-  q_sample_kernel<<<ew_grid(samples, per_sample), 256, 0, (cudaStream_t)stream>>>(
-      x0, noise, t, sqrt_ac, sqrt_1mac, out, per_sample);
-  return check_launch("q_sample_kernel");
+  if (noise == nullptr) return set_error(-2, "mri_q_sample: null noise");
+  return q_sample_impl(x0, noise, nullptr, t, sqrt_ac, sqrt_1mac, out, nullptr, samples, per_sample,
+                       stream);
+}
+
+extern "C" int mri_q_sample_rng(const float* x0, const uint64_t* rng, const int64_t* t,
+                                const float* sqrt_ac, const float* sqrt_1mac, float* out,
+                                float* noise_out, int samples, int64_t per_sample, void* stream) {
+  if (rng == nullptr) return set_error(-2, "mri_q_sample_rng: null generator state");
+  return q_sample_impl(x0, nullptr, rng, t, sqrt_ac, sqrt_1mac, out, noise_out, samples, per_sample,
+                       stream);
+}
+
+static int ddpm_step_impl(const float* x, const void* eps, int ldc, int channels, const float* noise,
+                          const uint64_t* rng, const int64_t* t, const float* betas,
+                          const float* sqrt_1mac, const float* sqrt_recip_alphas,
+                          const float* post_var, float* out, int samples, int64_t per_sample,
+                          void* stream) {
+  if (samples < 1 || per_sample < 1) return set_error(-2, "mri_ddpm_step: empty input");
+  if (ldc != 0 && (channels < 1 || per_sample % channels != 0))
+    return set_error(-2, "mri_ddpm_step: per_sample must be channels * spatial");
+  const long long numel = (long long)samples * per_sample;
+  int rc = device_props();
+  if (rc) return rc;
+  const AtenGrid g = aten_grid(numel);
+  StepTables T{t, betas, sqrt_1mac, sqrt_recip_alphas, post_var};
+  if (rng != nullptr)
+    ddpm_step_kernel<true><<<my_blocks(g), 256, 0, (cudaStream_t)stream>>>(
+        x, eps, ldc, channels, nullptr, rng, T, out, per_sample, numel, g.Tt, g.n_iter);
+  else
+    ddpm_step_kernel<false><<<my_blocks(g), 256, 0, (cudaStream_t)stream>>>(
+        x, eps, ldc, channels, noise, nullptr, T, out, per_sample, numel, g.Tt, g.n_iter);
+  return check_launch("ddpm_step_kernel");
 }
 
 extern "C" int mri_ddpm_step(const float* x, const void* eps, int eps_nhwc_ldc, int channels,
@@ -152,13 +472,19 @@ extern "C" int mri_ddpm_step(const float* x, const void* eps, int eps_nhwc_ldc, 
                              const float* sqrt_1mac, const float* sqrt_recip_alphas,
                              const float* post_var, float* out, int samples, int64_t per_sample,
                              void* stream) {
-  if (samples < 1 || per_sample < 1) return set_error(-2, "mri_ddpm_step: empty input");
-  if (eps_nhwc_ldc != 0 && (channels < 1 || per_sample % channels != 0))
-    return set_error(-2, "mri_ddpm_step: per_sample must be channels * spatial");
-  ddpm_step_kernel<<<ew_grid(samples, per_sample), 256, 0, (cudaStream_t)stream>>>(
-      x, eps, eps_nhwc_ldc, channels, noise, t, betas, sqrt_1mac, sqrt_recip_alphas, post_var, out,
-      per_sample);
-  return check_launch("ddpm_step_kernel");
+  if (noise == nullptr) return set_error(-2, "mri_ddpm_step: null noise");
+  return ddpm_step_impl(x, eps, eps_nhwc_ldc, channels, noise, nullptr, t, betas, sqrt_1mac,
+                        sqrt_recip_alphas, post_var, out, samples, per_sample, stream);
+}
+
+extern "C" int mri_ddpm_step_rng(const float* x, const void* eps, int eps_nhwc_ldc, int channels,
+                                 const uint64_t* rng, const int64_t* t, const float* betas,
+                                 const float* sqrt_1mac, const float* sqrt_recip_alphas,
+                                 const float* post_var, float* out, int samples, int64_t per_sample,
+                                 void* stream) {
+  if (rng == nullptr) return set_error(-2, "mri_ddpm_step_rng: null generator state");
+  return ddpm_step_impl(x, eps, eps_nhwc_ldc, channels, nullptr, rng, t, betas, sqrt_1mac,
+                        sqrt_recip_alphas, post_var, out, samples, per_sample, stream);
 }
 
 extern "C" int mri_ddim_step(const float* x, const void* eps, int eps_nhwc_ldc, int channels,
@@ -167,9 +493,22 @@ extern "C" int mri_ddim_step(const float* x, const void* eps, int eps_nhwc_ldc, 
   if (samples < 1 || per_sample < 1) return set_error(-2, "mri_ddim_step: empty input");
   if (eps_nhwc_ldc != 0 && (channels < 1 || per_sample % channels != 0))
     return set_error(-2, "mri_ddim_step: per_sample must be channels * spatial");
-  ddim_step_kernel<<<ew_grid(samples, per_sample), 256, 0, (cudaStream_t)stream>>>(
-      x, eps, eps_nhwc_ldc, channels, t, t_prev, alphas_cumprod, out, per_sample);
+  const long long numel = (long long)samples * per_sample;
+  int rc = device_props();
+  if (rc) return rc;
+  const AtenGrid g = aten_grid(numel);
+  ddim_step_kernel<<<my_blocks(g), 256, 0, (cudaStream_t)stream>>>(
+      x, eps, eps_nhwc_ldc, channels, t, t_prev, alphas_cumprod, out, per_sample, numel, g.Tt,
+      g.n_iter);
   return check_launch("ddim_step_kernel");
+}
+
+extern "C" int mri_step_advance(int64_t* t, int64_t* t_prev, int n, int64_t delta, uint64_t* rng,
+                                uint64_t rng_increment, void* stream) {
+  if (n < 1) return 0;
+  step_advance_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, t_prev, n, delta, rng,
+                                                                        rng_increment);
+  return check_launch("step_advance_kernel");
 }
 
 extern "C" int mri_minsnr_loss(const float* pred, const float* noise, const int64_t* t,

@@ -314,6 +314,37 @@ gather_pack_kernel(const MriGatherSeg* __restrict__ segs, int n_segs) {
   }
 }
 
+// ---- strided copy with dtype conversion (small layout shuffles of the backward launch list) ----
+struct Copy4 {
+  int64_t shape[4], ss[4], ds[4];
+};
+template <typename T> __device__ __forceinline__ float ld_as_float(const void* p, int64_t i);
+template <> __device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const void* p, int64_t i) {
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+template <> __device__ __forceinline__ float ld_as_float<float>(const void* p, int64_t i) {
+  return reinterpret_cast<const float*>(p)[i];
+}
+template <> __device__ __forceinline__ float ld_as_float<double>(const void* p, int64_t i) {
+  return (float)reinterpret_cast<const double*>(p)[i];
+}
+template <typename TS>
+__global__ void __launch_bounds__(256)
+copy_cast_kernel(const void* __restrict__ src, void* __restrict__ dst, int dst_dtype, Copy4 c,
+                 int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int64_t i3 = r % c.shape[3]; r /= c.shape[3];
+    const int64_t i2 = r % c.shape[2]; r /= c.shape[2];
+    const int64_t i1 = r % c.shape[1]; r /= c.shape[1];
+    const float v = ld_as_float<TS>(src, r * c.ss[0] + i1 * c.ss[1] + i2 * c.ss[2] + i3 * c.ss[3]);
+    const int64_t o = r * c.ds[0] + i1 * c.ds[1] + i2 * c.ds[2] + i3 * c.ds[3];
+    if (dst_dtype == 0) reinterpret_cast<__nv_bfloat16*>(dst)[o] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(dst)[o] = v;
+  }
+}
+
 static inline unsigned grid_for(int64_t total) {
   int64_t b = (total + 255) / 256;
   const int64_t cap = 148 * 16;
@@ -428,4 +459,32 @@ extern "C" int mri_softmax_rows(const float* S, void* P, int64_t rows, int cols,
   else if (per_lane <= 40) softmax_rows_kernel<40><<<grid, 256, 0, st>>>(S, Pp, rows, cols, ld_s, ld_p, scale);
   else softmax_rows_kernel<64><<<grid, 256, 0, st>>>(S, Pp, rows, cols, ld_s, ld_p, scale);
   return check_launch("softmax_rows_kernel");
+}
+
+extern "C" int mri_copy_cast(const void* src, int src_dtype, const int64_t* src_strides, void* dst,
+                             int dst_dtype, const int64_t* dst_strides, const int64_t* shape,
+                             void* stream) {
+  if (src_dtype < 0 || src_dtype > 2 || dst_dtype < 0 || dst_dtype > 1)
+    return set_error(-2, "mri_copy_cast: dtypes are 0 = bf16, 1 = f32, 2 = f64 (source only)");
+  Copy4 c;
+  int64_t total = 1;
+  for (int i = 0; i < 4; ++i) {
+    c.shape[i] = shape[i];
+    c.ss[i] = src_strides[i];
+    c.ds[i] = dst_strides[i];
+    if (shape[i] < 1) return set_error(-2, "mri_copy_cast: empty shape");
+    total *= shape[i];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = grid_for(total);
+  if (src_dtype == 0) copy_cast_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, dst, dst_dtype, c, total);
+  else if (src_dtype == 1) copy_cast_kernel<float><<<grid, 256, 0, st>>>(src, dst, dst_dtype, c, total);
+  else copy_cast_kernel<double><<<grid, 256, 0, st>>>(src, dst, dst_dtype, c, total);
+  return check_launch("copy_cast_kernel");
+}
+
+extern "C" int mri_memset_zero(void* ptr, int64_t bytes, void* stream) {
+  if (bytes <= 0) return 0;
+  cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : set_cuda_error(e, "cudaMemsetAsync");
 }

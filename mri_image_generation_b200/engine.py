@@ -119,7 +119,7 @@ class UNetProgram(BackwardMixin):
     def run_traced(self) -> List[Tuple[str, List[torch.Tensor]]]:
         """Debug: run op by op (synchronising) and return a copy of every op's outputs."""
         trace = []
-        self._arena[:max(self._arena_used, 4)].zero_()
+        ops.memset_zero(self._arena, max(self._arena_used, 4) * 8)
         for name, fn, outs in zip(self.op_names, self.ops, self.op_outs):
             fn()
             torch.cuda.synchronize(self.device)
@@ -289,7 +289,7 @@ class UNetProgram(BackwardMixin):
             self._run_eager()
 
     def _run_eager(self) -> None:
-        self._arena[:max(self._arena_used, 4)].zero_()
+        ops.memset_zero(self._arena, max(self._arena_used, 4) * 8)
         for fn in self.ops:
             fn()
 

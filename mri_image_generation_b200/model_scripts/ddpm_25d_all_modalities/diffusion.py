@@ -14,9 +14,10 @@ class GaussianDiffusion(_GD2):
 
     def p_losses(self, x_start, t, z_pos, context=None, noise=None):
         """ddpm_25d_all_modalities/diffusion.py:76-89: F.mse_loss(model(x_t, t, z, context), noise)."""
-        if noise is None:
-            noise = torch.randn_like(x_start)
-        x_noisy = self.q_sample(x_start=x_start, t=t, noise=noise)
+        if noise is None:  # noise = torch.randn_like(x_start), drawn inside the q_sample kernel
+            x_noisy, noise = self._q_sample_draw(x_start, t)
+        else:
+            x_noisy = self.q_sample(x_start=x_start, t=t, noise=noise)
         predicted_noise = self.model(x_noisy, t, z_pos, context=context)
         return self._loss(predicted_noise, noise, t, 0.0)
 
@@ -25,15 +26,14 @@ class GaussianDiffusion(_GD2):
         """ddpm_25d_all_modalities/diffusion.py:91-112."""
         _require_cuda(x, "p_sample")
         eps_theta = self.model(x, t, z_pos, context=context)
-        noise = torch.randn_like(x)
-        return self._p_update(x, t, eps_theta, noise)
+        return self._p_update(x, t, eps_theta)  # z = randn_like(x) drawn inside the kernel
 
     @torch.no_grad()
     def p_sample_loop(self, shape, z_pos, context=None):
         """ddpm_25d_all_modalities/diffusion.py:114-137."""
         device = self.betas.device
         B = shape[0]
-        img = torch.randn(shape, device=device)
+        img = self._randn(shape, device)
         z_pos = self._z_tensor(z_pos, B, device)
         if context is not None:
             context = context.to(device)

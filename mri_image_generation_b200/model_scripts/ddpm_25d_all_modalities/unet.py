@@ -4,6 +4,8 @@ from typing import Union
 
 import torch
 
+from ...modules import on_input_device
+
 from ..slice_cond_2d_ddpm.unet import (DownBlock, ResidualBlock, SinusoidalPosEmb,  # noqa: F401
                                        UpBlock, _UNet2DBase)
 
@@ -18,6 +20,7 @@ class UNet(_UNet2DBase):
         self.out_channels = out_channels
         self._build(in_channels, out_channels, base_channels, channel_mults, time_emb_dim)
 
+    @on_input_device
     def forward(self, x: torch.Tensor, t: torch.Tensor, z_pos: torch.Tensor,
                 context: Union[torch.Tensor, None] = None) -> torch.Tensor:
         """x: (B, C_target, H, W) noisy centre-slice modalities; context: (B, C_context, H, W)

@@ -8,7 +8,7 @@ import torch.nn as nn
 
 from ... import _lib
 from ...engine import UNet3DProgram
-from ...modules import EngineModule, SinusoidalHolder, UNetFunction
+from ...modules import EngineModule, SinusoidalHolder, UNetFunction, on_input_device
 
 # name kept for importers of the reference module (unet_attention.py:7)
 SinusoidalPositionEmbeddings = SinusoidalHolder
@@ -95,6 +95,7 @@ class _UNet3DBase(EngineModule):
         key = (int(batch), tuple(int(s) for s in spatial), bool(training))
         return self.get_program(key, lambda: UNet3DProgram(self, key[0], key[1], training=key[2]))
 
+    @on_input_device
     def forward(self, x, t):
         """x: (B, C, D, H, W) fp32, t: (B,) int64 -> predicted noise (B, C, D, H, W) fp32
         (unet_attention.py:157-200)."""

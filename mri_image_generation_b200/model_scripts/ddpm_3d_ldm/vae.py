@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from ... import _lib
-from ...modules import EngineModule
+from ...modules import EngineModule, on_input_device
 from ...vae_engine import VAE3DProgram
 
 
@@ -96,6 +96,7 @@ class VAE3D(EngineModule):
         key = (mode, int(x.shape[0]), tuple(int(s) for s in x.shape[2:]))
         return self.get_program(key, lambda: VAE3DProgram(self, mode, key[1], key[2]))
 
+    @on_input_device
     def encode(self, x):
         """vae.py:102-104: (mu, logvar), each (B, latent, D/4, H/4, W/4)."""
         cin = self.encoder.in_conv.weight.shape[1]
@@ -111,6 +112,7 @@ class VAE3D(EngineModule):
         eps = torch.randn_like(std)
         return mu + eps * std
 
+    @on_input_device
     def decode(self, z):
         """vae.py:111-112."""
         lat = self.decoder.from_latent.weight.shape[1]
@@ -118,6 +120,7 @@ class VAE3D(EngineModule):
             raise _lib.MriError(f"expected {lat} latent channels, got {z.shape[1]}")
         return self._program("decode", z).forward(z.float().contiguous()).clone()
 
+    @on_input_device
     def forward(self, x):
         """vae.py:114-118."""
         mu, logvar = self.encode(x)
@@ -126,12 +129,14 @@ class VAE3D(EngineModule):
         return recon, mu, logvar
 
     @torch.no_grad()
+    @on_input_device
     def encode_to_latent(self, x):
         """vae.py:120-124: deterministic latent mean for diffusion."""
         mu, logvar = self.encode(x)
         return mu
 
     @torch.no_grad()
+    @on_input_device
     def decode_from_latent(self, z):
         """vae.py:126-128."""
         return self.decode(z)

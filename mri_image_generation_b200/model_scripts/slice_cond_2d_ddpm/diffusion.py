@@ -29,8 +29,8 @@ class GaussianDiffusion(DiffusionBase):
 
     def q_sample(self, x_start, t, noise=None):
         """diffusion.py:60-75."""
-        if noise is None:
-            noise = torch.randn_like(x_start)
+        if noise is None:  # noise = torch.randn_like(x_start), drawn inside the kernel
+            return self._q_sample_draw(x_start, t)[0]
         return self._q_sample(x_start, t, noise)
 
     def p_losses(self, x_start, t, cond=None, noise=None, min_snr_gamma=5.0):
@@ -39,9 +39,10 @@ class GaussianDiffusion(DiffusionBase):
         training script passes z_pos there, model.py:164).  The reference's hard-coded
         mean(dim=(1,2,3,4)) raises IndexError on 4-D slices; this computes the same
         quantity rank-generically instead of reproducing the crash."""
-        if noise is None:
-            noise = torch.randn_like(x_start)
-        x_noisy = self.q_sample(x_start=x_start, t=t, noise=noise)
+        if noise is None:  # noise = torch.randn_like(x_start), drawn inside the q_sample kernel
+            x_noisy, noise = self._q_sample_draw(x_start, t)
+        else:
+            x_noisy = self.q_sample(x_start=x_start, t=t, noise=noise)
         predicted_noise = self.model(x_noisy, t) if cond is None else self.model(x_noisy, t, cond)
         return self._loss(predicted_noise, noise, t, float(min_snr_gamma))
 
@@ -55,8 +56,7 @@ class GaussianDiffusion(DiffusionBase):
             prog.z_in.copy_(self._z_tensor(z_pos, x.shape[0], x.device).reshape(-1, 1))
             return self._p_sample_on(prog, x, t)
         eps_theta = self.model(x, t, z_pos)
-        noise = torch.randn_like(x)
-        return self._p_update(x, t, eps_theta, noise)
+        return self._p_update(x, t, eps_theta)  # z = randn_like(x) drawn inside the kernel
 
     def _z_tensor(self, z_pos, B, device):
         if not torch.is_tensor(z_pos):
@@ -68,7 +68,7 @@ class GaussianDiffusion(DiffusionBase):
         """diffusion.py:134-155."""
         device = self.betas.device
         B = shape[0]
-        img = torch.randn(shape, device=device)
+        img = self._randn(shape, device)
         z_pos = self._z_tensor(z_pos, B, device)
         eng = self._engine_model()
         if eng is not None:

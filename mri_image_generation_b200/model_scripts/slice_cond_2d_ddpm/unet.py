@@ -7,7 +7,7 @@ import torch.nn as nn
 
 from ... import _lib
 from ...engine import UNet2DProgram
-from ...modules import EngineModule, SinusoidalHolder, UNetFunction
+from ...modules import EngineModule, SinusoidalHolder, UNetFunction, on_input_device
 
 SinusoidalPosEmb = SinusoidalHolder  # unet.py:7
 
@@ -113,6 +113,7 @@ class UNet(_UNet2DBase):
         super().__init__()
         self._build(img_channels, img_channels, base_channels, channel_mults, time_emb_dim)
 
+    @on_input_device
     def forward(self, x: torch.Tensor, t: torch.Tensor, z_pos: torch.Tensor) -> torch.Tensor:
         """unet.py:169-199."""
         return self._forward(x, t, z_pos)

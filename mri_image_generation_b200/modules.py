@@ -8,12 +8,27 @@ i.e. the sm_100a kernels behind the C ABI.
 """
 from __future__ import annotations
 
+import functools
 from typing import Dict, Tuple
 
 import torch
 import torch.nn as nn
 
 from . import _lib
+
+
+def on_input_device(fn):
+    """Run a module entry point with the input tensor's GPU as the current device: kernels are
+    launched on `torch.cuda.current_stream()` and TMA descriptors are encoded for the current
+    context, so a model living on cuda:1 while cuda:0 is current (model.to('cuda:1') without
+    set_device, nn.DataParallel replicas) would otherwise launch on the wrong device."""
+    @functools.wraps(fn)
+    def wrapped(self, x, *args, **kwargs):
+        if torch.is_tensor(x) and x.is_cuda and x.device.index != torch.cuda.current_device():
+            with torch.cuda.device(x.device):
+                return fn(self, x, *args, **kwargs)
+        return fn(self, x, *args, **kwargs)
+    return wrapped
 
 
 class SinusoidalHolder(nn.Module):
@@ -89,7 +104,11 @@ class UNetFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         prog = ctx.prog
-        prog.backward(dout.contiguous().float(), sync=getattr(prog, "grad_sync", None))
+        sync = getattr(prog, "grad_sync", None)
+        with torch.cuda.device(dout.device):
+            prog.backward(dout.contiguous().float(), sync=sync)
+        if sync is not None and sync.active():
+            sync.reduce_pending(prog.param_list)   # gradients left in .grad by no_sync() steps
         # one copy of the whole gradient arena (the program overwrites it next step); every
         # parameter's gradient is a view of that copy
         flat = prog.garena[:prog._garena_used].clone()

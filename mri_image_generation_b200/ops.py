@@ -143,6 +143,79 @@ def add_i64(t: torch.Tensor, delta: int) -> None:
     _lib.check(_lib.load().mri_add_i64(_p(t), t.numel(), delta, _s()), "mri_add_i64")
 
 
+# ------------------------------------------------------------------------------ in-kernel RNG
+def randn_offset_increment(numel: int) -> int:
+    """Philox offset consumed by one draw of `numel` normals (what torch.randn advances its CUDA
+    generator by for a tensor of that size on this device)."""
+    import ctypes as C
+    inc = C.c_uint64(0)
+    _lib.check(_lib.load().mri_randn_offset_increment(int(numel), C.byref(inc)),
+               "mri_randn_offset_increment")
+    return int(inc.value)
+
+
+class DeviceRng:
+    """Bridge between torch's CUDA generator and the kernels that draw their own noise.
+
+    The kernels read (seed, philox offset) from a small device tensor and reproduce ATen's
+    element mapping, so a draw through them equals torch.randn / randn_like under the same
+    torch.manual_seed; the host then advances torch's generator by the offset the draw consumed,
+    which keeps every LATER torch draw identical to the reference's as well."""
+
+    def __init__(self, device: torch.device):
+        self.device = torch.device(device)
+        self.state = torch.zeros(2, dtype=torch.int64, device=self.device)  # {seed, offset} bits
+
+    def generator(self) -> torch.Generator:
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        return torch.cuda.default_generators[idx]
+
+    def load(self) -> int:
+        """Copy torch's current (seed, offset) into the device state; returns the offset."""
+        g = self.generator()
+        seed, off = int(g.initial_seed()), int(g.get_offset())
+        if off % 4:
+            raise _lib.MriError("CUDA generator offset must be a multiple of 4")
+        if seed >= 1 << 63:
+            seed -= 1 << 64
+        self.state.copy_(torch.tensor([seed, off], dtype=torch.int64))
+        return off
+
+    def commit(self, offset: int) -> None:
+        self.generator().set_offset(int(offset))
+
+
+def randn(out: torch.Tensor, rng: DeviceRng) -> None:
+    _chk_contig(out)
+    assert out.dtype == torch.float32
+    _lib.check(_lib.load().mri_randn(_p(out), out.numel(), _p(rng.state), _s()), "mri_randn")
+
+
+def q_sample_rng(x0, rng: DeviceRng, t, sqrt_ac, sqrt_1mac, out, noise_out=None) -> None:
+    _chk_contig(x0, out, noise_out)
+    n = x0.shape[0]
+    _lib.check(_lib.load().mri_q_sample_rng(_p(x0), _p(rng.state), _p(t), _p(sqrt_ac), _p(sqrt_1mac),
+                                            _p(out), _p(noise_out), n, x0.numel() // n, _s()),
+               "mri_q_sample_rng")
+
+
+def ddpm_step_rng(x, eps, rng: DeviceRng, t, betas, sqrt_1mac, sqrt_recip_alphas, post_var, out,
+                  eps_nhwc_ldc: int = 0, channels: int = 0) -> None:
+    _chk_contig(x, eps, out)
+    n = x.shape[0]
+    _lib.check(_lib.load().mri_ddpm_step_rng(_p(x), _p(eps), eps_nhwc_ldc, channels, _p(rng.state),
+                                             _p(t), _p(betas), _p(sqrt_1mac), _p(sqrt_recip_alphas),
+                                             _p(post_var), _p(out), n, x.numel() // n, _s()),
+               "mri_ddpm_step_rng")
+
+
+def step_advance(t: torch.Tensor, delta: int, t_prev=None, rng: Optional[DeviceRng] = None,
+                 rng_increment: int = 0) -> None:
+    _lib.check(_lib.load().mri_step_advance(_p(t), _p(t_prev), t.numel(), delta,
+                                            _p(rng.state) if rng is not None else None,
+                                            rng_increment, _s()), "mri_step_advance")
+
+
 # ------------------------------------------------------------------------------ backward
 def gn_bwd_reduce(x, dy, stats, gamma, beta, sums, samples, spatial, C, groups, stats_cpg, eps,
                   silu: bool) -> None:
@@ -200,3 +273,28 @@ def minsnr_loss_bwd(pred, noise, t, snr, gamma, upstream, dpred) -> None:
     _lib.check(_lib.load().mri_minsnr_loss_bwd(_p(pred), _p(noise), _p(t), _p(snr), gamma,
                                                _p(upstream), _p(dpred), n, pred.numel() // n, _s()),
                "mri_minsnr_loss_bwd")
+
+
+
+_DT = {torch.bfloat16: 0, torch.float32: 1, torch.float64: 2}
+
+
+def copy_cast(src: torch.Tensor, dst: torch.Tensor) -> None:
+    """dst <- src (same shape, any strides, up to 4 dims after merging; bf16/f32/f64 -> bf16/f32):
+    what `dst.copy_(src)` does, through mri_copy_cast."""
+    import ctypes as C
+    if tuple(src.shape) != tuple(dst.shape) or src.dim() > 4:
+        raise _lib.MriError(f"copy_cast: shapes {tuple(src.shape)} -> {tuple(dst.shape)} unsupported")
+    pad = 4 - src.dim()
+    shape = (C.c_int64 * 4)(*([1] * pad + list(src.shape)))
+    ss = (C.c_int64 * 4)(*([0] * pad + list(src.stride())))
+    ds = (C.c_int64 * 4)(*([0] * pad + list(dst.stride())))
+    _lib.check(_lib.load().mri_copy_cast(_p(src), _DT[src.dtype], ss, _p(dst), _DT[dst.dtype], ds,
+                                         shape, _s()), "mri_copy_cast")
+
+
+def memset_zero(t: torch.Tensor, nbytes: Optional[int] = None) -> None:
+    """Zero the first `nbytes` bytes of t's storage view (cudaMemsetAsync on the current stream)."""
+    _chk_contig(t)
+    n = t.numel() * t.element_size() if nbytes is None else int(nbytes)
+    _lib.check(_lib.load().mri_memset_zero(_p(t), n, _s()), "mri_memset_zero")

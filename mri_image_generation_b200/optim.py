@@ -44,11 +44,44 @@ class Adam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
         # grad_scale / found_inf are set (and deleted again) by torch.amp.GradScaler around step()
         self._tables = {}
+        self._group_steps = {}
+
+    def load_state_dict(self, state_dict):
+        """Loaded moment tensors replace the ones the cached segment tables point at."""
+        out = super().load_state_dict(state_dict)
+        self._tables.clear()
+        self._group_steps.clear()
+        return out
+
+    def add_param_group(self, param_group):
+        out = super().add_param_group(param_group)
+        if hasattr(self, "_tables"):
+            self._tables.clear()
+        return out
+
+    def _group_step(self, gi: int, plist) -> torch.Tensor:
+        """ONE device-resident step counter per param group (the kernel applies one bias
+        correction per launch).  It starts from the LARGEST step any parameter of the group
+        already has -- after load_state_dict, or when parameters that had no gradient before
+        join -- never from whichever parameter happens to come first."""
+        st = self._group_steps.get(gi)
+        dev = plist[0].device
+        if st is None:
+            have = [self.state[p]["step"] for p in plist if "step" in self.state[p]]
+            if have:
+                st = torch.stack([h.detach().to(dev, torch.float32).reshape(()) for h in have]).max()
+            else:
+                st = torch.zeros((), dtype=torch.float32, device=dev)
+            st = st.clone()
+            self._group_steps[gi] = st
+        return st
 
     def _table(self, gi: int, plist, grads):
         """Device segment table of one param group; rebuilt when a pointer changed (new .grad
         tensors appear after zero_grad(set_to_none=True))."""
-        key = tuple((p.data_ptr(), g.data_ptr()) for p, g in zip(plist, grads))
+        # the table bakes in all four pointers: parameter, gradient AND both moments
+        key = tuple((p.data_ptr(), g.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
+                     self.state[p]["exp_avg_sq"].data_ptr()) for p, g in zip(plist, grads))
         hit = self._tables.get(gi)
         if hit is not None and hit[0] == key:
             return hit[1], hit[2], hit[3]
@@ -93,10 +126,8 @@ class Adam(torch.optim.Optimizer):
                 grads.append(p.grad)
             if not plist:
                 continue
-            # one counter per group: every parameter's state["step"] aliases the first one's
-            step_t = self.state[plist[0]]["step"]
-            if not step_t.is_cuda:
-                step_t = step_t.to(plist[0].device, torch.float32)
+            # one counter per group: every parameter's state["step"] aliases it
+            step_t = self._group_step(gi, plist)
             for p in plist:
                 self.state[p]["step"] = step_t
             table, n, blocks = self._table(gi, plist, grads)

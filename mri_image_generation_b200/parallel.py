@@ -101,6 +101,9 @@ class GradSync:
         self._works: list = []
         self._comm_stream = None
         self.buckets_last_step: List[Tuple[int, int]] = []
+        self._pending_local = False         # a backward ran under no_sync(): .grad holds local sums
+        self.bucket_events: list = []       # per bucket (ready, start, end) CUDA events when timing
+        self.time_buckets = False
 
     def take(self) -> Optional["GradSync"]:
         """Called by the UNet's forward: the next backward synchronises only if the call came
@@ -115,10 +118,33 @@ class GradSync:
     def active(self) -> bool:
         return self.enabled and self.world() > 1
 
+    def note_local_backward(self) -> None:
+        """A backward pass ran with the all-reduce disabled (no_sync()): its gradients were
+        accumulated into `.grad` rank-locally."""
+        if self.world() > 1:
+            self._pending_local = True
+
+    def reduce_pending(self, params) -> None:
+        """torch DDP semantics for gradient accumulation: the first synchronised backward after
+        no_sync() steps reduces what those steps left in `.grad` as well (mean of the sums = sum of
+        the means).  Called before autograd accumulates the new, already reduced gradients."""
+        if not self._pending_local:
+            return
+        self._pending_local = False
+        grads = [p.grad for p in params if p.grad is not None]
+        if not grads:
+            return
+        flat = torch._utils._flatten_dense_tensors(grads)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        flat.mul_(1.0 / self.world())
+        for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+            g.copy_(f)
+
     def begin(self, arena: torch.Tensor) -> None:
         self._arena = arena
         self._works = []
         self.buckets_last_step = []
+        self.bucket_events = []
         if arena.is_cuda and self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(arena.device)
 
@@ -133,14 +159,21 @@ class GradSync:
             buf.mul_(1.0 / self.world())
             return
         cur = torch.cuda.current_stream(buf.device)
-        ev = torch.cuda.Event()
+        timing = self.time_buckets
+        ev = torch.cuda.Event(enable_timing=timing)
         ev.record(cur)
         with torch.cuda.stream(self._comm_stream):
             self._comm_stream.wait_event(ev)
+            if timing:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(self._comm_stream)
             if backend == "nccl":
                 w = dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
             else:
                 w = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            if timing:
+                e1.record(self._comm_stream)
+                self.bucket_events.append((ev, e0, e1, (hi - lo) * buf.element_size()))
             self._works.append((w, buf, backend))
 
     def finish(self) -> None:
@@ -192,10 +225,10 @@ class DistributedDataParallel(torch.nn.Module):
     def no_sync(self):
         """Context manager: backward passes inside it skip the all-reduce (local gradients).
 
-        Difference from torch DDP: a later synchronised backward reduces only ITS OWN gradients
-        (the arena of that step), not what earlier no_sync() steps left in `.grad`.  For gradient
-        accumulation across ranks, all-reduce `.grad` yourself after the last micro-step, or use
-        torch's DDP (`wrap_ddp(overlap=False)`).  The reference scripts never use no_sync()."""
+        As with torch DDP, the first synchronised backward afterwards also mean-all-reduces what
+        the no_sync() steps accumulated in `.grad` (GradSync.reduce_pending), so gradient
+        accumulation gives the same result as torch's wrapper.  The reference scripts never use
+        no_sync()."""
         import contextlib
 
         @contextlib.contextmanager

@@ -66,3 +66,59 @@ def test_adam_with_grad_scaler_skips_on_inf_and_unscales():
         for x, y in zip(pa, pb):
             assert torch.allclose(x, y, rtol=5e-6, atol=1e-7), it
     assert sa.get_scale() == sb.get_scale()
+
+
+def test_adam_resume_from_state_dict_uses_the_loaded_moments():
+    """load_state_dict installs new moment tensors: the cached segment table must follow them
+    (it used to keep pointing at the freed ones), and the step counter must continue."""
+    import copy
+    from mri_image_generation_b200.optim import Adam
+    pa, pb = make_params(5), make_params(5)
+    oa = Adam(pa, lr=1e-3)
+    ob = torch.optim.Adam(pb, lr=1e-3)
+    g = torch.Generator().manual_seed(6)
+
+    def give_grads(ps_a, ps_b):
+        for x, y in zip(ps_a, ps_b):
+            gr = torch.randn(*x.shape, generator=g).cuda()
+            if x.grad is None:
+                x.grad, y.grad = gr.clone(), gr.clone()
+            else:  # same .grad storage as before: the table's (param, grad) pointers do not change
+                x.grad.copy_(gr)
+                y.grad.copy_(gr)
+
+    for _ in range(3):
+        give_grads(pa, pb)
+        oa.step()
+        ob.step()
+    saved = copy.deepcopy(oa.state_dict())
+    for _ in range(2):  # move on, then roll the optimizer state back
+        give_grads(pa, pb)
+        oa.step()
+    with torch.no_grad():
+        for x, y in zip(pa, pb):
+            x.copy_(y)
+    oa.load_state_dict(saved)
+    for _ in range(2):
+        give_grads(pa, pb)
+        oa.step()
+        ob.step()
+        for x, y in zip(pa, pb):
+            assert torch.allclose(x, y, rtol=5e-6, atol=1e-7), (x - y).abs().max().item()
+    assert float(oa.state_dict()["state"][0]["step"]) == 5.0
+
+
+def test_adam_late_parameter_does_not_reset_the_group_step():
+    """A parameter that gets its first gradient later (and is first in the list) must not alias
+    a fresh step = 0 onto the others."""
+    from mri_image_generation_b200.optim import Adam
+    pa = make_params(7)
+    oa = Adam(pa, lr=1e-3)
+    for _ in range(3):
+        for p in pa[1:]:
+            p.grad = torch.ones_like(p)
+        oa.step()
+    for p in pa:
+        p.grad = torch.ones_like(p)
+    oa.step()
+    assert float(oa.state[pa[1]]["step"]) == 4.0

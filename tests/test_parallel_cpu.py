@@ -165,6 +165,16 @@ def _sync_worker(rank, world, port, out_dir):
     sync.enabled = False      # no_sync(): plain local backward, one un-segmented launch list
     pr._backward(torch.zeros(1), 1, sync)
     out["local"] = pr.garena[:pr._garena_used].clone()
+    # gradient accumulation: what the no_sync() step left in .grad is reduced by the next
+    # synchronised backward (torch DDP semantics)
+    assert sync._pending_local
+    ps = [torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(5))]
+    ps[0].grad = torch.full((3, 2), float(rank + 1))
+    ps[1].grad = torch.arange(5, dtype=torch.float32) * (rank + 1)
+    sync.enabled = True
+    sync.reduce_pending(ps)
+    out["accum"] = [p.grad.clone() for p in ps]
+    assert not sync._pending_local
     torch.save(out, os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -190,6 +200,8 @@ def test_grad_sync_gloo_world2(tmp_path):
     assert len(b) >= 3 and b[0][0] == 0 and all(x[1] == y[0] for x, y in zip(b, b[1:]))
     assert b[-1][1] == r0["arena0"].numel()
     assert any(k.startswith("bwd_seg") for k in r0["replayed"])
+    assert torch.equal(r0["accum"][0], torch.full((3, 2), 1.5))
+    assert torch.equal(r1["accum"][1], torch.arange(5, dtype=torch.float32) * 1.5)
     # no_sync: rank-local gradients, whole-list launch
     for i, (off, n) in r1["off"].items():
         assert torch.allclose(r1["local"][off:off + n], (2.0 * r1["values"][i]).reshape(-1))

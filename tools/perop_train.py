@@ -4,6 +4,7 @@
 import collections, contextlib, io, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mri_image_generation_b200 import ops  # noqa: E402
 os.environ["MRI_NO_GRAPH"] = "1"
 cfg = os.environ.get("CFG", "25d")
 with contextlib.redirect_stdout(io.StringIO()):
@@ -30,7 +31,8 @@ def fwd():
     return [(n, a.elapsed_time(b)) for n, a, b in ev]
 def bwd():
     prog.dout_in.normal_()
-    torch._foreach_zero_(prog._zero_each_bwd)
+    for chunk, used in prog._zero_each_bwd:
+        ops.memset_zero(chunk, used)
     ev = []
     for n, fn in zip(prog.bwd_names, prog.bwd_ops):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
