@@ -198,6 +198,259 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------
+def family_times(torch, dev, seq, plain_graph, reps: int = 5, load_replays: int = 4):
+    """Per-family kernel time of ONE reverse step measured INSIDE a replayed CUDA graph.
+
+    `seq` = [(family, fn)] is the step's launch list.  The step is captured once more with an
+    external timing event (an event-record node) at every boundary between two families;
+    consecutive events bracket contiguous runs of one family, so the family sums telescope to the
+    instrumented step's duration by construction (sum <= step).  Each sample is taken right after
+    `load_replays` replays of the plain step graph so that clocks / power state are those of the
+    timed loop.  Falls back to one small graph per run with ordinary events between the graphs
+    if external events cannot be captured."""
+    fams = [f for f, _ in seq]
+    bounds = [0] + [i for i in range(1, len(seq)) if fams[i] != fams[i - 1]] + [len(seq)]
+    runs = [(fams[a], a, b) for a, b in zip(bounds, bounds[1:])]
+    acc = {}
+    steps = []
+    mode = "event-record nodes inside one graph"
+    try:
+        evs = []
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(dev)
+        with torch.cuda.graph(g):
+            for fam, a, b in runs:
+                e = torch.cuda.Event(enable_timing=True, external=True)
+                e.record()
+                evs.append(e)
+                for _, fn in seq[a:b]:
+                    fn()
+            e = torch.cuda.Event(enable_timing=True, external=True)
+            e.record()
+            evs.append(e)
+        for _ in range(reps):
+            for _ in range(load_replays):
+                plain_graph.replay()
+            g.replay()
+            torch.cuda.synchronize(dev)
+            for (fam, _, _), e0, e1 in zip(runs, evs, evs[1:]):
+                acc[fam] = acc.get(fam, 0.0) + e0.elapsed_time(e1)
+            steps.append(evs[0].elapsed_time(evs[-1]))
+    except Exception as exc:  # noqa: BLE001
+        mode = f"one graph per run, events between graph launches ({type(exc).__name__})"
+        acc, steps = {}, []
+        torch.cuda.synchronize(dev)
+        graphs = []
+        for fam, a, b in runs:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _, fn in seq[a:b]:
+                    fn()
+            graphs.append(g)
+        for _ in range(reps):
+            for _ in range(load_replays):
+                plain_graph.replay()
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(runs) + 1)]
+            evs[0].record()
+            for g, e in zip(graphs, evs[1:]):
+                g.replay()
+                e.record()
+            torch.cuda.synchronize(dev)
+            for (fam, _, _), e0, e1 in zip(runs, evs, evs[1:]):
+                acc[fam] = acc.get(fam, 0.0) + e0.elapsed_time(e1)
+            steps.append(evs[0].elapsed_time(evs[-1]))
+    out = {k: v / reps for k, v in acc.items()}
+    return out, sum(steps) / len(steps), (max(steps) - min(steps)) / (sum(steps) / len(steps)), mode, len(runs)
+
+
+def gpu_comparator(torch, dev, B: int, sd):
+    """SURVEY.md 8(d) "GPU comparator": the reference's own PyTorch graph (the oracle restatement:
+    the same ATen / cuDNN / cuBLAS calls the reference modules make) run EAGERLY on this GPU at
+    the benched shape -- fp32 with TF32 (train.py:72) and under autocast(bf16) (train.py:395),
+    cudnn.benchmark on (train.py:71).  A reported baseline like cpu_baseline; nothing of it is on
+    the product path."""
+    from oracle import reference_oracle as O
+    old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32,
+           torch.get_float32_matmul_precision())
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.set_float32_matmul_precision("high")
+    out = {"cudnn": torch.backends.cudnn.version(), "batch_per_step": B,
+           "what": "reference graph (oracle restatement) eager on the same GPU, one reverse step"}
+    try:
+        buf = {k: v.to(dev) for k, v in O.schedule_buffers(O.cosine_betas(T_STEPS)).items()}
+        x = torch.randn(B, *LATENT, device=dev)
+        t = torch.full((B,), 500, device=dev, dtype=torch.long)
+
+        def step(autocast):
+            ctx = torch.autocast("cuda", dtype=torch.bfloat16) if autocast else contextlib.nullcontext()
+            with torch.no_grad():
+                with ctx:
+                    eps = O.unet3d_forward(sd, x, t)
+                return O.p_sample_update(buf, x, t, eps.float(), torch.randn_like(x))
+
+        for name, ac in (("autocast_bf16", True), ("tf32", False)):
+            for _ in range(2):
+                step(ac)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(3):
+                step(ac)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / 3
+            out[name] = {"ms_per_step": ms, "value": B / (T_STEPS * ms * 1e-3), "unit": "volumes/s",
+                         "tflops": B * 1276.4e9 / (ms * 1e-3) / 1e12}
+    except Exception as exc:  # noqa: BLE001
+        out["error"] = repr(exc)
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32 = old[0], old[1]
+        torch.set_float32_matmul_precision(old[2])
+        torch.cuda.empty_cache()
+    return out
+
+
+def train_record(args, torch, dist, rank, world, dev, B: int, K: int, W: int):
+    """BASELINE.json cfg5: K timed DDP training steps of the 3D LDM UNet at B latents per GPU --
+    q_sample (noise drawn in-kernel) + forward + min-SNR loss + backward with the bucketed NCCL
+    all-reduce overlapped (ddpm_3d_ldm/train.py:232-233,395-400) + fused Adam.  Returns the
+    record that goes on the bench line (rank 0) or None."""
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.diffusion import GaussianDiffusionLatent3D
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.unet_attention import \
+        UNet3DModelWithAttention
+    from mri_image_generation_b200.parallel import wrap_ddp
+
+    torch.manual_seed(0)
+    model = UNet3DModelWithAttention(**MODEL_KW).to(dev).train()
+    overlap = not getattr(args, "torch_ddp", False)
+    net = wrap_ddp(model, dev, overlap=overlap) if world > 1 else model
+    diff = quiet(GaussianDiffusionLatent3D, net, LATENT[0], timesteps=T_STEPS).to(dev)
+    if getattr(args, "torch_adam", False):
+        opt = torch.optim.Adam(model.parameters(), lr=2e-4)
+    else:  # one-launch Adam (mri_adam_step), same update rule and state layout
+        from mri_image_generation_b200.optim import Adam
+        opt = Adam(model.parameters(), lr=2e-4)
+    torch.manual_seed(1234 + rank)
+    z = torch.randn(B, *LATENT, device=dev)
+
+    def step():
+        t = torch.randint(1, T_STEPS, (B,), device=dev)
+        opt.zero_grad(set_to_none=True)
+        loss = diff.p_losses(z, t, cond=None, min_snr_gamma=5.0)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def timed(n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        return e0.elapsed_time(e1), loss
+
+    for _ in range(max(W, 4)):   # two eager steps, the capturing one, a replayed one
+        step()
+    sampler = ClockSampler(dev.index) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_dev, loss = timed(K)
+    clocks = sampler.stop() if sampler else None
+    # end to end: every step's latents come from pinned host memory and every step's loss is read
+    # back to the host (a 4-byte D2H that also synchronises the step)
+    z_host = z.cpu().pin_memory()
+    Ke = min(K, 10)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(Ke):
+        z.copy_(z_host, non_blocking=True)
+        loss_host = step().item()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_e2e = e0.elapsed_time(e1)
+    # ---- communication: per-bucket events, exposed time, overlap on / off --------------------
+    comm = None
+    ms_noov = 0.0
+    prog = model.program(B, LATENT[1:], training=True)
+    if world > 1 and overlap:
+        gs = net.grad_sync
+        gs.time_buckets = True
+        reports = []
+        for _ in range(3):
+            step()
+            torch.cuda.synchronize(dev)
+            reports.append(gs.bucket_report())
+        gs.time_buckets = False
+        comm = reports[-1]
+        if comm is not None:
+            comm["exposed_comm_ms_samples"] = [r["exposed_comm_ms"] for r in reports if r]
+            comm["n_buckets"] = len(gs.buckets_last_step)
+            comm["bucket_cap_mb"] = gs.bucket_bytes / (1 << 20)
+        # A/B: one bucket = the all-reduce starts after the whole backward (no overlap)
+        cap = gs.bucket_bytes
+        gs.bucket_bytes = 1 << 40
+        prog.bwd_segments = []
+        for _ in range(4):
+            step()
+        ms_noov, _ = timed(min(K, 10))
+        ms_noov /= min(K, 10)
+        gs.bucket_bytes = cap
+        prog.bwd_segments = []
+    ms = torch.tensor([ms_dev, ms_e2e, ms_noov], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    ms_per_step = ms[0].item() / K
+    ms_e2e_step = ms[1].item() / Ke
+    flops = B * 3 * 1276.4e9  # fwd + bwd = 3 x fwd (SURVEY.md 8d: 30.62 TFLOP per 8-sample step)
+    peaks = load_peaks()
+    rec = {
+        "metric": "training samples/sec (3D LDM UNet DDP step)", "value": world * B / (ms_per_step / 1e3),
+        "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": max(W, 4), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "ddpm_3d_ldm_train_step", "latent": list(LATENT), "batch_per_gpu": B,
+                   "model": "UNet3DModelWithAttention(base 128, mults 1-2-4, 136.4M params)",
+                   "step": "q_sample (in-kernel Philox) + fwd + min-SNR loss + bwd + DDP all-reduce + Adam",
+                   "ddp": ("none (1 GPU)" if world == 1 else "torch DDP (reducer after backward)" if not overlap
+                           else "bucketed NCCL all-reduce (545.6 MB fp32) overlapped with the backward launch list"),
+                   "optimizer": "torch.optim.Adam" if getattr(args, "torch_adam", False) else "mri_b200 fused Adam",
+                   "loss": float(loss.item())},
+        "e2e": {"value": world * B / (ms_e2e_step / 1e3), "unit": "samples/s",
+                "h2d_bytes_per_step": z_host.numel() * 4, "d2h_bytes_per_step": 4, "steps": Ke,
+                "path": "pinned host latents -> p_losses -> backward -> Adam -> loss.item() on the host, every step",
+                "last_loss": loss_host},
+        # launches of this library per step: forward + backward launch lists (replayed as CUDA
+        # graphs), q_sample, loss forward / backward, weight re-pack, gradient finalisation, Adam
+        "gpu_launches": (len(prog.ops) + len(prog.bwd_ops) + 8) * K,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": flops / (ms_per_step * 1e-3) / 1e12,
+                     "peak": peaks["tflops"], "unit": "TFLOP/s",
+                     "frac": flops / (ms_per_step * 1e-3) / 1e12 / peaks["tflops"],
+                     "note": "whole step (all kernels + optimizer + all-reduce), algorithmic conv+attention FLOPs",
+                     "executed_gemm_flops": prog.gemm_flops + prog.bwd_flops},
+    }
+    if comm is not None:
+        rec["comm"] = comm
+        rec["no_overlap_ms_per_step"] = ms[2].item()
+        rec["overlap_gain_ms"] = ms[2].item() - ms_per_step
+    del opt, diff, net, model
+    torch.cuda.empty_cache()
+    return rec
+
+
+# ------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -226,7 +479,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- device-resident timing: K replays of the captured reverse step --------------------
     with torch.no_grad():
         diff._reverse_loop(prog, x_T, T_STEPS - 1, W, "ddpm")  # builds + captures + W warm-up steps
-        graph = diff._graphs()[(id(prog), "ddpm")]
+        graph = prog._step_graphs["ddpm"][2]
         prog.x_in.copy_(x_T)
         prog.t_in.fill_(T_STEPS - 1)
         sampler = ClockSampler(local_rank)
@@ -293,27 +546,41 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
         ms_e2e = e0.elapsed_time(e1)
 
-        # ---- per-kernel timing of the dominant kernel (tcgen05 implicit GEMM), CUDA events ---
+        # ---- per-family kernel time, measured INSIDE the replayed step graph ------------------
+        from mri_image_generation_b200 import ops as _ops
         gemm_idx = [i for i, n in enumerate(prog.op_names) if n.startswith("gemm:")]
         gn_idx = {i for i, _ in prog.gn_ops}   # GroupNorm-apply launches: the HBM-bound family
-        evs, gn_evs = [], []
-        reps = 3
-        stream = torch.cuda.current_stream(dev)
-        for r in range(reps + 1):
-            prog._arena[:max(prog._arena_used, 4)].zero_()
-            for i, fn in enumerate(prog.ops):
-                if (i in gemm_idx or i in gn_idx) and r > 0:
-                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record(stream)
-                    fn()
-                    b.record(stream)
-                    (evs if i in gemm_idx else gn_evs).append((a, b))
-                else:
-                    fn()
-        torch.cuda.synchronize(dev)
-        gemm_ms = sum(a.elapsed_time(b) for a, b in evs) / reps
-        gn_ms = sum(a.elapsed_time(b) for a, b in gn_evs) / reps
+        rng = diff._rng(dev)
+        inc = _ops.randn_offset_increment(prog.x_in.numel())
+        seq = [("other", lambda: _ops.memset_zero(prog._arena, max(prog._arena_used, 4) * 8))]
+        for i, fn in enumerate(prog.ops):
+            seq.append(("gemm" if i in set(gemm_idx) else "gn" if i in gn_idx else "other", fn))
+        seq.append(("other", lambda: _ops.ddpm_step_rng(
+            prog.x_in, prog.eps_nhwc, rng, prog.t_in, diff.betas, diff.sqrt_one_minus_alphas_cumprod,
+            diff.sqrt_recip_alphas, diff.posterior_variance, prog.x_in, eps_nhwc_ldc=prog.cout_pad,
+            channels=prog.cout)))
+        seq.append(("other", lambda: _ops.step_advance(prog.t_in, -1, rng=rng, rng_increment=inc)))
+        prog.x_in.copy_(x_T)
+        prog.t_in.fill_(T_STEPS - 1)
+        fam, inst_ms, inst_spread, fam_mode, n_runs = family_times(torch, dev, seq, graph)
+        gemm_ms, gn_ms, other_ms = fam.get("gemm", 0.0), fam.get("gn", 0.0), fam.get("other", 0.0)
         gn_bytes = sum(nb for _, nb in prog.gn_ops)
+        evs = []
+        if args.per_op:   # eager per-op events (each launch bracketed on its own): --per-op only
+            reps = 3
+            stream = torch.cuda.current_stream(dev)
+            for r in range(reps + 1):
+                _ops.memset_zero(prog._arena, max(prog._arena_used, 4) * 8)
+                for i, fn in enumerate(prog.ops):
+                    if i in gemm_idx and r > 0:
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record(stream)
+                        fn()
+                        b.record(stream)
+                        evs.append((a, b))
+                    else:
+                        fn()
+            torch.cuda.synchronize(dev)
         if args.per_op and rank == 0:
             per = {}
             for j, (a, b) in enumerate(evs):
@@ -331,6 +598,15 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t_ms.tolist()
+    comparator = None
+    if world == 1 and not args.no_gpu_comparator:
+        sd_dev = {k: v.detach() for k, v in model.state_dict().items()}
+        comparator = gpu_comparator(torch, dev, B, sd_dev)
+    # ---- secondary record: BASELINE cfg5 DDP training step on the same N GPUs --------------------
+    train = None
+    if not args.no_train:
+        train = train_record(args, torch, dist, rank, world, dev, args.train_batch,
+                             min(K, args.train_steps), W)
     if rank != 0:
         return
 
@@ -344,7 +620,7 @@ def run_ours(args, rank, world, local_rank):
     executed_flops = prog.gemm_flops
     achieved = conv_flops / (gemm_ms * 1e-3) / 1e12
     x_bytes = x_host.numel() * 4
-    launches_per_step = len(prog.ops) + 4  # + arena memset, noise draw, fused update, t -= 1
+    launches_per_step = len(prog.ops) + 2  # + fused update (in-kernel Philox), step advance
     cpu = None
     if world == 1 or rank == 0:
         if not args.no_cpu_baseline:
@@ -381,7 +657,12 @@ def run_ours(args, rank, world, local_rank):
                      "peak_source": peaks["source"] + " (bf16_tflops_sustained)",
                      "flops_per_step": conv_flops, "executed_flops_per_step": executed_flops,
                      "kernel_ms_per_step": gemm_ms,
-                     "share_of_step": gemm_ms / ms_per_step},
+                     "share_of_step": gemm_ms / inst_ms,
+                     "timing": {"how": "CUDA events at every family boundary INSIDE one replayed step graph ("
+                                       + fam_mode + "), mean of 5 samples each taken after 4 plain replays",
+                                "instrumented_step_ms": inst_ms, "plain_step_ms": ms_per_step,
+                                "spread": inst_spread, "event_pairs_per_step": n_runs,
+                                "families_ms": {"gemm_tc": gemm_ms, "gn_apply": gn_ms, "other": other_ms}}},
         # second kernel family of the step: GroupNorm-apply (+SiLU, + time-embedding add, + residual),
         # HBM-bound; algorithmic bytes = 2 B read + 2 B written per element (+2 B with a residual)
         "roofline_hbm": {"bound": "hbm", "kernel": "gn_apply_kernel (all GroupNorm+SiLU launches of the step)",
@@ -389,115 +670,30 @@ def run_ours(args, rank, world, local_rank):
                          "frac": gn_bytes / (gn_ms * 1e-3) / 1e9 / peaks["hbm"],
                          "traffic": tr_gn.get("dram_bytes"),
                          "bytes_per_step": gn_bytes, "kernel_ms_per_step": gn_ms,
-                         "share_of_step": gn_ms / ms_per_step, "launches_per_step": len(prog.gn_ops)},
+                         "share_of_step": gn_ms / inst_ms, "launches_per_step": len(prog.gn_ops)},
         "cpu_baseline": cpu,
     }
+    if comparator is not None:
+        line["gpu_comparator"] = comparator
+    if train is not None:
+        line["train"] = train
     print(json.dumps(line), flush=True)
 
 
 def run_train(args, rank, world, local_rank):
-    """Secondary workload (BASELINE.json cfg5): one DDP training step of the 3D LDM UNet --
-    q_sample + UNet fwd + min-SNR loss + bwd (+ NCCL gradient all-reduce through torch DDP when
-    world > 1) + Adam -- at `--batch` latents per GPU.  Prints samples/s; not the headline."""
+    """Secondary workload (BASELINE.json cfg5) on its own: `--mode train` prints the training
+    record (samples/s) as the line; the default sampling run carries the same record under
+    "train"."""
     import torch
     import torch.distributed as dist
     from mri_image_generation_b200 import _lib
-    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.diffusion import GaussianDiffusionLatent3D
-    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.unet_attention import \
-        UNet3DModelWithAttention
-    from mri_image_generation_b200.parallel import wrap_ddp
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _lib.require_device()
-    B, K, W = args.batch, args.steps, max(3, args.warmup)
-    torch.manual_seed(0)
-    model = UNet3DModelWithAttention(**MODEL_KW).to(dev).train()
-    net = wrap_ddp(model, dev, overlap=not args.torch_ddp) if world > 1 else model
-    diff = quiet(GaussianDiffusionLatent3D, net, LATENT[0], timesteps=T_STEPS).to(dev)
-    if args.torch_adam:
-        opt = torch.optim.Adam(model.parameters(), lr=2e-4)
-    else:  # one-launch Adam (mri_adam_step), same update rule and state layout
-        from mri_image_generation_b200.optim import Adam
-        opt = Adam(model.parameters(), lr=2e-4)
-    torch.manual_seed(1234 + rank)
-    z = torch.randn(B, *LATENT, device=dev)
-
-    def step():
-        t = torch.randint(1, T_STEPS, (B,), device=dev)
-        opt.zero_grad(set_to_none=True)
-        loss = diff.p_losses(z, t, cond=None, min_snr_gamma=5.0)
-        loss.backward()
-        opt.step()
-        return loss
-
-    for _ in range(W):
-        step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        loss = step()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    clocks = sampler.stop() if sampler else None
-    ms_dev = e0.elapsed_time(e1)
-    # end to end: every step's latents come from pinned host memory and every step's loss is read
-    # back to the host (a 4-byte D2H that also synchronises the step)
-    z_host = z.cpu().pin_memory()
-    Ke = min(K, 10)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    e0.record()
-    for _ in range(Ke):
-        z.copy_(z_host, non_blocking=True)
-        loss_host = step().item()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms = torch.tensor([ms_dev, e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    if rank != 0:
-        return
-    ms_per_step = ms[0].item() / K
-    ms_e2e_step = ms[1].item() / Ke
-    prog = model.program(B, LATENT[1:], training=True)
-    flops = B * 3 * 1276.4e9  # fwd + bwd = 3 x fwd (SURVEY.md 8d: 30.62 TFLOP per 8-sample step)
-    peaks = load_peaks()
-    line = {
-        "metric": "training samples/sec (3D LDM UNet DDP step)", "value": world * B / (ms_per_step / 1e3),
-        "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic",
-        "config": {"workload": "ddpm_3d_ldm_train_step", "latent": list(LATENT), "batch_per_gpu": B,
-                   "model": "UNet3DModelWithAttention(base 128, mults 1-2-4, 136.4M params)",
-                   "step": "q_sample + fwd + min-SNR loss + bwd + DDP all-reduce + Adam",
-                   "ddp": ("none (1 GPU)" if world == 1 else "torch DDP (reducer after backward)" if args.torch_ddp
-                           else "bucketed NCCL all-reduce overlapped with the backward launch list: buckets "
-                           + str(len(net.grad_sync.buckets_last_step))),
-                   "optimizer": "torch.optim.Adam" if args.torch_adam else "mri_b200 fused Adam",
-                   "loss": float(loss.item())},
-        "e2e": {"value": world * B / (ms_e2e_step / 1e3), "unit": "samples/s",
-                "h2d_bytes_per_step": z_host.numel() * 4, "d2h_bytes_per_step": 4, "steps": Ke,
-                "path": "pinned host latents -> p_losses -> backward -> Adam -> loss.item() on the host, every step",
-                "last_loss": loss_host},
-        # launches of this library per step: forward + backward launch lists (replayed as CUDA
-        # graphs), q_sample, loss forward / backward, weight re-pack, gradient finalisation, Adam (2)
-        "gpu_launches": (len(prog.ops) + len(prog.bwd_ops) + 8) * K,
-        "clocks": clocks,
-        "roofline": {"bound": "tensor", "achieved": flops / (ms_per_step * 1e-3) / 1e12,
-                     "peak": peaks["tflops"], "unit": "TFLOP/s",
-                     "frac": flops / (ms_per_step * 1e-3) / 1e12 / peaks["tflops"],
-                     "note": "whole step (all kernels + optimizer + all-reduce), algorithmic conv+attention FLOPs",
-                     "executed_gemm_flops": prog.gemm_flops + prog.bwd_flops},
-    }
-    print(json.dumps(line), flush=True)
+    rec = train_record(args, torch, dist, rank, world, dev, args.batch, args.steps, max(3, args.warmup))
+    if rank == 0:
+        print(json.dumps(rec), flush=True)
 
 
 def run_vae(args, rank, world, local_rank):
@@ -560,6 +756,12 @@ def main():
                     help="sample = headline (cfg4); train = DDP training step (cfg5); vae = VAE3D "
                          "encode / decode at the cfg4 volume size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-comparator", action="store_true",
+                    help="skip the eager cuDNN run of the reference graph on the same GPU (N = 1 only)")
+    ap.add_argument("--no-train", action="store_true",
+                    help="sample mode: skip the cfg5 DDP training-step record appended to the line")
+    ap.add_argument("--train-batch", type=int, default=8, help="latents per GPU of the training record")
+    ap.add_argument("--train-steps", type=int, default=20, help="timed steps of the training record (<= --steps)")
     ap.add_argument("--torch-adam", action="store_true", help="train mode: torch.optim.Adam instead of "
                     "mri_image_generation_b200.optim.Adam")
     ap.add_argument("--torch-ddp", action="store_true", help="train mode, N > 1: torch DDP instead of the "

@@ -265,6 +265,8 @@ int mri_add_i64(int64_t* t, int n, int64_t delta, void* stream);
  *                       i < n; rng[1] += rng_increment
  *                       (rng nullable) -- the bookkeeping between two replays of a captured step
  * ------------------------------------------------------------------------------------------ */
+/* mri_rng_seed: rng[0] = seed, rng[1] = offset, stream-ordered (no host synchronisation) */
+int mri_rng_seed(uint64_t* rng, uint64_t seed, uint64_t offset, void* stream);
 int mri_randn_offset_increment(int64_t numel, uint64_t* increment_out);
 int mri_randn(float* out, int64_t numel, const uint64_t* rng, void* stream);
 int mri_q_sample_rng(const float* x0, const uint64_t* rng, const int64_t* t, const float* sqrt_ac,

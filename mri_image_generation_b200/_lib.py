@@ -131,6 +131,7 @@ SIGNATURES = {
     "mri_minsnr_loss": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i64, _vp]),
     "mri_add_i64": (_i, [_vp, _i, _i64, _vp]),
     "mri_randn_offset_increment": (_i, [_i64, C.POINTER(C.c_uint64)]),
+    "mri_rng_seed": (_i, [_vp, _u64, _u64, _vp]),
     "mri_randn": (_i, [_vp, _i64, _vp, _vp]),
     "mri_q_sample_rng": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "mri_ddpm_step_rng": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),

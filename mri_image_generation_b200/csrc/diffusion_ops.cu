@@ -374,6 +374,13 @@ __global__ void add_i64_kernel(int64_t* t, int n, int64_t delta) {
   if (i < n) t[i] += delta;
 }
 
+__global__ void rng_seed_kernel(uint64_t* rng, uint64_t seed, uint64_t offset) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    rng[0] = seed;
+    rng[1] = offset;
+  }
+}
+
 static inline dim3 ew_grid(int samples, int64_t per_sample) {
   int64_t bx = (per_sample + 255) / 256;
   int64_t cap = (148 * 8 + samples - 1) / samples;
@@ -501,6 +508,13 @@ extern "C" int mri_ddim_step(const float* x, const void* eps, int eps_nhwc_ldc, 
       x, eps, eps_nhwc_ldc, channels, t, t_prev, alphas_cumprod, out, per_sample, numel, g.Tt,
       g.n_iter);
   return check_launch("ddim_step_kernel");
+}
+
+extern "C" int mri_rng_seed(uint64_t* rng, uint64_t seed, uint64_t offset, void* stream) {
+  if (rng == nullptr) return set_error(-2, "mri_rng_seed: null state");
+  if (offset % 4 != 0) return set_error(-2, "mri_rng_seed: philox offset must be a multiple of 4");
+  rng_seed_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(rng, seed, offset);
+  return check_launch("rng_seed_kernel");
 }
 
 extern "C" int mri_step_advance(int64_t* t, int64_t* t_prev, int n, int64_t delta, uint64_t* rng,

@@ -176,9 +176,10 @@ class DeviceRng:
         seed, off = int(g.initial_seed()), int(g.get_offset())
         if off % 4:
             raise _lib.MriError("CUDA generator offset must be a multiple of 4")
-        if seed >= 1 << 63:
-            seed -= 1 << 64
-        self.state.copy_(torch.tensor([seed, off], dtype=torch.int64))
+        # stream-ordered 1-thread launch: no host synchronisation, no pinned staging buffer
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().mri_rng_seed(_p(self.state), seed & ((1 << 64) - 1), off, _s()),
+                       "mri_rng_seed")
         return off
 
     def commit(self, offset: int) -> None:

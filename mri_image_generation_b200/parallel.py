@@ -178,11 +178,37 @@ class GradSync:
 
     def finish(self) -> None:
         """Compute stream waits for all buckets (no host synchronisation with NCCL)."""
+        timing = self.time_buckets and self._works and self._works[0][1].is_cuda
+        if timing:  # how long the compute stream stalls here = the exposed communication
+            cur = torch.cuda.current_stream(self._works[0][1].device)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(cur)
         for w, buf, backend in self._works:
             w.wait()
             if backend != "nccl":
                 buf.mul_(1.0 / self.world())
+        if timing:
+            b.record(cur)
+            self.finish_events = (a, b)
         self._works = []
+
+    def bucket_report(self) -> Optional[dict]:
+        """After a step run with time_buckets = True (and a device synchronise): per-bucket
+        queueing / transfer times, the time the compute stream stalled in finish() (exposed
+        communication) and the bucket that ended last."""
+        if not self.bucket_events or getattr(self, "finish_events", None) is None:
+            return None
+        a, b = self.finish_events
+        rows = []
+        for i, (ready, e0, e1, nbytes) in enumerate(self.bucket_events):
+            rows.append({"bucket": i, "mbytes": round(nbytes / 1e6, 2),
+                         "queue_ms": round(ready.elapsed_time(e0), 4),
+                         "comm_ms": round(e0.elapsed_time(e1), 4),
+                         # > 0: this bucket was still in flight when the backward launch list ended
+                         "end_after_backward_ms": round(a.elapsed_time(e1), 4)})
+        last = max(rows, key=lambda r: r["end_after_backward_ms"])
+        return {"exposed_comm_ms": round(a.elapsed_time(b), 4), "limiting_bucket": last["bucket"],
+                "buckets": rows}
 
 
 class DistributedDataParallel(torch.nn.Module):

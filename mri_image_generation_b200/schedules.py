@@ -4,7 +4,7 @@ the CPU exactly as the reference builds them, then moved with the module).
 linear:  slice_cond_2d_ddpm/diffusion.py:23-49, ddpm_25d_all_modalities/diffusion.py:22-47
 cosine:  ddpm_3d_ldm/diffusion.py:23-56
 These must stay bit-identical to the reference (checkpoints carry them; metrics.py:291-294
-infers `timesteps` from betas.numel()), which tests/test_schedules.py checks against
+infers `timesteps` from betas.numel()), which tests/test_oracle_golden.py and tests/test_host_api.py check against
 tests/golden/schedules.pt.
 """
 import math

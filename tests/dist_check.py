@@ -1,4 +1,5 @@
-"""Multi-GPU checks (run under torchrun on a multi-GPU box; not collected by pytest):
+"""Multi-GPU checks (run under torchrun on a multi-GPU box; tests/test_gpu_dist.py launches this
+script as a collected `-m gpu` test when at least 2 GPUs are visible):
 
   torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_check.py
 
@@ -123,9 +124,16 @@ def main():
     dist.all_gather(gathered, g_local)
     assert rel(sum(gathered) / world, grads_ddp["mid_attn.qkv.weight"]) < 1e-5
     assert world == 1 or not torch.equal(gathered[0], gathered[1])
+    # gradient accumulation: the next synchronised backward also reduces what no_sync() left in
+    # .grad (torch DDP semantics) -> .grad == 2 x the averaged gradient on every rank
+    diff_o.p_losses(x0[sl].to(dev), t[sl].to(dev), noise=noise[sl].to(dev)).backward()
+    for n in ("mid_attn.qkv.weight", "in_conv.weight", "out_conv.bias"):
+        p = dict(model.named_parameters())[n]
+        assert rel(p.grad, 2 * grads_ddp[n]) < 1e-5, (n, rel(p.grad, 2 * grads_ddp[n]))
     if rank == 0:
         print(f"[dist_check] overlapped all-reduce ({nb} buckets, eager + captured + replayed steps) == "
-              f"torch DDP gradients (rel-L2 < 2e-6 per tensor); no_sync() keeps local gradients")
+              f"torch DDP gradients (rel-L2 < 2e-6 per tensor); no_sync() keeps local gradients and the next "
+              f"synchronised step reduces the accumulated ones")
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
