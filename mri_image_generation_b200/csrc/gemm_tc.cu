@@ -251,6 +251,10 @@ __device__ __forceinline__ float4* partial_ptr(const MriGemmArgs& p, int cta, in
 // than the element-wise stores on the cfg2 forward (29.6 vs 28.3 ms, same GPU, back to back), so
 // the staging stores are not what paces the epilogue -- see profiles/README.md item 8.
 __constant__ int g_frag_epilogue = 0;
+// Probing switch (tools/gemm_probe.py, MRI_GEMM_DBG): removes parts of the swap_ab epilogue to
+// attribute its cost.  1: no statistics math, 2: no staging stores, 4: no TMA store, 8: no TMEM
+// loads.  Results are garbage with any bit set; 0 (default) is the product path.
+__constant__ int g_dbg = 0;
 
 // 16 TMEM lanes x 16 columns: thread T gets rows T/4 and T/4 + 8, columns 2(T%4) + {0, 1} (+8):
 // r0 r1 = (row, c) (row, c+1), r2 r3 = (row+8, ..), r4..r7 = the same for columns + 8
@@ -1091,14 +1095,15 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
               b = 0.f;
             };
             uint32_t v[16];
-            if (!frag) tmem_ld16(tacc + (uint32_t)(h * 128), v);  // software pipeline: next chunk's TMEM load
+            const int dbg = g_dbg;
+            if (!frag && !(dbg & 8)) tmem_ld16(tacc + (uint32_t)(h * 128), v);  // software pipeline: next chunk's TMEM load
             for (int c0 = 0; c0 < kBlockM; c0 += 16) { // is in flight while this one is processed
               if (frag || c0 >= rows_in_box) break;
-              tmem_ld_wait();
+              if (!(dbg & 8)) tmem_ld_wait();
               float f[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + add_c;
-              if (c0 + 16 < rows_in_box) tmem_ld16(tacc + (uint32_t)(h * 128 + c0 + 16), v);
+              if (c0 + 16 < rows_in_box && !(dbg & 8)) tmem_ld16(tacc + (uint32_t)(h * 128 + c0 + 16), v);
               const uint32_t vm = (s_vmask[c0 >> 5] >> (c0 & 31)) & 0xffffu;  // valid positions
               const uint32_t rowb = (uint32_t)c0 * 128u;
               if (has_res) {  // TMA zero-filled the positions outside the tensor
@@ -1151,6 +1156,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
                     }
                   }
                 }
+              } else if (dbg & 1) {
               } else if (vm == 0xffffu) {
                 float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};  // short dependency chains
 #pragma unroll
@@ -1168,12 +1174,14 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
                   s_sq = fmaf(x, x, s_sq);
                 }
               }
+              if (!(dbg & 2)) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const __nv_bfloat16 o = __float2bfloat16_rn(f[i]);
-                asm volatile("st.shared.u16 [%0], %1;" ::"r"(swz8[i & 7] + rowb + (uint32_t)i * 128u),
-                             "h"(*reinterpret_cast<const uint16_t*>(&o))
-                             : "memory");
+                for (int i = 0; i < 16; ++i) {
+                  const __nv_bfloat16 o = __float2bfloat16_rn(f[i]);
+                  asm volatile("st.shared.u16 [%0], %1;" ::"r"(swz8[i & 7] + rowb + (uint32_t)i * 128u),
+                               "h"(*reinterpret_cast<const uint16_t*>(&o))
+                               : "memory");
+                }
               }
             }
             if (per_pos_sample) flush_pp(s_sum, s_sq, pp_sample);
@@ -1193,9 +1201,11 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
             fence_proxy_async_smem();
             named_bar_sync(1, 128);
             if (epi_tid == 0) {
-              tma_store_5d(o_map, sset, t.n0, oh[0], oh[1], oh[2], oh[3]);
-              if (chunk1)
-                tma_store_5d(o_map, sset + kChunkBytes, t.n0 + 64, oh[0], oh[1], oh[2], oh[3]);
+              if (!(dbg & 4)) {
+                tma_store_5d(o_map, sset, t.n0, oh[0], oh[1], oh[2], oh[3]);
+                if (chunk1)
+                  tma_store_5d(o_map, sset + kChunkBytes, t.n0 + 64, oh[0], oh[1], oh[2], oh[3]);
+              }
               tma_store_commit();
             }
           }
@@ -1305,6 +1315,17 @@ extern "C" int mri_gemm_launch(const MriGemmArgs* a, void* stream) {
     cudaError_t ce = cudaMemcpyToSymbol(g_frag_epilogue, &v, sizeof(int));
     if (ce != cudaSuccess) return set_cuda_error(ce, "cudaMemcpyToSymbol(g_frag_epilogue)");
     frag_configured = 1;
+  }
+  {  // probing switch: re-read on every launch (tools/gemm_probe.py changes it between variants)
+    static int dbg_last = 0;
+    const char* e = getenv("MRI_GEMM_DBG");
+    const int v = e != nullptr ? atoi(e) : 0;
+    if (v != dbg_last) {
+      cudaError_t ce = cudaMemcpyToSymbolAsync(g_dbg, &v, sizeof(int), 0, cudaMemcpyHostToDevice,
+                                               (cudaStream_t)stream);
+      if (ce != cudaSuccess) return set_cuda_error(ce, "cudaMemcpyToSymbol(g_dbg)");
+      dbg_last = v;
+    }
   }
   MriGemmArgs k = *a;
   // short K loops (2D convolutions: 9 taps): the epilogue, not the main loop, paces the CTA ->

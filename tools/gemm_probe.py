@@ -25,6 +25,11 @@ SHAPES = [
     ("L0 256->128", (40, 48, 40), [128, 128], 128, 3),
     ("L1 256->256", (20, 24, 20), [256], 256, 3),
     ("L2 512->512", (10, 12, 10), [512], 512, 3),
+    # epilogue-bound shapes: thin K (a 1x1x1 convolution, n_kb = 2, like in_conv / out_conv.taps /
+    # the attention logits) and the 2D models' top levels (9 taps x 1-2 slabs)
+    ("T0 1x1 128->128", (40, 48, 40), [128], 128, 1),
+    ("2D 64->64 240", (240, 240), [64], 64, 3),
+    ("2D 128->128 120", (120, 120), [128], 128, 3),
 ]
 
 
@@ -73,10 +78,13 @@ def main():
             continue
         for vs in args.variants.split(","):
             var = {}
+            os.environ["MRI_GEMM_DBG"] = "0"
             if vs != "base":
                 for kv in vs.split("+"):
                     a, b = kv.split("=")
                     var[a] = int(b)
+            if "dbg" in var:   # epilogue attribution switch, read by mri_gemm_launch on every launch
+                os.environ["MRI_GEMM_DBG"] = str(var["dbg"])
             try:
                 pl, keep = build(args.batch, sp, cins, cout, k, var)
             except Exception as e:  # noqa: BLE001
