@@ -674,7 +674,13 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
       decode_tile(p, geom, tile, t);
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
 
-      mbar_wait(tmem_full_bar(buf), ((uint32_t)seg >> 1) & 1u);
+      if (trace != nullptr && epi_tid == 0) {   // [12]: epilogue waiting for accumulators
+        const long long t0 = clock64();
+        mbar_wait(tmem_full_bar(buf), ((uint32_t)seg >> 1) & 1u);
+        trace[12] += (uint64_t)(clock64() - t0);
+      } else {
+        mbar_wait(tmem_full_bar(buf), ((uint32_t)seg >> 1) & 1u);
+      }
       tc_fence_after();
       if (trace != nullptr && epi_tid == 0) trace[4] = (uint64_t)clock64();
 
@@ -955,7 +961,9 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
             }
             // this set of staging buffers must have been read out by the store that last used it
             if (epi_tid == 0) {
+              const long long t0 = trace != nullptr ? clock64() : 0;
               if (staging2) tma_store_wait_read1(); else tma_store_wait_read0();
+              if (trace != nullptr) trace[13] += (uint64_t)(clock64() - t0);  // [13]: staging busy
             }
             named_bar_sync(1, 128);  // also publishes the position tables
             if (has_res) {

@@ -142,7 +142,8 @@ def main():
                     d = tr[:, col] - tr[:, 1]
                     print(f"    {nm:22s} min {int(d.min()):8d}  median {int(np.median(d)):8d}  max {int(d.max()):8d} cycles")
                 for nm, col in (("MMA waits for operands", 7), ("MMA waits for epilogue", 8),
-                                ("producer waits (ring full)", 9), ("producer waits (x ring)", 10), ("segments", 11)):
+                                ("producer waits (ring full)", 9), ("producer waits (x ring)", 10), ("segments", 11),
+                                ("epilogue waits for MMA", 12), ("epilogue waits for staging", 13)):
                     d = tr[:, col]
                     print(f"    {nm:26s} min {int(d.min()):8d}  median {int(np.median(d)):8d}  max {int(d.max()):8d}")
             del pl, keep
