@@ -308,7 +308,11 @@ gather_pack_kernel(const MriGatherSeg* __restrict__ segs, int n_segs) {
     if (i >= sg.n) break;
     const int32_t e = __ldg(sg.idx + i);
     float v = 0.f;
-    if (e >= 0) v = __ldg(sg.src[(e >> 28) & 3] + (e & 0x0fffffff));
+    if (e >= 0) {  // select, not a dynamically indexed copy of the array (that would live in local memory)
+      const int sl = (e >> 28) & 3;
+      const float* sp = sl == 0 ? sg.src[0] : (sl == 1 ? sg.src[1] : (sl == 2 ? sg.src[2] : sg.src[3]));
+      v = __ldg(sp + (e & 0x0fffffff));
+    }
     if (sg.dst_bf16) reinterpret_cast<__nv_bfloat16*>(sg.dst)[i] = __float2bfloat16_rn(v);
     else reinterpret_cast<float*>(sg.dst)[i] = v;
   }

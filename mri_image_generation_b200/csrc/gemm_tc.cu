@@ -84,6 +84,14 @@ __device__ __forceinline__ Geom make_geom(const MriGemmArgs& p) {
   return g;
 }
 
+// a[i] for a run-time i WITHOUT indexing the array: a dynamically indexed local array lives in
+// local memory (a stack frame), and with 227 KB of shared memory per CTA the L1 that is left cannot
+// hold 192 stack frames -- every access then costs an L2 round trip (measured: ~10 k cycles of
+// epilogue per tile with NO work in it, profiles/r02b_epi_trace.txt).  Selects keep it in registers.
+__device__ __forceinline__ int pick4(const int (&a)[4], int i) {
+  return i == 0 ? a[0] : (i == 1 ? a[1] : (i == 2 ? a[2] : a[3]));
+}
+
 __device__ __forceinline__ void decode_tile(const MriGemmArgs& p, const Geom& g, int tile, Work& w) {
   const int nt = tile % p.n_tiles_n;
   int pr = tile / p.n_tiles_n;
@@ -96,23 +104,29 @@ __device__ __forceinline__ void decode_tile(const MriGemmArgs& p, const Geom& g,
     b0 = 2 * pr;
     w.nbox = (b0 + 1 < g.boxes_per_class) ? 2 : 1;
   }
-  const int f = p.tile_fast_dim;  // boxes advance along this dim first, then x1..x4 in order
+  // boxes advance along dim f first, then along x1..x4 in order: enumeration step k visits dim
+  // ord(k) = f, then the others ascending
+  const int f = p.tile_fast_dim;
+  int te[4], od[4];  // extents / dims in enumeration order (static indices only)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    od[k] = (f == 0) ? k : (k == 0 ? f : (k <= f ? k - 1 : k));
+    te[k] = od[k] == 0 ? p.tiles[0] : (od[k] == 1 ? p.tiles[1] : (od[k] == 2 ? p.tiles[2] : p.tiles[3]));
+  }
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     int b = b0 + h;
-    if (f != 0) {
-      w.tix[h][f] = b % p.tiles[f];
-      b /= p.tiles[f];
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = b % te[k];
+      b /= te[k];
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      if (i != f || f == 0) {
-        w.tix[h][i] = b % p.tiles[i];
-        b /= p.tiles[i];
-      }
+      w.tix[h][i] = od[0] == i ? v[0] : (od[1] == i ? v[1] : (od[2] == i ? v[2] : v[3]));
+      w.org[h][i] = w.tix[h][i] * p.box[i];
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) w.org[h][i] = w.tix[h][i] * p.box[i];
   }
 }
 
@@ -458,7 +472,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
       while (it.next(tile, kb0, len, seg_end)) {
         Work t;
         decode_tile(p, geom, tile, t);
-        auto sel = [&](int s) { return s == 0 ? 0 : (s == 1 ? t.cls : t.tix[0][s - 2]); };
+        auto sel = [&](int s) { return s == 0 ? 0 : (s == 1 ? t.cls : pick4(t.tix[0], s - 2)); };
         const int bz1 = sel(p.bz_sel[0]);
         const int bz2 = sel(p.bz_sel[1]);
         const uint32_t tx_bytes = (uint32_t)(rows_in_box * t.nbox) * 128u + (uint32_t)block_n * 128u;
@@ -760,8 +774,8 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
           bool valid = r < rows_in_box;
 #pragma unroll
           for (int i = 0; i < 4; ++i) valid = valid && (t.org[0][i] + rl[i] < p.ext[i]);
-          const int sample = sd > 0 ? t.org[0][sd - 1] + rl[sd - 1] : 0;
-          const int tile_sample = sd > 0 ? t.org[0][sd - 1] : 0;
+          const int tile_sample = sd > 0 ? pick4(t.org[0], sd - 1) : 0;
+          const int sample = sd > 0 ? tile_sample + pick4(rl, sd - 1) : 0;
           if (smem_stats && tile_sample != cur_sample) {
             flush_smem_stats();
             cur_sample = tile_sample;
@@ -949,12 +963,12 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
               bool ok = epi_tid < rows_in_box;
 #pragma unroll
               for (int i = 0; i < 4; ++i) ok = ok && (oh[i] + pl[i] < p.ext[i]);
-              const int smp = sd > 0 ? oh[sd - 1] + pl[sd - 1] : 0;
+              const int smp = sd > 0 ? pick4(oh, sd - 1) + pick4(pl, sd - 1) : 0;
               s_pos_info[epi_tid] = ok ? smp : -1;
               const uint32_t bal = __ballot_sync(0xffffffffu, ok);
               if (lane == 0) s_vmask[warp - 2] = bal;  // positions 32*(warp-2) .. +31
             }
-            const int tile_sample = sd > 0 ? oh[sd - 1] : 0;
+            const int tile_sample = sd > 0 ? pick4(oh, sd - 1) : 0;
             if (smem_stats && tile_sample != cur_sample) {
               flush_smem_stats();
               cur_sample = tile_sample;
