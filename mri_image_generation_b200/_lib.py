@@ -11,6 +11,8 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmri_b200.so")
+if os.environ.get("MRI_B200_LIB"):   # kernel-probe builds (tools/): an explicitly named library
+    LIB_PATH = os.environ["MRI_B200_LIB"]
 
 
 class MriGemmArgs(C.Structure):

@@ -43,13 +43,41 @@
 #include "common.h"
 #include "ptx.cuh"
 
+// Fine-grained epilogue trace (tools/gemm_probe.py ft=1; compile with -DMRI_GEMM_FINE_TRACE): per-phase
+// cycle sums of epilogue threads 0 and 96 in trace rows [gridDim + block] and [2 gridDim + block].
+#ifdef MRI_GEMM_FINE_TRACE
+#define FT_START() do { if (trace != nullptr) ft_t = clock64(); } while (0)
+#define FT_ADD(k) do { if (trace != nullptr) { const long long n_ = clock64(); ft[k] += (unsigned long long)(n_ - ft_t); ft_t = n_; } } while (0)
+#else
+#define FT_START() do { } while (0)
+#define FT_ADD(k) do { } while (0)
+#endif
+
 namespace mri {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // bf16 -> 128-byte rows = one swizzle span
 constexpr int kUmmaK = 16;
 constexpr int kSlabBytes = kBlockM * 128;        // 128 rows x 64 bf16
-constexpr int kThreads = 192;
+// Warp roles.  Default (MRI_EPI_WARPS = 4): 6 warps -- TMA producer, MMA issuer, four epilogue warps
+// (a warp may only read the TMEM lane quadrant warp % 4).  MRI_EPI_WARPS = 8 builds the variant with
+// 12 warps = 3 warpgroups: WG0 = {producer, MMA issuer, 2 idle warps}, WG1 + WG2 = 8 epilogue warps
+// in PAIRS per quadrant that split the columns of every tile, registers re-balanced with setmaxnreg
+// (the CTA launches at 168 per thread; 104 + 2 * 200 = 3 * 168 is what one sub-partition's three
+// warps own).  Measured on B200 (profiles/README.md, round 2): the pairs hide each other's latencies
+// only on partial-box tiles; everywhere else the variant LOSES 4 % on the cfg4 step, because the
+// values shared by all roles end up in a stack frame and the single-thread producer / MMA loops
+// re-load them every k-step.  What made the epilogue ~1.6x faster instead was doing less per box.
+#ifndef MRI_EPI_WARPS
+#define MRI_EPI_WARPS 4
+#endif
+constexpr int kEpiWarps = MRI_EPI_WARPS;
+static_assert(kEpiWarps == 4 || kEpiWarps == 8, "one or two epilogue warps per TMEM lane quadrant");
+constexpr int kSplit = kEpiWarps / 4;                   // warps sharing a quadrant split a tile's columns
+constexpr int kEpiWarp0 = kEpiWarps == 8 ? 4 : 2;       // first epilogue warp
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;  // 384 / 192
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kRegsProducer = 104, kRegsEpilogue = 200;  // 104 + 2 * 200 = 3 * 168: what one sub-partition's three warps own
 constexpr int kMaxStages = 8;
 constexpr int kChunkBytes = kBlockM * 128;       // one staging buffer: 128 rows x 128 bytes
 constexpr int kStagingBytes = 2 * kChunkBytes;
@@ -74,13 +102,41 @@ struct Geom {
   int boxes_per_class;   // boxes of positions per output class
   int groups_per_class;  // tiles along the position axis per class (box pairs when swap_ab)
   long long n_tiles;
+  // reciprocals for fdivmod (tile index -> class / channel block / box coordinates): a generic
+  // 32-bit division is ~25 instructions and decode_tile needs a dozen of them per tile
+  float rcp_ntn, rcp_gpc, rcp_te[4];
+  int te[4], od[4];      // box-grid extents / dims in enumeration order
 };
+
+// n / d and n % d for 0 <= n < 2^24, d >= 1 through one float multiply and a fix-up
+__device__ __forceinline__ void fdivmod(int n, int d, float rcp, int& q, int& r) {
+  q = __float2int_rz(__int2float_rn(n) * rcp);
+  r = n - q * d;
+  if (r < 0) {
+    --q;
+    r += d;
+  } else if (r >= d) {
+    ++q;
+    r -= d;
+  }
+}
 
 __device__ __forceinline__ Geom make_geom(const MriGemmArgs& p) {
   Geom g;
   g.boxes_per_class = p.tiles[0] * p.tiles[1] * p.tiles[2] * p.tiles[3];
   g.groups_per_class = p.swap_ab ? (g.boxes_per_class + 1) / 2 : g.boxes_per_class;
   g.n_tiles = (long long)p.n_tiles_n * p.n_class * g.groups_per_class;
+  g.rcp_ntn = 1.0f / (float)p.n_tiles_n;
+  g.rcp_gpc = 1.0f / (float)g.groups_per_class;
+  // boxes advance along dim f first, then along x1..x4 in order: enumeration step k visits dim
+  // od[k] = f, then the others ascending
+  const int f = p.tile_fast_dim;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    g.od[k] = (f == 0) ? k : (k == 0 ? f : (k <= f ? k - 1 : k));
+    g.te[k] = g.od[k] == 0 ? p.tiles[0] : (g.od[k] == 1 ? p.tiles[1] : (g.od[k] == 2 ? p.tiles[2] : p.tiles[3]));
+    g.rcp_te[k] = 1.0f / (float)g.te[k];
+  }
   return g;
 }
 
@@ -93,25 +149,16 @@ __device__ __forceinline__ int pick4(const int (&a)[4], int i) {
 }
 
 __device__ __forceinline__ void decode_tile(const MriGemmArgs& p, const Geom& g, int tile, Work& w) {
-  const int nt = tile % p.n_tiles_n;
-  int pr = tile / p.n_tiles_n;
-  w.cls = pr / g.groups_per_class;
-  pr -= w.cls * g.groups_per_class;
+  int nt, pr;
+  fdivmod(tile, p.n_tiles_n, g.rcp_ntn, pr, nt);
+  int rem;
+  fdivmod(pr, g.groups_per_class, g.rcp_gpc, w.cls, rem);
   w.n0 = nt * p.block_n;
-  int b0 = pr;
+  int b0 = rem;
   w.nbox = 1;
   if (p.swap_ab) {
-    b0 = 2 * pr;
+    b0 = 2 * rem;
     w.nbox = (b0 + 1 < g.boxes_per_class) ? 2 : 1;
-  }
-  // boxes advance along dim f first, then along x1..x4 in order: enumeration step k visits dim
-  // ord(k) = f, then the others ascending
-  const int f = p.tile_fast_dim;
-  int te[4], od[4];  // extents / dims in enumeration order (static indices only)
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    od[k] = (f == 0) ? k : (k == 0 ? f : (k <= f ? k - 1 : k));
-    te[k] = od[k] == 0 ? p.tiles[0] : (od[k] == 1 ? p.tiles[1] : (od[k] == 2 ? p.tiles[2] : p.tiles[3]));
   }
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -119,12 +166,13 @@ __device__ __forceinline__ void decode_tile(const MriGemmArgs& p, const Geom& g,
     int v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      v[k] = b % te[k];
-      b /= te[k];
+      int qn;
+      fdivmod(b, g.te[k], g.rcp_te[k], qn, v[k]);
+      b = qn;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      w.tix[h][i] = od[0] == i ? v[0] : (od[1] == i ? v[1] : (od[2] == i ? v[2] : v[3]));
+      w.tix[h][i] = g.od[0] == i ? v[0] : (g.od[1] == i ? v[1] : (g.od[2] == i ? v[2] : v[3]));
       w.org[h][i] = w.tix[h][i] * p.box[i];
     }
   }
@@ -259,39 +307,6 @@ __device__ __forceinline__ float4* partial_ptr(const MriGemmArgs& p, int cta, in
          ((size_t)cta * (kPartialLd / 4) + (size_t)(col >> 2)) * kBlockM + lane128;
 }
 
-// swap_ab epilogue through accumulator FRAGMENTS: experimental, OFF unless MRI_GEMM_FRAG_EPI=1.
-// tools/tmem_frag_probe.cu establishes the two layouts used here; the path is parity-tested
-// (tests/test_gpu_gemm.py::test_fragment_epilogue_in_a_subprocess) but measured 4.5 % SLOWER
-// than the element-wise stores on the cfg2 forward (29.6 vs 28.3 ms, same GPU, back to back), so
-// the staging stores are not what paces the epilogue -- see profiles/README.md item 8.
-__constant__ int g_frag_epilogue = 0;
-// Probing switch (tools/gemm_probe.py, MRI_GEMM_DBG): removes parts of the swap_ab epilogue to
-// attribute its cost.  1: no statistics math, 2: no staging stores, 4: no TMA store, 8: no TMEM
-// loads.  Results are garbage with any bit set; 0 (default) is the product path.
-__constant__ int g_dbg = 0;
-
-// 16 TMEM lanes x 16 columns: thread T gets rows T/4 and T/4 + 8, columns 2(T%4) + {0, 1} (+8):
-// r0 r1 = (row, c) (row, c+1), r2 r3 = (row+8, ..), r4..r7 = the same for columns + 8
-__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-}
-// four 8x8 b16 matrices, transposed on the way: register i of thread T holds (rows 2(T%4) + {0, 1},
-// column T/4) of matrix i; lanes 8i .. 8i+7 give the addresses of that matrix's eight 16-byte rows
-__device__ __forceinline__ void stmatrix_x4_trans(uint32_t addr, const uint32_t (&m)[4]) {
-  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-               "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3])
-               : "memory");
-}
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&m)[4]) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(m[3])
-               : "r"(addr)
-               : "memory");
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -332,9 +347,18 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
   const int n_kb = p.n_kb;
   const int G = (int)gridDim.x;
   const int my_r = G - 1 - (int)blockIdx.x;  // waiters (tile heads) wait on LOWER block indices
-  const Geom geom = make_geom(p);
-  const long long n_tiles = geom.n_tiles;
-  const Sched sch = make_sched(p, n_tiles, G);
+  // tile geometry and schedule live in shared memory, not in registers: they are read once per
+  // tile (decode_tile, SegIter), and the single-thread producer / MMA loops run on a small
+  // register budget after setmaxnreg -- values kept live across their k-loops would be spilled
+  // to local memory and re-loaded every k-step
+  __shared__ Geom s_geom;
+  __shared__ Sched s_sch;
+  if (threadIdx.x == 0) {
+    s_geom = make_geom(p);
+    s_sch = make_sched(p, s_geom.n_tiles, G);
+  }
+  const Geom& geom = s_geom;
+  const Sched& sch = s_sch;
   const int rows_in_box = p.box[0] * p.box[1] * p.box[2] * p.box[3];
   const bool dual = !swap && block_n <= 128;  // two accumulators per tile (k-step parity)
 
@@ -346,7 +370,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tmem_full_bar(b), 1);
-      mbar_init(tmem_empty_bar(b), 4);  // one arrive per epilogue warp
+      mbar_init(tmem_empty_bar(b), kEpiThreads / 32);  // one arrive per epilogue warp
     }
     mbar_init(resid_bar, 1);
     for (int xs = 0; xs < kXStages; ++xs) mbar_init(xempty_bar(xs), 1);
@@ -389,6 +413,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
   };
 
   if (warp == 0) {
+    if (kEpiWarps == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
     // ================================ TMA producer ==================================
     // ONE elected thread owns the whole loop (barrier waits, table reads, TMA issue).  Measured
     // with tools/feed_probe.cu: keeping the warp converged around a per-step elect.sync costs
@@ -511,6 +536,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
       }
     }
   } else if (warp == 1) {
+    if (kEpiWarps == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
     // ================================ MMA issuer ====================================
     // one elected thread owns the loop as well (see the producer): waits, tcgen05.mma, commits
     if (!elect_one_sync()) {
@@ -618,11 +644,16 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
         trace[11] = (uint64_t)seg;
       }
     }
+  } else if (warp < kEpiWarp0) {
+    if (kEpiWarps == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));  // idle warps of WG0
   } else {
+    if (kEpiWarps == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue));
     // ================================ epilogue ======================================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int ew = warp - kEpiWarp0;  // epilogue warp 0..7
+    const int half = ew >> 2;         // which half of a tile's columns this warp of the pair takes
     const int r = q * 32 + lane;  // TMEM lane: position (normal) or channel (swap_ab) of this thread
-    const int epi_tid = (warp - 2) * 32 + lane;
+    const int epi_tid = ew * 32 + lane;   // 0..255; threads 0..127 also describe positions
     const int esize = p.out_f32 ? 4 : 2;
     const int chunk_cols_full = p.out_f32 ? 32 : 64;
     const int chunk_cols = block_n < chunk_cols_full ? block_n : chunk_cols_full;
@@ -635,6 +666,13 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
     const int cpg = p.stats_cpg;
     const float* bias = p.bias;
     int cur_sample = -1;       // sample whose statistics s_stats currently accumulates
+    float rb_val = 0.f;        // swap_ab: cached rowbias[(rb_sample, rb_ch)]
+    int rb_sample = -1, rb_ch = -1;
+    // swap_ab, uniform sample: fp32 statistics sums of channel acc_ch over sample acc_sample
+    float s_sum = 0.f, s_sq = 0.f;
+    int acc_sample = -1, acc_ch = -1;
+    const bool pow2 = cpg > 0 && (cpg & (cpg - 1)) == 0 && cpg <= 32;
+    const int span = pow2 ? cpg : ((cpg > 0 && cpg % 32 == 0) ? 32 : 1);  // lanes sharing a stats group
     uint32_t chunk_ctr = 0;    // staging buffer alternation across tiles (normal mode)
     uint32_t resid_phase = 0;  // swap_ab: parity of the residual-tile barrier
 
@@ -665,13 +703,33 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
     uint32_t box_ctr = 0;
 
     auto flush_smem_stats = [&]() {  // all 128 epilogue threads
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kEpiThreads);
       if (cur_sample >= 0 && epi_tid < 2 * p.stats_ld) {
         const double v = s_stats[epi_tid];
         if (v != 0.0) atomicAdd(p.stats + (size_t)cur_sample * p.stats_ld * 2 + epi_tid, v);
         s_stats[epi_tid] = 0.0;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kEpiThreads);
+    };
+
+    // reduce the lanes that share a statistics group, then one fp64 atomic pair per group
+    // (warp-uniform call: acc_sample and the validity of a warp's 32 channels are warp-uniform)
+    auto reduce_acc_stats = [&]() {
+      if (p.stats != nullptr && acc_sample >= 0 && acc_ch >= 0) {
+        for (int o = span >> 1; o > 0; o >>= 1) {
+          s_sum += __shfl_xor_sync(0xffffffffu, s_sum, o);
+          s_sq += __shfl_xor_sync(0xffffffffu, s_sq, o);
+        }
+        if (acc_ch < p.n_total && (lane & (span - 1)) == 0) {
+          const int g = acc_ch / cpg;
+          double* dstp = smem_stats ? &s_stats[g * 2]
+                                    : p.stats + ((size_t)acc_sample * p.stats_ld + g) * 2;
+          atomicAdd(dstp, (double)s_sum);
+          atomicAdd(dstp + 1, (double)s_sq);
+        }
+      }
+      s_sum = 0.f;
+      s_sq = 0.f;
     };
 
     int seg = 0;
@@ -679,6 +737,11 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
     it.init(p, sch, my_r);
     int tile, kb0, len;
     long long seg_end;
+#ifdef MRI_GEMM_FINE_TRACE
+    long long ft_t = 0;
+    unsigned long long ft[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+    FT_START();
     while (it.next(tile, kb0, len, seg_end)) {
       const int buf = seg & 1;
       const bool head = (kb0 == 0);
@@ -686,6 +749,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
       const int acc_cols = swap ? 256 : block_n;
       Work t;
       decode_tile(p, geom, tile, t);
+      FT_ADD(0);
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
 
       if (trace != nullptr && epi_tid == 0) {   // [12]: epilogue waiting for accumulators
@@ -697,10 +761,11 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
       }
       tc_fence_after();
       if (trace != nullptr && epi_tid == 0) trace[4] = (uint64_t)clock64();
+      FT_ADD(1);
 
       if (!head) {
         // ---------- partial tile: raw fp32 sums -> workspace, flag -> the tile's head CTA ------
-        for (int c0 = 0; c0 < acc_cols; c0 += 16) {
+        for (int c0 = half * 16; c0 < acc_cols; c0 += 16 * kSplit) {   // a pair interleaves 16-column groups
           float4* dst = partial_ptr(p, (int)blockIdx.x, r, c0);
           uint32_t v[16], w[16];
           tmem_ld16(tacc + (uint32_t)c0, v);
@@ -726,7 +791,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
         __threadfence();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpiThreads);
         if (epi_tid == 0) st_release_gpu(p.sk_flags + blockIdx.x, 1u);
       } else {
         // ---------- head of the tile: gather partials (if split), fused epilogue --------------
@@ -735,22 +800,23 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
         if (len < n_kb) {
           n_contrib = count_contributors(sch, my_r, seg_end, (long long)(tile + 1) * n_kb);
           if (epi_tid == 0) wait_contributors(p, contrib_cta0, n_contrib);
-          named_bar_sync(1, 128);
+          named_bar_sync(1, kEpiThreads);
           // add the partial tiles into accumulator 0 (fixed order -> deterministic); loads of the
           // next 16 columns are in flight while the current ones are folded into TMEM
           for (int j = 0; j < n_contrib; ++j) {
             const int cta = contrib_cta0 - j;
             float4 nx[4];
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) nx[k4] = __ldcg(partial_ptr(p, cta, r, 0) + (size_t)k4 * kBlockM);
-            for (int c0 = 0; c0 < acc_cols; c0 += 16) {
+            for (int k4 = 0; k4 < 4; ++k4)
+              nx[k4] = __ldcg(partial_ptr(p, cta, r, half * 16) + (size_t)k4 * kBlockM);
+            for (int c0 = half * 16; c0 < acc_cols; c0 += 16 * kSplit) {
               float4 cur[4];
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) cur[k4] = nx[k4];
-              if (c0 + 16 < acc_cols) {
+              if (c0 + 16 * kSplit < acc_cols) {
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4)
-                  nx[k4] = __ldcg(partial_ptr(p, cta, r, c0 + 16) + (size_t)k4 * kBlockM);
+                  nx[k4] = __ldcg(partial_ptr(p, cta, r, c0 + 16 * kSplit) + (size_t)k4 * kBlockM);
               }
               uint32_t v[16];
               tmem_ld16(tacc + (uint32_t)c0, v);
@@ -766,6 +832,11 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
             }
             tmem_st_wait();
           }
+          // the fused epilogue below splits the columns differently from the interleaved fold:
+          // every warp must see its partner's TMEM stores
+          tc_fence_before();
+          named_bar_sync(1, kEpiThreads);
+          tc_fence_after();
         }
         const CUtensorMap* o_map = reinterpret_cast<const CUtensorMap*>(p.o_maps) + t.cls;
 
@@ -828,8 +899,8 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
             const uint32_t sbuf = stag + (chunk_ctr & 1u) * kChunkBytes;
             // the TMA store that last used this buffer (two chunks ago) must have read it out
             if (epi_tid == 0) tma_store_wait_read1();
-            named_bar_sync(1, 128);
-            for (int c0 = cbase; c0 < cbase + chunk_cols; c0 += 16) {
+            named_bar_sync(1, kEpiThreads);
+            for (int c0 = cbase + half * 16; c0 < cbase + chunk_cols; c0 += 16 * kSplit) {
               uint32_t v[16], w[16];
               tmem_ld16(tacc + (uint32_t)c0, v);
               if (two_acc) tmem_ld16(tacc + 128u + (uint32_t)c0, w);
@@ -925,7 +996,7 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
               }
             }
             fence_proxy_async_smem();
-            named_bar_sync(1, 128);
+            named_bar_sync(1, kEpiThreads);
             if (epi_tid == 0) {
               tma_store_5d(o_map, sbuf, t.n0 + cbase, t.org[0][0], t.org[0][1], t.org[0][2],
                            t.org[0][3]);
@@ -949,6 +1020,14 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
           // staging: chunk buffer (q >> 1) holds channels [64*(q>>1), +64); 128B rows, swizzled.
           // Position c0 + i (c0 % 16 == 0) lives in row c0 + i, 16-byte unit (cunit ^ (i & 7)).
           const uint32_t cbyte = (uint32_t)(((q & 1) * 32 + lane) * 2);
+          // statistics sums live in registers ACROSS boxes and tiles for as long as the thread's
+          // channel and the sample stay the same (with one channel block per position -- Cout <= 128 --
+          // that is until the sample changes): the lane shuffles and the two fp64 shared-memory
+          // atomics of the reduction cost ~1 k cycles, which used to be paid per box
+          if (acc_ch != ch) {
+            reduce_acc_stats();
+            acc_ch = ch;
+          }
           for (int h = 0; h < t.nbox; ++h, ++box_ctr) {
             const uint32_t sset = stag + ((staging2 && (box_ctr & 1u)) ? (uint32_t)kStagingBytes : 0u);
             const uint32_t sbuf = sset + (uint32_t)(q >> 1) * kChunkBytes;
@@ -958,17 +1037,28 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
             int oh[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) oh[i] = h ? t.org[1][i] : t.org[0][i];
-            // per-position tables of this box (thread epi_tid describes position epi_tid)
-            {
+            // is the box entirely inside the tensor?  (Then every position is valid and, with a
+            // uniform sample, no per-position table is needed.)
+            bool full = rows_in_box == kBlockM;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) full = full && (oh[i] + p.box[i] <= p.ext[i]);
+            const bool tables = !full || per_pos_sample;
+            if (tables) {  // per-position tables of this box (thread epi_tid describes position epi_tid)
               bool ok = epi_tid < rows_in_box;
 #pragma unroll
               for (int i = 0; i < 4; ++i) ok = ok && (oh[i] + pl[i] < p.ext[i]);
               const int smp = sd > 0 ? pick4(oh, sd - 1) + pick4(pl, sd - 1) : 0;
-              s_pos_info[epi_tid] = ok ? smp : -1;
-              const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-              if (lane == 0) s_vmask[warp - 2] = bal;  // positions 32*(warp-2) .. +31
+              if (ew < 4) {  // threads 0..127 describe the box's 128 positions
+                s_pos_info[epi_tid] = ok ? smp : -1;
+                const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+                if (lane == 0) s_vmask[ew] = bal;  // positions 32 * ew .. + 31
+              }
             }
             const int tile_sample = sd > 0 ? pick4(oh, sd - 1) : 0;
+            if (uniform_sample && tile_sample != acc_sample) {
+              reduce_acc_stats();  // sums of the previous box belong to another sample
+              acc_sample = tile_sample;
+            }
             if (smem_stats && tile_sample != cur_sample) {
               flush_smem_stats();
               cur_sample = tile_sample;
@@ -979,7 +1069,8 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
               if (staging2) tma_store_wait_read1(); else tma_store_wait_read0();
               if (trace != nullptr) trace[13] += (uint64_t)(clock64() - t0);  // [13]: staging busy
             }
-            named_bar_sync(1, 128);  // also publishes the position tables
+            named_bar_sync(1, kEpiThreads);  // also publishes the position tables
+            FT_ADD(2);
             if (has_res) {
               // residual box -> the staging buffers (same layout as the output), by TMA
               if (epi_tid == 0) {
@@ -992,115 +1083,16 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
               mbar_wait(resid_bar, resid_phase);
               resid_phase ^= 1u;
             }
-            const float add_c = bias_c + ((p.rowbias != nullptr && uniform_sample && ch_ok)
-                                              ? __ldg(p.rowbias + (size_t)tile_sample * p.rowbias_ld + ch)
-                                              : 0.f);
-            // ---- fragment path: boxes inside one sample, statistics groups of whole 8-channel blocks.
-            // Per 16 positions a warp issues 2 TMEM loads (16 lanes x 16 columns each) and 2
-            // stmatrix.x4.trans instead of 16 16-bit shared-memory stores per thread: the fragment
-            // of thread T is (channels T/4 + 8k, positions 2(T%4) + {0, 1} (+8)), which stmatrix
-            // writes as 16-byte units of 8 channels into the position rows of the staging tile.
-            const bool frag = g_frag_epilogue != 0 && !per_pos_sample &&
-                              (p.stats == nullptr || (cpg & 7) == 0);
-            if (frag) {
-              float add4[4], fs[4], fq[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int chk = t.n0 + q * 32 + (lane >> 2) + 8 * k;
-                float a = 0.f;
-                if (chk < p.n_total) {
-                  if (bias != nullptr) a += __ldg(bias + chk);
-                  if (p.rowbias != nullptr) a += __ldg(p.rowbias + (size_t)tile_sample * p.rowbias_ld + chk);
-                }
-                add4[k] = a;
-                fs[k] = 0.f;
-                fq[k] = 0.f;
-              }
-              const int tp = (lane & 3) * 2;           // first position of my pairs in an 8-group
-              const int mi = lane >> 3, mr = lane & 7;  // stmatrix: my matrix and row
-              uint32_t ra[2][8];
-              tmem_ld_16x256b_x2(tacc + (uint32_t)(h * 128), ra[0]);   // software pipeline: the next
-              tmem_ld_16x256b_x2(tacc + (16u << 16) + (uint32_t)(h * 128), ra[1]);  // chunk is in flight
-              for (int c0 = 0; c0 < rows_in_box; c0 += 16) {
-                tmem_ld_wait();
-                float xa[2][8];
-#pragma unroll
-                for (int L = 0; L < 2; ++L) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) xa[L][e] = __uint_as_float(ra[L][e]);
-                }
-                if (c0 + 16 < rows_in_box) {
-                  tmem_ld_16x256b_x2(tacc + (uint32_t)(h * 128 + c0 + 16), ra[0]);
-                  tmem_ld_16x256b_x2(tacc + (16u << 16) + (uint32_t)(h * 128 + c0 + 16), ra[1]);
-                }
-                const uint32_t vm = (s_vmask[c0 >> 5] >> (c0 & 31)) & 0xffffu;
-                const uint32_t pos = (uint32_t)(c0 + 8 * (mi >> 1) + mr);
-#pragma unroll
-                for (int L = 0; L < 2; ++L) {
-                  const uint32_t unit = (uint32_t)((q & 1) * 4 + 2 * L + (mi & 1));
-                  const uint32_t addr = sbuf + pos * 128u + ((unit ^ (pos & 7u)) << 4);
-                  uint32_t rm[4] = {0u, 0u, 0u, 0u};
-                  if (has_res) ldmatrix_x4_trans(addr, rm);
-                  uint32_t m[4];
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {   // i: (half = i & 1 -> channel slot 2L + half, j = i >> 1)
-                    const int k = 2 * L + (i & 1);
-                    float x0 = xa[L][2 * i] + add4[k];
-                    float x1 = xa[L][2 * i + 1] + add4[k];
-                    if (has_res) {
-                      x0 += __uint_as_float(rm[i] << 16);
-                      x1 += __uint_as_float(rm[i] & 0xffff0000u);
-                    }
-                    const int b = 8 * (i >> 1) + tp;
-                    const float v0 = ((vm >> b) & 1u) ? x0 : 0.f;
-                    const float v1 = ((vm >> (b + 1)) & 1u) ? x1 : 0.f;
-                    fs[k] += v0 + v1;
-                    fq[k] = fmaf(v0, v0, fmaf(v1, v1, fq[k]));
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
-                    m[i] = *reinterpret_cast<uint32_t*>(&h2);
-                  }
-                  stmatrix_x4_trans(addr, m);
-                }
-              }
-              if (stats_p != nullptr) {
-                // my 4 slots are 4 blocks of 8 channels (lanes T/4 = 0..7): fold the 4 lanes of a
-                // channel and the 8 channels of a block; lane 0 adds one pair per statistics group
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-#pragma unroll
-                  for (int o = 1; o < 32; o <<= 1) {
-                    fs[k] += __shfl_xor_sync(0xffffffffu, fs[k], o);
-                    fq[k] += __shfl_xor_sync(0xffffffffu, fq[k], o);
-                  }
-                }
-                if (lane == 0) {
-                  double a = 0.0, b = 0.0;
-                  int g_prev = (t.n0 + q * 32) / cpg;
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    const int g = (t.n0 + q * 32 + 8 * k) / cpg;
-                    if (g != g_prev) {
-                      double* dstp = smem_stats ? &s_stats[g_prev * 2]
-                                                : p.stats + ((size_t)tile_sample * p.stats_ld + g_prev) * 2;
-                      atomicAdd(dstp, a);
-                      atomicAdd(dstp + 1, b);
-                      a = b = 0.0;
-                      g_prev = g;
-                    }
-                    a += (double)fs[k];
-                    b += (double)fq[k];
-                  }
-                  double* dstp = smem_stats ? &s_stats[g_prev * 2]
-                                            : p.stats + ((size_t)tile_sample * p.stats_ld + g_prev) * 2;
-                  atomicAdd(dstp, a);
-                  atomicAdd(dstp + 1, b);
-                }
-              }
+            // bias + time-embedding projection of (sample, channel): reloaded only when either changes
+            if (p.rowbias != nullptr && uniform_sample && ch_ok &&
+                (tile_sample != rb_sample || ch != rb_ch)) {
+              rb_val = __ldg(p.rowbias + (size_t)tile_sample * p.rowbias_ld + ch);
+              rb_sample = tile_sample;
+              rb_ch = ch;
             }
-            float s_sum = 0.f, s_sq = 0.f;
-            int pp_sample = -1;  // per_pos_sample: sample the register sums belong to
-            const bool pow2 = (cpg & (cpg - 1)) == 0 && cpg <= 32;
-            const int span = pow2 ? cpg : (cpg % 32 == 0 ? 32 : 1);  // lanes sharing a stats group
+            const float add_c = bias_c + ((p.rowbias != nullptr && uniform_sample && ch_ok) ? rb_val : 0.f);
+            int pp_sample = -1;  // per_pos_sample: sample the register sums pp_sum / pp_sq belong to
+            float pp_sum = 0.f, pp_sq = 0.f;
             auto flush_pp = [&](float& a, float& b, int smp) {  // warp-uniform call
               if (stats_p != nullptr && smp >= 0) {
                 for (int o = span >> 1; o > 0; o >>= 1) {
@@ -1116,87 +1108,124 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
               a = 0.f;
               b = 0.f;
             };
-            uint32_t v[16];
-            const int dbg = g_dbg;
-            if (!frag && !(dbg & 8)) tmem_ld16(tacc + (uint32_t)(h * 128), v);  // software pipeline: next chunk's TMEM load
-            for (int c0 = 0; c0 < kBlockM; c0 += 16) { // is in flight while this one is processed
-              if (frag || c0 >= rows_in_box) break;
-              if (!(dbg & 8)) tmem_ld_wait();
-              float f[16];
+            FT_ADD(3);
+            // this warp's half of the box's positions: [c_lo, c_hi)
+            const int c_lo = half * (kBlockM / kSplit);
+            const int c_hi = rows_in_box < c_lo + kBlockM / kSplit ? rows_in_box : c_lo + kBlockM / kSplit;
+            if (full && !has_res && !per_pos_sample) {
+              // ---- fast path: every position valid, one sample, nothing to add from memory.  32
+              // positions per step (one 32-column TMEM load, the next one in flight): long
+              // straight-line blocks give the two warps of a sub-partition independent work to issue
+              const bool want_stats = stats_p != nullptr;
+              uint32_t v[32];
+              tmem_ld32(tacc + (uint32_t)(h * 128 + c_lo), v);
+#pragma unroll 1
+              for (int c0 = c_lo; c0 < c_hi; c0 += 32) {   // full box: c_hi - c_lo = 128 / kSplit
+                tmem_ld_wait();
+                float f[32];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + add_c;
-              if (c0 + 16 < rows_in_box && !(dbg & 8)) tmem_ld16(tacc + (uint32_t)(h * 128 + c0 + 16), v);
-              const uint32_t vm = (s_vmask[c0 >> 5] >> (c0 & 31)) & 0xffffu;  // valid positions
-              const uint32_t rowb = (uint32_t)c0 * 128u;
-              if (has_res) {  // TMA zero-filled the positions outside the tensor
+                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + add_c;
+                if (c0 + 32 < c_hi) tmem_ld32(tacc + (uint32_t)(h * 128 + c0 + 32), v);
+                if (want_stats) {
+                  float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};  // short dependency chains
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  uint16_t rv;
-                  asm volatile("ld.shared.u16 %0, [%1];"
-                               : "=h"(rv)
-                               : "r"(swz8[i & 7] + rowb + (uint32_t)i * 128u));
-                  f[i] += __uint_as_float((uint32_t)rv << 16);
+                  for (int i = 0; i < 32; ++i) {
+                    ps[i & 3] += f[i];
+                    pq[i & 3] = fmaf(f[i], f[i], pq[i & 3]);
+                  }
+                  s_sum += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+                  s_sq += (pq[0] + pq[1]) + (pq[2] + pq[3]);
+                }
+                const uint32_t rowb = (uint32_t)c0 * 128u;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const __nv_bfloat16 o = __float2bfloat16_rn(f[i]);
+                  asm volatile("st.shared.u16 [%0], %1;" ::"r"(swz8[i & 7] + rowb + (uint32_t)i * 128u),
+                               "h"(*reinterpret_cast<const uint16_t*>(&o))
+                               : "memory");
                 }
               }
-              if (per_pos_sample) {
-                // the box spans several samples (sample = slowest box coordinate): a 16-position
-                // chunk normally lies inside one sample -> register sums, flushed on change
-                int smp = -1;
-                bool same = true;
+            } else {
+              // ---- general path: partial boxes, residual tile, boxes spanning several samples ----
+              uint32_t v[16];
+              if (c_lo < c_hi) tmem_ld16(tacc + (uint32_t)(h * 128 + c_lo), v);  // software pipeline
+              for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+                tmem_ld_wait();
+                float f[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const int info = s_pos_info[c0 + i];
-                  if (info >= 0) {
-                    same = same && (smp < 0 || smp == info);
-                    smp = info;
+                for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + add_c;
+                if (c0 + 16 < c_hi) tmem_ld16(tacc + (uint32_t)(h * 128 + c0 + 16), v);
+                const uint32_t vm = tables ? ((s_vmask[c0 >> 5] >> (c0 & 31)) & 0xffffu) : 0xffffu;  // valid positions
+                const uint32_t rowb = (uint32_t)c0 * 128u;
+                if (has_res) {  // TMA zero-filled the positions outside the tensor
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    uint16_t rv;
+                    asm volatile("ld.shared.u16 %0, [%1];"
+                                 : "=h"(rv)
+                                 : "r"(swz8[i & 7] + rowb + (uint32_t)i * 128u));
+                    f[i] += __uint_as_float((uint32_t)rv << 16);
                   }
                 }
-                if (smp >= 0 && same) {
-                  if (smp != pp_sample) {
-                    flush_pp(s_sum, s_sq, pp_sample);
-                    pp_sample = smp;
-                  }
-                  const float rbv = (p.rowbias != nullptr && ch_ok)
-                                        ? __ldg(p.rowbias + (size_t)smp * p.rowbias_ld + ch)
-                                        : 0.f;
+                if (per_pos_sample) {
+                  // the box spans several samples (sample = slowest box coordinate): a 16-position
+                  // chunk normally lies inside one sample -> register sums, flushed on change
+                  int smp = -1;
+                  bool same = true;
 #pragma unroll
                   for (int i = 0; i < 16; ++i) {
-                    f[i] += rbv;
-                    const float x = ((vm >> i) & 1u) ? f[i] : 0.f;
-                    s_sum += x;
-                    s_sq = fmaf(x, x, s_sq);
-                  }
-                } else if (smp >= 0) {  // chunk straddles a sample boundary: element-wise
-                  for (int i = 0; i < 16; ++i) {
                     const int info = s_pos_info[c0 + i];
-                    if (info < 0) continue;
-                    if (p.rowbias != nullptr && ch_ok) f[i] += __ldg(p.rowbias + (size_t)info * p.rowbias_ld + ch);
-                    if (stats_p != nullptr) {
-                      double* dstp = p.stats + ((size_t)info * p.stats_ld + grp) * 2;
-                      atomicAdd(dstp, (double)f[i]);
-                      atomicAdd(dstp + 1, (double)f[i] * (double)f[i]);
+                    if (info >= 0) {
+                      same = same && (smp < 0 || smp == info);
+                      smp = info;
+                    }
+                  }
+                  if (smp >= 0 && same) {
+                    if (smp != pp_sample) {
+                      flush_pp(pp_sum, pp_sq, pp_sample);
+                      pp_sample = smp;
+                    }
+                    const float rbv = (p.rowbias != nullptr && ch_ok)
+                                          ? __ldg(p.rowbias + (size_t)smp * p.rowbias_ld + ch)
+                                          : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                      f[i] += rbv;
+                      const float x = ((vm >> i) & 1u) ? f[i] : 0.f;
+                      pp_sum += x;
+                      pp_sq = fmaf(x, x, pp_sq);
+                    }
+                  } else if (smp >= 0) {  // chunk straddles a sample boundary: element-wise
+                    for (int i = 0; i < 16; ++i) {
+                      const int info = s_pos_info[c0 + i];
+                      if (info < 0) continue;
+                      if (p.rowbias != nullptr && ch_ok) f[i] += __ldg(p.rowbias + (size_t)info * p.rowbias_ld + ch);
+                      if (stats_p != nullptr) {
+                        double* dstp = p.stats + ((size_t)info * p.stats_ld + grp) * 2;
+                        atomicAdd(dstp, (double)f[i]);
+                        atomicAdd(dstp + 1, (double)f[i] * (double)f[i]);
+                      }
+                    }
+                  }
+                } else if (stats_p != nullptr) {
+                  if (vm == 0xffffu) {
+                    float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                      ps[i & 3] += f[i];
+                      pq[i & 3] = fmaf(f[i], f[i], pq[i & 3]);
+                    }
+                    s_sum += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+                    s_sq += (pq[0] + pq[1]) + (pq[2] + pq[3]);
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                      const float x = ((vm >> i) & 1u) ? f[i] : 0.f;
+                      s_sum += x;
+                      s_sq = fmaf(x, x, s_sq);
                     }
                   }
                 }
-              } else if (dbg & 1) {
-              } else if (vm == 0xffffu) {
-                float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};  // short dependency chains
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  ps[i & 3] += f[i];
-                  pq[i & 3] = fmaf(f[i], f[i], pq[i & 3]);
-                }
-                s_sum += (ps[0] + ps[1]) + (ps[2] + ps[3]);
-                s_sq += (pq[0] + pq[1]) + (pq[2] + pq[3]);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const float x = ((vm >> i) & 1u) ? f[i] : 0.f;
-                  s_sum += x;
-                  s_sq = fmaf(x, x, s_sq);
-                }
-              }
-              if (!(dbg & 2)) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                   const __nv_bfloat16 o = __float2bfloat16_rn(f[i]);
@@ -1206,30 +1235,21 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
                 }
               }
             }
-            if (per_pos_sample) flush_pp(s_sum, s_sq, pp_sample);
-            if (stats_p != nullptr && uniform_sample && !frag) {
-              // reduce the lanes that share a statistics group, then one atomic per group
-              for (int o = span >> 1; o > 0; o >>= 1) {
-                s_sum += __shfl_xor_sync(0xffffffffu, s_sum, o);
-                s_sq += __shfl_xor_sync(0xffffffffu, s_sq, o);
-              }
-              if ((lane & (span - 1)) == 0) {
-                double* dstp = smem_stats ? &s_stats[grp * 2]
-                                          : p.stats + ((size_t)tile_sample * p.stats_ld + grp) * 2;
-                atomicAdd(dstp, (double)s_sum);
-                atomicAdd(dstp + 1, (double)s_sq);
-              }
-            }
+            FT_ADD(4);
+            if (per_pos_sample) flush_pp(pp_sum, pp_sq, pp_sample);
+            if (uniform_sample && !smem_stats) reduce_acc_stats();  // global atomics: no CTA-level table
+            FT_ADD(5);
             fence_proxy_async_smem();
-            named_bar_sync(1, 128);
+            FT_ADD(9);
+            named_bar_sync(1, kEpiThreads);
+            FT_ADD(6);
             if (epi_tid == 0) {
-              if (!(dbg & 4)) {
-                tma_store_5d(o_map, sset, t.n0, oh[0], oh[1], oh[2], oh[3]);
-                if (chunk1)
-                  tma_store_5d(o_map, sset + kChunkBytes, t.n0 + 64, oh[0], oh[1], oh[2], oh[3]);
-              }
+              tma_store_5d(o_map, sset, t.n0, oh[0], oh[1], oh[2], oh[3]);
+              if (chunk1)
+                tma_store_5d(o_map, sset + kChunkBytes, t.n0 + 64, oh[0], oh[1], oh[2], oh[3]);
               tma_store_commit();
             }
+            FT_ADD(7);
           }
         }
         // TMEM buffer drained -> the MMA warp may start the tile after next in it
@@ -1241,7 +1261,15 @@ gemm_tc_kernel(const __grid_constant__ MriGemmArgs p) {
         }
       }
       ++seg;
+      FT_ADD(8);
     }
+#ifdef MRI_GEMM_FINE_TRACE
+    if (trace != nullptr && (epi_tid == 0 || epi_tid == 96)) {
+      uint64_t* row = p.trace + (size_t)((epi_tid == 0 ? 1 : 2) * gridDim.x + blockIdx.x) * 16;
+      for (int k = 0; k < 12; ++k) row[k] = ft[k];
+    }
+#endif
+    if (swap) reduce_acc_stats();
     if (smem_stats) flush_smem_stats();
     if (epi_tid == 0) tma_store_wait_all();
     if (trace != nullptr && epi_tid == 0) {
@@ -1310,6 +1338,8 @@ extern "C" int mri_gemm_launch(const MriGemmArgs* a, void* stream) {
   }
   const long long tiles = (long long)a->n_tiles_n * a->n_class * (swap ? (boxes + 1) / 2 : boxes);
   if (rows > kBlockM) return set_error(-2, "mri_gemm_launch: box has more than 128 rows");
+  if (tiles >= (1LL << 24) || boxes + 1 >= (1LL << 24))
+    return set_error(-2, "mri_gemm_launch: more than 2^24 tiles (tile decoding uses float reciprocals)");
   if (tiles > 0x7fffffffLL / a->n_kb) return set_error(-2, "mri_gemm_launch: too many work units");
   if (a->n_total % 8 != 0) return set_error(-2, "mri_gemm_launch: n_total must be a multiple of 8");
   if (a->stats != nullptr && !a->swap_ab && (a->stats_cpg < 8 || a->stats_cpg % 8 != 0))
@@ -1329,25 +1359,6 @@ extern "C" int mri_gemm_launch(const MriGemmArgs* a, void* stream) {
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaDeviceGetAttribute(SM count)");
-  }
-  static int frag_configured = 0;
-  if (!frag_configured) {
-    const char* e = getenv("MRI_GEMM_FRAG_EPI");
-    const int v = (e != nullptr && atoi(e) != 0) ? 1 : 0;
-    cudaError_t ce = cudaMemcpyToSymbol(g_frag_epilogue, &v, sizeof(int));
-    if (ce != cudaSuccess) return set_cuda_error(ce, "cudaMemcpyToSymbol(g_frag_epilogue)");
-    frag_configured = 1;
-  }
-  {  // probing switch: re-read on every launch (tools/gemm_probe.py changes it between variants)
-    static int dbg_last = 0;
-    const char* e = getenv("MRI_GEMM_DBG");
-    const int v = e != nullptr ? atoi(e) : 0;
-    if (v != dbg_last) {
-      cudaError_t ce = cudaMemcpyToSymbolAsync(g_dbg, &v, sizeof(int), 0, cudaMemcpyHostToDevice,
-                                               (cudaStream_t)stream);
-      if (ce != cudaSuccess) return set_cuda_error(ce, "cudaMemcpyToSymbol(g_dbg)");
-      dbg_last = v;
-    }
   }
   MriGemmArgs k = *a;
   // short K loops (2D convolutions: 9 taps): the epilogue, not the main loop, paces the CTA ->

@@ -264,21 +264,6 @@ def test_box_order_does_not_change_results(P):
         outs.append((y, stats))
     for y, st in outs[1:]:
         assert torch.equal(y, outs[0][0])
-        assert torch.allclose(st, outs[0][1], rtol=1e-12, atol=1e-9)
-
-
-def test_fragment_epilogue_in_a_subprocess():
-    """The experimental swap-mode epilogue (tcgen05.ld.16x256b fragments + stmatrix.trans,
-    MRI_GEMM_FRAG_EPI=1; off by default because it measured slower) must stay correct: the
-    stride-1 convolution cases -- bias, row bias, residual, statistics, ragged boxes -- run again in a
-    process that enables it (the switch is read once per process)."""
-    import os
-    import subprocess
-    import sys
-    env = dict(os.environ, MRI_GEMM_FRAG_EPI="1")
-    here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_gemm.py"), "-q", "-x",
-                        "-k", "test_conv_stride1 or test_down_conv or test_up_conv", "-p", "no:cacheprovider"],
-                       env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert " passed" in r.stdout
+        # per-thread fp32 partial sums now span the (up to two) boxes of a tile before they enter the
+        # fp64 accumulators, and which boxes share a tile depends on the box order: fp32 rounding
+        assert torch.allclose(st, outs[0][1], rtol=2e-6, atol=1e-6)

@@ -57,7 +57,7 @@ def build(B, sp, cins, cout, k, var):
         if key in var and hasattr(pl, key):
             setattr(pl, key, var[key])
     if var.get("trace"):
-        pl.trace = torch.zeros(148, 16, dtype=torch.int64, device=dev)
+        pl.trace = torch.zeros(148 * 3, 16, dtype=torch.int64, device=dev)
     pl.materialize(dev)
     return pl, (acts, wm, y, bias, stats)
 
@@ -78,13 +78,10 @@ def main():
             continue
         for vs in args.variants.split(","):
             var = {}
-            os.environ["MRI_GEMM_DBG"] = "0"
             if vs != "base":
                 for kv in vs.split("+"):
                     a, b = kv.split("=")
                     var[a] = int(b)
-            if "dbg" in var:   # epilogue attribution switch, read by mri_gemm_launch on every launch
-                os.environ["MRI_GEMM_DBG"] = str(var["dbg"])
             try:
                 pl, keep = build(args.batch, sp, cins, cout, k, var)
             except Exception as e:  # noqa: BLE001
@@ -131,7 +128,17 @@ def main():
                 pl.trace.zero_()
                 pl.launch()
                 torch.cuda.synchronize()
-                tr = pl.trace.cpu().numpy().astype(np.int64)
+                full = pl.trace.cpu().numpy().astype(np.int64)
+                G = min(148, pl.grid())
+                tr = full[:148]
+                if full[G:3 * G].any():  # fine epilogue trace (library built with -DMRI_GEMM_FINE_TRACE)
+                    names = ["decode_tile", "wait tmem_full", "box head + bar 1", "residual / add_c",
+                             "chunk loop", "stats tail", "bar 2", "store issue", "tile tail", "proxy fence"]
+                    for who, rows in (("thread 0", full[G:2 * G]), ("thread 96", full[2 * G:3 * G])):
+                        tot = rows[:, :10].sum(1)
+                        print(f"    fine trace, epilogue {who}: total {int(np.median(tot))} cycles (median over CTAs)")
+                        for k, nm in enumerate(names):
+                            print(f"        {nm:20s} {int(np.median(rows[:, k])):9d}")
                 tr = tr[tr[:, 0] > 0]
                 t0 = tr[:, 0].min()
                 print(f"    trace over {len(tr)} CTAs (ns from first CTA entry / cycles from CTA setup):")
