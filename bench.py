@@ -550,11 +550,13 @@ def run_ours(args, rank, world, local_rank):
         from mri_image_generation_b200 import ops as _ops
         gemm_idx = [i for i, n in enumerate(prog.op_names) if n.startswith("gemm:")]
         gn_idx = {i for i, _ in prog.gn_ops}   # GroupNorm-apply launches: the HBM-bound family
+        gemm_set = set(gemm_idx)
         rng = diff._rng(dev)
         inc = _ops.randn_offset_increment(prog.x_in.numel())
         seq = [("other", lambda: _ops.memset_zero(prog._arena, max(prog._arena_used, 4) * 8))]
         for i, fn in enumerate(prog.ops):
-            seq.append(("gemm" if i in set(gemm_idx) else "gn" if i in gn_idx else "other", fn))
+            tc = i in gemm_set or prog.op_names[i].startswith("attn:")   # tcgen05 kernels
+            seq.append(("gemm" if tc else "gn" if i in gn_idx else "other", fn))
         seq.append(("other", lambda: _ops.ddpm_step_rng(
             prog.x_in, prog.eps_nhwc, rng, prog.t_in, diff.betas, diff.sqrt_one_minus_alphas_cumprod,
             diff.sqrt_recip_alphas, diff.posterior_variance, prog.x_in, eps_nhwc_ldc=prog.cout_pad,
@@ -649,7 +651,7 @@ def run_ours(args, rank, world, local_rank):
                         "copies on two copy streams, double-buffered against the compute stream"},
         "gpu_launches": launches_per_step * K,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM, all convs + attention GEMMs)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM, all convolutions) + attn_flash_kernel (tcgen05 fused attention)",
                      "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["tflops"], "traffic": tr_gemm.get("dram_bytes"),
                      "traffic_note": ("DRAM bytes read + written by the %d GEMM launches of one step, ncu capture %s"

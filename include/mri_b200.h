@@ -211,6 +211,35 @@ int mri_copy_cast(const void* src, int src_dtype, const int64_t* src_strides, vo
                   int dst_dtype, const int64_t* dst_strides, const int64_t* shape, void* stream);
 int mri_memset_zero(void* ptr, int64_t bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused bottleneck attention, inference (AttentionBlock3D.forward, ddpm_3d_ldm/unet_attention.py:
+ * 44-52: q, k, v = qkv.chunk(3); attn = softmax(einsum('bhcn,bhcm->bhnm') * d^-0.5); out =
+ * einsum('bhnm,bhcm->bhcn')): O = softmax(Q K^T * scale) V per (sample, head) in ONE kernel --
+ * tcgen05 MMAs with S and O in TMEM, online softmax between them, logits and probabilities never
+ * written to HBM (csrc/attn_flash.cu).
+ *   qk_map: CUtensorMap over the token-major qkv tensor, bf16, dims {row length, n, batch}, box
+ *           {64, 128, 1}, 128B swizzle; head h reads q at columns [h*d, (h+1)*d) and k at
+ *           [k_col0 + h*d, ...).
+ *   vt_map: CUtensorMap over v^T, bf16, dims {npad (keys, contiguous), rows, batch}, box
+ *           {64, d, 1}, 128B swizzle; head h reads rows [v_row0 + h*d, ...).  Keys >= n must be
+ *           outside the tensor or zero.
+ *   out:    bf16 [batch][n][ld_out]; head h writes columns [h*d, (h+1)*d).
+ * d must be 64 or 128 (mri_attn_flash_supported).  Training keeps the unfused GEMM / softmax
+ * launches: its backward pass needs the probabilities.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MriAttnArgs {
+  const void* qk_map;
+  const void* vt_map;
+  void* out;
+  int32_t batch, heads, n, d;
+  int32_t C;        /* heads * d */
+  int32_t k_col0, v_row0, ld_out;
+  float scale;      /* d^-0.5 */
+  int32_t reserved;
+} MriAttnArgs;
+int mri_attn_flash_supported(int d);
+int mri_attn_flash_launch(const MriAttnArgs* args, void* stream);
+
 /* Row softmax for the bottleneck attention (unet_attention.py:50): P = softmax(S * scale),
  * S fp32 [rows][ld_s], P bf16 [rows][ld_p], `cols` valid columns (padding columns written 0). */
 int mri_softmax_rows(const float* S, void* P, int64_t rows, int cols, int ld_s, int ld_p,

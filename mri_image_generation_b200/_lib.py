@@ -77,6 +77,13 @@ class MriWgradArgs(C.Structure):
     ]
 
 
+class MriAttnArgs(C.Structure):
+    _fields_ = [("qk_map", C.c_void_p), ("vt_map", C.c_void_p), ("out", C.c_void_p),
+                ("batch", C.c_int32), ("heads", C.c_int32), ("n", C.c_int32), ("d", C.c_int32),
+                ("C", C.c_int32), ("k_col0", C.c_int32), ("v_row0", C.c_int32), ("ld_out", C.c_int32),
+                ("scale", C.c_float), ("reserved", C.c_int32)]
+
+
 class MriGatherSeg(C.Structure):
     _fields_ = [
         ("dst", C.c_void_p),
@@ -123,6 +130,8 @@ SIGNATURES = {
     "mri_tap_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mri_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i64, _i, _i, _vp]),
     "mri_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i64, _i, _i, _vp]),
+    "mri_attn_flash_supported": (_i, [_i]),
+    "mri_attn_flash_launch": (_i, [C.POINTER(MriAttnArgs), _vp]),
     "mri_softmax_rows": (_i, [_vp, _vp, _i64, _i, _i, _i, _f, _vp]),
     "mri_copy_cast": (_i, [_vp, _i, C.POINTER(C.c_int64), _vp, _i, C.POINTER(C.c_int64),
                            C.POINTER(C.c_int64), _vp]),

@@ -699,6 +699,9 @@ class UNet3DProgram(UNetProgram):
         qkv = self.conv([P.ConvSource(hn)], wqkv, C3, 1, blk.qkv.bias, with_stats=False,
                         name=f"{name}.qkv")
         qkv_plan = self.plans[-1]
+        if (not self.training and d in (64, 128) and _lib.load().mri_attn_flash_supported(d)
+                and os.environ.get("MRI_ATTN_FLASH", "1") != "0"):
+            return self._attention_flash(x, blk, name, hn, qkv, heads, d, n, npad)
         # [k^T; v^T][b] = W[C:3C] . hn[b]^T  (+ bias along rows): classes = samples
         wkv = self.packed(lambda: blk.qkv.weight.detach()[C:].reshape(2 * C, C).to(torch.bfloat16).contiguous())
         bkv = self.packed(lambda: blk.qkv.bias.detach()[C:].contiguous())
@@ -747,6 +750,56 @@ class UNet3DProgram(UNetProgram):
         # the norm's GnRec was recorded before the attention record; backward order must be
         # attention first, then the norm: move the norm record after... (tape is reversed, so
         # the later-recorded AttnRec is already processed first)
+        self.pool.release(hn)
+        self.pool.release(qkv.t)
+        self.pool.release(O)
+        self.pool.release(x.t)
+        return out
+
+    def _attention_flash(self, x: Act, blk, name: str, hn: torch.Tensor, qkv: Act, heads: int,
+                         d: int, n: int, npad: int) -> Act:
+        """Inference: softmax(q^T k / sqrt(d)) v in ONE kernel (mri_attn_flash_launch: S and O in
+        TMEM, online softmax between the two MMAs; no logits / probabilities in HBM).  q and k are
+        read straight from the token-major qkv rows; v^T [B, C, npad] comes from one extra GEMM
+        W_v . hn^T (keys contiguous = the K-major B operand of P V)."""
+        import ctypes as C_
+        B, C, dev = self.B, x.C, self.device
+        C3 = 3 * C
+        wv = self.packed(lambda: blk.qkv.weight.detach()[2 * C:].reshape(C, C).to(torch.bfloat16).contiguous())
+        bv = self.packed(lambda: blk.qkv.bias.detach()[2 * C:].contiguous())
+        vT = torch.zeros(B, C, npad, dtype=torch.bfloat16, device=dev)
+        a = P.TView(wv, (C, C, 1, 1, 1), (1, C, C * C, C * C, C * C))
+        b = P.TView(hn, (C, n, B, 1), (1, C, n * C, B * n * C))
+        sz = C * npad
+        o_views = [P.TView(vT, (npad, C, 1, 1, 1), (1, npad, sz, sz, sz), offset=bi * sz)
+                   for bi in range(B)]
+        pl = P.matrix_plan(a, (128, 1, 1, 1), b, o_views[0], K=C, n_total=npad, block_n=128,
+                           ext=(C, 1, 1, 1), tiles=(C // 128, 1, 1, 1), bz_sel=(1, 0),
+                           bias_m=bv, name=f"{name}.vT", flops=2 * B * n * C * C)
+        chunk_box, swz = pl.o_maps[0].box, pl.o_maps[0].swizzle
+        pl.o_maps = [P.MapSpec(v, chunk_box, swz) for v in o_views]
+        pl.ktable = pl.ktable.repeat(B, axis=0)
+        self.gemm(pl)
+        O = self.pool.get(tuple(x.t.shape))
+        maps = P.encode_maps([
+            P.MapSpec(P.TView(qkv.t, (C3, n, B), (1, C3, n * C3)), (64, 128, 1), 3),
+            P.MapSpec(P.TView(vT, (npad, C, B), (1, npad, C * npad)), (64, d, 1), 3)], dev)
+        args = _lib.MriAttnArgs()
+        args.qk_map, args.vt_map, args.out = maps.data_ptr(), maps.data_ptr() + 128, O.data_ptr()
+        args.batch, args.heads, args.n, args.d, args.C = B, heads, n, d, C
+        args.k_col0, args.v_row0, args.ld_out = C, 0, C
+        args.scale = float(d) ** -0.5
+        self._keep_alive = getattr(self, "_keep_alive", []) + [maps, args, vT]
+        lib = _lib.load()
+
+        def flash():
+            _lib.check(lib.mri_attn_flash_launch(C_.byref(args), _lib.current_stream_ptr()),
+                       f"mri_attn_flash_launch[{name}]")
+
+        self._add(f"attn:{name}.flash", flash, [O])
+        self.gemm_flops += 2 * 2 * B * heads * n * n * d
+        wp = self.packed(lambda: P.pack_conv_weight(blk.proj.weight.detach()))
+        out = self.conv([P.ConvSource(O)], wp, C, 1, blk.proj.bias, residual=x.t, name=f"{name}.proj")
         self.pool.release(hn)
         self.pool.release(qkv.t)
         self.pool.release(O)

@@ -267,3 +267,44 @@ def test_box_order_does_not_change_results(P):
         # per-thread fp32 partial sums now span the (up to two) boxes of a tile before they enter the
         # fp64 accumulators, and which boxes share a tile depends on the box order: fp32 rounding
         assert torch.allclose(st, outs[0][1], rtol=2e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,d,heads", [(1200, 128, 2), (700, 64, 3), (100, 128, 1)])
+def test_attn_flash_kernel_with_growing_logits(n, d, heads):
+    """mri_attn_flash_launch alone against fp32 torch attention.  The keys grow in norm along the
+    sequence, so that the running row maximum keeps rising across key tiles and the lazy
+    reference-maximum update (rescaling l and the O accumulator in TMEM) is exercised, not just
+    the no-rescale fast path."""
+    import ctypes as C
+    from mri_image_generation_b200 import _lib, plan as PL
+    B, Cc = 2, heads * d
+    npad = (n + 7) // 8 * 8
+    g = torch.Generator().manual_seed(n + d)
+    q = torch.randn(B, n, Cc, generator=g)
+    ramp = torch.linspace(0.2, 6.0, n).view(1, n, 1)        # later keys are much "louder"
+    k = torch.randn(B, n, Cc, generator=g) * ramp
+    v = torch.randn(B, n, Cc, generator=g)
+    qkv = torch.cat([q, k, v], dim=-1).to(torch.bfloat16).cuda().contiguous()     # [B, n, 3C]
+    vT = torch.zeros(B, Cc, npad, dtype=torch.bfloat16, device="cuda")
+    vT[:, :, :n] = qkv[:, :, 2 * Cc:].transpose(1, 2)
+    out = torch.zeros(B, n, Cc, dtype=torch.bfloat16, device="cuda")
+    maps = PL.encode_maps([
+        PL.MapSpec(PL.TView(qkv, (3 * Cc, n, B), (1, 3 * Cc, n * 3 * Cc)), (64, 128, 1), 3),
+        PL.MapSpec(PL.TView(vT, (npad, Cc, B), (1, npad, Cc * npad)), (64, d, 1), 3)], "cuda")
+    a = _lib.MriAttnArgs()
+    a.qk_map, a.vt_map, a.out = maps.data_ptr(), maps.data_ptr() + 128, out.data_ptr()
+    a.batch, a.heads, a.n, a.d, a.C = B, heads, n, d, Cc
+    a.k_col0, a.v_row0, a.ld_out = Cc, 0, Cc
+    a.scale = float(d) ** -0.5
+    _lib.check(_lib.load().mri_attn_flash_launch(C.byref(a), _lib.current_stream_ptr()), "attn")
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().view(B, n, heads, d).transpose(1, 2) for t in
+                  (qkv[..., :Cc], qkv[..., Cc:2 * Cc], qkv[..., 2 * Cc:]))
+    logits = (qf @ kf.transpose(-1, -2)) * a.scale
+    # the row maximum really does climb by far more than 8 / log2(e) between the first and last tile
+    if n > 256:
+        assert (logits[..., 128:].amax(-1) - logits[..., :128].amax(-1)).median().item() > 8.0
+    want = (torch.softmax(logits, -1) @ vf).transpose(1, 2).reshape(B, n, Cc)
+    err = rel_l2(out, want)
+    print(f"attn_flash n={n} d={d} heads={heads}: rel-L2 {err:.3e}")
+    assert err < 1e-2, err

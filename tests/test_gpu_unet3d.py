@@ -128,3 +128,39 @@ def test_sampling_loop_graph_equals_eager_and_teacher_forced_oracle():
         t = torch.full((B,), i, device="cuda", dtype=torch.long)
         img = diff.p_sample_ddim(img, t, t - 1)
     assert rel_l2(y, img) < 5e-3
+
+
+@pytest.mark.parametrize("spatial,base,heads", [((8, 8, 8), 64, 4), ((24, 20, 24), 64, 4), ((40, 48, 40), 64, 2),
+                                                ((16, 24, 20), 128, 4)])
+def test_fused_attention_matches_unfused_and_oracle(spatial, base, heads, monkeypatch):
+    """Inference runs the bottleneck attention as ONE kernel (mri_attn_flash_launch: S and O in
+    TMEM, online softmax with a lazily updated reference maximum).  It must agree with the
+    unfused GEMM / softmax / GEMM launches (bf16 rounding of P differs: un-normalised vs
+    normalised) and with the fp32 oracle, for token counts below, at and above the 128-token tile
+    (8, 180, 1200, 120 tokens) and for head dimensions 64 and 128."""
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.unet_attention import UNet3DModelWithAttention
+    m = UNet3DModelWithAttention(3, base_channels=base, time_emb_dim=64, num_heads=heads)
+    sd = synthetic_state_dict(shapes_of(m), seed=81)
+    # larger qkv weights: logits with a real spread, so the softmax is far from uniform
+    for k in sd:
+        if "mid_attn.qkv.weight" in k:
+            sd[k] = sd[k] * 6.0
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 3, *spatial, generator=g)
+    t = torch.tensor([3, 700])
+    with torch.no_grad():
+        fused = m(x.cuda(), t.cuda()).clone()
+        names = next(iter(m._programs().values())).op_names
+        d = 4 * base // heads
+        assert any(nm.startswith("attn:") for nm in names) == (d in (64, 128)), names
+        m.__dict__.pop("_mri_programs", None)
+        monkeypatch.setenv("MRI_ATTN_FLASH", "0")
+        unfused = m(x.cuda(), t.cuda()).clone()
+        assert not any(nm.startswith("attn:") for nm in next(iter(m._programs().values())).op_names)
+        ref = O.unet3d_forward(sd, x, t, heads=heads)
+    e_f, e_u, cross = rel_l2(fused, ref), rel_l2(unfused, ref), rel_l2(fused, unfused)
+    print(f"attention {spatial} base {base} heads {heads}: fused {e_f:.3e}, unfused {e_u:.3e}, fused vs unfused {cross:.3e}")
+    assert e_f < 2e-2 and e_u < 2e-2, (e_f, e_u)
+    assert cross < 1e-2, cross
