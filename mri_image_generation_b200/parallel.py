@@ -172,6 +172,9 @@ class GradSync:
             else:
                 w = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             if timing:
+                # NCCL runs the collective on its own stream: make the communication stream wait
+                # for it, so that the second event fires when the bucket has really been reduced
+                w.wait()
                 e1.record(self._comm_stream)
                 self.bucket_events.append((ev, e0, e1, (hi - lo) * buf.element_size()))
             self._works.append((w, buf, backend))

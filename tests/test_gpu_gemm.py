@@ -276,6 +276,7 @@ def test_attn_flash_kernel_with_growing_logits(n, d, heads):
     reference-maximum update (rescaling l and the O accumulator in TMEM) is exercised, not just
     the no-rescale fast path."""
     import ctypes as C
+    from helpers import rel_l2
     from mri_image_generation_b200 import _lib, plan as PL
     B, Cc = 2, heads * d
     npad = (n + 7) // 8 * 8
