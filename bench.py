@@ -554,13 +554,21 @@ def run_ours(args, rank, world, local_rank):
         rng = diff._rng(dev)
         inc = _ops.randn_offset_increment(prog.x_in.numel())
         seq = [("other", lambda: _ops.memset_zero(prog._arena, max(prog._arena_used, 4) * 8))]
-        for i, fn in enumerate(prog.ops):
+        fh = prog.fused_head if os.environ.get("MRI_FUSED_STEP", "1") != "0" else None
+        for i, fn in enumerate(prog.ops[:-1] if fh is not None else prog.ops):
             tc = i in gemm_set or prog.op_names[i].startswith("attn:")   # tcgen05 kernels
             seq.append(("gemm" if tc else "gn" if i in gn_idx else "other", fn))
-        seq.append(("other", lambda: _ops.ddpm_step_rng(
-            prog.x_in, prog.eps_nhwc, rng, prog.t_in, diff.betas, diff.sqrt_one_minus_alphas_cumprod,
-            diff.sqrt_recip_alphas, diff.posterior_variance, prog.x_in, eps_nhwc_ldc=prog.cout_pad,
-            channels=prog.cout)))
+        if fh is not None:   # out_conv's tap sum + DDPM update (in-kernel Philox) in one launch
+            seq.append(("other", lambda: _ops.tap_gather_step(
+                fh["y"], fh["bias"], prog.B, fh["D"], fh["H"], fh["W"], fh["ndim"], fh["cout"], fh["ldy"],
+                prog.x_in, 0, rng=rng, t=prog.t_in, betas=diff.betas,
+                sqrt_1mac=diff.sqrt_one_minus_alphas_cumprod, sqrt_recip_alphas=diff.sqrt_recip_alphas,
+                post_var=diff.posterior_variance)))
+        else:
+            seq.append(("other", lambda: _ops.ddpm_step_rng(
+                prog.x_in, prog.eps_nhwc, rng, prog.t_in, diff.betas, diff.sqrt_one_minus_alphas_cumprod,
+                diff.sqrt_recip_alphas, diff.posterior_variance, prog.x_in, eps_nhwc_ldc=prog.cout_pad,
+                channels=prog.cout)))
         seq.append(("other", lambda: _ops.step_advance(prog.t_in, -1, rng=rng, rng_increment=inc)))
         prog.x_in.copy_(x_T)
         prog.t_in.fill_(T_STEPS - 1)
@@ -622,7 +630,8 @@ def run_ours(args, rank, world, local_rank):
     executed_flops = prog.gemm_flops
     achieved = conv_flops / (gemm_ms * 1e-3) / 1e12
     x_bytes = x_host.numel() * 4
-    launches_per_step = len(prog.ops) + 2  # + fused update (in-kernel Philox), step advance
+    # forward launch list (its last launch replaced by the fused gather + DDPM update) + step advance
+    launches_per_step = len(prog.ops) + (1 if prog.fused_head is not None else 2)
     cpu = None
     if world == 1 or rank == 0:
         if not args.no_cpu_baseline:

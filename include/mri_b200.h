@@ -296,6 +296,20 @@ int mri_add_i64(int64_t* t, int n, int64_t delta, void* stream);
  * ------------------------------------------------------------------------------------------ */
 /* mri_rng_seed: rng[0] = seed, rng[1] = offset, stream-ordered (no host synchronisation) */
 int mri_rng_seed(uint64_t* rng, uint64_t seed, uint64_t offset, void* stream);
+/* mri_tap_gather_step: the thin output convolution finished INSIDE the reverse step
+ * (ddpm_3d_ldm/unet_attention.py:155,199 out_conv -> diffusion.py:118-126 / 168-186).  Y is the
+ * "GEMM over all taps" of out_conv (see mri_tap_gather): eps[q][co] = bias[co] + sum over taps of
+ * Y[q + off(tap)][tap * cout + co], rounded to bf16 exactly as mri_tap_gather stores it, and
+ *   mode 0: x <- DDPM update with z drawn in the kernel (ATen mapping over the whole state tensor),
+ *   mode 1: x <- DDIM update (t_prev, alphas_cumprod),
+ *   mode 2: eps only (eps_out bf16 [positions][ldo] required; otherwise optional).
+ * x is the fp32 NC[D]HW sampler state [samples][cout][D][H][W], updated in place; 3^ndim taps,
+ * ndim 2 (D = 1) or 3, cout 1..4.  The predicted noise never goes to HBM in modes 0 / 1. */
+int mri_tap_gather_step(const void* y, const float* bias, int samples, int D, int H, int W, int ndim,
+                        int cout, int ldy, float* x, void* eps_out, int ldo, int mode,
+                        const uint64_t* rng, const int64_t* t, const int64_t* t_prev,
+                        const float* betas, const float* sqrt_1mac, const float* sqrt_recip_alphas,
+                        const float* post_var, const float* alphas_cumprod, void* stream);
 int mri_randn_offset_increment(int64_t numel, uint64_t* increment_out);
 int mri_randn(float* out, int64_t numel, const uint64_t* rng, void* stream);
 int mri_q_sample_rng(const float* x0, const uint64_t* rng, const int64_t* t, const float* sqrt_ac,

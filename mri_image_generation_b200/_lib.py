@@ -147,6 +147,8 @@ SIGNATURES = {
     "mri_q_sample_rng": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "mri_ddpm_step_rng": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "mri_step_advance": (_i, [_vp, _vp, _i, _i64, _vp, _u64, _vp]),
+    "mri_tap_gather_step": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp,
+                                 _vp, _vp, _vp, _vp, _vp, _vp]),
     "mri_wgrad_launch": (_i, [C.POINTER(MriWgradArgs), _vp]),
     "mri_gn_bwd_reduce": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _i, _f, _i, _vp]),
     "mri_gn_bwd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _i, _f,

@@ -312,6 +312,176 @@ ddim_step_kernel(const float* x, const void* eps, int ldc, int channels, const i
       one);
 }
 
+// ------------------------------------------------------------------------------------------
+// Thin output convolution finished INSIDE the reverse step.  The k^d convolution with 1..4 output
+// channels (out_conv) is computed as one GEMM over all taps, Y[q][tap * cout + co] = W[tap][co] . a[q]
+// (the activation is read once); this kernel sums the shifted taps -- eps[q][co] = bias[co] +
+// sum_tap Y[q + off(tap)][tap][co], in the same order and with the same bf16 rounding of the result
+// as mri_tap_gather -- and applies the DDPM (noise drawn in-kernel, ATen mapping) or DDIM update to
+// the fp32 NC[D]HW sampler state in place, so the predicted noise never goes to HBM.
+// One CTA = a tile of (TD x TH x TW) output positions; the Y rows of the tile plus a one-voxel halo
+// are staged in shared memory (odd word pitch: conflict-free), one thread per output position.
+// ------------------------------------------------------------------------------------------
+struct FusedStepArgs {
+  const __nv_bfloat16* y;
+  const float* bias;
+  float* x;
+  __nv_bfloat16* eps_out;   // optional bf16 [positions][ldo]
+  const uint64_t* rng;
+  const int64_t* t;
+  const int64_t* t_prev;    // DDIM
+  const float *betas, *sqrt_1mac, *sqrt_recip_alphas, *post_var, *alphas_cumprod;
+  int samples, D, H, W, ndim, cout, ldy, ldo, mode;  // mode 0: DDPM, 1: DDIM, 2: eps only
+  int TD, TH, TW, pitch_w;  // tile and shared-memory row pitch in 32-bit words
+  long long Tt;             // ATen launch geometry of a randn over the whole state
+};
+
+template <int CH>   // 16-byte chunks per Y row that hold the tap products (0: run-time value)
+__global__ void __launch_bounds__(256)
+tap_gather_step_kernel(const FusedStepArgs a) {
+  extern __shared__ uint32_t ysm[];
+  const int hd = a.ndim == 3 ? 1 : 0;             // halo along depth only for 3-D filters
+  const int RD = a.TD + 2 * hd, RH = a.TH + 2, RW = a.TW + 2;
+  const int rows = RD * RH * RW;
+  const int taps = a.ndim == 3 ? 27 : 9;
+  const int row_elems = taps * a.cout;            // bf16 per Y row that matter
+  const int row_words = (row_elems + 1) >> 1;
+  const int chunks = CH > 0 ? CH : (row_words + 3) >> 2;
+  // tile origin
+  const int tiles_w = (a.W + a.TW - 1) / a.TW, tiles_h = (a.H + a.TH - 1) / a.TH;
+  const int tiles_d = (a.D + a.TD - 1) / a.TD;
+  int tix = (int)blockIdx.x;
+  const int tw0 = (tix % tiles_w) * a.TW;
+  tix /= tiles_w;
+  const int th0 = (tix % tiles_h) * a.TH;
+  tix /= tiles_h;
+  const int td0 = (tix % tiles_d) * a.TD;
+  const int n = tix / tiles_d;
+  const long long spatial = (long long)a.D * a.H * a.W;
+  const uint4* yn = reinterpret_cast<const uint4*>(a.y + (size_t)n * spatial * a.ldy);
+  const int ldq = a.ldy >> 3;                     // Y row pitch in 16-byte units (ldy % 8 == 0)
+
+  // ---- stage the halo tile -----------------------------------------------------------------------
+  // (1) per halo row: its offset in Y (16-byte units) or -1 outside the tensor
+  int* row_off = reinterpret_cast<int*>(ysm + (size_t)rows * a.pitch_w);
+  for (int r = threadIdx.x; r < rows; r += 256) {
+    int rr = r;
+    const int w = tw0 + rr % RW - 1;
+    rr /= RW;
+    const int h = th0 + rr % RH - 1;
+    const int d = td0 + rr / RH - hd;
+    const bool ok = (unsigned)w < (unsigned)a.W && (unsigned)h < (unsigned)a.H && (unsigned)d < (unsigned)a.D;
+    row_off[r] = ok ? (int)((((long long)d * a.H + h) * a.W + w) * ldq) : -1;
+  }
+  __syncthreads();
+  // (2) 16-byte loads, four in flight per thread, scattered into rows of odd word pitch
+  const int total = rows * chunks;
+  for (int base = 0; base < total; base += 256 * 4) {
+    uint4 v[4];
+    int dst[4], jw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * 256 + (int)threadIdx.x;
+      v[u] = make_uint4(0u, 0u, 0u, 0u);
+      dst[u] = -1;
+      jw[u] = 0;
+      if (i < total) {
+        const int r = i / chunks;
+        const int j = i - r * chunks;
+        const int off = row_off[r];
+        if (off >= 0) v[u] = __ldg(yn + off + j);
+        dst[u] = r * a.pitch_w + 4 * j;
+        jw[u] = 4 * j;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (dst[u] >= 0) {
+        const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (jw[u] + k < row_words) ysm[dst[u] + k] = w4[k];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- one output position per thread -------------------------------------------------------------
+  int q = threadIdx.x;
+  const int lw = q % a.TW;
+  q /= a.TW;
+  const int lh = q % a.TH;
+  const int ld_ = q / a.TH;
+  const int w0 = tw0 + lw, h0 = th0 + lh, d0 = td0 + ld_;
+  if (ld_ >= a.TD || w0 >= a.W || h0 >= a.H || d0 >= a.D) return;
+  float acc[4];
+#pragma unroll
+  for (int co = 0; co < 4; ++co) acc[co] = (co < a.cout && a.bias != nullptr) ? __ldg(a.bias + co) : 0.f;
+  const __nv_bfloat16* ys = reinterpret_cast<const __nv_bfloat16*>(ysm);
+  int tap = 0;
+  const int kd_n = a.ndim == 3 ? 3 : 1;
+  for (int kd = 0; kd < kd_n; ++kd)
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw, ++tap) {
+        const int r = ((ld_ + kd) * RH + lh + kh) * RW + lw + kw;
+        const __nv_bfloat16* row = ys + (size_t)r * a.pitch_w * 2 + tap * a.cout;
+#pragma unroll
+        for (int co = 0; co < 4; ++co)
+          if (co < a.cout) acc[co] += __bfloat162float(row[co]);   // halo rows outside the tensor are 0
+      }
+  const long long s = ((long long)d0 * a.H + h0) * a.W + w0;
+  const long long per_sample = (long long)a.cout * spatial;
+  // per-sample coefficients
+  float q_c = 0.f, c1 = 0.f, wn = 0.f, sqrt_a_t = 0.f, s1m_t = 0.f, denom = 1.f, sqrt_a_p = 0.f, s1m_p = 0.f;
+  if (a.mode == 0) {
+    StepTables T{a.t, a.betas, a.sqrt_1mac, a.sqrt_recip_alphas, a.post_var};
+    const StepCoef c = step_coef(T, n);
+    q_c = c.q;
+    c1 = c.c1;
+    wn = c.w;
+  } else if (a.mode == 1) {
+    const float a_t = __ldg(a.alphas_cumprod + a.t[n]);
+    const float a_p = __ldg(a.alphas_cumprod + a.t_prev[n]);
+    sqrt_a_t = __fsqrt_rn(a_t);
+    s1m_t = __fsqrt_rn(__fsub_rn(1.0f, a_t));
+    denom = fmaxf(sqrt_a_t, 1e-8f);
+    sqrt_a_p = __fsqrt_rn(a_p);
+    s1m_p = __fsqrt_rn(__fsub_rn(1.0f, a_p));
+  }
+  uint64_t seed = 0, ctr0 = 0;
+  if (a.mode == 0) {
+    seed = a.rng[0];
+    ctr0 = a.rng[1] >> 2;
+  }
+#pragma unroll
+  for (int co = 0; co < 4; ++co) {
+    if (co >= a.cout) break;
+    const __nv_bfloat16 eb = __float2bfloat16_rn(acc[co]);
+    if (a.eps_out != nullptr) a.eps_out[((size_t)n * spatial + s) * a.ldo + co] = eb;
+    if (a.mode == 2) continue;
+    const float e = __bfloat162float(eb);
+    const long long idx = (long long)n * per_sample + (long long)co * spatial + s;   // NC[D]HW element
+    const float xv = a.x[idx];
+    if (a.mode == 0) {
+      // z of element idx under ATen's mapping: call it, component ii of subsequence j
+      const long long it = idx / (4 * a.Tt);
+      const long long rem = idx - it * 4 * a.Tt;
+      const int ii = (int)(rem / a.Tt);
+      const long long j = rem - (long long)ii * a.Tt;
+      const uint64_t cc = ctr0 + (uint64_t)it;
+      const uint4 rr = philox4x32_10(
+          make_uint4((uint32_t)cc, (uint32_t)(cc >> 32), (uint32_t)j, (uint32_t)((uint64_t)j >> 32)),
+          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+      const float2 bm = (ii < 2) ? box_muller(rr.x, rr.y) : box_muller(rr.z, rr.w);
+      const float z = (ii & 1) ? bm.y : bm.x;
+      a.x[idx] = __fadd_rn(__fmul_rn(c1, __fsub_rn(xv, __fmul_rn(q_c, e))), __fmul_rn(wn, z));
+    } else {
+      const float x0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(s1m_t, e)), denom);
+      a.x[idx] = __fadd_rn(__fmul_rn(sqrt_a_p, x0), __fmul_rn(s1m_p, e));
+    }
+  }
+}
+
 // one thread: t -= 1 for every sample (and t_prev), generator offset += rng_inc -- the bookkeeping
 // between two replays of the captured reverse step
 __global__ void step_advance_kernel(int64_t* t, int64_t* t_prev, int n, int64_t delta,
@@ -544,4 +714,72 @@ extern "C" int mri_add_i64(int64_t* t, int n, int64_t delta, void* stream) {
   if (n < 1) return 0;
   add_i64_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, n, delta);
   return check_launch("add_i64_kernel");
+}
+
+extern "C" int mri_tap_gather_step(const void* y, const float* bias, int samples, int D, int H, int W,
+                                   int ndim, int cout, int ldy, float* x, void* eps_out, int ldo,
+                                   int mode, const uint64_t* rng, const int64_t* t,
+                                   const int64_t* t_prev, const float* betas, const float* sqrt_1mac,
+                                   const float* sqrt_recip_alphas, const float* post_var,
+                                   const float* alphas_cumprod, void* stream) {
+  if (ndim != 2 && ndim != 3) return set_error(-2, "mri_tap_gather_step: ndim must be 2 or 3");
+  if (cout < 1 || cout > 4) return set_error(-2, "mri_tap_gather_step: 1..4 output channels");
+  const int taps = ndim == 3 ? 27 : 9;
+  if (ldy % 2 != 0 || taps * cout > ldy) return set_error(-2, "mri_tap_gather_step: bad Y row layout");
+  if (samples < 1 || D < 1 || H < 1 || W < 1) return set_error(-2, "mri_tap_gather_step: empty input");
+  if (ndim == 2 && D != 1) return set_error(-2, "mri_tap_gather_step: 2-D problems have D = 1");
+  if (mode < 0 || mode > 2) return set_error(-2, "mri_tap_gather_step: mode 0 (DDPM) / 1 (DDIM) / 2 (eps only)");
+  if (mode == 0 && (rng == nullptr || t == nullptr || betas == nullptr || sqrt_1mac == nullptr ||
+                    sqrt_recip_alphas == nullptr || post_var == nullptr || x == nullptr))
+    return set_error(-2, "mri_tap_gather_step: DDPM mode needs x, rng, t and the four schedule tables");
+  if (mode == 1 && (t == nullptr || t_prev == nullptr || alphas_cumprod == nullptr || x == nullptr))
+    return set_error(-2, "mri_tap_gather_step: DDIM mode needs x, t, t_prev and alphas_cumprod");
+  if (mode == 2 && eps_out == nullptr) return set_error(-2, "mri_tap_gather_step: eps-only mode needs eps_out");
+  if (eps_out != nullptr && ldo < cout) return set_error(-2, "mri_tap_gather_step: ldo < cout");
+  int rc = device_props();
+  if (rc) return rc;
+  FusedStepArgs a;
+  a.y = reinterpret_cast<const __nv_bfloat16*>(y);
+  a.bias = bias;
+  a.x = x;
+  a.eps_out = reinterpret_cast<__nv_bfloat16*>(eps_out);
+  a.rng = rng;
+  a.t = t;
+  a.t_prev = t_prev;
+  a.betas = betas;
+  a.sqrt_1mac = sqrt_1mac;
+  a.sqrt_recip_alphas = sqrt_recip_alphas;
+  a.post_var = post_var;
+  a.alphas_cumprod = alphas_cumprod;
+  a.samples = samples; a.D = D; a.H = H; a.W = W; a.ndim = ndim; a.cout = cout; a.ldy = ldy; a.ldo = ldo;
+  a.mode = mode;
+  a.TD = ndim == 3 ? 4 : 1;
+  a.TH = ndim == 3 ? 8 : 16;
+  a.TW = ndim == 3 ? 8 : 16;
+  const int row_words = (taps * cout + 1) / 2;
+  a.pitch_w = row_words | 1;                         // odd pitch: consecutive rows hit different banks
+  const long long numel = (long long)samples * cout * D * H * W;
+  a.Tt = aten_grid(numel).Tt;
+  const int rows = (a.TD + (ndim == 3 ? 2 : 0)) * (a.TH + 2) * (a.TW + 2);
+  const int smem = rows * a.pitch_w * 4 + rows * 4;   // staged rows + the row-offset table
+  if (ldy % 8 != 0) return set_error(-2, "mri_tap_gather_step: ldy must be a multiple of 8");
+  if ((long long)D * H * W * (ldy / 8) > 0x7fffffffLL)
+    return set_error(-2, "mri_tap_gather_step: sample too large for 32-bit row offsets");
+  const long long tiles = (long long)samples * ((D + a.TD - 1) / a.TD) * ((H + a.TH - 1) / a.TH) *
+                          ((W + a.TW - 1) / a.TW);
+  if (tiles > 0x7fffffffLL) return set_error(-2, "mri_tap_gather_step: too many tiles");
+  const int chunks = (row_words + 3) / 4;
+  void (*kern)(const FusedStepArgs) = chunks == 11 ? tap_gather_step_kernel<11>
+                                      : chunks == 5 ? tap_gather_step_kernel<5>
+                                      : chunks == 2 ? tap_gather_step_kernel<2>
+                                                    : tap_gather_step_kernel<0>;
+  static int configured[4] = {0, 0, 0, 0};   // per instantiation (not re-done inside a graph capture)
+  const int slot = chunks == 11 ? 0 : chunks == 5 ? 1 : chunks == 2 ? 2 : 3;
+  if (smem > configured[slot]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(tap_gather_step_kernel)");
+    configured[slot] = smem;
+  }
+  kern<<<(unsigned)tiles, 256, smem, (cudaStream_t)stream>>>(a);
+  return check_launch("tap_gather_step_kernel");
 }

@@ -14,6 +14,7 @@ model arguments (z_pos, context) and the loss; everything that touches the GPU i
 """
 from __future__ import annotations
 
+import os
 import weakref
 from typing import Callable, Dict, Optional, Tuple
 
@@ -227,7 +228,21 @@ class DiffusionBase(nn.Module):
         # the graph bakes the stride in: one graph per (mode, stride)
         gkey = mode if stride == 1 else f"{mode}/{stride}"
 
+        fused = (getattr(prog, "fused_head", None) is not None and not prog.training
+                 and os.environ.get("MRI_FUSED_STEP", "1") != "0")
+
         def one_step():
+            if fused:  # out_conv's tap sum + the update in one kernel: eps never goes to HBM
+                if mode == "ddpm":
+                    prog.run_fused_step(0, rng=rng, t=prog.t_in, betas=self.betas,
+                                        sqrt_1mac=self.sqrt_one_minus_alphas_cumprod,
+                                        sqrt_recip_alphas=self.sqrt_recip_alphas,
+                                        post_var=self.posterior_variance)
+                    ops.step_advance(prog.t_in, -1, rng=rng, rng_increment=inc)
+                else:
+                    prog.run_fused_step(1, t=prog.t_in, t_prev=tprev, alphas_cumprod=self.alphas_cumprod)
+                    ops.step_advance(prog.t_in, -stride, t_prev=tprev)
+                return
             prog.run()
             if mode == "ddpm":
                 ops.ddpm_step_rng(prog.x_in, prog.eps_nhwc, rng, prog.t_in, self.betas,

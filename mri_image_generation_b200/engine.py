@@ -109,6 +109,7 @@ class UNetProgram(BackwardMixin):
         self.gn_ops: List[Tuple[int, int]] = []
         self._param_versions: Optional[Tuple] = None
         self._params: List[torch.Tensor] = []
+        self.fused_head: Optional[dict] = None   # set by thin_out_conv (inference programs)
 
     # ------------------------------------------------------------------ bookkeeping
     def _add(self, name: str, fn: Callable[[], None], outs: Sequence[torch.Tensor] = ()) -> None:
@@ -293,6 +294,18 @@ class UNetProgram(BackwardMixin):
         for fn in self.ops:
             fn()
 
+    def run_fused_step(self, mode: int, **step_kw) -> None:
+        """Inference programs with a thin output convolution: the whole forward EXCEPT the final
+        tap gather, then mri_tap_gather_step, which finishes out_conv and applies the DDPM (mode 0)
+        or DDIM (mode 1) update to self.x_in in place."""
+        fh = self.fused_head
+        assert fh["op_index"] == len(self.ops) - 1 and not self.training
+        ops.memset_zero(self._arena, max(self._arena_used, 4) * 8)
+        for fn in self.ops[:-1]:
+            fn()
+        ops.tap_gather_step(fh["y"], fh["bias"], self.B, fh["D"], fh["H"], fh["W"], fh["ndim"],
+                            fh["cout"], fh["ldy"], self.x_in, mode, **step_kw)
+
     def _replay(self, key: str, body: Callable[[], None]) -> None:
         """`body` is a fixed launch sequence over static buffers: run it eagerly twice, then
         capture it once and replay the graph (removes ~10^2..10^3 launch overheads per step)."""
@@ -436,6 +449,11 @@ class UNetProgram(BackwardMixin):
         self._add(f"{name}.gather",
                   lambda: ops.tap_gather(y.t, eps, bias, B, sp3[0], sp3[1], sp3[2], ksize, nd, cout,
                                          n_y, ldo), [eps])
+        # the samplers replace this last launch by mri_tap_gather_step (gather + reverse-step update
+        # in one kernel: the predicted noise never goes to HBM); see DiffusionBase._reverse_loop_on
+        if ksize == 3 and 1 <= cout <= 4:
+            self.fused_head = dict(y=y.t, bias=bias, D=sp3[0], H=sp3[1], W=sp3[2], ndim=nd, cout=cout,
+                                   ldy=n_y, op_index=len(self.ops) - 1)
         self.cout, self.cout_pad, self.eps_nhwc = cout, ldo, eps
         self.hbm_bytes_elementwise += y.t.numel() * 2 + eps.numel() * 2
 

@@ -210,6 +210,18 @@ def ddpm_step_rng(x, eps, rng: DeviceRng, t, betas, sqrt_1mac, sqrt_recip_alphas
                "mri_ddpm_step_rng")
 
 
+def tap_gather_step(y, bias, samples, D, H, W, ndim, cout, ldy, x, mode: int, rng=None, t=None,
+                    t_prev=None, betas=None, sqrt_1mac=None, sqrt_recip_alphas=None, post_var=None,
+                    alphas_cumprod=None, eps_out=None, ldo: int = 0) -> None:
+    """Finish the thin out_conv (sum of shifted tap products) and apply the reverse-step update to
+    the sampler state x in place: mode 0 DDPM (noise drawn in-kernel), 1 DDIM, 2 eps only."""
+    _chk_contig(y, x, eps_out)
+    _lib.check(_lib.load().mri_tap_gather_step(
+        _p(y), _p(bias), samples, D, H, W, ndim, cout, ldy, _p(x), _p(eps_out), ldo, mode,
+        _p(rng.state) if rng is not None else None, _p(t), _p(t_prev), _p(betas), _p(sqrt_1mac),
+        _p(sqrt_recip_alphas), _p(post_var), _p(alphas_cumprod), _s()), "mri_tap_gather_step")
+
+
 def step_advance(t: torch.Tensor, delta: int, t_prev=None, rng: Optional[DeviceRng] = None,
                  rng_increment: int = 0) -> None:
     _lib.check(_lib.load().mri_step_advance(_p(t), _p(t_prev), t.numel(), delta,

@@ -114,3 +114,51 @@ def test_strided_ddim_graph_loop_equals_step_by_step():
         assert torch.equal(got, img), (stride, (got - img).abs().max().item())
     vol = diff.sample_ddim(2, 8, num_steps=5)
     assert vol.shape == (2, 3, 8, 8, 8) and torch.isfinite(vol).all()
+
+
+@pytest.mark.parametrize("kind", ["3d", "2d", "25d"])
+def test_fused_gather_step_equals_unfused_bit_exactly(kind, monkeypatch):
+    """The sampling loop finishes out_conv and applies the update in ONE kernel
+    (mri_tap_gather_step): same tap order, same bf16 rounding of eps, same Philox draws ->
+    bit-identical to the unfused launches (tap gather, then mri_ddpm_step_rng / mri_ddim_step)."""
+    if kind == "3d":
+        from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.diffusion import GaussianDiffusionLatent3D
+        from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.unet import UNet3DModel
+        m = UNet3DModel(3, base_channels=64, time_emb_dim=64)
+        mk = lambda mm: quiet(GaussianDiffusionLatent3D, mm, 3, timesteps=12).cuda()
+        run = lambda d: d.sample(2, (8, 12, 8))
+    elif kind == "2d":
+        from mri_image_generation_b200.model_scripts.slice_cond_2d_ddpm.diffusion import GaussianDiffusion
+        from mri_image_generation_b200.model_scripts.slice_cond_2d_ddpm.unet import UNet
+        m = quiet(UNet, img_channels=1, base_channels=64, time_emb_dim=64)
+        mk = lambda mm: quiet(GaussianDiffusion, mm, 40, channels=1, timesteps=12).cuda()
+        run = lambda d: d.sample(3, z_pos=0.3)
+    else:
+        from mri_image_generation_b200.model_scripts.ddpm_25d_all_modalities.diffusion import GaussianDiffusion
+        from mri_image_generation_b200.model_scripts.ddpm_25d_all_modalities.unet import UNet
+        m = quiet(UNet, in_channels=20, out_channels=4, base_channels=64, time_emb_dim=64)
+        mk = lambda mm: quiet(GaussianDiffusion, mm, 24, channels=4, timesteps=12).cuda()
+        ctx = torch.randn(2, 16, 24, 24, generator=torch.Generator().manual_seed(1)).cuda()
+        run = lambda d: d.sample(2, z_pos=0.6, context=ctx)
+    sd = synthetic_state_dict(shapes_of(m), seed=91)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    outs = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("MRI_FUSED_STEP", fused)
+        m.__dict__.pop("_mri_programs", None)      # fresh program: fresh step graph
+        diff = mk(m)
+        torch.manual_seed(17)
+        outs.append(run(diff).clone())
+        prog = next(iter(m._programs().values()))
+        assert (prog.fused_head is not None)
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1]), (outs[0] - outs[1]).abs().max().item()
+    if kind == "3d":   # DDIM (strided) through the fused kernel as well
+        x = torch.randn(2, 3, 8, 12, 8, generator=torch.Generator().manual_seed(2)).cuda()
+        res = []
+        for fused in ("1", "0"):
+            monkeypatch.setenv("MRI_FUSED_STEP", fused)
+            m.__dict__.pop("_mri_programs", None)
+            res.append(mk(m).sample_from_ddim(x, 11, stride=3).clone())
+        assert torch.equal(res[0], res[1])
