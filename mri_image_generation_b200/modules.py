@@ -67,6 +67,18 @@ class EngineModule(nn.Module):
         return super()._apply(fn, *args, **kwargs)
 
     def _check_input(self, x: torch.Tensor) -> None:
+        if getattr(self, "_is_replica", False):
+            # nn.DataParallel (slice_cond_2d_ddpm/model.py:113-115) re-creates shallow replicas of
+            # the module on every forward; a UNetProgram is a static launch list bound to ONE set of
+            # parameter tensors, so replicas would rebuild it every step -- and share the cached
+            # programs of the original through the copied __dict__.  Refuse instead of being slow
+            # and wrong: the multi-GPU path is one process per GPU.
+            raise _lib.MriError(
+                "nn.DataParallel replication is not supported by the B200 drop-in: run one process "
+                "per GPU (torchrun) and wrap the UNet in DistributedDataParallel "
+                "(mri_image_generation_b200.parallel.DistributedDataParallel or torch's), as "
+                "ddpm_3d_ldm/train.py:232-233 does.  With a single visible GPU DataParallel calls "
+                "the module directly and works.")
         if not x.is_cuda:
             raise _lib.MriError(
                 f"{type(self).__name__} runs on B200 GPUs only (input is on {x.device}); this "

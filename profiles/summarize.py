@@ -62,6 +62,52 @@ def launches(src, dst):
         f.write(f"{'TOTAL':48s} {sum(v[0] for v in agg.values()):8d} {tot:12.1f}\n")
 
 
+def traffic(src, dst, batch="16", note=""):
+    """Per-family DRAM bytes and serialised time of ONE step from the CSV of
+    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum` over the
+    NVTX range of tools/one_step.py -> the JSON bench.py reads for roofline.traffic."""
+    import json
+    rows = list(csv.reader(open(src, errors="replace")))
+    hdr = None
+    fam = collections.OrderedDict()
+
+    def family(name):
+        if "gemm_tc" in name or "attn_flash" in name:
+            return "gemm_tc"
+        if "gn_apply" in name:
+            return "gn_apply"
+        return "other"
+
+    launches_seen = collections.defaultdict(set)
+    for r in rows:
+        if len(r) > 5 and r[0] == "ID":
+            hdr = r
+            continue
+        if hdr and len(r) == len(hdr):
+            d = dict(zip(hdr, r))
+            name = d["Kernel Name"].split("(")[0]
+            f_ = fam.setdefault(family(name), collections.defaultdict(float))
+            v = float(d["Metric Value"].replace(",", ""))
+            unit = d.get("Metric Unit", "")
+            m = d["Metric Name"]
+            if m.startswith("dram__bytes"):
+                v *= {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+                f_["dram_bytes_read" if "read" in m else "dram_bytes_write"] += v
+            elif m == "gpu__time_duration.sum":
+                v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(unit, 1e-6)
+                f_["ncu_time_ms_serialised"] += v
+                launches_seen[family(name)].add(d["ID"])
+            f_.setdefault("kernels", 0)
+    out = {"source": note or f"ncu over the NVTX range of tools/one_step.py; raw CSV: {src}",
+           "batch_per_gpu": int(batch)}
+    for k, f_ in fam.items():
+        out[k] = {"launches_per_step": len(launches_seen[k]),
+                  "dram_bytes_read": f_["dram_bytes_read"], "dram_bytes_write": f_["dram_bytes_write"],
+                  "dram_bytes": f_["dram_bytes_read"] + f_["dram_bytes_write"],
+                  "ncu_time_ms_serialised": f_["ncu_time_ms_serialised"]}
+    json.dump(out, open(dst, "w"), indent=1)
+
+
 def _ncu(args):
     return subprocess.run(["ncu"] + args, check=True, capture_output=True, text=True).stdout
 
@@ -92,4 +138,4 @@ def full(src, dst):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])

@@ -118,3 +118,15 @@ def test_vae_state_dict_keys_and_shapes_match_reference(name):
     got = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
     assert got == [(k, tuple(s)) for k, s in g["shapes"]]
     pickle.loads(pickle.dumps(m))
+
+
+def test_data_parallel_replicas_are_refused_loudly():
+    """nn.DataParallel (slice_cond_2d_ddpm/model.py:113-115) replicates the module on every forward;
+    static launch programs cannot follow that.  A replica must raise a clear error (the
+    supported multi-GPU path is one process per GPU), never run with another replica's buffers."""
+    from mri_image_generation_b200 import _lib
+    from mri_image_generation_b200.model_scripts.slice_cond_2d_ddpm.unet import UNet
+    m = quiet(UNet)
+    m._is_replica = True       # what torch.nn.parallel.replicate sets on every replica
+    with pytest.raises(_lib.MriError, match="DataParallel"):
+        m(torch.zeros(1, 1, 16, 16), torch.zeros(1, dtype=torch.long), torch.zeros(1))
