@@ -556,7 +556,7 @@ def run_ours(args, rank, world, local_rank):
         seq = [("other", lambda: _ops.memset_zero(prog._arena, max(prog._arena_used, 4) * 8))]
         fh = prog.fused_head if os.environ.get("MRI_FUSED_STEP", "1") != "0" else None
         for i, fn in enumerate(prog.ops[:-1] if fh is not None else prog.ops):
-            tc = i in gemm_set or prog.op_names[i].startswith("attn:")   # tcgen05 kernels
+            tc = i in gemm_set or prog.op_names[i].startswith(("attn:", "tc:"))   # tcgen05 kernels
             seq.append(("gemm" if tc else "gn" if i in gn_idx else "other", fn))
         if fh is not None:   # out_conv's tap sum + DDPM update (in-kernel Philox) in one launch
             seq.append(("other", lambda: _ops.tap_gather_step(
@@ -660,7 +660,7 @@ def run_ours(args, rank, world, local_rank):
                         "copies on two copy streams, double-buffered against the compute stream"},
         "gpu_launches": launches_per_step * K,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM, all convolutions) + attn_flash_kernel (tcgen05 fused attention)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM: every convolution) + thin_in_conv_kernel + attn_flash_kernel (tcgen05 first convolution / fused attention)",
                      "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["tflops"], "traffic": tr_gemm.get("dram_bytes"),
                      "traffic_note": ("DRAM bytes read + written by the %d GEMM launches of one step, ncu capture %s"

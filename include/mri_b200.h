@@ -201,6 +201,17 @@ int mri_nhwc_to_nchw(const void* src, float* dst, int samples, int64_t spatial, 
 int mri_nchw_to_nhwc(const float* src, void* dst, int samples, int64_t spatial, int C, int ldc,
                      void* stream);
 
+/* First convolution of the UNets for inference (in_conv / init_conv with 1..4 input channels, 3^ndim
+ * taps, padding 1: ddpm_3d_ldm/unet_attention.py:114,161; slice_cond_2d_ddpm/unet.py:137,185) as ONE
+ * tcgen05 kernel that builds the patch matrix in shared memory from the fp32 NC[D]HW input
+ * (csrc/thin_conv.cu): y bf16 [samples][D*H*W][cout] = conv(x) + bias, plus the GroupNorm(8, cout)
+ * partial sums (sum, sum of squares per (sample, group), fp64 [samples][stats_ld][2], ADDED to --
+ * zero them first) when stats != NULL.  w_packed: bf16 [cout][128], column = tap * 4 + channel with
+ * taps in (kd, kh, kw) order, zero padded.  cout must be 64 or 128. */
+int mri_thin_in_conv(const float* x, const void* w_packed, const float* bias, void* y, double* stats,
+                     int stats_ld, int samples, int cin, int D, int H, int W, int ndim, int cout,
+                     void* stream);
+
 /* Strided 4-D copy with dtype conversion, dst[i0,i1,i2,i3] = (dst_dtype) src[i0,i1,i2,i3] with
  * element strides src_strides / dst_strides (host int64[4]) and `shape` (host int64[4]); dtypes
  * 0 = bf16, 1 = f32, 2 = f64 (source only).  Used for the few layout shuffles of the backward

@@ -133,6 +133,7 @@ SIGNATURES = {
     "mri_attn_flash_supported": (_i, [_i]),
     "mri_attn_flash_launch": (_i, [C.POINTER(MriAttnArgs), _vp]),
     "mri_softmax_rows": (_i, [_vp, _vp, _i64, _i, _i, _i, _f, _vp]),
+    "mri_thin_in_conv": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mri_copy_cast": (_i, [_vp, _i, C.POINTER(C.c_int64), _vp, _i, C.POINTER(C.c_int64),
                            C.POINTER(C.c_int64), _vp]),
     "mri_memset_zero": (_i, [_vp, _i64, _vp]),

@@ -418,6 +418,34 @@ class UNetProgram(BackwardMixin):
 
         return col, self.packed(make), kpad
 
+    def thin_in_conv(self, x_in: torch.Tensor, conv, sp: Sequence[int], name: str, with_stats: bool) -> Optional[Act]:
+        """Inference: the first convolution (<= 4 input channels, 64 / 128 output channels, 3^d taps)
+        as ONE launch of mri_thin_in_conv -- no layout pass, no im2col buffer, no generic GEMM whose
+        K = 128 tiles are epilogue-bound.  Returns None when the shape is not covered."""
+        cout, cin, ksize = conv.weight.shape[0], conv.weight.shape[1], conv.weight.shape[2]
+        nd = len(sp)
+        if (self.training or cin > 4 or cout not in (64, 128) or ksize != 3
+                or os.environ.get("MRI_THIN_IN_CONV", "1") == "0"):
+            return None
+        B = self.B
+        self.track(conv.weight, conv.bias)
+
+        def make():
+            w = conv.weight.detach()
+            wp = torch.zeros(cout, 4, *w.shape[2:], dtype=w.dtype, device=w.device)
+            wp[:, :cin] = w
+            return _pad_k(P.pack_conv_weight(wp), 128)
+
+        w128 = self.packed(make)
+        y = self.new_act(sp, cout, with_stats)
+        sp3 = (1,) * (3 - nd) + tuple(sp)
+        bias, st = conv.bias, y.stats
+        self._add(f"tc:{name}", lambda: ops.thin_in_conv(x_in, w128, bias, y.t, st, B, cin, sp3[0], sp3[1],
+                                                         sp3[2], nd, cout), [y.t, st])
+        S = sp3[0] * sp3[1] * sp3[2]
+        self.gemm_flops += 2 * B * S * cout * (ksize ** nd) * cin
+        return y
+
     def thin_out_conv(self, a: torch.Tensor, oc, name: str = "out_conv", cin_pad: int = 0) -> None:
         """Inference head for a k^d convolution with 1..8 output channels (out_conv): one GEMM
         computes every tap's product Y[q][tap*cout + co] = W[tap][co] . a[q] (K = Cin, the
@@ -550,14 +578,16 @@ class UNet3DProgram(UNetProgram):
             x_in = self.x_in
             self._add("im2col", lambda: ops.im2col(x_in, col, B, cin, D, H, W, 3, 3, kpad), [col])
             w_in = self.packed(lambda: _pad_k(P.pack_conv_weight(ic.weight.detach()), kpad))
-        else:
-            col, w_in, kpad = self.thin_patch_matrix(self.x_in, ic, self.sp, "in_conv")
-        h = self.new_act(self.sp, chs[0])
-        pl = self._matrix_conv(col, w_in, h, S, kpad, ic.bias, "in_conv")
-        self.gemm(pl)
-        self.tape.append(ConvRec(kind="matrix", plan=pl, y=h.t, ksize=3, sources=[(col, True)],
-                                 weight=ic.weight, splits=[cin], bias_params=[ic.bias], cout=chs[0],
-                                 need_dgrad=False, kpad=kpad, name="in_conv"))
+        h = self.thin_in_conv(self.x_in, ic, self.sp, "in_conv", with_stats=True)
+        if h is None:
+            if not training:
+                col, w_in, kpad = self.thin_patch_matrix(self.x_in, ic, self.sp, "in_conv")
+            h = self.new_act(self.sp, chs[0])
+            pl = self._matrix_conv(col, w_in, h, S, kpad, ic.bias, "in_conv")
+            self.gemm(pl)
+            self.tape.append(ConvRec(kind="matrix", plan=pl, y=h.t, ksize=3, sources=[(col, True)],
+                                     weight=ic.weight, splits=[cin], bias_params=[ic.bias], cout=chs[0],
+                                     need_dgrad=False, kpad=kpad, name="in_conv"))
 
         # ---- down path -----------------------------------------------------------------------
         skips: List[Act] = []
@@ -919,14 +949,17 @@ class UNet2DProgram(UNetProgram):
             self._add("im2col", lambda: ops.im2col(x_in, col, B, x_channels, 1, H, W, 3, 2, kpad,
                                                    src2=ctx_in, cin2=ctx_channels), [col])
             w_in = self.packed(lambda: _pad_k(P.pack_conv_weight(ic.weight.detach()), kpad))
-        else:
-            col, w_in, kpad = self.thin_patch_matrix(self.x_in, ic, self.sp, "init_conv")
-        h = self.new_act(self.sp, chs[0], with_stats=False)
-        pl = self._matrix_conv2d(col, w_in, h, S, kpad, ic.bias, "init_conv")
-        self.gemm(pl)
-        self.tape.append(ConvRec(kind="matrix", plan=pl, y=h.t, ksize=3, sources=[(col, True)],
-                                 weight=ic.weight, splits=[cin], bias_params=[ic.bias], cout=chs[0],
-                                 need_dgrad=False, kpad=kpad, name="init_conv"))
+        h = None if (training or ctx_channels) else self.thin_in_conv(self.x_in, ic, self.sp, "init_conv",
+                                                                      with_stats=False)
+        if h is None:
+            if not (training or ctx_channels):
+                col, w_in, kpad = self.thin_patch_matrix(self.x_in, ic, self.sp, "init_conv")
+            h = self.new_act(self.sp, chs[0], with_stats=False)
+            pl = self._matrix_conv2d(col, w_in, h, S, kpad, ic.bias, "init_conv")
+            self.gemm(pl)
+            self.tape.append(ConvRec(kind="matrix", plan=pl, y=h.t, ksize=3, sources=[(col, True)],
+                                     weight=ic.weight, splits=[cin], bias_params=[ic.bias], cout=chs[0],
+                                     need_dgrad=False, kpad=kpad, name="init_conv"))
 
         skips: List[Act] = []
         for i, d in enumerate(model.downs):

@@ -82,6 +82,14 @@ def im2col4(src, dst, samples, cp, D, H, W, ksize, ndim, kpad) -> None:
                "mri_im2col4")
 
 
+def thin_in_conv(x, w_packed, bias, y, stats, samples, cin, D, H, W, ndim, cout) -> None:
+    """in_conv / init_conv (<= 4 input channels) in one tcgen05 launch: patch matrix built in smem."""
+    _chk_contig(x, w_packed, y, stats)
+    _lib.check(_lib.load().mri_thin_in_conv(_p(x), _p(w_packed), _p(bias), _p(y), _p(stats),
+                                            stats.shape[1] if stats is not None else 0, samples, cin,
+                                            D, H, W, ndim, cout, _s()), "mri_thin_in_conv")
+
+
 def tap_gather(y, out, bias, samples, D, H, W, ksize, ndim, cout, ldy, ldo) -> None:
     _chk_contig(y, out, bias)
     _lib.check(_lib.load().mri_tap_gather(_p(y), _p(out), _p(bias), samples, D, H, W, ksize, ndim,

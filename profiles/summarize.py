@@ -72,7 +72,7 @@ def traffic(src, dst, batch="16", note=""):
     fam = collections.OrderedDict()
 
     def family(name):
-        if "gemm_tc" in name or "attn_flash" in name:
+        if "gemm_tc" in name or "attn_flash" in name or "thin_in_conv" in name:
             return "gemm_tc"
         if "gn_apply" in name:
             return "gn_apply"

@@ -309,3 +309,44 @@ def test_attn_flash_kernel_with_growing_logits(n, d, heads):
     err = rel_l2(out, want)
     print(f"attn_flash n={n} d={d} heads={heads}: rel-L2 {err:.3e}")
     assert err < 1e-2, err
+
+
+@pytest.mark.parametrize("sp,cin,cout", [((8, 12, 8), 3, 128), ((5, 7, 9), 3, 64), ((40, 48, 40), 3, 128),
+                                         ((37, 50), 1, 64), ((128, 128), 1, 64), ((16, 24), 4, 128)])
+def test_thin_in_conv_kernel(sp, cin, cout):
+    """mri_thin_in_conv (patch matrix built in shared memory, one tcgen05 launch) against torch's
+    convolution on the same bf16-rounded operands, and its GroupNorm partial sums against the
+    sums of the stored output; spatial sizes that are not multiples of the 128-position tile."""
+    from helpers import rel_l2
+    from mri_image_generation_b200 import ops, plan as PL
+    nd = len(sp)
+    B = 2
+    g = torch.Generator().manual_seed(sum(sp) + cin + cout)
+    x = torch.randn(B, cin, *sp, generator=g).cuda()
+    w = (torch.randn(cout, cin, *([3] * nd), generator=g) * 0.2).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    wp = torch.zeros(cout, 4, *([3] * nd), device="cuda")
+    wp[:, :cin] = w
+    packed = PL.pack_conv_weight(wp)
+    w128 = torch.zeros(cout, 128, dtype=torch.bfloat16, device="cuda")
+    w128[:, :packed.shape[1]] = packed
+    S = 1
+    for e in sp:
+        S *= e
+    y = torch.zeros(B, S, cout, dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(B, 8, 2, dtype=torch.float64, device="cuda")
+    sp3 = (1,) * (3 - nd) + tuple(sp)
+    ops.thin_in_conv(x, w128, bias, y, stats, B, cin, sp3[0], sp3[1], sp3[2], nd, cout)
+    torch.cuda.synchronize()
+    conv = F.conv3d if nd == 3 else F.conv2d
+    want = conv(x.bfloat16().float(), w.bfloat16().float(), bias, padding=1)       # [B, cout, *sp]
+    want = want.reshape(B, cout, S).transpose(1, 2)
+    err = rel_l2(y, want)
+    yf = y.double().view(B, S, 8, cout // 8)
+    # the sums are taken over the fp32 values BEFORE the bf16 rounding of the stored output
+    wf = want.double().reshape(B, S, 8, cout // 8)
+    assert torch.allclose(stats[..., 0], wf.sum((1, 3)), rtol=1e-4, atol=1e-2), (stats[0, :, 0], wf.sum((1, 3))[0])
+    assert torch.allclose(stats[..., 1], (wf * wf).sum((1, 3)), rtol=1e-4, atol=1e-2)
+    print(f"thin_in_conv {sp} {cin}->{cout}: rel-L2 {err:.3e}")
+    assert err < 5e-3, err
+    del yf
