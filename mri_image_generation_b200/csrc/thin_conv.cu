@@ -52,13 +52,14 @@ struct ThinConvArgs {
   long long n_tiles;
 };
 
-template <int COUT>
+template <int COUT, int CIN, int NDIM>
 __global__ void __launch_bounds__(kTcThreads, 3)
 thin_in_conv_kernel(const ThinConvArgs a) {
   constexpr int CPG = COUT / 8;                 // GroupNorm(8, COUT): channels per group
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_holder;
+  __shared__ __align__(16) float s_bias[COUT];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_smem = smem_base;                       // 2 slabs of COUT rows
@@ -83,6 +84,7 @@ thin_in_conv_kernel(const ThinConvArgs a) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
   }
+  for (int i = tid; i < COUT; i += kTcThreads) s_bias[i] = a.bias != nullptr ? __ldg(a.bias + i) : 0.f;
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -93,13 +95,13 @@ thin_in_conv_kernel(const ThinConvArgs a) {
   // contiguous range of tiles per CTA (tiles of one sample stay together: few statistics flushes)
   const long long t0 = a.n_tiles * blockIdx.x / gridDim.x;
   const long long t1 = a.n_tiles * (blockIdx.x + 1) / gridDim.x;
-  const int taps = a.ndim == 3 ? 27 : 9;
-  const int kd_n = a.ndim == 3 ? 3 : 1;
+  constexpr int taps = NDIM == 3 ? 27 : 9;
   const long long plane = (long long)a.H * a.W;
   const float rcp_w = 1.0f / (float)a.W;
-  float gs[8], gq[8];
+  float2 gs[8], gq[8];   // per group: sums / sums of squares of the even and the odd channels
 #pragma unroll
-  for (int g = 0; g < 8; ++g) gs[g] = gq[g] = 0.f;
+  for (int g = 0; g < 8; ++g) gs[g] = gq[g] = make_float2(0.f, 0.f);
+  const int sp32 = (int)a.spatial, plane32 = (int)plane;
   int acc_sample = -1;
   uint32_t phase = 0;
   const uint32_t row_smem = a_smem + (uint32_t)tid * 128u;
@@ -109,7 +111,7 @@ thin_in_conv_kernel(const ThinConvArgs a) {
     if (a.stats != nullptr && acc_sample >= 0) {
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
-        float s = gs[g], q = gq[g];
+        float s = gs[g].x + gs[g].y, q = gq[g].x + gq[g].y;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -123,7 +125,7 @@ thin_in_conv_kernel(const ThinConvArgs a) {
       }
     }
 #pragma unroll
-    for (int g = 0; g < 8; ++g) gs[g] = gq[g] = 0.f;
+    for (int g = 0; g < 8; ++g) gs[g] = gq[g] = make_float2(0.f, 0.f);
   };
 
   for (long long t = t0; t < t1; ++t) {
@@ -138,7 +140,7 @@ thin_in_conv_kernel(const ThinConvArgs a) {
     int d0 = 0, h0 = 0, w0 = 0;
     {
       long long rest = s;
-      if (a.ndim == 3) {
+      if (NDIM == 3) {
         d0 = (int)(rest / plane);
         rest -= (long long)d0 * plane;
       }
@@ -147,25 +149,30 @@ thin_in_conv_kernel(const ThinConvArgs a) {
       h0 = qh;
       w0 = rw;
     }
-    const float* xn = a.x + (size_t)n * a.cin * a.spatial;
-    int tap = 0;
-    for (int kd = 0; kd < kd_n; ++kd) {
-      const int d = a.ndim == 3 ? d0 + kd - 1 : 0;
-      const bool okd = valid && (unsigned)d < (unsigned)a.D;
+    // x[n][c][s + off]: 32-bit offsets from my own voxel; per-axis validity computed once
+    const float* xs = a.x + (size_t)n * CIN * a.spatial + (valid ? s : 0);
+    bool vd[3], vh[3], vw[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      vd[k] = valid && (NDIM != 3 ? k == 1 : (unsigned)(d0 + k - 1) < (unsigned)a.D);
+      vh[k] = (unsigned)(h0 + k - 1) < (unsigned)a.H;
+      vw[k] = (unsigned)(w0 + k - 1) < (unsigned)a.W;
+    }
+    int tap = 0;   // compile-time after unrolling
+#pragma unroll
+    for (int kd = (NDIM == 3 ? 0 : 1); kd < (NDIM == 3 ? 3 : 2); ++kd) {
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
-        const int h = h0 + kh - 1;
-        const bool okh = okd && (unsigned)h < (unsigned)a.H;
+        const bool okdh = vd[kd] && vh[kh];
+        const int base = (kd - 1) * plane32 + (kh - 1) * a.W - 1;
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw, ++tap) {
-          const int w = w0 + kw - 1;
-          const bool ok = okh && (unsigned)w < (unsigned)a.W;
-          const long long off = ((long long)d * a.H + h) * a.W + w;
+          const bool ok = okdh && vw[kw];
           float v[4] = {0.f, 0.f, 0.f, 0.f};
           if (ok) {
+            const float* px = xs + (base + kw);
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-              if (c < a.cin) v[c] = __ldg(xn + (size_t)c * a.spatial + off);
+            for (int c = 0; c < CIN; ++c) v[c] = __ldg(px + c * sp32);
           }
           const __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]);
           const __nv_bfloat162 p1 = __floats2bfloat162_rn(v[2], v[3]);
@@ -180,6 +187,7 @@ thin_in_conv_kernel(const ThinConvArgs a) {
       }
     }
     // zero the K padding [taps * 4, 128)
+#pragma unroll
     for (int k8 = taps; k8 < 32; ++k8) {
       const uint32_t dst = row_smem + (uint32_t)(k8 >> 4) * kTcSlab +
                            (((uint32_t)((k8 >> 1) & 7) ^ xr) << 4) + (uint32_t)(k8 & 1) * 8u;
@@ -216,22 +224,21 @@ thin_in_conv_kernel(const ThinConvArgs a) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
       if (c0 + 32 < COUT) tmem_ld32(tacc + (uint32_t)(c0 + 32), v);
-      if (a.bias != nullptr) {
+      float2 f2[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + i));
-          f[i] += b4.x;
-          f[i + 1] += b4.y;
-          f[i + 2] += b4.z;
-          f[i + 3] += b4.w;
-        }
+      for (int i = 0; i < 16; i += 2) {   // bias from shared memory, channel pairs on the packed fp32 pipe
+        const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + 2 * i]);
+        f2[i] = __fadd2_rn(make_float2(f[2 * i], f[2 * i + 1]), make_float2(b4.x, b4.y));
+        f2[i + 1] = __fadd2_rn(make_float2(f[2 * i + 2], f[2 * i + 3]), make_float2(b4.z, b4.w));
       }
       if (valid) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int g = (c0 + i) / CPG;       // compile-time after unrolling
-          gs[g] += f[i];
-          gq[g] = fmaf(f[i], f[i], gq[g]);
+        for (int i = 0; i < 16; ++i) {
+          const int g = (c0 + 2 * i) / CPG;     // compile-time after unrolling; CPG is even
+          gs[g] = __fadd2_rn(gs[g], f2[i]);
+          gq[g] = __ffma2_rn(f2[i], f2[i], gq[g]);
+          f[2 * i] = f2[i].x;
+          f[2 * i + 1] = f2[i].y;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -296,22 +303,22 @@ extern "C" int mri_thin_in_conv(const float* x, const void* w_packed, const floa
   if (grid > a.n_tiles) grid = a.n_tiles;
   const int smem = 2 * cout * 128 + 2 * kTcSlab + 1024;
   cudaStream_t st = (cudaStream_t)stream;
-  if (cout == 128) {
-    static int conf = 0;
-    if (!conf) {
-      cudaError_t e = cudaFuncSetAttribute(thin_in_conv_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(thin_in_conv_kernel<128>)");
-      conf = 1;
-    }
-    thin_in_conv_kernel<128><<<(unsigned)grid, kTcThreads, smem, st>>>(a);
-  } else {
-    static int conf = 0;
-    if (!conf) {
-      cudaError_t e = cudaFuncSetAttribute(thin_in_conv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(thin_in_conv_kernel<64>)");
-      conf = 1;
-    }
-    thin_in_conv_kernel<64><<<(unsigned)grid, kTcThreads, smem, st>>>(a);
+  if (a.spatial * cin >= (1LL << 31)) return set_error(-2, "mri_thin_in_conv: sample too large");
+  typedef void (*Kern)(const ThinConvArgs);
+#define MRI_TC_ROW(CO, ND) \
+  {thin_in_conv_kernel<CO, 1, ND>, thin_in_conv_kernel<CO, 2, ND>, thin_in_conv_kernel<CO, 3, ND>, \
+   thin_in_conv_kernel<CO, 4, ND>}
+  static const Kern kerns[2][2][4] = {{MRI_TC_ROW(64, 2), MRI_TC_ROW(128, 2)},
+                                      {MRI_TC_ROW(64, 3), MRI_TC_ROW(128, 3)}};
+#undef MRI_TC_ROW
+  static int configured[2][2][4] = {{{0, 0, 0, 0}, {0, 0, 0, 0}}, {{0, 0, 0, 0}, {0, 0, 0, 0}}};
+  const int ci = cout == 128 ? 1 : 0;
+  Kern kern = kerns[ndim - 2][ci][cin - 1];
+  if (!configured[ndim - 2][ci][cin - 1]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(thin_in_conv_kernel)");
+    configured[ndim - 2][ci][cin - 1] = 1;
   }
+  kern<<<(unsigned)grid, kTcThreads, smem, st>>>(a);
   return check_launch("thin_in_conv_kernel");
 }
