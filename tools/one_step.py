@@ -7,7 +7,7 @@
   ncu --nvtx --nvtx-include "measured_step/" --set full --import-source on -k regex:attn_flash ... python tools/one_step.py
 
 MODE=train runs one cfg5 training step (q_sample + forward + loss + backward + Adam, 8 latents)
-in the range instead."""
+inside the start/end range "measured_train_step" instead (--nvtx-include "measured_train_step")."""
 import contextlib
 import io
 import os
@@ -56,8 +56,10 @@ else:
     for _ in range(2):
         step()
     torch.cuda.synchronize()
-    torch.cuda.nvtx.range_push("measured_step")
+    # start / end range, not push / pop: the backward launches come from the autograd thread, and
+    # push / pop ranges are per thread (ncu: --nvtx-include "measured_train_step", no trailing slash)
+    rid = torch.cuda.nvtx.range_start("measured_train_step")
     loss = step()
     torch.cuda.synchronize()
-    torch.cuda.nvtx.range_pop()
+    torch.cuda.nvtx.range_end(rid)
     print("one training step done; loss", float(loss))
