@@ -22,6 +22,7 @@ import os
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib, ops
@@ -231,37 +232,60 @@ class UNetProgram(BackwardMixin):
             valid = a >= 0
             which = torch.searchsorted(offs_t, a.clamp_min(0), right=True) - 1
             used = torch.unique(which[valid]).tolist() if bool(valid.any().item()) else []
-            if len(used) > 4 or bool((a >= tot).any().item()):
+            if bool((a >= tot).any().item()):
                 fallback.append(i)
                 continue
-            slot_of = {pi: s_ for s_, pi in enumerate(used)}
-            slot = torch.zeros_like(a)
+            # a segment addresses at most 4 source tensors: a buffer that gathers from more (the
+            # concatenated block projections) is cut into contiguous pieces of <= 4 sources each
+            pieces = [(0, buf.numel(), used)]
+            if len(used) > 4:
+                wc = torch.where(valid, which, torch.full_like(which, -1)).cpu().numpy()
+                cuts = np.flatnonzero(np.diff(wc)) + 1
+                starts = np.concatenate([[0], cuts])
+                ends = np.concatenate([cuts, [wc.size]])
+                pieces, lo, cur = [], 0, []
+                for st_, en_ in zip(starts.tolist(), ends.tolist()):
+                    src_ = int(wc[st_])
+                    if src_ >= 0 and src_ not in cur:
+                        if len(cur) == 4:
+                            pieces.append((lo, st_, cur))
+                            lo, cur = st_, []
+                        cur.append(src_)
+                pieces.append((lo, wc.size, cur))
             local = torch.zeros_like(a)
             for pi in used:
                 m = valid & (which == pi)
-                slot[m] = slot_of[pi]
                 local[m] = a[m] - offs[pi]
             if bool((local >= (1 << 28)).any().item()):
                 fallback.append(i)
                 continue
+            slot = torch.zeros_like(a)
+            for lo, hi, srcs_ in pieces:
+                for s_, pi in enumerate(srcs_):
+                    m = torch.zeros_like(valid)
+                    m[lo:hi] = valid[lo:hi] & (which[lo:hi] == pi)
+                    slot[m] = s_
             idx = torch.where(valid, (slot << 28) | local, torch.full_like(a, -1)).to(torch.int32)
             # verify against the real expression before trusting the map
-            flat_srcs = [params[pi].detach().reshape(-1) for pi in used]
             got = torch.zeros(buf.numel(), dtype=torch.float32, device=self.device)
-            for s_, src in enumerate(flat_srcs):
-                m = valid & (slot == s_)
-                got[m] = src[local[m]]
+            for pi in used:
+                m = valid & (which == pi)
+                got[m] = params[pi].detach().reshape(-1)[local[m]]
             if not torch.equal(got.to(buf.dtype), make().reshape(-1)):
                 fallback.append(i)
                 continue
-            sg = _lib.MriGatherSeg()
-            sg.dst, sg.idx, sg.n = buf.data_ptr(), idx.data_ptr(), buf.numel()
-            for s_, pi in enumerate(used):
-                sg.src[s_] = params[pi].data_ptr()
-            sg.block0 = blocks
-            sg.dst_bf16 = 1 if buf.dtype == torch.bfloat16 else 0
-            blocks += -(-buf.numel() // 2048)
-            segs.append(sg)
+            esz = buf.element_size()
+            for lo, hi, srcs_ in pieces:
+                if hi <= lo:
+                    continue
+                sg = _lib.MriGatherSeg()
+                sg.dst, sg.idx, sg.n = buf.data_ptr() + lo * esz, idx.data_ptr() + lo * 4, hi - lo
+                for s_, pi in enumerate(srcs_):
+                    sg.src[s_] = params[pi].data_ptr()
+                sg.block0 = blocks
+                sg.dst_bf16 = 1 if buf.dtype == torch.bfloat16 else 0
+                blocks += -(-(hi - lo) // 2048)
+                segs.append(sg)
             keep.append(idx)
         table = None
         if segs:
@@ -711,9 +735,12 @@ class UNet3DProgram(UNetProgram):
             w2 = self.packed(lambda: P.pack_conv_weight(
                 c2.weight.detach(),
                 extra=[sk.weight.detach().reshape(cout, -1)[:, a:a + n] for a, n in extras]))
-            b2 = self.packed(lambda: (c2.bias.detach() + sk.bias.detach()).contiguous())
+            # the two bias vectors are added in the epilogue (skip bias as a row bias whose row
+            # pitch is 0: the same row for every sample) -- no derived "sum of parameters" buffer
+            # that would need a torch expression to refresh after every optimizer step
             sources = [P.ConvSource(a2)] + [P.ConvSource(s.t, taps=False) for s in srcs]
-            out = self.conv(sources, w2, cout, 3, b2, name=f"{name}.conv2+skip",
+            out = self.conv(sources, w2, cout, 3, c2.bias, rowbias=sk.bias, rowbias_ld=0,
+                            name=f"{name}.conv2+skip",
                             rec=dict(weight=c2.weight, splits=[cout], extra_weight=sk.weight,
                                      bias_params=[c2.bias, sk.bias]))
         else:

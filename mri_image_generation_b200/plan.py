@@ -341,8 +341,11 @@ class GemmPlan:
                         x1 = (org[0] + rl[0]).clamp(max=self.bias_m.numel() - 1)
                         acc += torch.where(valid, self.bias_m[x1], torch.zeros(()))[:, None]
                     if self.rowbias is not None:
-                        rb = self.rowbias.reshape(-1, self.rowbias_ld) if self.rowbias.dim() == 1 \
-                            else self.rowbias
+                        if self.rowbias_ld == 0:      # one row for every sample (a second bias vector)
+                            rb = self.rowbias.reshape(1, -1)
+                        else:
+                            rb = self.rowbias.reshape(-1, self.rowbias_ld) if self.rowbias.dim() == 1 \
+                                else self.rowbias
                         smp = sample.clamp(max=rb.shape[0] - 1)
                         add = rb[smp][:, ncols.clamp(max=rb.shape[1] - 1)]
                         acc += torch.where(valid[:, None] & colok[None, :], add, torch.zeros(()))

@@ -122,3 +122,21 @@ def test_adam_late_parameter_does_not_reset_the_group_step():
         p.grad = torch.ones_like(p)
     oa.step()
     assert float(oa.state[pa[1]]["step"]) == 4.0
+
+
+def test_weight_repack_after_a_step_is_pure_gather():
+    """After an optimizer step every derived weight buffer (packed bf16 matrices, the concatenated
+    block projections, padded biases) is refreshed by ONE mri_gather_pack launch: no buffer is left
+    on the torch-expression fallback, and the refreshed buffers equal a fresh packing."""
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.unet_attention import UNet3DModelWithAttention
+    torch.manual_seed(3)
+    m = UNet3DModelWithAttention(3, base_channels=64, time_emb_dim=64).cuda().train()
+    prog = m.program(2, (8, 8, 8), training=True)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(torch.randn_like(p) * 0.01)
+    prog.do_refresh()
+    info = prog.gather_info
+    assert info["fallback"] == 0, info
+    for buf, make in prog._packed:
+        assert torch.equal(buf, make().reshape(buf.shape).to(buf.dtype)), "stale packed buffer"
