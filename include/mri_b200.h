@@ -443,6 +443,49 @@ typedef struct MriFinalSeg {
 } MriFinalSeg;
 int mri_grad_finalize(const MriFinalSeg* segs_dev, int n_segs, int64_t total_blocks, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The data path in front of the UNets (the reference's Dataset.__getitem__ arithmetic, batched on
+ * the device; reading NIfTI files stays with the host).
+ *
+ * mri_masked_stats: per item, over its NON-ZERO elements, mean and (population) standard deviation
+ * as fp32 (two passes with fp64 sums, like numpy's) -- `mask = x != 0; mean = x[mask].mean();
+ * std = x[mask].std()`
+ * (slice_cond_2d_ddpm/dataset.py:71-76, ddpm_25d_all_modalities/dataset.py:84-88,
+ * ddpm_3d_ldm/dataset.py:18-24).  Item i is the rows x cols view at x + i * item_stride with
+ * element strides (row_stride, col_stride); either col_stride == 1 (contiguous slices / a whole
+ * volume as one row) or item_stride == 1 (the slices vol[:, :, z] of an (H, W, D) NIfTI array).
+ * std is replaced by 1 when it is not positive or below eps (eps = 0: the 2-D rule `std if std > 0
+ * else 1.0`; eps = 1e-6: the 3-D rule `if std < eps: std = 1.0`).  An item without non-zero
+ * elements gets (0, 1).  acc: fp64 scratch [items][3] (count, sum, sum of squared deviations; zeroed by the
+ * call); mean_std: fp32 [items][2].
+ *
+ * mri_slice_normalize_resize: out[i] = 2 * bilinear(clip01(x_i)) - 1 with
+ * clip01(v) = (clip(v != 0 ? (v - mean_i) / std_i : v, -5, 5) + 5) / 10 and torch's
+ * F.interpolate(size=(out_h, out_w), mode="bilinear", align_corners=False)
+ * (slice_cond_2d_ddpm/dataset.py:78-96, ddpm_25d_all_modalities/dataset.py:91-103).  out item i
+ * is the contiguous [out_h][out_w] block at out + i * out_item_stride (so that centre and context
+ * slices land directly in the channels of a [B, C, S, S] batch).
+ *
+ * mri_volume_normalize_patch: one modality of BraTS3DVolumeDataset._load_volume
+ * (ddpm_3d_ldm/dataset.py:11-41 _normalize_volume, 44-77 _pad_to_min_shape, 80-105
+ * _random_or_center_crop, 160-185) in one pass: out[z][y][x] = n(vol[z + off_d, y + off_h,
+ * x + off_w]) inside the volume and 0 in the zero padding, n(v) = 2 * (clip(zscore(v), -clip,
+ * clip) + clip) / (2 clip) - 1.  The volume is addressed through element strides along (D, H, W),
+ * so nibabel's (H, W, D) array is read in place (stride_d = 1: transposed through shared memory);
+ * off_* = crop start - pad_before (negative inside the padding).
+ * ------------------------------------------------------------------------------------------ */
+int mri_masked_stats(const float* x, int items, int64_t item_stride, int64_t rows, int64_t cols,
+                     int64_t row_stride, int64_t col_stride, float eps, double* acc,
+                     float* mean_std, void* stream);
+int mri_slice_normalize_resize(const float* x, int items, int64_t item_stride, int H, int W,
+                               int64_t row_stride, int64_t col_stride, const float* mean_std,
+                               int out_h, int out_w, float* out, int64_t out_item_stride,
+                               void* stream);
+int mri_volume_normalize_patch(const float* vol, int D, int H, int W, int64_t stride_d,
+                               int64_t stride_h, int64_t stride_w, const float* mean_std,
+                               float clip, int off_d, int off_h, int off_w, int pd, int ph, int pw,
+                               float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -137,6 +137,11 @@ SIGNATURES = {
     "mri_copy_cast": (_i, [_vp, _i, C.POINTER(C.c_int64), _vp, _i, C.POINTER(C.c_int64),
                            C.POINTER(C.c_int64), _vp]),
     "mri_memset_zero": (_i, [_vp, _i64, _vp]),
+    "mri_masked_stats": (_i, [_vp, _i, _i64, _i64, _i64, _i64, _i64, _f, _vp, _vp, _vp]),
+    "mri_slice_normalize_resize": (_i, [_vp, _i, _i64, _i, _i, _i64, _i64, _vp, _i, _i, _vp, _i64,
+                                        _vp]),
+    "mri_volume_normalize_patch": (_i, [_vp, _i, _i, _i, _i64, _i64, _i64, _vp, _f, _i, _i, _i, _i,
+                                        _i, _i, _vp, _vp]),
     "mri_q_sample": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "mri_ddpm_step": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "mri_ddim_step": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i64, _vp]),

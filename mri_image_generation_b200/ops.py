@@ -319,3 +319,83 @@ def memset_zero(t: torch.Tensor, nbytes: Optional[int] = None) -> None:
     _chk_contig(t)
     n = t.numel() * t.element_size() if nbytes is None else int(nbytes)
     _lib.check(_lib.load().mri_memset_zero(_p(t), n, _s()), "mri_memset_zero")
+
+
+# ---- data path (csrc/data_path.cu) ---------------------------------------------------------------
+def _f32_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise _lib.MriError(f"{what}: needs a CUDA tensor (no CPU path)")
+    if t.dtype != torch.float32:
+        raise _lib.MriError(f"{what}: needs float32, got {t.dtype}")
+
+
+def masked_stats(x: torch.Tensor, item_dim: Optional[int] = None, eps: float = 0.0) -> torch.Tensor:
+    """fp32 [items, 2] = (mean, std) over the non-zero elements of each item of x (any strides).
+    x is 2-D (one item) / 3-D with the item axis `item_dim`; or any contiguous tensor with
+    item_dim=None (one item: the whole tensor).  Rules for std: see mri_masked_stats."""
+    _f32_cuda(x, "masked_stats")
+    if item_dim is None:
+        if not x.is_contiguous():
+            raise _lib.MriError("masked_stats: a whole-tensor item must be contiguous")
+        items, ist, rows, cols, rs, cs = 1, 0, 1, x.numel(), 0, 1
+    else:
+        if x.dim() != 3:
+            raise _lib.MriError("masked_stats: item_dim needs a 3-D tensor")
+        item_dim %= 3
+        r, c = [d for d in range(3) if d != item_dim]
+        items, ist = x.shape[item_dim], x.stride(item_dim)
+        rows, cols, rs, cs = x.shape[r], x.shape[c], x.stride(r), x.stride(c)
+        if cs != 1 and rs == 1:          # statistics do not care which axis is called "row"
+            rows, cols, rs, cs = cols, rows, cs, rs
+        if items == 1 and cs != 1:       # a single strided slice: the item-major kernel, one lane
+            ist = 1
+    with torch.cuda.device(x.device):
+        acc = torch.empty(items, 3, dtype=torch.float64, device=x.device)
+        out = torch.empty(items, 2, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().mri_masked_stats(_p(x), items, ist, rows, cols, rs, cs,
+                                                float(eps), _p(acc), _p(out), _s()),
+                   "mri_masked_stats")
+    return out
+
+
+def slice_normalize_resize(x: torch.Tensor, item_dim: int, mean_std: torch.Tensor,
+                           out: torch.Tensor) -> None:
+    """out[i] (a contiguous [S_h, S_w] block per item; out is [items, S_h, S_w] or any view whose
+    last two dims are contiguous, e.g. batch[:, c0:c0+items] of a [B, C, S, S] tensor with B == 1,
+    or batch[:, c] with one item per sample) <- normalised, bilinearly resized slice i of the 3-D
+    tensor x, mapped to [-1, 1]."""
+    _f32_cuda(x, "slice_normalize_resize")
+    _f32_cuda(out, "slice_normalize_resize")
+    if x.dim() != 3 or out.dim() != 3:
+        raise _lib.MriError("slice_normalize_resize: x and out must be 3-D (items on one axis)")
+    item_dim %= 3
+    r, c = [d for d in range(3) if d != item_dim]
+    items = x.shape[item_dim]
+    if out.shape[0] != items or out.stride(2) != 1 or out.stride(1) != out.shape[2]:
+        raise _lib.MriError("slice_normalize_resize: out must be [items, S_h, S_w] with contiguous "
+                            "slices")
+    if tuple(mean_std.shape) != (items, 2) or not mean_std.is_contiguous():
+        raise _lib.MriError("slice_normalize_resize: mean_std must be contiguous [items, 2]")
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().mri_slice_normalize_resize(
+            _p(x), items, x.stride(item_dim), x.shape[r], x.shape[c], x.stride(r), x.stride(c),
+            _p(mean_std), out.shape[1], out.shape[2], _p(out), out.stride(0), _s()),
+            "mri_slice_normalize_resize")
+
+
+def volume_normalize_patch(vol_dhw: torch.Tensor, mean_std: torch.Tensor, origin, out: torch.Tensor,
+                           clip: float = 5.0) -> None:
+    """out (contiguous [pd, ph, pw]) <- normalised patch of the (D, H, W)-indexed view vol_dhw (any
+    strides, e.g. nib_array.permute(2, 0, 1)) whose first voxel is vol_dhw[origin]; positions
+    outside the volume are the zero padding."""
+    _f32_cuda(vol_dhw, "volume_normalize_patch")
+    _f32_cuda(out, "volume_normalize_patch")
+    if vol_dhw.dim() != 3 or out.dim() != 3 or not out.is_contiguous():
+        raise _lib.MriError("volume_normalize_patch: vol must be 3-D, out contiguous 3-D")
+    D, H, W = vol_dhw.shape
+    sd, sh, sw = vol_dhw.stride()
+    od, oh, ow = (int(v) for v in origin)
+    with torch.cuda.device(vol_dhw.device):
+        _lib.check(_lib.load().mri_volume_normalize_patch(
+            _p(vol_dhw), D, H, W, sd, sh, sw, _p(mean_std), float(clip), od, oh, ow, out.shape[0],
+            out.shape[1], out.shape[2], _p(out), _s()), "mri_volume_normalize_patch")

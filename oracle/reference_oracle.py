@@ -308,3 +308,77 @@ def sample_loop(buf: SD, model_fn, x_T, noises: Sequence[torch.Tensor], T: int):
         t = torch.full((B,), i, dtype=torch.long)
         img = p_sample_update(buf, img, t, model_fn(img, t), noises[k])
     return img
+
+
+# ------------------------------------------------------------------------------------------
+# data path: what Dataset.__getitem__ does to a loaded volume (numpy + F.interpolate on the CPU)
+# ------------------------------------------------------------------------------------------
+def _zscore_nonzero(a, floor):
+    """In place: a[a != 0] <- (a - mean) / std over those entries; `floor(std)` is the reference's
+    guard against a vanishing deviation.  Returns False when there is no non-zero entry."""
+    import numpy as np
+    nz = a != 0
+    if not np.any(nz):
+        return False
+    m, s = a[nz].mean(), floor(a[nz].std())
+    a[nz] = (a[nz] - m) / s
+    return True
+
+
+def preprocess_slice(slice_2d, image_size: int) -> torch.Tensor:
+    """slice_cond_2d_ddpm/dataset.py:71-98 == ddpm_25d_all_modalities/dataset.py:79-103:
+    z-score of the non-zero pixels, clip +-5, [0, 1], bilinear resize, [-1, 1] -> (1, S, S).
+    (Works on a copy: the 2-D reference mutates its cached volume through the view, see
+    mri_image_generation_b200/model_scripts/slice_cond_2d_ddpm/dataset.py.)"""
+    import numpy as np
+    a = np.array(slice_2d, dtype=np.float32, copy=True)
+    _zscore_nonzero(a, lambda s: s if s > 0 else 1.0)
+    a = (np.clip(a, -5, 5) + 5) / 10.0
+    t = F.interpolate(torch.from_numpy(a)[None, None], size=(image_size, image_size),
+                      mode="bilinear", align_corners=False)[0]
+    return t * 2.0 - 1.0
+
+
+def normalize_volume(vol, eps: float = 1e-6, clip_val: float = 5.0):
+    """ddpm_3d_ldm/dataset.py:11-41 (float32 numpy in, float32 numpy out, input untouched)."""
+    import numpy as np
+    a = np.array(vol, dtype=np.float32, copy=True)
+    floor = lambda s: 1.0 if s < eps else s
+    if not _zscore_nonzero(a, floor):
+        a = (a - a.mean()) / floor(a.std())      # dataset.py:26-32: nothing but background
+    a = np.clip(a, -clip_val, clip_val)
+    a = (a + clip_val) / (2.0 * clip_val)
+    return a * 2.0 - 1.0
+
+
+def pad_to_min_shape(vol, target_shape):
+    """ddpm_3d_ldm/dataset.py:44-77: symmetric zero padding of (C, D, H, W), the odd voxel after."""
+    import numpy as np
+    widths = [(0, 0)]
+    for have, want in zip(vol.shape[1:], target_shape):
+        missing = max(want - have, 0)
+        widths.append((missing // 2, missing - missing // 2))
+    return np.pad(vol, widths, mode="constant") if any(b or a for b, a in widths) else vol
+
+
+def crop_patch(vol, patch_size, random_crop: bool = True, rng=None):
+    """ddpm_3d_ldm/dataset.py:80-105: centre crop, or a random one drawing z, y, x starts from
+    Python's `random` (only along axes with room)."""
+    import random as _random
+    rng = rng or _random
+    starts = []
+    for have, want in zip(vol.shape[1:], patch_size):
+        if have < want:
+            raise ValueError("Volume is smaller than patch even after padding.")
+        room = have - want
+        starts.append((rng.randint(0, room) if room > 0 else 0) if random_crop else room // 2)
+    z, y, x = starts
+    return vol[:, z:z + patch_size[0], y:y + patch_size[1], x:x + patch_size[2]]
+
+
+def load_volume_patch(vols_hwd, patch_size, random_crop: bool = True, rng=None):
+    """ddpm_3d_ldm/dataset.py:160-185 after the file read: (H, W, D) modality arrays ->
+    (C, pd, ph, pw) float32."""
+    import numpy as np
+    stack = np.stack([normalize_volume(np.transpose(v, (2, 0, 1))) for v in vols_hwd], axis=0)
+    return crop_patch(pad_to_min_shape(stack, patch_size), patch_size, random_crop, rng)
