@@ -47,6 +47,8 @@ class ResidualBlock3D(nn.Module):
 
 
 class _UNet3DBase(EngineModule):
+    SUPPORTS_GRAD_SYNC = True   # backward can hand gradient buckets to parallel.GradSync
+
     def _build(self, in_channels, base_channels, channel_mults, time_emb_dim, groups, num_heads):
         self.in_channels = in_channels
         self.time_mlp = nn.Sequential(

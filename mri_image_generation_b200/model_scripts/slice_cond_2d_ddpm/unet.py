@@ -48,6 +48,8 @@ class UpBlock(nn.Module):
 
 
 class _UNet2DBase(EngineModule):
+    SUPPORTS_GRAD_SYNC = True   # backward can hand gradient buckets to parallel.GradSync
+
     def _build(self, in_channels, out_channels, base_channels, channel_mults, time_emb_dim):
         self.time_mlp = nn.Sequential(
             SinusoidalHolder(time_emb_dim),

@@ -280,3 +280,19 @@ def wrap_ddp(module: torch.nn.Module, device: torch.device, overlap: bool = True
     from torch.nn.parallel import DistributedDataParallel as DDP
     return DDP(module, device_ids=[device.index], output_device=device.index,
                find_unused_parameters=False, **kw)
+
+
+def ddp_for_scripts(torch_ddp):
+    """What `overlay.install(overlap_ddp=True)` binds `torch.nn.parallel.DistributedDataParallel`
+    to: `DDP(unet, device_ids=[local_rank], ...)` (ddpm_3d_ldm/train.py:232-233) gives the
+    overlapped wrapper for the drop-in UNets and torch's own wrapper for every other module (the
+    VAE, train.py:232), with the reference's call signature."""
+    from .modules import EngineModule
+
+    def DDP(module, *args, **kwargs):
+        if isinstance(module, EngineModule) and getattr(module, "SUPPORTS_GRAD_SYNC", False):
+            return DistributedDataParallel(module, *args, **kwargs)
+        return torch_ddp(module, *args, **kwargs)
+
+    DDP.__wrapped__ = torch_ddp
+    return DDP
