@@ -42,6 +42,13 @@ class ConvRec:
     w_rows: Optional[Tuple[int, int]] = None     # use only weight rows [a, b) (qkv slices)
     kpad: int = 0                                # 'matrix': padded K of the im2col'd weight
     dgrad_dy: Optional[torch.Tensor] = None      # 64-channel copy of dY when Cout is thin (out_conv)
+    # channel-padded layers (the VAE's 32-channel level runs zero-padded to 64, vae_engine.py):
+    # how to read the parameter gradients out of the packed wgrad matrix, and the zero-padded
+    # reference-layout weights the adjoint plans are packed from
+    unpack: Optional[Callable[[torch.Tensor], torch.Tensor]] = None
+    unpack_extra: Optional[Callable[[torch.Tensor], torch.Tensor]] = None
+    wfull: Optional[Callable[[], torch.Tensor]] = None
+    efull: Optional[Callable[[], torch.Tensor]] = None
     name: str = ""
 
 
@@ -58,6 +65,8 @@ class GnRec:
     tproj_off: Optional[int] = None
     residual: Optional[torch.Tensor] = None
     name: str = ""
+    gparam: Optional[torch.Tensor] = None   # the nn.Parameters when gamma / beta are zero-padded
+    bparam: Optional[torch.Tensor] = None   # packed copies (vae_engine.py)
 
 
 @dataclass
@@ -302,7 +311,11 @@ class BackwardMixin:
             self.badd(f"wgrad:{r.name}", wg.launch)
             gw = self.pg(r.weight)
             wshape = tuple(r.weight.shape)
-            if r.kind == "up":
+            if r.unpack is not None:
+                self.bfinal_gather(gw, dw, r.unpack)
+                if r.unpack_extra is not None:
+                    self.bfinal_gather(self.pg(r.extra_weight), dw, r.unpack_extra)
+            elif r.kind == "up":
                 self.bfinal_gather(gw, dw, lambda d: P.unpack_convT_wgrad(d, wshape))
             else:
                 taps_splits = r.splits
@@ -329,15 +342,16 @@ class BackwardMixin:
         if not r.need_dgrad:
             return
         w = r.weight
+        wfull = r.wfull if r.wfull is not None else (lambda: w.detach())
         if r.kind == "down":
             (src, _), = r.sources
-            wT = self.packed(lambda: P.pack_convT_weight(w.detach()))
+            wT = self.packed(lambda: P.pack_convT_weight(wfull()))
             self.emit_grad(src, lambda out, add: self.bgemm(
                 P.up_conv_plan(dy, wT, out, residual=add, name=f"dgrad:{r.name}")))
             return
         if r.kind == "up":
             (src, _), = r.sources
-            wT = self.packed(lambda: P.pack_conv_weight(w.detach()))
+            wT = self.packed(lambda: P.pack_conv_weight(wfull()))
             self.emit_grad(src, lambda out, add: self.bgemm(
                 P.down_conv_plan(dy, wT, out, residual=add, name=f"dgrad:{r.name}")))
             return
@@ -353,7 +367,7 @@ class BackwardMixin:
                 rows = r.w_rows
 
                 def make(a=a, b=b, rows=rows):
-                    ww = w.detach() if rows is None else w.detach()[rows[0]:rows[1]]
+                    ww = wfull() if rows is None else wfull()[rows[0]:rows[1]]
                     wt = ww[:, a:b].transpose(0, 1).flip(*range(2, 2 + nd))  # [Ci, Co, *k]
                     if wt.shape[1] < cy:  # thin Cout padded to the 64-channel dY copy
                         pad = torch.zeros(wt.shape[0], cy - wt.shape[1], *wt.shape[2:],
@@ -368,10 +382,11 @@ class BackwardMixin:
                 c0 += Ci
             else:
                 a, b = e0, e0 + Ci
-                ew = r.extra_weight
+                efull = r.efull if r.efull is not None else (lambda: r.extra_weight.detach())
 
                 def make_e(a=a, b=b):
-                    wt = ew.detach().reshape(ew.shape[0], -1)[:, a:b].t().contiguous()
+                    ew = efull()
+                    wt = ew.reshape(ew.shape[0], -1)[:, a:b].t().contiguous()
                     return P.pack_conv_weight(wt.reshape(b - a, ew.shape[0], *([1] * nd)))
 
                 wTe = self.packed(make_e)
@@ -394,8 +409,11 @@ class BackwardMixin:
         xs, st, cpg = x.t, x.stats, x.cpg
         self.badd(f"gn_bwd_reduce:{r.name}", lambda: ops.gn_bwd_reduce(
             xs, dy, st, gamma, beta, sums, B, S, C, r.groups, cpg, r.eps, r.silu))
-        gg = self.pg(r.gamma)[r.c_off:r.c_off + C]
-        gb = self.pg(r.beta)[r.c_off:r.c_off + C]
+        if r.gparam is not None:   # padded copies feed the kernels; the real channels come first
+            gg, gb = self.pg(r.gparam), self.pg(r.bparam)
+        else:
+            gg = self.pg(r.gamma)[r.c_off:r.c_off + C]
+            gb = self.pg(r.beta)[r.c_off:r.c_off + C]
         self.bfinal_bsum(gg, sums[2], "gn_param_grad")
         self.bfinal_bsum(gb, sums[1], "gn_param_grad")
         if r.tproj_off is not None:
@@ -618,6 +636,9 @@ class BackwardMixin:
         ops.nchw_to_nhwc(self.dout_in, self.deps16, self.B, S, self.cout, self.cout_pad)
         ops.nchw_to_nhwc(self.dout_in, self.deps64, self.B, S, self.cout, 64)
 
+    def _bwd_tail(self) -> None:
+        """After the last backward op (programs that return an input gradient override this)."""
+
     def _backward(self, dout: torch.Tensor, S: int, sync) -> None:
         self.dout_in.copy_(dout)
         if sync is None or not sync.active():
@@ -627,6 +648,7 @@ class BackwardMixin:
             def body():
                 self._bwd_head(S)
                 self.run_backward()
+                self._bwd_tail()
             self._replay("bwd", body)
             return
         # segmented: one replayed graph per segment; after each, its (contiguous) slice of the
@@ -639,6 +661,8 @@ class BackwardMixin:
                 if lo == 0:
                     self._bwd_head(S)
                 self.run_backward(lo, hi)
+                if hi == len(self.bwd_ops):
+                    self._bwd_tail()
             self._replay(f"bwd_seg{i}/{len(segs)}", body)
             sync.bucket_ready(a_lo, a_hi)
         sync.finish()

@@ -86,7 +86,9 @@ __device__ __forceinline__ GnCoef gn_coef(const double* stats, int sample, int s
 // produced (plain column sum).  grid (chunks, samples); thread = fixed 8-channel vector.
 // sums: fp64 [3][samples][C] (fp64 atomics: the result does not depend on arrival order)
 // ---------------------------------------------------------------------------------------
-template <bool kSilu, bool kHasX>
+// kFine: groups of 4 channels (GroupNorm(8, 32) of the VAE's full-resolution level,
+// ddpm_3d_ldm/vae.py:8): the two halves of a thread's 8-channel vector belong to different groups.
+template <bool kSilu, bool kHasX, bool kFine>
 __global__ void __launch_bounds__(256)
 gn_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
                      const double* __restrict__ stats, const float* __restrict__ gamma,
@@ -102,12 +104,22 @@ gn_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
   const int c = cv * 8;
 
   float2 sc[4], sh[4];
-  float2 rs2 = make_float2(1.f, 1.f), nmr2 = make_float2(0.f, 0.f);  // xh = x * rstd - mean * rstd
+  constexpr int NH = kFine ? 2 : 1;
+  float2 rs2[NH], nmr2[NH];  // xh = x * rstd - mean * rstd
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    rs2[h] = make_float2(1.f, 1.f);
+    nmr2[h] = make_float2(0.f, 0.f);
+  }
   if (kHasX) {
     const int cpg = C / groups;
-    const GnCoef k = gn_coef(stats, sample, stats_ld, c / cpg, cpg / stats_cpg, cpg, spatial, eps);
-    rs2 = make_float2(k.rstd, k.rstd);
-    nmr2 = make_float2(-k.mean * k.rstd, -k.mean * k.rstd);
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      const GnCoef k = gn_coef(stats, sample, stats_ld, (c + 4 * h) / cpg, cpg / stats_cpg, cpg,
+                               spatial, eps);
+      rs2[h] = make_float2(k.rstd, k.rstd);
+      nmr2[h] = make_float2(-k.mean * k.rstd, -k.mean * k.rstd);
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       sc[j] = make_float2(__ldg(gamma + c + 2 * j), __ldg(gamma + c + 2 * j + 1));
@@ -125,7 +137,8 @@ gn_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
       const float2 d = bf2_to_f2(dw[j]);
       a0[j] = __fadd2_rn(a0[j], d);
       if (kHasX) {
-        const float2 xh = __ffma2_rn(bf2_to_f2(xw[j]), rs2, nmr2);
+        const int h = kFine ? (j >> 1) : 0;
+        const float2 xh = __ffma2_rn(bf2_to_f2(xw[j]), rs2[h], nmr2[h]);
         const float2 du = kSilu ? silu_bwd2(d, xh, sc[j], sh[j]) : d;
         a1[j] = __fadd2_rn(a1[j], du);
         a2[j] = __ffma2_rn(du, xh, a2[j]);
@@ -188,7 +201,7 @@ gn_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
 // Pass B.  dx = rstd * (gamma*du - m1 - xhat*m2) (+ add), with per (sample, group)
 // m1 = mean(gamma*du), m2 = mean(gamma*du*xhat) from the pass-A sums.
 // ---------------------------------------------------------------------------------------
-template <bool kSilu>
+template <bool kSilu, bool kFine>
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
                     const uint4* __restrict__ add, uint4* __restrict__ dx,
@@ -205,11 +218,14 @@ gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
   const int rows_step = blockDim.x / vec_per_row;
   const int c = cv * 8;
   const int cpg = C / groups;
-  const int g = c / cpg;
+  constexpr int NH = kFine ? 2 : 1;   // kFine: cpg == 4, the vector's halves are two groups
   float csum[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) csum[j] = 0.f;
-  const GnCoef k = gn_coef(stats, sample, stats_ld, g, cpg / stats_cpg, cpg, spatial, eps);
+  GnCoef k[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h)
+    k[h] = gn_coef(stats, sample, stats_ld, (c + 4 * h) / cpg, cpg / stats_cpg, cpg, spatial, eps);
   {  // one warp per group folds the pass-A sums (every thread used to walk cpg channels itself)
     const double* S1 = sums + ((size_t)1 * samples + sample) * C;
     const double* S2 = sums + ((size_t)2 * samples + sample) * C;
@@ -237,20 +253,26 @@ gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
     }
     __syncthreads();
   }
-  const float m1 = (float)gmean[0][g];
-  const float m2 = (float)gmean[1][g];
   // dx = (gamma * rstd) * du - rstd * m1 - (rstd * m2) * xh, on channel pairs
   float2 sc[4], sh[4], grs[4];
+  float2 rs2[NH], nmr2[NH], nrm1[NH], nrm2[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    const int g = (c + 4 * h) / cpg;
+    const float m1 = (float)gmean[0][g];
+    const float m2 = (float)gmean[1][g];
+    rs2[h] = make_float2(k[h].rstd, k[h].rstd);
+    nmr2[h] = make_float2(-k[h].mean * k[h].rstd, -k[h].mean * k[h].rstd);
+    nrm1[h] = make_float2(-k[h].rstd * m1, -k[h].rstd * m1);
+    nrm2[h] = make_float2(-k[h].rstd * m2, -k[h].rstd * m2);
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
+    const int h = kFine ? (j >> 1) : 0;
     sc[j] = make_float2(__ldg(gamma + c + 2 * j), __ldg(gamma + c + 2 * j + 1));
     sh[j] = make_float2(__ldg(beta + c + 2 * j), __ldg(beta + c + 2 * j + 1));
-    grs[j] = make_float2(sc[j].x * k.rstd, sc[j].y * k.rstd);
+    grs[j] = make_float2(sc[j].x * k[h].rstd, sc[j].y * k[h].rstd);
   }
-  const float2 rs2 = make_float2(k.rstd, k.rstd);
-  const float2 nmr2 = make_float2(-k.mean * k.rstd, -k.mean * k.rstd);
-  const float2 nrm1 = make_float2(-k.rstd * m1, -k.rstd * m1);
-  const float2 nrm2 = make_float2(-k.rstd * m2, -k.rstd * m2);
   float2 cs2[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) cs2[j] = make_float2(0.f, 0.f);
@@ -280,11 +302,12 @@ gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
       uint32_t ow[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
+        const int h = kFine ? (j >> 1) : 0;
         const float2 d = bf2_to_f2(dw[j]);
-        const float2 xh = __ffma2_rn(bf2_to_f2(xw[j]), rs2, nmr2);
+        const float2 xh = __ffma2_rn(bf2_to_f2(xw[j]), rs2[h], nmr2[h]);
         const float2 du = kSilu ? silu_bwd2(d, xh, sc[j], sh[j]) : d;
-        float2 o = __ffma2_rn(du, grs[j], nrm1);
-        o = __ffma2_rn(xh, nrm2, o);
+        float2 o = __ffma2_rn(du, grs[j], nrm1[h]);
+        o = __ffma2_rn(xh, nrm2[h], o);
         if (add != nullptr) o = __fadd2_rn(o, bf2_to_f2(aw[j]));
         ow[j] = f2_to_bf2(o);
         if (colsum != nullptr)  // column sums of the bf16 values a later pass would read
@@ -587,13 +610,18 @@ extern "C" int mri_gn_bwd_reduce(const void* x, const void* dy, const double* st
   const uint4* dp = reinterpret_cast<const uint4*>(dy);
   if (spatial * vpr > 0x7fffffffLL) return set_error(-2, "mri_gn_bwd_reduce: sample too large");
   cudaStream_t st = (cudaStream_t)stream;
-#define MRI_GN_RED(S, X)                                                                        \
-  gn_bwd_reduce_kernel<S, X><<<grid, threads, smem, st>>>(xp, dp, stats, gamma, beta, sums,     \
-                                                          samples, spatial, C, groups, stats_ld, \
-                                                          stats_cpg, eps, rpb)
-  if (x == nullptr) MRI_GN_RED(false, false);
-  else if (silu) MRI_GN_RED(true, true);
-  else MRI_GN_RED(false, true);
+#define MRI_GN_RED(S, X, F)                                                                     \
+  gn_bwd_reduce_kernel<S, X, F><<<grid, threads, smem, st>>>(xp, dp, stats, gamma, beta, sums,  \
+                                                             samples, spatial, C, groups,       \
+                                                             stats_ld, stats_cpg, eps, rpb)
+  const bool fine = x != nullptr && C / groups == 4;
+  if (x != nullptr && (C / groups) % 8 != 0 && !fine)
+    return set_error(-2, "mri_gn_bwd_reduce: channels per group must be 4 or a multiple of 8");
+  if (x == nullptr) MRI_GN_RED(false, false, false);
+  else if (silu && fine) MRI_GN_RED(true, true, true);
+  else if (silu) MRI_GN_RED(true, true, false);
+  else if (fine) MRI_GN_RED(false, true, true);
+  else MRI_GN_RED(false, true, false);
 #undef MRI_GN_RED
   return check_launch("gn_bwd_reduce_kernel");
 }
@@ -615,14 +643,18 @@ extern "C" int mri_gn_bwd_apply(const void* x, const void* dy, const void* add, 
   uint4* op = reinterpret_cast<uint4*>(dx);
   if (groups > 64) return set_error(-2, "mri_gn_bwd_apply: more than 64 groups");
   const size_t csm = colsum != nullptr ? (size_t)threads * 8 * sizeof(float) : 0;
-  if (silu)
-    gn_bwd_apply_kernel<true><<<grid, threads, csm, (cudaStream_t)stream>>>(
-        xp, dp, ap, op, stats, gamma, beta, sums, samples, spatial, C, groups, stats_ld, stats_cpg,
-        eps, rpb, colsum);
-  else
-    gn_bwd_apply_kernel<false><<<grid, threads, csm, (cudaStream_t)stream>>>(
-        xp, dp, ap, op, stats, gamma, beta, sums, samples, spatial, C, groups, stats_ld, stats_cpg,
-        eps, rpb, colsum);
+  const bool fine = C / groups == 4;
+  if ((C / groups) % 8 != 0 && !fine)
+    return set_error(-2, "mri_gn_bwd_apply: channels per group must be 4 or a multiple of 8");
+#define MRI_GN_APP(S, F)                                                                          \
+  gn_bwd_apply_kernel<S, F><<<grid, threads, csm, (cudaStream_t)stream>>>(                        \
+      xp, dp, ap, op, stats, gamma, beta, sums, samples, spatial, C, groups, stats_ld, stats_cpg, \
+      eps, rpb, colsum)
+  if (silu && fine) MRI_GN_APP(true, true);
+  else if (silu) MRI_GN_APP(true, false);
+  else if (fine) MRI_GN_APP(false, true);
+  else MRI_GN_APP(false, false);
+#undef MRI_GN_APP
   return check_launch("gn_bwd_apply_kernel");
 }
 

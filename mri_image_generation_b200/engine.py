@@ -361,7 +361,8 @@ class UNetProgram(BackwardMixin):
     def gn(self, x: Act, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float,
            silu: bool, rowbias: Optional[torch.Tensor] = None, rowbias_ld: int = 0,
            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-           name: str = "gn", c_off: int = 0, tproj_off: Optional[int] = None) -> torch.Tensor:
+           name: str = "gn", c_off: int = 0, tproj_off: Optional[int] = None,
+           gparam: Optional[torch.Tensor] = None, bparam: Optional[torch.Tensor] = None) -> torch.Tensor:
         """y = act(GroupNorm(x)) (+ rowbias[n, c]) (+ residual).  Uses x.stats (fine groups).
         gamma / beta are the module parameters; channels [c_off, c_off + C) of them apply."""
         assert x.stats is not None, f"{name}: input has no statistics"
@@ -379,7 +380,8 @@ class UNetProgram(BackwardMixin):
 
         self._add(name, fn, [y])
         self.tape.append(GnRec(x=x, y=y, gamma=gamma, beta=beta, c_off=c_off, groups=groups, eps=eps,
-                               silu=silu, tproj_off=tproj_off, residual=residual, name=name))
+                               silu=silu, tproj_off=tproj_off, residual=residual, name=name,
+                               gparam=gparam, bparam=bparam))
         return y
 
     def stats_of(self, x: Act, name: str = "gn_stats") -> None:
@@ -409,7 +411,9 @@ class UNetProgram(BackwardMixin):
                                      bias_params=rec.get("bias_params", []), residual=residual,
                                      tproj_off=rec.get("tproj_off"), cout=rec.get("cout", cout),
                                      need_dgrad=rec.get("need_dgrad", True),
-                                     dgrad_dy=rec.get("dgrad_dy"), name=name))
+                                     dgrad_dy=rec.get("dgrad_dy"), unpack=rec.get("unpack"),
+                                     unpack_extra=rec.get("unpack_extra"), wfull=rec.get("wfull"),
+                                     efull=rec.get("efull"), name=name))
         return y
 
     def thin_patch_matrix(self, x_in: torch.Tensor, conv, sp: Sequence[int], name: str):

@@ -2,16 +2,17 @@
 
 Same classes, constructor signatures, attributes and state_dict keys.  `encode`,
 `encode_to_latent`, `decode`, `decode_from_latent` and `forward` run the B200 engine
-(vae_engine.VAE3DProgram) whenever no gradient is required -- which is every use on the diffusion
-path: latents for LDM training (train.py:386-388, frozen VAE under no_grad), latent statistics
-(train.py:351-364), decoding samples (show_model.py:255).  The VAE's own training stage
-(train.py:258-300) is off the hot path; calling the model with gradients enabled raises.
+(vae_engine.VAE3DProgram): inference programs whenever no gradient is required -- latents for LDM
+training (train.py:386-388, frozen VAE under no_grad), latent statistics (train.py:351-364),
+decoding samples (show_model.py:255) -- and training programs (forward + backward launch lists
+behind one autograd node each for the encoder and the decoder) for the VAE's own training stage
+(train.py:258-300: `recon, mu, logvar = vae(x)`, L1 + KL loss, GradScaler, DDP).
 """
 import torch
 import torch.nn as nn
 
 from ... import _lib
-from ...modules import EngineModule, on_input_device
+from ...modules import EngineModule, ProgramFunction, on_input_device
 from ...vae_engine import VAE3DProgram
 
 
@@ -76,6 +77,8 @@ class Decoder3D(nn.Module):
 class VAE3D(EngineModule):
     """vae.py:90-127."""
 
+    MAX_PROGRAMS = 6   # stage 1 alternates encoder / decoder training and inference programs
+
     def __init__(self, in_channels=4, base_channels=32, num_down=3, latent_channels=8, groups=8):
         super().__init__()
         self.encoder = Encoder3D(in_channels, base_channels, num_down, latent_channels, groups)
@@ -83,18 +86,23 @@ class VAE3D(EngineModule):
                                  enc_out_channels=self.encoder.out_channels, groups=groups)
 
     # ------------------------------------------------------------------ engine plumbing
-    def _program(self, mode: str, x: torch.Tensor) -> VAE3DProgram:
+    def _program(self, mode: str, x: torch.Tensor, training: bool = False) -> VAE3DProgram:
         self._check_input(x)
         if x.dim() != 5:
             raise _lib.MriError(f"VAE3D expects (B, C, D, H, W), got {tuple(x.shape)}")
-        if self._needs_grad() or x.requires_grad:
-            raise _lib.MriError(
-                "VAE3D on the B200 path is inference-only (encode_to_latent / decode_from_latent / "
-                "no_grad forward): the VAE training stage (ddpm_3d_ldm/train.py:258-300) is not on "
-                "the diffusion hot path -- train the VAE with the reference implementation and load "
-                "its state_dict here (identical keys).")
-        key = (mode, int(x.shape[0]), tuple(int(s) for s in x.shape[2:]))
-        return self.get_program(key, lambda: VAE3DProgram(self, mode, key[1], key[2]))
+        key = (mode, int(x.shape[0]), tuple(int(s) for s in x.shape[2:]), bool(training))
+        return self.get_program(key, lambda: VAE3DProgram(self, mode, key[1], key[2], training=key[3]))
+
+    def _run(self, mode: str, x: torch.Tensor, part: nn.Module) -> torch.Tensor:
+        xf = x.float().contiguous()
+        needs = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in part.parameters()))
+        if not needs:
+            return self._program(mode, x).forward(xf).clone()
+        # training (train.py:258-300): forward + backward launch lists behind one autograd node
+        prog = self._program(mode, x, training=True)
+        prog.param_list = list(part.parameters())
+        return ProgramFunction.apply(prog, lambda: prog.forward(xf), xf if mode == "decode" else None,
+                                     *prog.param_list)
 
     @on_input_device
     def encode(self, x):
@@ -102,8 +110,8 @@ class VAE3D(EngineModule):
         cin = self.encoder.in_conv.weight.shape[1]
         if x.shape[1] != cin:
             raise _lib.MriError(f"expected {cin} input channels, got {x.shape[1]}")
-        stats = self._program("encode", x).forward(x.float().contiguous())
-        mu, logvar = torch.chunk(stats.clone(), 2, dim=1)
+        stats = self._run("encode", x, self.encoder)
+        mu, logvar = torch.chunk(stats, 2, dim=1)
         return mu, logvar
 
     def reparameterize(self, mu, logvar):
@@ -118,7 +126,7 @@ class VAE3D(EngineModule):
         lat = self.decoder.from_latent.weight.shape[1]
         if z.shape[1] != lat:
             raise _lib.MriError(f"expected {lat} latent channels, got {z.shape[1]}")
-        return self._program("decode", z).forward(z.float().contiguous()).clone()
+        return self._run("decode", z, self.decoder)
 
     @on_input_device
     def forward(self, x):

@@ -87,11 +87,13 @@ class EngineModule(nn.Module):
     def _needs_grad(self) -> bool:
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
+    MAX_PROGRAMS = 4  # static-shape programs own their activation memory: keep few
+
     def get_program(self, key: Tuple, build):
         progs = self._programs()
         prog = progs.get(key)
         if prog is None:
-            if len(progs) >= 4:  # static-shape programs own their activation memory: keep few
+            if len(progs) >= self.MAX_PROGRAMS:
                 progs.pop(next(iter(progs)))
             prog = build()
             progs[key] = prog
@@ -133,3 +135,30 @@ class UNetFunction(torch.autograd.Function):
                 grads.append(flat[loc[0]:loc[0] + loc[1]].view(p.shape))
         extra = len(ctx.needs_input_grad) - 3 - len(grads)
         return (None, None, None, *grads, *([None] * extra))
+
+
+class ProgramFunction(torch.autograd.Function):
+    """UNetFunction for programs that may also return the gradient of their input (the VAE
+    decoder's latent, ddpm_3d_ldm/vae.py:106-118): apply(prog, run_forward, x_or_None, *params).
+    The program leaves the input gradient in `prog.dz_out`."""
+
+    @staticmethod
+    def forward(ctx, prog, run_forward, x, *params):
+        ctx.prog = prog
+        return run_forward().clone()
+
+    @staticmethod
+    def backward(ctx, dout):
+        prog = ctx.prog
+        with torch.cuda.device(dout.device):
+            prog.backward(dout.contiguous().float())
+        flat = prog.garena[:prog._garena_used].clone()
+        grads = []
+        for p in prog.param_list:
+            loc = prog._g_off.get(id(p))
+            if loc is None or not p.requires_grad:
+                grads.append(None)
+            else:
+                grads.append(flat[loc[0]:loc[0] + loc[1]].view(p.shape))
+        dx = prog.dz_out.clone() if (ctx.needs_input_grad[2] and prog.dz_out is not None) else None
+        return (None, None, dx, *grads)

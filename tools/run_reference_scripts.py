@@ -129,7 +129,7 @@ def stage_checkpoints(work: Path, name: str) -> str:
     return note.strip()
 
 
-LOSS_RE = re.compile(r"(?:loss|Loss)[^0-9\-naNif]*:?\s*(-?(?:\d+\.\d+(?:e[-+]?\d+)?|nan|inf))")
+LOSS_RE = re.compile(r"(?:loss|Loss|eps-MSE)[^0-9\-naNif]*[:=]?\s*(-?(?:\d+\.\d+(?:e[-+]?\d+)?|nan|inf))")
 
 
 def check_log(text: str) -> dict:
