@@ -737,10 +737,64 @@ def run_vae(args, rank, world, local_rank):
             prog = vae._program(name, inp)
             res[name] = {"ms": e0.elapsed_time(e1) / K, "executed_gemm_tflop": prog.gemm_flops / 1e12,
                          "finite": bool(torch.isfinite(out).all().item())}
+    # ---- stage 1 of ddpm_3d_ldm/train.py:258-300: one VAE training step at the script's patch size
+    # (4 x 128 x 160 x 160, batch 1, VAE3D(4, 32, 3, latent 16)): vae(x) + L1 + KL + backward
+    import torch.nn.functional as F
+
+    def vae_loss(recon, xx, mu, logvar):
+        kl = -0.5 * torch.mean(1 + logvar - mu.pow(2) - logvar.exp())
+        return F.l1_loss(recon, xx) + 1e-4 * kl
+
+    torch.manual_seed(0)
+    tv = VAE3D(4, 32, 3, 16).to(dev).train()
+    xt = torch.randn(1, 4, 128, 160, 160, device=dev).clamp_(-1, 1)
+
+    def ours_step():
+        tv.zero_grad(set_to_none=True)
+        recon, mu, logvar = tv(xt)
+        vae_loss(recon, xt, mu, logvar).backward()
+
+    def timed(fn, warm, iters):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / iters
+
+    train = {"ms": timed(ours_step, 4, K), "batch": 1, "patch": [128, 160, 160],
+             "model": "VAE3D(4, base 32, num_down 3, latent 16) (train.py:43-46)"}
+    progs = [p_ for k_, p_ in tv._programs().items() if k_[-1]]
+    train["executed_gemm_tflop"] = sum(p_.gemm_flops + p_.bwd_flops for p_ in progs) / 1e12
+    train["finite_grads"] = all(bool(torch.isfinite(p_.grad).all().item()) for p_ in tv.parameters())
+    if rank == 0 and not args.no_gpu_comparator:
+        # the reference's graph (oracle restatement = the same ATen / cuDNN calls) eagerly, autocast bf16
+        from oracle import reference_oracle as O
+        torch.backends.cudnn.benchmark = True
+        sd = {k: v.detach().clone().requires_grad_(True) for k, v in tv.state_dict().items()}
+
+        def eager_step():
+            for v in sd.values():
+                v.grad = None
+            with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
+                mu, logvar = O.vae3d_encode(sd, xt)
+                zz = mu + torch.randn_like(mu) * torch.exp(0.5 * logvar)
+                recon = O.vae3d_decode(sd, zz)
+                loss = vae_loss(recon.float(), xt, mu.float(), logvar.float())
+            loss.backward()
+
+        train["eager_cudnn_autocast_bf16_ms"] = timed(eager_step, 2, max(2, K // 3))
+        del sd
+    del tv
+    torch.cuda.empty_cache()
     if rank != 0:
         return
     peaks = load_peaks()
-    for r in res.values():
+    for r in list(res.values()) + [train]:
         r["tflops_executed"] = r["executed_gemm_tflop"] / (r["ms"] * 1e-3)
     line = {"metric": "volumes/sec (VAE3D decode_from_latent, 3x40x48x40 -> 4x160x192x160)",
             "value": world * B / (res["decode"]["ms"] / 1e3), "unit": "volumes/s", "n_gpus": world,
@@ -749,7 +803,8 @@ def run_vae(args, rank, world, local_rank):
             "config": {"workload": "vae3d_decode", "batch_per_gpu": B,
                        "model": "VAE3D(4, base 32, num_down 3, latent 3)",
                        "note": "executed FLOPs include the zero padding of 32-channel layers to 64"},
-            "decode": res["decode"], "encode": res["encode"], "peak_tflops": peaks["tflops"]}
+            "decode": res["decode"], "encode": res["encode"], "train_step": train,
+            "peak_tflops": peaks["tflops"]}
     print(json.dumps(line), flush=True)
 
 

@@ -219,7 +219,7 @@ def main() -> int:
         print("no reference checkout found (--reference / MRI_REFERENCE_DIR / baseline/_ref)")
         return 2
     work = Path(args.work) if args.work else Path(tempfile.mkdtemp(prefix="mri_scripts_"))
-    out = Path(args.out)
+    out = Path(args.out).resolve()
     out.mkdir(parents=True, exist_ok=True)
     stage_tree(ref, work)
     stage_datasets(work, *[int(v) for v in args.cases.split(",")])
