@@ -384,6 +384,21 @@ int mri_gn_bwd_apply(const void* x, const void* dy, const void* add, void* dx, c
                      const float* gamma, const float* beta, const double* sums, int samples,
                      int64_t spatial, int C, int groups, int stats_ld, int stats_cpg, float eps,
                      int silu, double* colsum, void* stream);
+/* Image sizes the down-sampling factor does not divide (slice_cond_2d_ddpm/unet.py:95-99,
+ * ddpm_25d_all_modalities/unet.py:95-99: `F.interpolate(x, size=skip.shape[-2:], mode="bilinear",
+ * align_corners=False)` after the transposed convolution).  Channels-last bf16 [B, H, W, C], C % 8 == 0.
+ * mri_copy_window_nhwc: dst[b, dh0+i, dw0+j, :] = src[b, sh0+i, sw0+j, :] (+ add at the dst index; add
+ *   may alias dst) for i < nH, j < nW; the rest of dst is left alone (zero padding in front of the
+ *   stride-2 convolution, cropping its output, and the adjoints of both).
+ * mri_resize_bilinear_nhwc: ATen's upsample_bilinear2d with align_corners = false.
+ * mri_resize_bilinear_nhwc_bwd: its adjoint, dx [B, sH, sW, C] = R^T dy [B, dH, dW, C] (+ add). */
+int mri_copy_window_nhwc(const void* src, void* dst, const void* add, int B, int sH, int sW, int dH,
+                         int dW, int C, int sh0, int sw0, int dh0, int dw0, int nH, int nW,
+                         void* stream);
+int mri_resize_bilinear_nhwc(const void* src, void* dst, int B, int sH, int sW, int dH, int dW, int C,
+                             void* stream);
+int mri_resize_bilinear_nhwc_bwd(const void* dy, void* dx, const void* add, int B, int sH, int sW,
+                                 int dH, int dW, int C, void* stream);
 /* out = a + b, bf16, n elements (multiple of 8) */
 int mri_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
 /* attention: dS = scale * P * (dP - rowsum(dP * P)); P, dS bf16 [rows][ld_p], dP fp32 [rows][ld_dp] */

@@ -70,6 +70,26 @@ class GnRec:
 
 
 @dataclass
+class WindowRec:
+    """dst[:, d0:d0+n] = src[:, s0:s0+n] over (H, W) of channels-last tensors (zero padding an odd
+    level in front of the stride-2 convolution / cropping its output)."""
+    src: torch.Tensor
+    dst: torch.Tensor
+    src_off: Tuple[int, int]
+    dst_off: Tuple[int, int]
+    size: Tuple[int, int]
+    name: str = ""
+
+
+@dataclass
+class ResizeRec:
+    """dst = bilinear resize of src (slice_cond_2d_ddpm/unet.py:98-99)."""
+    src: torch.Tensor
+    dst: torch.Tensor
+    name: str = ""
+
+
+@dataclass
 class AttnRec:
     x: object
     hn: torch.Tensor
@@ -425,6 +445,22 @@ class BackwardMixin:
             colsum=holder[0])))
         self._gn_writer[id(self.grads[id(xs)])] = holder
 
+    def bwd_window(self, r: "WindowRec") -> None:
+        dy = self.grads.get(id(r.dst))
+        if dy is None:
+            raise _lib.MriError(f"backward: no gradient reached {r.name}")
+        # the adjoint of a window copy is the window copied back; outside the window the gradient
+        # buffer keeps what it held (zeros when this is its only producer)
+        self.emit_grad(r.src, lambda out, add: self.badd(
+            f"window_bwd:{r.name}", lambda: ops.copy_window(dy, out, r.dst_off, r.src_off, r.size, add=add)))
+
+    def bwd_resize(self, r: "ResizeRec") -> None:
+        dy = self.grads.get(id(r.dst))
+        if dy is None:
+            raise _lib.MriError(f"backward: no gradient reached {r.name}")
+        self.emit_grad(r.src, lambda out, add: self.badd(
+            f"resize_bwd:{r.name}", lambda: ops.resize_bilinear_bwd(dy, out, add=add)))
+
     def bwd_attention(self, r: AttnRec) -> None:
         dev, B = self.device, self.B
         blk = r.blk
@@ -576,6 +612,10 @@ class BackwardMixin:
                 self.bwd_attention(rec)
             elif isinstance(rec, TimeRec):
                 self.bwd_time(rec)
+            elif isinstance(rec, WindowRec):
+                self.bwd_window(rec)
+            elif isinstance(rec, ResizeRec):
+                self.bwd_resize(rec)
             else:  # pragma: no cover
                 raise _lib.MriError(f"unknown tape record {type(rec)}")
             self._close_record()

@@ -124,6 +124,8 @@ class SliceDatasetBase(torch.utils.data.Dataset):
     """Shared by the 2-D and 2.5-D BraTSSliceDataset mirrors: volume discovery, the (path, z)
     index and the device cache of preprocessed volumes."""
 
+    MRI_DEVICE_DATASET = True
+
     flair_suffix = "_flair.nii.gz"
 
     def _build_index(self, anchor_suffix: str, radius: int):
@@ -248,3 +250,42 @@ def load_patch(vols_hwd: Sequence[torch.Tensor], patch_size, random_crop: bool =
             ms = stats[c] if stats is not None else _volume_stats(v, eps)
             ops.volume_normalize_patch(v.permute(2, 0, 1), ms, origin, out[c], clip=clip_val)
     return out
+
+
+# ---- DataLoader over device-resident datasets ---------------------------------------------------
+def is_device_dataset(ds) -> bool:
+    """True for the Dataset mirrors of this package, also behind torch's Subset / random_split /
+    ConcatDataset wrappers (slice_cond_2d_ddpm/model.py:71-82, ddpm_3d_ldm/train.py:160-167)."""
+    seen = 0
+    while ds is not None and seen < 8:
+        if getattr(ds, "MRI_DEVICE_DATASET", False):
+            return True
+        if hasattr(ds, "datasets"):
+            return any(is_device_dataset(d) for d in ds.datasets)
+        ds = getattr(ds, "dataset", None)
+        seen += 1
+    return False
+
+
+def device_dataloader(base):
+    """A `torch.utils.data.DataLoader` whose worker / pinning options are overridden when the
+    dataset hands out CUDA tensors: the reference's scripts ask for `num_workers=8,
+    pin_memory=True` (ddpm_3d_ldm/train.py:180-188), which is how a CPU dataset is fed to a GPU;
+    items that are already device tensors are batched in the main process (torch.stack on the
+    device) and need neither.  Everything else (batch size, shuffling, samplers) is untouched."""
+
+    class DataLoader(base):
+        def __init__(self, dataset, *args, **kwargs):
+            if is_device_dataset(dataset):
+                if len(args) > 4:
+                    raise _lib.MriError("DataLoader over a device dataset: pass num_workers / "
+                                        "pin_memory by keyword")
+                kwargs["num_workers"] = 0
+                kwargs["pin_memory"] = False
+                kwargs["persistent_workers"] = False
+                kwargs.pop("prefetch_factor", None)
+                kwargs.pop("worker_init_fn", None)
+            super().__init__(dataset, *args, **kwargs)
+
+    DataLoader.__qualname__ = "DataLoader"
+    return DataLoader

@@ -27,7 +27,7 @@ import torch
 
 from . import _lib, ops
 from . import plan as P
-from .backward import AttnRec, BackwardMixin, ConvRec, GnRec, TimeRec
+from .backward import AttnRec, BackwardMixin, ConvRec, GnRec, ResizeRec, TimeRec, WindowRec
 
 
 def _rup(n: int, m: int) -> int:
@@ -930,9 +930,8 @@ class UNet2DProgram(UNetProgram):
         B, (H, W) = batch, self.sp
         chs = list(model.chs)
         n_down = len(model.downs)
-        if H % (2 ** n_down) or W % (2 ** n_down):
-            raise _lib.MriError(f"image size {self.sp} must be divisible by {2 ** n_down} (the bilinear "
-                                "resize branch of UpBlock, unet.py:98-99, is not implemented)")
+        if min(H, W) >> n_down < 1:
+            raise _lib.MriError(f"image size {self.sp} is too small for {n_down} stride-2 levels")
         eps = model.out_norm.eps
         cin = model.init_conv.weight.shape[1]
         if x_channels + ctx_channels != cin:
@@ -1000,12 +999,30 @@ class UNet2DProgram(UNetProgram):
             dn = d.down
             self.track(dn.weight, dn.bias)
             wd = self.packed(lambda dn=dn: P.pack_conv_weight(dn.weight.detach()))
-            y = self.new_act([s // 2 for s in h.t.shape[1:-1]], dn.weight.shape[0], with_stats=False)
-            pl = P.down_conv_plan(h.t, wd, y.t, bias=dn.bias, name=f"downs.{i}.down")
+            hh, ww = h.t.shape[1:-1]
+            src = h.t
+            if hh % 2 or ww % 2:
+                # odd level: Conv2d(k=4, s=2, p=1) gives floor(n / 2) outputs, and output o reads
+                # inputs 2o-1 .. 2o+2 <= n-1 -- the same values as on the level zero-padded to an
+                # even size, whose extra last output is dropped again
+                src = torch.zeros(B, hh + hh % 2, ww + ww % 2, h.C, dtype=torch.bfloat16, device=dev)
+                self._add(f"downs.{i}.pad", lambda s_=h.t, d_=src, n=(hh, ww): ops.copy_window(
+                    s_, d_, (0, 0), (0, 0), n), [src])
+                self.tape.append(WindowRec(h.t, src, (0, 0), (0, 0), (hh, ww), name=f"downs.{i}.pad"))
+            y = self.new_act([s // 2 for s in src.shape[1:-1]], dn.weight.shape[0], with_stats=False)
+            pl = P.down_conv_plan(src, wd, y.t, bias=dn.bias, name=f"downs.{i}.down")
             self.gemm(pl)
-            self.tape.append(ConvRec(kind="down", plan=pl, y=y.t, ksize=4, sources=[(h.t, True)],
+            self.tape.append(ConvRec(kind="down", plan=pl, y=y.t, ksize=4, sources=[(src, True)],
                                      weight=dn.weight, splits=[h.C], bias_params=[dn.bias],
                                      cout=dn.weight.shape[0], name=f"downs.{i}.down"))
+            if src is not h.t:
+                yc = self.new_act([hh // 2, ww // 2], dn.weight.shape[0], with_stats=False)
+                self._add(f"downs.{i}.crop", lambda s_=y.t, d_=yc.t, n=(hh // 2, ww // 2): ops.copy_window(
+                    s_, d_, (0, 0), (0, 0), n), [yc.t])
+                self.tape.append(WindowRec(y.t, yc.t, (0, 0), (0, 0), (hh // 2, ww // 2),
+                                           name=f"downs.{i}.crop"))
+                self.pool.release(y.t)
+                y = yc
             h = y
         h = self.resblock2d(h, None, model.mid_block1, eps, "mid_block1")
         h = self.resblock2d(h, None, model.mid_block2, eps, "mid_block2")
@@ -1022,7 +1039,12 @@ class UNet2DProgram(UNetProgram):
                                      cout=up.weight.shape[1], name=f"ups.{j}.up"))
             self.pool.release(h.t)
             if tuple(y.t.shape[1:-1]) != tuple(skip.t.shape[1:-1]):
-                raise _lib.MriError("UpBlock bilinear-resize branch (unet.py:98-99) not implemented")
+                # unet.py:98-99: F.interpolate(x, size=skip.shape[-2:], mode="bilinear")
+                y2 = self.pool.get((B, *skip.t.shape[1:-1], y.C))
+                self._add(f"ups.{j}.resize", lambda s_=y.t, d_=y2: ops.resize_bilinear(s_, d_), [y2])
+                self.tape.append(ResizeRec(y.t, y2, name=f"ups.{j}.resize"))
+                self.pool.release(y.t)
+                y = Act(y2)
             h = self.resblock2d(y, skip, u.res1, eps, f"ups.{j}.res1")
             h = self.resblock2d(h, None, u.res2, eps, f"ups.{j}.res2")
 

@@ -20,6 +20,8 @@ class BraTS3DVolumeDataset(torch.utils.data.Dataset):
     per modality.  Random crops consume Python's `random` exactly as the reference does.  Tensors
     live on `device`: DataLoader with num_workers=0, pin_memory=False."""
 
+    MRI_DEVICE_DATASET = True
+
     def __init__(self, root_dir, patch_size=(128, 160, 160), random_crop=True,
                  modalities=("flair", "t1", "t1ce", "t2"), device=None, source=None, cache_size=32):
         super().__init__()

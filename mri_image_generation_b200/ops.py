@@ -269,6 +269,31 @@ def add_bf16(a, b, out) -> None:
     _lib.check(_lib.load().mri_add_bf16(_p(a), _p(b), _p(out), a.numel(), _s()), "mri_add_bf16")
 
 
+def copy_window(src, dst, src_off, dst_off, size, add=None) -> None:
+    """dst[:, dh0:dh0+nH, dw0:dw0+nW] = src[:, sh0:sh0+nH, sw0:sw0+nW] (+ add), [B, H, W, C] bf16."""
+    _chk_contig(src, dst)
+    B, sH, sW, C = src.shape
+    _lib.check(_lib.load().mri_copy_window_nhwc(_p(src), _p(dst), _p(add) if add is not None else None,
+                                                B, sH, sW, dst.shape[1], dst.shape[2], C, src_off[0],
+                                                src_off[1], dst_off[0], dst_off[1], size[0], size[1],
+                                                _s()), "mri_copy_window_nhwc")
+
+
+def resize_bilinear(src, dst) -> None:
+    _chk_contig(src, dst)
+    B, sH, sW, C = src.shape
+    _lib.check(_lib.load().mri_resize_bilinear_nhwc(_p(src), _p(dst), B, sH, sW, dst.shape[1],
+                                                    dst.shape[2], C, _s()), "mri_resize_bilinear_nhwc")
+
+
+def resize_bilinear_bwd(dy, dx, add=None) -> None:
+    _chk_contig(dy, dx)
+    B, sH, sW, C = dx.shape
+    _lib.check(_lib.load().mri_resize_bilinear_nhwc_bwd(_p(dy), _p(dx), _p(add) if add is not None else None,
+                                                        B, sH, sW, dy.shape[1], dy.shape[2], C, _s()),
+               "mri_resize_bilinear_nhwc_bwd")
+
+
 def softmax_bwd(P, dP, dS, rows, cols, ld_p, ld_dp, scale) -> None:
     _lib.check(_lib.load().mri_softmax_bwd(_p(P), _p(dP), _p(dS), rows, cols, ld_p, ld_dp, scale,
                                            _s()), "mri_softmax_bwd")

@@ -37,7 +37,9 @@ def install(packages: Optional[Iterable[str]] = None, *, vae: bool = True, datas
     """Alias the drop-in modules as `<root>.<pkg>.<module>`.  Returns the aliased names.
 
     vae=False keeps the reference's `vae.py` (stage 1 of ddpm_3d_ldm/train.py on the reference
-    implementation); datasets=True also replaces `dataset.py` by the device data path;
+    implementation); datasets=True also replaces `dataset.py` by the device data path and
+    `torch.utils.data.DataLoader` by one that drops the worker / pinning options for datasets
+    whose items already are device tensors (data.device_dataloader);
     overlap_ddp=True makes `from torch.nn.parallel import DistributedDataParallel` in the scripts
     (ddpm_3d_ldm/train.py:16) resolve to the wrapper that overlaps the gradient all-reduce with
     the backward launch list (modules it does not know are handed to torch's wrapper)."""
@@ -55,6 +57,14 @@ def install(packages: Optional[Iterable[str]] = None, *, vae: bool = True, datas
                                    "already holds the reference classes")
             sys.modules[name] = importlib.import_module(f"{__package__}.model_scripts.{pkg}.{mod}")
             done.append(name)
+    if datasets:
+        import torch.utils.data as tud
+
+        from . import data
+        if not hasattr(tud, "_mri_torch_dataloader"):
+            tud._mri_torch_dataloader = tud.DataLoader
+        tud.DataLoader = data.device_dataloader(tud._mri_torch_dataloader)
+        done.append("torch.utils.data.DataLoader")
     if overlap_ddp:
         import torch.nn.parallel as tnp
 
@@ -71,9 +81,13 @@ def uninstall(root: str = "model_scripts") -> None:
                  if n.startswith(root + ".") and m.__name__.startswith(__package__ + ".")]:
         del sys.modules[name]
     import torch.nn.parallel as tnp
+    import torch.utils.data as tud
     if hasattr(tnp, "_mri_torch_ddp"):
         tnp.DistributedDataParallel = tnp._mri_torch_ddp
         del tnp._mri_torch_ddp
+    if hasattr(tud, "_mri_torch_dataloader"):
+        tud.DataLoader = tud._mri_torch_dataloader
+        del tud._mri_torch_dataloader
 
 
 def main(argv=None) -> None:

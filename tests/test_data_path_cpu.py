@@ -105,3 +105,37 @@ def test_no_cpu_path():
         ops.masked_stats(torch.zeros(4, 4, 4), 2)
     with pytest.raises(_lib.MriError):
         data.preprocess_slices(torch.zeros(4, 4, 4), 8)
+
+
+def test_device_dataloader_drops_worker_options_only_for_device_datasets():
+    """overlay --device-datasets: the scripts' DataLoader(..., num_workers=8, pin_memory=True)
+    (ddpm_3d_ldm/train.py:180-188) must not fork workers / pin when items are device tensors,
+    also behind Subset and random_split (slice_cond_2d_ddpm/model.py:73-82)."""
+    import torch
+    import torch.utils.data as tud
+
+    from mri_image_generation_b200 import data
+
+    class Dev(tud.Dataset):
+        MRI_DEVICE_DATASET = True
+
+        def __len__(self):
+            return 10
+
+        def __getitem__(self, i):
+            return torch.full((2,), float(i))
+
+    class Host(Dev):
+        MRI_DEVICE_DATASET = False
+
+    DL = data.device_dataloader(tud.DataLoader)
+    sub = tud.Subset(Dev(), list(range(8)))
+    a, b = tud.random_split(sub, [6, 2])
+    for ds in (Dev(), sub, a, tud.ConcatDataset([Host(), Dev()])):
+        dl = DL(ds, batch_size=4, shuffle=True, num_workers=8, pin_memory=True, worker_init_fn=print,
+                prefetch_factor=2)
+        assert dl.num_workers == 0 and dl.pin_memory is False and dl.worker_init_fn is None
+        assert next(iter(dl)).shape == (4, 2)
+    dl = DL(Host(), batch_size=2, num_workers=2, pin_memory=False)
+    assert dl.num_workers == 2
+    assert not data.is_device_dataset(Host()) and data.is_device_dataset(a)

@@ -169,6 +169,8 @@ def run_one(name: str, work: Path, out: Path, args) -> dict:
         overlay.append("--keep-vae")
     if args.overlap_ddp:
         overlay.append("--overlap-ddp")
+    if args.device_datasets:
+        overlay.append("--device-datasets")
     overlay += ["-m", module]
     if args.nproc > 1 and name == "train3d":
         cmd = [sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1",
@@ -210,6 +212,8 @@ def main() -> int:
     ap.add_argument("--out", default=str(REPO / "gpurun_out" / "scripts"))
     ap.add_argument("--keep-vae", action="store_true", help="leave vae.py to the reference")
     ap.add_argument("--overlap-ddp", action="store_true")
+    ap.add_argument("--device-datasets", action="store_true",
+                    help="dataset.py -> the device data path (normalise / resize / pad / crop kernels)")
     ap.add_argument("--nproc", type=int, default=1, help="train3d under torchrun with this many ranks")
     ap.add_argument("--timeout", type=int, default=1500, help="seconds per script")
     ap.add_argument("--cases", default="6,3,4", help="synthetic subjects in datasets/train,val,dataset")
@@ -224,6 +228,7 @@ def main() -> int:
     stage_tree(ref, work)
     stage_datasets(work, *[int(v) for v in args.cases.split(",")])
     summary = {"reference": str(ref), "work": str(work), "keep_vae": args.keep_vae, "nproc": args.nproc,
+               "device_datasets": args.device_datasets, "overlap_ddp": args.overlap_ddp,
                "results": {}}
     for name in [s for s in args.scripts.split(",") if s]:
         summary["results"][name] = run_one(name, work, out, args)
