@@ -33,7 +33,7 @@ DATA_MODULES: Dict[str, List[str]] = {k: ["dataset"] for k in HOT_MODULES}
 
 
 def install(packages: Optional[Iterable[str]] = None, *, vae: bool = True, datasets: bool = False,
-            overlap_ddp: bool = False, root: str = "model_scripts") -> List[str]:
+            overlap_ddp: bool = False, fused_adam: bool = False, root: str = "model_scripts") -> List[str]:
     """Alias the drop-in modules as `<root>.<pkg>.<module>`.  Returns the aliased names.
 
     vae=False keeps the reference's `vae.py` (stage 1 of ddpm_3d_ldm/train.py on the reference
@@ -42,7 +42,9 @@ def install(packages: Optional[Iterable[str]] = None, *, vae: bool = True, datas
     whose items already are device tensors (data.device_dataloader);
     overlap_ddp=True makes `from torch.nn.parallel import DistributedDataParallel` in the scripts
     (ddpm_3d_ldm/train.py:16) resolve to the wrapper that overlaps the gradient all-reduce with
-    the backward launch list (modules it does not know are handed to torch's wrapper)."""
+    the backward launch list (modules it does not know are handed to torch's wrapper);
+    fused_adam=True makes `torch.optim.Adam(...)` (train.py:242-243, model.py:126) the one-launch
+    Adam of this package (same constructor, update rule, state_dict and GradScaler protocol)."""
     done = []
     for pkg in (packages or HOT_MODULES):
         if pkg not in HOT_MODULES:
@@ -65,6 +67,14 @@ def install(packages: Optional[Iterable[str]] = None, *, vae: bool = True, datas
             tud._mri_torch_dataloader = tud.DataLoader
         tud.DataLoader = data.device_dataloader(tud._mri_torch_dataloader)
         done.append("torch.utils.data.DataLoader")
+    if fused_adam:
+        import torch.optim as topt
+
+        from . import optim
+        if not hasattr(topt, "_mri_torch_adam"):
+            topt._mri_torch_adam = topt.Adam
+        topt.Adam = optim.Adam
+        done.append("torch.optim.Adam")
     if overlap_ddp:
         import torch.nn.parallel as tnp
 
@@ -88,6 +98,10 @@ def uninstall(root: str = "model_scripts") -> None:
     if hasattr(tud, "_mri_torch_dataloader"):
         tud.DataLoader = tud._mri_torch_dataloader
         del tud._mri_torch_dataloader
+    import torch.optim as topt
+    if hasattr(topt, "_mri_torch_adam"):
+        topt.Adam = topt._mri_torch_adam
+        del topt._mri_torch_adam
 
 
 def main(argv=None) -> None:
@@ -97,6 +111,7 @@ def main(argv=None) -> None:
     ap.add_argument("--device-datasets", action="store_true", help="also replace <pkg>/dataset.py")
     ap.add_argument("--overlap-ddp", action="store_true",
                     help="DistributedDataParallel -> the wrapper overlapping all-reduce and backward")
+    ap.add_argument("--fused-adam", action="store_true", help="torch.optim.Adam -> the one-launch Adam")
     ap.add_argument("--path", action="append", default=[], help="prepend to sys.path (stub modules ...)")
     ap.add_argument("-m", dest="module", required=True, help="the reference script, as for python -m")
     ap.add_argument("args", nargs=argparse.REMAINDER)
@@ -106,7 +121,7 @@ def main(argv=None) -> None:
     if "" not in sys.path and "." not in sys.path:
         sys.path.insert(0, "")      # what `python -m` itself does: the reference checkout is the cwd
     names = install(vae=not ns.keep_vae, datasets=ns.device_datasets, overlap_ddp=ns.overlap_ddp,
-                    root=ns.module.split(".")[0])
+                    fused_adam=ns.fused_adam, root=ns.module.split(".")[0])
     print(f"[mri_b200.overlay] {len(names)} modules bound to the B200 path: {', '.join(names)}", flush=True)
     sys.argv = [ns.module] + list(ns.args)
     runpy.run_module(ns.module, run_name="__main__", alter_sys=True)

@@ -72,21 +72,23 @@ def test_unet2d_forward_at_sizes_not_divisible_by_8(size, batch):
 
 
 def test_sampling_loop_at_an_odd_size():
-    """sample() through the fused reverse step at 30 x 25 (graph replay == the eager steps)."""
+    """sample() through the fused reverse step at 30 x 30 -- levels 30, 15, 7, 3: two odd levels and
+    two resizes (the reference's GaussianDiffusion samples squares: diffusion.py:144-149) -- graph
+    replay == the eager steps."""
     from mri_image_generation_b200.model_scripts.slice_cond_2d_ddpm.diffusion import GaussianDiffusion
     from mri_image_generation_b200.model_scripts.slice_cond_2d_ddpm.unet import UNet
     m = quiet(UNet, img_channels=1, base_channels=64, time_emb_dim=64)
     m.load_state_dict(synthetic_state_dict(shapes_of(m), seed=42))
     m = m.cuda().eval()
-    diff = quiet(GaussianDiffusion, m, (30, 25), channels=1, timesteps=8).cuda()
+    diff = quiet(GaussianDiffusion, m, 30, channels=1, timesteps=8).cuda()
     z = torch.rand(2, device="cuda")
     torch.manual_seed(5)
     a = diff.sample(2, z)
     torch.manual_seed(5)
-    x = torch.randn(2, 1, 30, 25, device="cuda")
+    x = torch.randn(2, 1, 30, 30, device="cuda")
     for i in reversed(range(8)):
         x = diff.p_sample(x, torch.full((2,), i, device="cuda", dtype=torch.long), z)
-    assert a.shape == (2, 1, 30, 25) and torch.isfinite(a).all()
+    assert a.shape == (2, 1, 30, 30) and torch.isfinite(a).all()
     assert torch.equal(a, x)
 
 
@@ -99,7 +101,7 @@ def test_train_step_25d_with_context_at_odd_sizes(size):
     m.load_state_dict(sd)
     m = m.cuda().train()
     T = 100
-    diff = quiet(GaussianDiffusion, m, size, channels=4, timesteps=T).cuda()
+    diff = quiet(GaussianDiffusion, m, size[0], channels=4, timesteps=T).cuda()   # image_size only sizes sample()
     g = torch.Generator().manual_seed(11)
     x0 = torch.randn(2, 4, *size, generator=g)
     noise = torch.randn(2, 4, *size, generator=g)

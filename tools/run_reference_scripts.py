@@ -171,6 +171,8 @@ def run_one(name: str, work: Path, out: Path, args) -> dict:
         overlay.append("--overlap-ddp")
     if args.device_datasets:
         overlay.append("--device-datasets")
+    if args.fused_adam:
+        overlay.append("--fused-adam")
     overlay += ["-m", module]
     if args.nproc > 1 and name == "train3d":
         cmd = [sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1",
@@ -212,6 +214,7 @@ def main() -> int:
     ap.add_argument("--out", default=str(REPO / "gpurun_out" / "scripts"))
     ap.add_argument("--keep-vae", action="store_true", help="leave vae.py to the reference")
     ap.add_argument("--overlap-ddp", action="store_true")
+    ap.add_argument("--fused-adam", action="store_true", help="torch.optim.Adam -> the one-launch Adam")
     ap.add_argument("--device-datasets", action="store_true",
                     help="dataset.py -> the device data path (normalise / resize / pad / crop kernels)")
     ap.add_argument("--nproc", type=int, default=1, help="train3d under torchrun with this many ranks")
@@ -229,6 +232,7 @@ def main() -> int:
     stage_datasets(work, *[int(v) for v in args.cases.split(",")])
     summary = {"reference": str(ref), "work": str(work), "keep_vae": args.keep_vae, "nproc": args.nproc,
                "device_datasets": args.device_datasets, "overlap_ddp": args.overlap_ddp,
+               "fused_adam": args.fused_adam,
                "results": {}}
     for name in [s for s in args.scripts.split(",") if s]:
         summary["results"][name] = run_one(name, work, out, args)
