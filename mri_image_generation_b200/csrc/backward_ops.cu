@@ -559,7 +559,10 @@ static inline int rows_per_block_for(int samples, int64_t spatial, int rows_step
     return e != nullptr ? atoi(e) : 0;
   }();
   if (env_bps > 0) blocks_per_sm = env_bps;
-  int64_t want_blocks = (148 * blocks_per_sm + samples - 1) / samples;
+  // chunks per sample rounded DOWN: the grid must fit ONE resident wave -- rounding up gives
+  // e.g. 320 blocks on 296 slots at batch 64 (or 32), whose 24 stragglers run as a second wave
+  int64_t want_blocks = (148 * blocks_per_sm) / samples;
+  if (want_blocks < 1) want_blocks = 1;
   int64_t rows_per = (spatial + want_blocks - 1) / want_blocks;
   const int64_t quantum = (int64_t)rows_step * 4;
   rows_per = (rows_per + quantum - 1) / quantum * quantum;

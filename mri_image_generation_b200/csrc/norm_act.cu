@@ -78,27 +78,40 @@ gn_stats_kernel(const uint4* __restrict__ x, double* __restrict__ stats, int64_t
 }
 
 // ---------------------------------------------------------------------------------------
-// Apply.  grid (chunks, samples).  A thread owns one 8-channel vector position (fixed channel
-// group), so mean / rstd / gamma / beta collapse into 8 (scale, shift) pairs computed once;
-// the thread then streams rows with 4 independent 16-byte loads in flight.
+// Apply.  ONE resident wave of blocks (148 x occupancy, mri_gn_apply) over the flattened
+// (sample, row) space: block b owns rows [b * rows_per_block, ...) of that space, i.e. a range of
+// one sample or the tail of one and the head of the next -- every block has the same amount of
+// work for ANY batch size (a (chunks, samples) grid leaves a ragged second wave whenever the slot
+// count is not a multiple of the batch: 640 blocks on 592 slots at batch 64).  A thread owns one
+// 8-channel vector position (fixed channel group), so mean / rstd / gamma / beta collapse into 8
+// (scale, shift) pairs computed once per sample segment; the thread then streams rows with 4
+// independent 16-byte loads in flight.
 // ---------------------------------------------------------------------------------------
 template <bool kSilu, bool kResidual>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, kResidual ? 3 : 4)
 gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double* __restrict__ stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta,
                 const float* __restrict__ rowbias, int rowbias_ld, const uint4* __restrict__ residual,
-                int64_t spatial, int C, int groups, int stats_ld, int stats_g0, int stats_cpg,
-                float eps, int rows_per_block) {
+                int samples, int64_t spatial, int C, int groups, int stats_ld, int stats_g0,
+                int stats_cpg, float eps, int64_t rows_per_block) {
   const int vec_per_row = C >> 3;
   const int cpg = C / groups;        // channels per normalisation group
   const int comb = cpg / stats_cpg;  // fine groups per normalisation group
-  const int sample = blockIdx.y;
   const int cv = threadIdx.x % vec_per_row;
   const int rsub = threadIdx.x / vec_per_row;
   const int rows_step = blockDim.x / vec_per_row;
   const int c = cv * 8;
-  float sc[8], sh[8], rb[8];
   const double inv_cnt = 1.0 / ((double)cpg * (double)spatial);
+  const int64_t total_rows = (int64_t)samples * spatial;
+  int64_t g0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t g1 = g0 + rows_per_block;
+  if (g1 > total_rows) g1 = total_rows;
+  while (g0 < g1) {
+  const int sample = (int)(g0 / spatial);
+  const int r0 = (int)(g0 - (int64_t)sample * spatial);
+  const int r1 = (g1 - g0) < (spatial - r0) ? r0 + (int)(g1 - g0) : (int)spatial;
+  g0 += r1 - r0;
+  float sc[8], sh[8], rb[8];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {  // the two halves of the vector may lie in different groups
     const int g = (c + 4 * h) / cpg;
@@ -156,8 +169,6 @@ gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double
     return make_uint4(ow[0], ow[1], ow[2], ow[3]);
   };
   // rows [r0, r1) of the sample; whole batches of U rows without predicates, then the ragged end
-  const int r0 = blockIdx.x * rows_per_block;
-  const int r1 = (int64_t)r0 + rows_per_block > spatial ? (int)spatial : r0 + rows_per_block;
   const size_t base = (size_t)sample * spatial * vec_per_row + cv;
   const uint4* xp = x + base;
   const uint4* rp = kResidual ? residual + base : xp;
@@ -181,6 +192,14 @@ gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double
     const uint4 q = kResidual ? __ldg(rp + r * vec_per_row) : v;
     yp[r * vec_per_row] = apply(v, q);
   }
+  }  // sample segments of this block's row range
+}
+
+template <typename K>
+static int blocks_per_sm(K kernel, int threads) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n < 1) n = 1;
+  return n;
 }
 
 }  // namespace mri
@@ -220,27 +239,32 @@ extern "C" int mri_gn_apply(const void* x, void* y, const double* stats, const f
   if (vec_per_row > 256) return set_error(-2, "mri_gn_apply: C > 2048 unsupported");
   const int threads = (256 / vec_per_row) * vec_per_row;
   const int rows_step = threads / vec_per_row;
-  // ~4 blocks of 256 threads per SM (3 resident; measured best of 2/3/4/6), each covering a
-  // multiple of 4*rows_step rows
   if (spatial * vec_per_row > 0x7fffffffLL) return set_error(-2, "mri_gn_apply: sample too large");
   static const int env_bps = [] {
     const char* e = getenv("MRI_GN_BLOCKS_PER_SM");  // tuning probe (tools/gn_probe.py)
     return e != nullptr ? atoi(e) : 0;
   }();
-  int64_t want_blocks = (148 * (env_bps > 0 ? env_bps : 4) + samples - 1) / samples;
-  int64_t rows_per = (spatial + want_blocks - 1) / want_blocks;
-  const int64_t quantum = (int64_t)rows_step * 4;
-  rows_per = (rows_per + quantum - 1) / quantum * quantum;
-  const int chunks = (int)((spatial + rows_per - 1) / rows_per);
-  dim3 grid(chunks, samples);
   const uint4* xp = reinterpret_cast<const uint4*>(x);
   uint4* yp = reinterpret_cast<uint4*>(y);
   const uint4* rp = reinterpret_cast<const uint4*>(residual);
   cudaStream_t st = (cudaStream_t)stream;
-#define MRI_GN_LAUNCH(S, R)                                                                     \
-  gn_apply_kernel<S, R><<<grid, threads, 0, st>>>(xp, yp, stats, gamma, beta, rowbias,          \
-                                                  rowbias_ld, rp, spatial, C, groups, stats_ld, \
-                                                  stats_g0, stats_cpg, eps, (int)rows_per)
+  // exactly one resident wave (62 registers: 4 blocks per SM, 70-74 with a residual: 3), every
+  // block the same multiple of 4 * rows_step rows of the flattened (sample, row) space
+  const int64_t total_rows = (int64_t)samples * spatial;
+  const int64_t quantum = (int64_t)rows_step * 4;
+#define MRI_GN_LAUNCH(S, R)                                                                       \
+  do {                                                                                            \
+    static int occ = 0; /* per instantiation; the block size only depends on C / 8 <= 256 */       \
+    if (occ == 0) occ = blocks_per_sm(gn_apply_kernel<S, R>, 256);                                \
+    const int bps = env_bps > 0 ? env_bps : occ;                                                  \
+    int64_t blocks = 148LL * bps;                                                                 \
+    int64_t rows_per = (total_rows + blocks - 1) / blocks;                                        \
+    rows_per = (rows_per + quantum - 1) / quantum * quantum;                                      \
+    blocks = (total_rows + rows_per - 1) / rows_per;                                              \
+    gn_apply_kernel<S, R><<<(unsigned)blocks, threads, 0, st>>>(                                  \
+        xp, yp, stats, gamma, beta, rowbias, rowbias_ld, rp, samples, spatial, C, groups,         \
+        stats_ld, stats_g0, stats_cpg, eps, rows_per);                                            \
+  } while (0)
   if (silu) {
     if (residual) MRI_GN_LAUNCH(true, true); else MRI_GN_LAUNCH(true, false);
   } else {
