@@ -98,6 +98,9 @@ class VAE3D(EngineModule):
         needs = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in part.parameters()))
         if not needs:
             return self._program(mode, x).forward(xf).clone()
+        if mode == "encode" and x.requires_grad:
+            raise _lib.MriError("VAE3D.encode: a gradient w.r.t. the input volume is not provided (the "
+                                "reference's training never asks for one, train.py:262-276)")
         # training (train.py:258-300): forward + backward launch lists behind one autograd node
         prog = self._program(mode, x, training=True)
         prog.param_list = list(part.parameters())
