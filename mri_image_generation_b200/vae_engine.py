@@ -26,14 +26,14 @@ decoder program returns the gradient of its input latent.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 
 from . import _lib, ops
 from . import plan as P
 from .backward import ConvRec
-from .engine import Act, UNetProgram, _pad_k, _pad_vec, _rup
+from .engine import Act, UNetProgram, _pad_vec, _rup
 
 
 def _pad_cin(w: torch.Tensor, cin_pad: int) -> torch.Tensor:
