@@ -8,6 +8,7 @@ import torch.nn as nn
 
 from ... import _lib
 from ...engine import UNet3DProgram
+from ...split_engine import UNet3DSplitProgram
 from ...modules import EngineModule, SinusoidalHolder, UNetFunction, on_input_device
 
 # name kept for importers of the reference module (unet_attention.py:7)
@@ -93,7 +94,20 @@ class _UNet3DBase(EngineModule):
         self.out_act = nn.SiLU()
         self.out_conv = nn.Conv3d(chs[0], in_channels, 3, padding=1)
 
-    def program(self, batch: int, spatial, training: bool = False) -> UNet3DProgram:
+    # "bf16": bf16 operands / fp32 accumulation (the reference's training precision, autocast(bf16));
+    # "split": parity with its fp32 / TF32 sampling path (show_model.py:254) -- every operand travels
+    # as two bf16 numbers through the same kernels (split_engine.py); inference only, ~6x the time
+    precision = "bf16"
+
+    def program(self, batch: int, spatial, training: bool = False):
+        if self.precision == "split":
+            if training:
+                raise _lib.MriError("precision = 'split' is an inference mode (run under torch.no_grad(), "
+                                    "or set model.precision = 'bf16' for training)")
+            key = (int(batch), tuple(int(s) for s in spatial), "split")
+            return self.get_program(key, lambda: UNet3DSplitProgram(self, key[0], key[1]))
+        if self.precision != "bf16":
+            raise _lib.MriError(f"unknown precision {self.precision!r}: 'bf16' or 'split'")
         key = (int(batch), tuple(int(s) for s in spatial), bool(training))
         return self.get_program(key, lambda: UNet3DProgram(self, key[0], key[1], training=key[2]))
 

@@ -269,6 +269,39 @@ def add_bf16(a, b, out) -> None:
     _lib.check(_lib.load().mri_add_bf16(_p(a), _p(b), _p(out), a.numel(), _s()), "mri_add_bf16")
 
 
+# ---- split precision mode (csrc/split_precision.cu) ----------------------------------------------
+def gn_split(x, y, stats, gamma, beta, samples, spatial, C, groups, stats_cpg, eps, silu, rowbias=None,
+             rowbias_ld=0) -> None:
+    """x fp32 [samples, spatial, C] -> y bf16 [samples, spatial, 3C] = [hi | lo | hi] of
+    act(GroupNorm(x)) (+ rowbias); stats None: plain split."""
+    _chk_contig(x, y)
+    _lib.check(_lib.load().mri_gn_split(_p(x), _p(y), _p(stats) if stats is not None else None,
+                                        _p(gamma) if gamma is not None else None,
+                                        _p(beta) if beta is not None else None,
+                                        _p(rowbias) if rowbias is not None else None, rowbias_ld, samples,
+                                        spatial, C, groups, stats.shape[1] if stats is not None else 0,
+                                        stats_cpg, eps, 1 if silu else 0, _s()), "mri_gn_split")
+
+
+def split3(src, dst, outer, inner, width, src_outer_ld, src_inner_ld, dst_outer_ld, dst_inner_ld, seg,
+           pattern, src_off=0, dst_off=0) -> None:
+    lib = _lib.load()
+    _lib.check(lib.mri_split3(src.data_ptr() + 4 * src_off, dst.data_ptr() + 2 * dst_off, outer, inner, width,
+                              src_outer_ld, src_inner_ld, dst_outer_ld, dst_inner_ld, seg, pattern, _s()),
+               "mri_split3")
+
+
+def softmax_rows_split(S, P, rows, cols, ld_s, ld_p, seg, scale) -> None:
+    _lib.check(_lib.load().mri_softmax_rows_split(_p(S), _p(P), rows, cols, ld_s, ld_p, seg, scale, _s()),
+               "mri_softmax_rows_split")
+
+
+def bf16_residual_nchw(x, out, samples, per_sample) -> None:
+    _chk_contig(x, out)
+    _lib.check(_lib.load().mri_bf16_residual_nchw(_p(x), _p(out), samples, per_sample, _s()),
+               "mri_bf16_residual_nchw")
+
+
 def copy_window(src, dst, src_off, dst_off, size, add=None) -> None:
     """dst[:, dh0:dh0+nH, dw0:dw0+nW] = src[:, sh0:sh0+nH, sw0:sw0+nW] (+ add), [B, H, W, C] bf16."""
     _chk_contig(src, dst)

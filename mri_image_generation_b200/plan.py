@@ -500,11 +500,14 @@ def _spatial_ext(y: torch.Tensor, ndim: int):
 def conv_plan(sources: Sequence[ConvSource], wmat: torch.Tensor, y: torch.Tensor, ksize: int,
               *, bias=None, rowbias=None, rowbias_ld=0, residual: Optional[torch.Tensor] = None,
               stats=None, stats_cpg=0, block_n: Optional[int] = None, stages=0, name="",
-              xreuse=None) -> GemmPlan:
+              xreuse=None, out_f32: bool = False) -> GemmPlan:
     """Stride-1, pad k//2 convolution over the channel-concatenation of `sources`.
 
     wmat: packed weights [Cout_pad, K] bf16, K = sum over sources of (taps * C_i), see
-    pack_conv_weight().  y: [N, *sp, Cout_pad] bf16."""
+    pack_conv_weight().  y: [N, *sp, Cout_pad] bf16 (fp32 with out_f32: the split precision mode,
+    plain tiles only)."""
+    assert y.dtype == (torch.float32 if out_f32 else torch.bfloat16)
+    assert not (out_f32 and residual is not None)
     ndim = y.dim() - 2
     ext, sample_dim = _spatial_ext(y, ndim)
     box = choose_box(ext, prefer_unit=(sample_dim - 1,))
@@ -525,7 +528,8 @@ def conv_plan(sources: Sequence[ConvSource], wmat: torch.Tensor, y: torch.Tensor
     else:
         level = int(xreuse)
     use_x = bool(level >= 1 and ksize == 3 and bn == 128 and cout_pad % 64 == 0 and box[0] == 8
-                 and int(np.prod(box)) == BLOCK_M and os.environ.get("MRI_GEMM_SWAP", "1") != "0")
+                 and int(np.prod(box)) == BLOCK_M and os.environ.get("MRI_GEMM_SWAP", "1") != "0"
+                 and not out_f32)
     # level 2: boxes of exactly 8 x 16 x 1 x 1 positions load a 10 x 18 tile once per (kd, channel
     # slab) and all nine (kh, kw) taps read shifted views of it
     use_xy = bool(use_x and level >= 2 and box[1] == 16)
@@ -576,8 +580,8 @@ def conv_plan(sources: Sequence[ConvSource], wmat: torch.Tensor, y: torch.Tensor
     assert wmat.shape == (cout_pad, bk), (wmat.shape, cout_pad, bk)
     kt = np.asarray(rows, dtype=np.int32)[None]
     bview = TView(wmat, (bk, cout_pad, 1, 1), (1, bk, _rup8(bk * cout_pad), _rup8(bk * cout_pad)))
-    chunk = _out_chunk(bn, False)
-    omap = MapSpec(_act_view(y, ndim), (chunk,) + box, _out_swizzle(chunk * 2))
+    chunk = _out_chunk(bn, out_f32)
+    omap = MapSpec(_act_view(y, ndim), (chunk,) + box, _out_swizzle(chunk * (4 if out_f32 else 2)))
     rmaps = None
     if residual is not None:
         assert residual.shape == y.shape
@@ -585,7 +589,7 @@ def conv_plan(sources: Sequence[ConvSource], wmat: torch.Tensor, y: torch.Tensor
     tiles = tuple(-(-e // b) for e, b in zip(ext, box))
     m_rows = int(np.prod(ext))
     return GemmPlan(a_maps=a_maps, b_map=MapSpec(bview, (BLOCK_K, bn, 1, 1), 3), o_maps=[omap],
-                    r_maps=rmaps, ktable=kt, tiles=tiles, box=box, ext=ext, block_n=bn,
+                    r_maps=rmaps, ktable=kt, tiles=tiles, box=box, ext=ext, block_n=bn, out_f32=out_f32,
                     n_total=cout_pad, sample_dim=sample_dim, bias=bias, rowbias=rowbias,
                     rowbias_ld=rowbias_ld, stats=stats, stats_ld=(stats.shape[1] if stats is not None else 0),
                     stats_cpg=stats_cpg, stages=stages, name=name, flops=2 * m_rows * cout_pad * bk,
@@ -607,7 +611,7 @@ def _rup8(n: int) -> int:
 
 def down_conv_plan(x: torch.Tensor, wmat: torch.Tensor, y: torch.Tensor, *, bias=None, stats=None,
                    stats_cpg=0, block_n=None, stages=0, name="",
-                   residual: Optional[torch.Tensor] = None) -> GemmPlan:
+                   residual: Optional[torch.Tensor] = None, out_f32: bool = False) -> GemmPlan:
     """Conv k=4, stride 2, pad 1 (slice_cond_2d_ddpm/unet.py:70, unet_attention.py:123): input
     index 2*o - 1 + k = 2*(o + a) + par with (par, a) = (1,-1), (0,0), (1,0), (0,1) for k = 0..3,
     i.e. tap k reads the parity-`par` sub-lattice shifted by a."""
@@ -632,14 +636,15 @@ def down_conv_plan(x: torch.Tensor, wmat: torch.Tensor, y: torch.Tensor, *, bias
     assert wmat.shape == (cout_pad, bk)
     kt = np.asarray(rows, dtype=np.int32)[None]
     bview = TView(wmat, (bk, cout_pad, 1, 1), (1, bk, _rup8(bk * cout_pad), _rup8(bk * cout_pad)))
-    chunk = _out_chunk(bn, False)
-    omap = MapSpec(_act_view(y, ndim), (chunk,) + box, _out_swizzle(chunk * 2))
+    assert y.dtype == (torch.float32 if out_f32 else torch.bfloat16) and not (out_f32 and residual is not None)
+    chunk = _out_chunk(bn, out_f32)
+    omap = MapSpec(_act_view(y, ndim), (chunk,) + box, _out_swizzle(chunk * (4 if out_f32 else 2)))
     tiles = tuple(-(-e // b) for e, b in zip(ext, box))
     rmaps = None
     if residual is not None:
         assert residual.shape == y.shape
         rmaps = [MapSpec(_act_view(residual, ndim), (chunk,) + box, _out_swizzle(chunk * 2))]
-    return GemmPlan(a_maps=a_maps, b_map=MapSpec(bview, (BLOCK_K, bn, 1, 1), 3), o_maps=[omap],
+    return GemmPlan(a_maps=a_maps, b_map=MapSpec(bview, (BLOCK_K, bn, 1, 1), 3), o_maps=[omap], out_f32=out_f32,
                     r_maps=rmaps, ktable=kt, tiles=tiles, box=box, ext=ext, block_n=bn, n_total=cout_pad,
                     sample_dim=sample_dim, bias=bias, stats=stats,
                     stats_ld=(stats.shape[1] if stats is not None else 0), stats_cpg=stats_cpg,
@@ -652,7 +657,7 @@ _CT_TAPS = {0: [(1, 0), (3, -1)], 1: [(0, 1), (2, 0)]}
 
 def up_conv_plan(x: torch.Tensor, wmat: torch.Tensor, y: torch.Tensor, *, bias=None, stats=None,
                  stats_cpg=0, block_n=None, stages=0, name="",
-                 residual: Optional[torch.Tensor] = None) -> GemmPlan:
+                 residual: Optional[torch.Tensor] = None, out_f32: bool = False) -> GemmPlan:
     """ConvTranspose k=4, stride 2, pad 1 (slice_cond_2d_ddpm/unet.py:89, unet_attention.py:142)
     as 2^d output-parity classes, each a 2^d-tap stride-1 convolution of the input written to
     the parity sub-lattice of the output.  wmat: [n_class, Cout_pad, 2^d * Cin]."""
@@ -681,8 +686,9 @@ def up_conv_plan(x: torch.Tensor, wmat: torch.Tensor, y: torch.Tensor, *, bias=N
     ncls = len(classes)
     assert wmat.shape == (ncls, cout_pad, K), (wmat.shape, (ncls, cout_pad, K))
     bview = TView(wmat, (K, cout_pad, ncls, 1), (1, K, K * cout_pad, _rup8(K * cout_pad * ncls)))
-    chunk = _out_chunk(bn, False)
-    o_maps = [MapSpec(_parity_view(y, ndim, rho), (chunk,) + box, _out_swizzle(chunk * 2))
+    assert y.dtype == (torch.float32 if out_f32 else torch.bfloat16) and not (out_f32 and residual is not None)
+    chunk = _out_chunk(bn, out_f32)
+    o_maps = [MapSpec(_parity_view(y, ndim, rho), (chunk,) + box, _out_swizzle(chunk * (4 if out_f32 else 2)))
               for rho in classes]
     tiles = tuple(-(-e // b) for e, b in zip(in_ext, box))
     rmaps = None
@@ -690,7 +696,7 @@ def up_conv_plan(x: torch.Tensor, wmat: torch.Tensor, y: torch.Tensor, *, bias=N
         assert residual.shape == y.shape
         rmaps = [MapSpec(_parity_view(residual, ndim, rho), (chunk,) + box, _out_swizzle(chunk * 2))
                  for rho in classes]
-    return GemmPlan(a_maps=a_maps, b_map=MapSpec(bview, (BLOCK_K, bn, 1, 1), 3), o_maps=o_maps,
+    return GemmPlan(a_maps=a_maps, b_map=MapSpec(bview, (BLOCK_K, bn, 1, 1), 3), o_maps=o_maps, out_f32=out_f32,
                     r_maps=rmaps, ktable=kt, tiles=tiles, box=box, ext=in_ext, block_n=bn, n_total=cout_pad,
                     bz_sel=(1, 0), sample_dim=sample_dim, bias=bias, stats=stats,
                     stats_ld=(stats.shape[1] if stats is not None else 0), stats_cpg=stats_cpg,

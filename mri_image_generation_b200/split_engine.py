@@ -1,0 +1,344 @@
+"""Split precision mode of the 3D latent UNet (inference): parity with the reference's fp32 / TF32
+sampling path.
+
+`ddpm_3d_ldm/show_model.py:254` samples WITHOUT autocast, i.e. with fp32 tensors and TF32 cuDNN
+convolutions (1.1e-3 rel-L2 from fp32 on a B200, profiles/r04g_reference_precision_modes.json); the
+default path of this package computes with bf16 operands like the reference's training path
+(1.2e-2).  This mode closes the gap on the SAME tensor-core kernel, which only takes bf16
+operands: an fp32 value v travels as two bf16 numbers hi = bf16(v), lo = bf16(v - hi) and a
+product a * w is evaluated as a_hi * w_hi + a_lo * w_hi + a_hi * w_lo by widening the contraction
+-- an activation with C channels is stored channels-last as [hi | lo | hi] (3C channels), the
+weights as [w_hi | w_hi | w_lo] along their input-channel axis, which is an ordinary convolution
+with 3C input channels for the implicit-GEMM plans; accumulation is fp32 and the output is written
+as fp32 (`out_f32`, plain tiles).  Everything between two convolutions runs on fp32 tensors
+(csrc/split_precision.cu): GroupNorm (+ SiLU, exact sigmoid) reads the fp32 convolution output and
+writes the widened operand; the residual / skip connections enter conv2's K loop as centre-tap
+sources with identity weights; the attention logits, probabilities and values are widened the
+same way.  Cost: 3x the contraction length on plain (non-`swap_ab`) tiles, about 6x the bf16
+path -- a parity mode, selected per model with `model.precision = "split"`.
+
+Reference graph: ddpm_3d_ldm/unet_attention.py:157-200 (the same walk as engine.UNet3DProgram).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib, ops
+from . import plan as P
+from .engine import UNetProgram, _pad_k, _pad_vec, _rup
+
+
+# ---- host-side helpers (weights are widened on the host when they are packed) ------------------
+def _hi_lo(w: torch.Tensor):
+    hi = w.to(torch.bfloat16).to(torch.float32)
+    lo = (w - hi).to(torch.bfloat16).to(torch.float32)
+    return hi, lo
+
+
+def widen_weight(w: torch.Tensor, splits: Optional[Sequence[int]] = None, transposed: bool = False) -> torch.Tensor:
+    """nn.ConvNd weight [Cout, Cin, *k] (transposed: nn.ConvTransposeNd [Cin, Cout, *k]) -> the same
+    layout with 3 * Cin input channels: per concatenated source (`splits`) [w_hi | w_hi | w_lo].
+    The values are bf16-exact fp32, so the bf16 packers store them unchanged."""
+    dim = 0 if transposed else 1
+    cin = w.shape[dim]
+    splits = list(splits) if splits else [cin]
+    assert sum(splits) == cin
+    hi, lo = _hi_lo(w.detach().to(torch.float32))
+    parts, c0 = [], 0
+    for c in splits:
+        sl = [slice(None)] * w.dim()
+        sl[dim] = slice(c0, c0 + c)
+        parts += [hi[tuple(sl)], hi[tuple(sl)], lo[tuple(sl)]]
+        c0 += c
+    return torch.cat(parts, dim=dim).contiguous()
+
+
+def identity_weight(C: int, device=None) -> torch.Tensor:
+    """1x1 weight [C, 3C] that adds hi + lo of a widened activation: [I | I | 0]."""
+    eye = torch.eye(C, device=device)
+    return torch.cat([eye, eye, torch.zeros(C, C, device=device)], dim=1).contiguous()
+
+
+def widen_activation(x_cl: torch.Tensor) -> torch.Tensor:
+    """[..., C] fp32 -> [..., 3C] bf16 = [hi | lo | hi] (host reference of mri_gn_split / mri_split3)."""
+    hi = x_cl.to(torch.bfloat16)
+    lo = (x_cl - hi.to(torch.float32)).to(torch.bfloat16)
+    return torch.cat([hi, lo, hi], dim=-1).contiguous()
+
+
+class F32Act:
+    """fp32 channels-last activation [N, *spatial, C] (+ GroupNorm partial sums of its producer)
+    and, once somebody needs it as a convolution operand, its plain widened copy."""
+
+    def __init__(self, t: torch.Tensor, stats: Optional[torch.Tensor] = None, cpg: int = 0):
+        self.t, self.stats, self.cpg = t, stats, cpg
+        self.raw3: Optional[torch.Tensor] = None
+
+    @property
+    def C(self) -> int:
+        return self.t.shape[-1]
+
+    @property
+    def spatial(self) -> int:
+        n = 1
+        for s in self.t.shape[1:-1]:
+            n *= s
+        return n
+
+
+class UNet3DSplitProgram(UNetProgram):
+    """ddpm_3d_ldm/unet_attention.py:88-200 and ddpm_3d_ldm/unet.py:57-158 in split precision."""
+
+    def __init__(self, model, batch: int, spatial: Sequence[int]):
+        dev = next(model.parameters()).device
+        super().__init__(dev, batch, spatial, groups=model.out_norm.num_groups, training=False)
+        self.model = model
+        B, (D, H, W) = batch, self.sp
+        cin = model.in_channels
+        chs = list(model.chs)
+        L = len(chs)
+        for s in self.sp:
+            if s % (2 ** (L - 1)) != 0:
+                raise _lib.MriError(f"spatial size {self.sp} must be divisible by {2 ** (L - 1)}")
+        eps = model.out_norm.eps
+        self.x_in = torch.zeros(B, cin, D, H, W, device=dev)
+        self.t_in = torch.zeros(B, dtype=torch.int64, device=dev)
+
+        tdim = model.time_mlp[1].in_features
+        temb = self.time_embedding(self.t_in, model.time_mlp, tdim)
+        blocks = []
+        for blk in model.downs:
+            blocks += [blk["res1"], blk["res2"]]
+        blocks += [model.mid1, model.mid2]
+        for blk in model.ups:
+            blocks += [blk["res1"], blk["res2"]]
+        tproj, toffs, tld = self.block_projections(temb, blocks, act=0)
+        self._tproj = {id(b): (tproj[:, o:], tld, o) for b, o in zip(blocks, toffs)}
+        self.tape.clear()        # inference only: nothing is differentiated in this mode
+
+        # ---- in_conv: patch matrix over the channels [x | x - bf16(x) | x] ----------------------
+        S = D * H * W
+        ic = model.in_conv
+        self.track(ic.weight, ic.bias)
+        x6 = torch.zeros(B, 2 * cin, D, H, W, device=dev)
+        kpad = _rup(27 * 3 * cin, 64)
+        col = torch.zeros(B * S, kpad, dtype=torch.bfloat16, device=dev)
+        x_in = self.x_in
+        self._add("in_conv.lo", lambda: ops.bf16_residual_nchw(x_in, x6, B, cin * S), [x6])
+        self._add("in_conv.im2col", lambda: ops.im2col(x_in, col, B, cin, D, H, W, 3, 3, kpad,
+                                                       src2=x6, cin2=2 * cin), [col])
+        w_in = self.packed(lambda: _pad_k(P.pack_conv_weight(widen_weight(ic.weight)), kpad))
+        h = self.new_f32(self.sp, chs[0])
+        a = P.TView(col, (kpad, S, B, 1, 1), (1, kpad, S * kpad, B * S * kpad, B * S * kpad))
+        bv = P.TView(w_in, (kpad, chs[0], 1, 1), (1, kpad, kpad * chs[0], kpad * chs[0]))
+        o = P.TView(h.t, (chs[0], S, B, 1, 1), (1, chs[0], S * chs[0], B * S * chs[0], B * S * chs[0]))
+        self.gemm(P.matrix_plan(a, (128, 1, 1, 1), bv, o, K=kpad, n_total=chs[0],
+                                block_n=P.pick_block_n(chs[0]), ext=(S, B, 1, 1),
+                                tiles=(-(-S // 128), B, 1, 1), sample_dim=2, bias=ic.bias, stats=h.stats,
+                                stats_cpg=h.cpg, out_f32=True, name="in_conv", flops=2 * B * S * chs[0] * kpad))
+
+        # ---- down path ---------------------------------------------------------------------------
+        skips: List[F32Act] = []
+        for i, blk in enumerate(model.downs):
+            h = self.resblock(h, None, blk["res1"], eps, f"downs.{i}.res1")
+            h = self.resblock(h, None, blk["res2"], eps, f"downs.{i}.res2")
+            skips.append(h)
+            if i != L - 1:
+                dn = blk["down"]
+                self.track(dn.weight, dn.bias)
+                wd = self.packed(lambda dn=dn: P.pack_conv_weight(widen_weight(dn.weight)))
+                y = self.new_f32([s // 2 for s in h.t.shape[1:-1]], chs[i + 1])
+                self.gemm(P.down_conv_plan(self.raw(h, f"downs.{i}.down.in"), wd, y.t, bias=dn.bias,
+                                           stats=y.stats, stats_cpg=y.cpg, out_f32=True, name=f"downs.{i}.down"))
+                h = y
+
+        # ---- bottleneck ----------------------------------------------------------------------------
+        h = self.resblock(h, None, model.mid1, eps, "mid1")
+        if hasattr(model, "mid_attn"):
+            h = self.attention(h, model.mid_attn, "mid_attn")
+        h = self.resblock(h, None, model.mid2, eps, "mid2")
+
+        # ---- up path -------------------------------------------------------------------------------
+        for j, blk in enumerate(model.ups):
+            i = L - 1 - j
+            if i != L - 1:
+                up = blk["up"]
+                self.track(up.weight, up.bias)
+                wu = self.packed(lambda up=up: P.pack_convT_weight(widen_weight(up.weight, transposed=True)))
+                u = self.new_f32([s * 2 for s in h.t.shape[1:-1]], chs[i])
+                self.gemm(P.up_conv_plan(self.raw(h, f"ups.{j}.up.in"), wu, u.t, bias=up.bias, stats=u.stats,
+                                         stats_cpg=u.cpg, out_f32=True, name=f"ups.{j}.up"))
+                h = u
+            skip = skips.pop()
+            if tuple(skip.t.shape[1:-1]) != tuple(h.t.shape[1:-1]):
+                raise _lib.MriError("skip/upsample shape mismatch (centre-crop path not supported)")
+            h = self.resblock(h, skip, blk["res1"], eps, f"ups.{j}.res1")
+            h = self.resblock(h, None, blk["res2"], eps, f"ups.{j}.res2")
+
+        # ---- head: fp32 eps, channels-last [.., cout_pad] -> NCDHW -----------------------------------
+        on, oc = model.out_norm, model.out_conv
+        self.track(on.weight, on.bias, oc.weight, oc.bias)
+        a3 = self.gn_split(h, on.weight, on.bias, self.groups, eps, True, name="out_norm")
+        cout = oc.weight.shape[0]
+        cp = _rup(cout, 16)
+        w_out = self.packed(lambda: P.pack_conv_weight(widen_weight(oc.weight), cout_pad=cp))
+        b_out = self.packed(lambda: _pad_vec(oc.bias.detach(), cp))
+        y = torch.zeros(B, D, H, W, cp, device=dev)
+        self.gemm(P.conv_plan([P.ConvSource(a3)], w_out, y, 3, bias=b_out, out_f32=True, name="out_conv"))
+        self.out = torch.zeros(B, cout, D, H, W, device=dev)
+        src = y.view(B, S, cp)[:, :, :cout].permute(0, 2, 1)
+        dst = self.out.view(B, cout, S)
+        self._add("out.nchw", lambda: ops.copy_cast(src, dst), [self.out])
+        # what the samplers read (diffusion_base._reverse_loop_on): eps in the state's own layout
+        self.eps_nhwc, self.cout, self.cout_pad = self.out, cout, 0
+        self.fused_head = None
+        self.params_changed()
+
+    # ------------------------------------------------------------------ buffers
+    def new_f32(self, sp: Sequence[int], C: int, with_stats: bool = True) -> F32Act:
+        t = torch.zeros(self.B, *sp, C, dtype=torch.float32, device=self.device)
+        if with_stats and C % (8 * self.groups) == 0:
+            return F32Act(t, self.new_stats(self.groups), C // self.groups)
+        return F32Act(t)
+
+    def wide(self, like: torch.Tensor) -> torch.Tensor:
+        return torch.zeros(*like.shape[:-1], 3 * like.shape[-1], dtype=torch.bfloat16, device=self.device)
+
+    # ------------------------------------------------------------------ op emitters
+    def gn_split(self, x: F32Act, gamma, beta, groups: int, eps: float, silu: bool, name: str,
+                 c_off: int = 0) -> torch.Tensor:
+        """[hi | lo | hi] of act(GroupNorm(x)); gamma / beta channels [c_off, c_off + C) apply."""
+        assert x.stats is not None, f"{name}: input has no statistics"
+        y = self.wide(x.t)
+        B, S, C, xs, st, cpg = self.B, x.spatial, x.C, x.t, x.stats, x.cpg
+        gm, bt = gamma[c_off:c_off + C], beta[c_off:c_off + C]
+        self._add(name, lambda: ops.gn_split(xs, y, st, gm, bt, B, S, C, groups, cpg, eps, silu), [y])
+        return y
+
+    def raw(self, x: F32Act, name: str) -> torch.Tensor:
+        """[hi | lo | hi] of x itself (convolution operand of the skip / down / up paths)."""
+        if x.raw3 is None:
+            y = self.wide(x.t)
+            B, S, C, xs = self.B, x.spatial, x.C, x.t
+            self._add(f"{name}.split", lambda: ops.gn_split(xs, y, None, None, None, B, S, C, 1, 1, 0.0, False), [y])
+            x.raw3 = y
+        return x.raw3
+
+    def conv(self, sources, wmat, cout: int, ksize: int, bias, *, rowbias=None, rowbias_ld=0,
+             with_stats=True, name="conv") -> F32Act:
+        sp = sources[0].x.shape[1:-1]
+        y = self.new_f32(sp, cout, with_stats)
+        self.gemm(P.conv_plan(sources, wmat, y.t, ksize, bias=bias, rowbias=rowbias, rowbias_ld=rowbias_ld,
+                              stats=y.stats, stats_cpg=y.cpg, out_f32=True, name=name))
+        return y
+
+    def resblock(self, x: F32Act, skip: Optional[F32Act], blk, eps: float, name: str) -> F32Act:
+        """ResidualBlock3D (unet_attention.py:59-85); with `skip` the input is cat([x, skip], 1)."""
+        n1, n2, c1, c2 = blk.norm1, blk.norm2, blk.conv1, blk.conv2
+        self.track(n1.weight, n1.bias, n2.weight, n2.bias, c1.weight, c1.bias, c2.weight, c2.bias)
+        cout = c1.weight.shape[0]
+        rowbias, rb_ld, _ = self._tproj[id(blk)]
+        srcs = [x] if skip is None else [x, skip]
+        cins = [s.C for s in srcs]
+        g_each = self.groups // len(srcs)   # GN(8, 2C) over a concat == GN(4) + GN(4) over the halves
+        normed, c0 = [], 0
+        for k, s in enumerate(srcs):
+            normed.append(self.gn_split(s, n1.weight, n1.bias, g_each, eps, True, f"{name}.norm1.{k}", c_off=c0))
+            c0 += s.C
+        w1 = self.packed(lambda: P.pack_conv_weight(widen_weight(c1.weight, splits=cins),
+                                                    splits=[3 * c for c in cins]))
+        h = self.conv([P.ConvSource(a) for a in normed], w1, cout, 3, c1.bias, rowbias=rowbias,
+                      rowbias_ld=rb_ld, name=f"{name}.conv1")
+        a2 = self.gn_split(h, n2.weight, n2.bias, self.groups, eps, True, f"{name}.norm2")
+        raws = [self.raw(s, f"{name}.in{k}") for k, s in enumerate(srcs)]
+        if not isinstance(blk.skip, torch.nn.Identity):
+            sk = blk.skip
+            self.track(sk.weight, sk.bias)
+            w2 = self.packed(lambda: P.pack_conv_weight(
+                widen_weight(c2.weight),
+                extra=[widen_weight(sk.weight.detach().reshape(cout, -1), splits=cins)]))
+            sources = [P.ConvSource(a2)] + [P.ConvSource(r, taps=False) for r in raws]
+            return self.conv(sources, w2, cout, 3, c2.bias, rowbias=sk.bias, rowbias_ld=0,
+                             name=f"{name}.conv2+skip")
+        assert skip is None and x.C == cout
+        w2 = self.packed(lambda: P.pack_conv_weight(widen_weight(c2.weight),
+                                                    extra=[identity_weight(cout, self.device)]))
+        return self.conv([P.ConvSource(a2), P.ConvSource(raws[0], taps=False)], w2, cout, 3, c2.bias,
+                         name=f"{name}.conv2+x")
+
+    def attention(self, x: F32Act, blk, name: str) -> F32Act:
+        """AttentionBlock3D (unet_attention.py:28-56) with every product in split precision."""
+        B, C, dev = self.B, x.C, self.device
+        heads = blk.num_heads
+        d = C // heads
+        n = x.spatial
+        npad = _rup(n, 64)       # segment length of the widened key axis: whole K slabs
+        C3 = 3 * C
+        sp = tuple(x.t.shape[1:-1])
+        self.track(blk.norm.weight, blk.norm.bias, blk.qkv.weight, blk.qkv.bias, blk.proj.weight,
+                   blk.proj.bias)
+        hn3 = self.gn_split(x, blk.norm.weight, blk.norm.bias, self.groups, blk.norm.eps, False, f"{name}.norm")
+        wqkv = self.packed(lambda: P.pack_conv_weight(widen_weight(blk.qkv.weight)))
+        qkv = self.conv([P.ConvSource(hn3)], wqkv, C3, 1, blk.qkv.bias, with_stats=False, name=f"{name}.qkv")
+        # q -> [hi | lo | hi], k -> [hi | hi | lo] per head along d: [B, n, heads, 3d]
+        q3 = torch.zeros(B, n, heads, 3 * d, dtype=torch.bfloat16, device=dev)
+        k3 = torch.zeros(B, n, heads, 3 * d, dtype=torch.bfloat16, device=dev)
+        qt = qkv.t
+        self._add(f"{name}.q.split", lambda: ops.split3(qt, q3, B * n, heads, d, C3, d, heads * 3 * d, 3 * d, d, 0), [q3])
+        self._add(f"{name}.k.split", lambda: ops.split3(qt, k3, B * n, heads, d, C3, d, heads * 3 * d, 3 * d, d, 1,
+                                                        src_off=C), [k3])
+        # S = q k^T (fp32 logits)
+        Sm = torch.zeros(B, heads, n, npad, dtype=torch.float32, device=dev)
+        ld = heads * 3 * d
+        qa = P.TView(q3, (3 * d, n, heads, B, 1), (1, ld, 3 * d, n * ld, B * n * ld))
+        kb = P.TView(k3, (3 * d, n, heads, B), (1, ld, 3 * d, n * ld))
+        so = P.TView(Sm, (npad, n, heads, B, 1), (1, npad, n * npad, heads * n * npad, B * heads * n * npad))
+        tiles = (-(-n // 128), heads, B, 1)
+        self.gemm(P.matrix_plan(qa, (128, 1, 1, 1), kb, so, K=3 * d, n_total=npad, block_n=128,
+                                ext=(n, heads, B, 1), tiles=tiles, bz_sel=(3, 4), out_f32=True,
+                                name=f"{name}.qk^T", flops=2 * B * heads * n * n * 3 * d))
+        P3 = torch.zeros(B, heads, n, 3 * npad, dtype=torch.bfloat16, device=dev)
+        scale = float(d) ** -0.5
+        self._add(f"{name}.softmax", lambda: ops.softmax_rows_split(Sm, P3, B * heads * n, n, npad, 3 * npad,
+                                                                    npad, scale), [P3])
+        # v^T [B, C, npad] fp32 = W_v . hn^T + b_v (keys contiguous), then widened [hi | hi | lo]
+        wv = self.packed(lambda: widen_weight(blk.qkv.weight.detach()[2 * C:].reshape(C, C)).to(torch.bfloat16))
+        bvv = self.packed(lambda: blk.qkv.bias.detach()[2 * C:].contiguous())
+        vT = torch.zeros(B, C, npad, dtype=torch.float32, device=dev)
+        a = P.TView(wv, (C3, C, 1, 1, 1), (1, C3, C * C3, C * C3, C * C3))
+        b = P.TView(hn3, (C3, n, B, 1), (1, C3, n * C3, B * n * C3))
+        sz = C * npad
+        o_views = [P.TView(vT, (npad, C, 1, 1, 1), (1, npad, sz, sz, sz), offset=bi * sz) for bi in range(B)]
+        pl = P.matrix_plan(a, (128, 1, 1, 1), b, o_views[0], K=C3, n_total=npad, block_n=128,
+                           ext=(C, 1, 1, 1), tiles=(C // 128, 1, 1, 1), bz_sel=(1, 0), bias_m=bvv,
+                           out_f32=True, name=f"{name}.vT", flops=2 * B * n * C * C3)
+        chunk_box, swz = pl.o_maps[0].box, pl.o_maps[0].swizzle
+        pl.o_maps = [P.MapSpec(v, chunk_box, swz) for v in o_views]
+        pl.ktable = pl.ktable.repeat(B, axis=0)
+        self.gemm(pl)
+        vT3 = torch.zeros(B, C, 3 * npad, dtype=torch.bfloat16, device=dev)
+        self._add(f"{name}.v.split", lambda: ops.split3(vT, vT3, B * C, 1, n, npad, 0, 3 * npad, 0, npad, 1), [vT3])
+        # O = P v (fp32, token-major [B, n, C])
+        O = F32Act(torch.zeros(B, *sp, C, dtype=torch.float32, device=dev))
+        pa = P.TView(P3, (3 * npad, n, heads, B, 1),
+                     (1, 3 * npad, n * 3 * npad, heads * n * 3 * npad, B * heads * n * 3 * npad))
+        vb = P.TView(vT3, (3 * npad, d, heads, B), (1, 3 * npad, d * 3 * npad, C * 3 * npad))
+        oo = P.TView(O.t, (d, n, heads, B, 1), (1, C, d, n * C, B * n * C))
+        self.gemm(P.matrix_plan(pa, (128, 1, 1, 1), vb, oo, K=3 * npad, n_total=d, block_n=min(d, 128),
+                                ext=(n, heads, B, 1), tiles=tiles, bz_sel=(3, 4), out_f32=True,
+                                name=f"{name}.pv", flops=2 * B * heads * n * 3 * npad * d))
+        wp = self.packed(lambda: P.pack_conv_weight(widen_weight(blk.proj.weight),
+                                                    extra=[identity_weight(C, self.device)]))
+        return self.conv([P.ConvSource(self.raw(O, f"{name}.O")), P.ConvSource(self.raw(x, f"{name}.x"), taps=False)],
+                         wp, C, 1, blk.proj.bias, name=f"{name}.proj+x")
+
+    # ------------------------------------------------------------------ entry
+    def forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        if self.params_changed():
+            self.do_refresh()
+        self.x_in.copy_(x)
+        self.t_in.copy_(t)
+        self.run()
+        return self.out
