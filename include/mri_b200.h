@@ -389,24 +389,34 @@ int mri_gn_bwd_apply(const void* x, const void* dy, const void* add, void* dx, c
  * bf16 numbers hi = bf16(v), lo = bf16(v - hi); an activation with C channels is stored
  * channels-last as [hi | lo | hi] (3C channels) against weights [w_hi | w_hi | w_lo], so the
  * implicit-GEMM kernel (fp32 accumulation, out_f32) evaluates a_hi*w_hi + a_lo*w_hi + a_hi*w_lo.
- * mri_gn_split: x fp32 [samples, spatial, C] -> y bf16 [samples, spatial, 3C] of
- *   act(GroupNorm(x)) (+ rowbias[sample, c]); stats == NULL: plain split of x.  Replaces
- *   nn.GroupNorm + nn.SiLU (unet_attention.py:62-63,76-80) in this mode; exact sigmoid.
+ * mri_gn_split: v = act(GroupNorm(x)) (+ rowbias[sample, c]) (+ residual, fp32 [.., C]) of x fp32
+ *   [samples, spatial, C]; stats == NULL: v = x (+ ...).  Written widened as y bf16 [samples,
+ *   spatial, 3C] (y != NULL) and / or as fp32 y32 [samples, spatial, C] (y32 != NULL).  Replaces
+ *   nn.GroupNorm + nn.SiLU and the adds around them (unet_attention.py:62-63,76-85;
+ *   slice_cond_2d_ddpm/unet.py:44-56) in this mode; exact sigmoid.
+ * mri_stats_f32: GroupNorm partial sums (sum, sum of squares; fp64 [samples][groups][2], zero it
+ *   first) of an fp32 channels-last tensor whose producer is not a convolution epilogue (the 2D
+ *   out_norm, slice_cond_2d_ddpm/unet.py:196).
  * mri_split3: dst[o, i, p*seg + j] = part_p(src[o, i, j]) for j < width; pattern 0 = (hi, lo, hi)
  *   (activation side), 1 = (hi, hi, lo) (weight side); leading dimensions in elements.
  * mri_softmax_rows_split: P = softmax(scale * S) per row in fp32 (unet_attention.py:49-50), written
  *   widened [hi | lo | hi] with segment length seg (ld_p >= 3 * seg).
- * mri_bf16_residual_nchw: x fp32 [B, C, S] -> out fp32 [B, 2C, S] = [x - bf16(x) | x]: the extra
- *   input channels of the first convolution (unet_attention.py:114). */
-int mri_gn_split(const float* x, void* y, const double* stats, const float* gamma, const float* beta,
-                 const float* rowbias, int rowbias_ld, int samples, int64_t spatial, int C, int groups,
-                 int stats_ld, int stats_cpg, float eps, int silu, void* stream);
+ * mri_bf16_residual_nchw: x fp32 [B, C, S] (per_sample = C * S) -> out[b] = [x - bf16(x) | x]
+ *   (2C channels; samples out_sample_stride elements apart): the extra input channels of the first
+ *   convolution (unet_attention.py:114, slice_cond_2d_ddpm/unet.py:184). */
+int mri_gn_split(const float* x, void* y, float* y32, const double* stats, const float* gamma,
+                 const float* beta, const float* rowbias, int rowbias_ld, const float* residual,
+                 int samples, int64_t spatial, int C, int groups, int stats_ld, int stats_cpg, float eps,
+                 int silu, void* stream);
+int mri_stats_f32(const float* x, double* stats, int samples, int64_t spatial, int C, int groups,
+                  void* stream);
 int mri_split3(const float* src, void* dst, int64_t outer, int inner, int width, int64_t src_outer_ld,
                int64_t src_inner_ld, int64_t dst_outer_ld, int64_t dst_inner_ld, int seg, int pattern,
                void* stream);
 int mri_softmax_rows_split(const float* S, void* P, int64_t rows, int cols, int ld_s, int ld_p, int seg,
                            float scale, void* stream);
-int mri_bf16_residual_nchw(const float* x, float* out, int samples, int64_t per_sample, void* stream);
+int mri_bf16_residual_nchw(const float* x, float* out, int samples, int64_t per_sample,
+                           int64_t out_sample_stride, void* stream);
 /* Image sizes the down-sampling factor does not divide (slice_cond_2d_ddpm/unet.py:95-99,
  * ddpm_25d_all_modalities/unet.py:95-99: `F.interpolate(x, size=skip.shape[-2:], mode="bilinear",
  * align_corners=False)` after the transposed convolution).  Channels-last bf16 [B, H, W, C], C % 8 == 0.

@@ -160,10 +160,11 @@ SIGNATURES = {
     "mri_gn_bwd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _i, _f,
                               _i, _vp, _vp]),
     "mri_add_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
-    "mri_gn_split": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _i, _i, _i, _f, _i, _vp]),
+    "mri_gn_split": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i64, _i, _i, _i, _i, _f, _i, _vp]),
+    "mri_stats_f32": (_i, [_vp, _vp, _i, _i64, _i, _i, _vp]),
     "mri_split3": (_i, [_vp, _vp, _i64, _i, _i, _i64, _i64, _i64, _i64, _i, _i, _vp]),
     "mri_softmax_rows_split": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _f, _vp]),
-    "mri_bf16_residual_nchw": (_i, [_vp, _vp, _i, _i64, _vp]),
+    "mri_bf16_residual_nchw": (_i, [_vp, _vp, _i, _i64, _i64, _vp]),
     "mri_copy_window_nhwc": (_i, [_vp, _vp, _vp] + [_i] * 12 + [_vp]),
     "mri_resize_bilinear_nhwc": (_i, [_vp, _vp] + [_i] * 6 + [_vp]),
     "mri_resize_bilinear_nhwc_bwd": (_i, [_vp, _vp, _vp] + [_i] * 6 + [_vp]),

@@ -26,14 +26,15 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
-// x fp32 [samples, spatial, C] -> y bf16 [samples, spatial, 3C] = [hi | lo | hi] of
-// act(GroupNorm(x)) (+ rowbias); stats == nullptr: y = split(x) (no normalisation, no act).
+// x fp32 [samples, spatial, C] -> v = act(GroupNorm(x)) (+ rowbias) (+ residual, fp32 [.., C]);
+// stats == nullptr: v = x (+ ...).  Written as y bf16 [samples, spatial, 3C] = [hi | lo | hi] of v
+// (y != nullptr) and / or as fp32 y32 [samples, spatial, C] (y32 != nullptr).
 __global__ void __launch_bounds__(256)
-gn_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+gn_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, float* __restrict__ y32,
                 const double* __restrict__ stats, const float* __restrict__ gamma,
                 const float* __restrict__ beta, const float* __restrict__ rowbias, int rowbias_ld,
-                int64_t spatial, int C, int groups, int stats_ld, int stats_cpg, float eps, int silu,
-                int64_t rows_per_block) {
+                const float* __restrict__ residual, int64_t spatial, int C, int groups, int stats_ld,
+                int stats_cpg, float eps, int silu, int64_t rows_per_block) {
   const int sample = blockIdx.y;
   const int c = threadIdx.x % C;           // host: blockDim.x is a multiple of C (C <= 256) or
   const int rsub = threadIdx.x / C;        // C is a multiple of blockDim.x handled by the c loop
@@ -68,12 +69,16 @@ gn_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
         if (silu) v = v / (1.f + expf(-v));
       }
       v += rb;
-      __nv_bfloat16 hi, lo;
-      split_bf16(v, hi, lo);
-      __nv_bfloat16* o = y + row * (size_t)(3 * C);
-      o[cc] = hi;
-      o[C + cc] = lo;
-      o[2 * C + cc] = hi;
+      if (residual != nullptr) v += residual[row * C + cc];
+      if (y32 != nullptr) y32[row * C + cc] = v;
+      if (y != nullptr) {
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        __nv_bfloat16* o = y + row * (size_t)(3 * C);
+        o[cc] = hi;
+        o[C + cc] = lo;
+        o[2 * C + cc] = hi;
+      }
     }
   }
 }
@@ -129,17 +134,50 @@ softmax_split_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P,
   }
 }
 
-// x fp32 [B, C, S] -> out fp32 [B, 2C, S]: channels [0, C) = x - bf16(x), [C, 2C) = x
+// x fp32 [B, C, S] (per_sample = C * S) -> out[b] (samples out_sample_stride elements apart):
+// channels [0, C) = x - bf16(x), [C, 2C) = x
 __global__ void __launch_bounds__(256)
-nchw_lo_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t per_sample, int64_t total) {
+nchw_lo_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t per_sample,
+               int64_t out_sample_stride, int64_t total) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = i / per_sample, r = i - b * per_sample;
     const float v = x[i];
-    float* o = out + b * 2 * per_sample + r;
+    float* o = out + b * out_sample_stride + r;
     o[0] = v - __bfloat162float(__float2bfloat16_rn(v));
     o[per_sample] = v;
   }
+}
+
+// GroupNorm partial sums of an fp32 channels-last tensor: stats[sample][group] += (sum, sum of squares)
+__global__ void __launch_bounds__(256)
+stats_f32_kernel(const float* __restrict__ x, double* __restrict__ stats, int64_t spatial, int C,
+                 int groups, int64_t rows_per_block) {
+  extern __shared__ double red[];  // [groups][2]
+  const int sample = blockIdx.y;
+  const int cpg = C / groups;
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) red[i] = 0.0;
+  __syncthreads();
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > spatial) r1 = spatial;
+  const float* base = x + (size_t)sample * spatial * C;
+  for (int g = 0; g < groups; ++g) {
+    double s = 0.0, ss = 0.0;
+    const int64_t n = (r1 - r0) * cpg;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const int64_t r = r0 + i / cpg;
+      const int c = g * cpg + (int)(i % cpg);
+      const double v = (double)base[r * C + c];
+      s += v;
+      ss += v * v;
+    }
+    atomicAdd(&red[2 * g], s);
+    atomicAdd(&red[2 * g + 1], ss);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x)
+    atomicAdd(stats + ((size_t)sample * groups) * 2 + i, red[i]);
 }
 
 static unsigned blocks_for(int64_t total) {
@@ -153,11 +191,12 @@ static unsigned blocks_for(int64_t total) {
 
 using namespace mri;
 
-extern "C" int mri_gn_split(const float* x, void* y, const double* stats, const float* gamma,
-                            const float* beta, const float* rowbias, int rowbias_ld, int samples,
-                            int64_t spatial, int C, int groups, int stats_ld, int stats_cpg, float eps,
-                            int silu, void* stream) {
+extern "C" int mri_gn_split(const float* x, void* y, float* y32, const double* stats, const float* gamma,
+                            const float* beta, const float* rowbias, int rowbias_ld,
+                            const float* residual, int samples, int64_t spatial, int C, int groups,
+                            int stats_ld, int stats_cpg, float eps, int silu, void* stream) {
   if (C < 1 || samples < 1 || spatial < 1) return set_error(-2, "mri_gn_split: bad shape");
+  if (y == nullptr && y32 == nullptr) return set_error(-2, "mri_gn_split: no output");
   if (stats != nullptr && (groups < 1 || C % groups != 0 || stats_cpg < 1 || (C / groups) % stats_cpg != 0))
     return set_error(-2, "mri_gn_split: bad group configuration");
   const int threads = C >= 256 ? 256 : (256 / C) * C;
@@ -168,8 +207,8 @@ extern "C" int mri_gn_split(const float* x, void* y, const double* stats, const 
   const int64_t chunks = (spatial + rows_per - 1) / rows_per;
   if (samples > 65535) return set_error(-2, "mri_gn_split: too many samples");
   gn_split_kernel<<<dim3((unsigned)chunks, (unsigned)samples), threads, 0, (cudaStream_t)stream>>>(
-      x, reinterpret_cast<__nv_bfloat16*>(y), stats, gamma, beta, rowbias, rowbias_ld, spatial, C, groups,
-      stats_ld, stats_cpg, eps, silu, rows_per);
+      x, reinterpret_cast<__nv_bfloat16*>(y), y32, stats, gamma, beta, rowbias, rowbias_ld, residual,
+      spatial, C, groups, stats_ld, stats_cpg, eps, silu, rows_per);
   return check_launch("gn_split_kernel");
 }
 
@@ -195,9 +234,24 @@ extern "C" int mri_softmax_rows_split(const float* S, void* P, int64_t rows, int
 }
 
 extern "C" int mri_bf16_residual_nchw(const float* x, float* out, int samples, int64_t per_sample,
-                                      void* stream) {
-  if (samples < 1 || per_sample < 1) return set_error(-2, "mri_bf16_residual_nchw: bad shape");
+                                      int64_t out_sample_stride, void* stream) {
+  if (samples < 1 || per_sample < 1 || out_sample_stride < 2 * per_sample)
+    return set_error(-2, "mri_bf16_residual_nchw: bad shape");
   const int64_t total = (int64_t)samples * per_sample;
-  nchw_lo_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(x, out, per_sample, total);
+  nchw_lo_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(x, out, per_sample,
+                                                                      out_sample_stride, total);
   return check_launch("nchw_lo_kernel");
+}
+
+extern "C" int mri_stats_f32(const float* x, double* stats, int samples, int64_t spatial, int C,
+                             int groups, void* stream) {
+  if (C < 1 || samples < 1 || spatial < 1 || groups < 1 || C % groups != 0 || groups > 512 || samples > 65535)
+    return set_error(-2, "mri_stats_f32: bad shape");
+  int64_t want = (148 * 4 + samples - 1) / samples;
+  int64_t rows_per = (spatial + want - 1) / want;
+  if (rows_per < 1) rows_per = 1;
+  const int64_t chunks = (spatial + rows_per - 1) / rows_per;
+  stats_f32_kernel<<<dim3((unsigned)chunks, (unsigned)samples), 256, 2 * groups * sizeof(double),
+                     (cudaStream_t)stream>>>(x, stats, spatial, C, groups, rows_per);
+  return check_launch("stats_f32_kernel");
 }

@@ -7,6 +7,7 @@ import torch.nn as nn
 
 from ... import _lib
 from ...engine import UNet2DProgram
+from ...split_engine import UNet2DSplitProgram
 from ...modules import EngineModule, SinusoidalHolder, UNetFunction, on_input_device
 
 SinusoidalPosEmb = SinusoidalHolder  # unet.py:7
@@ -80,8 +81,20 @@ class _UNet2DBase(EngineModule):
         self.out_norm = nn.GroupNorm(8, self.chs[0])
         self.out_conv = nn.Conv2d(self.chs[0], out_channels, 3, padding=1)
 
+    # "bf16" (default) | "split": parity with the fp32 / TF32 sampling of the reference's show_model /
+    # metrics scripts (no autocast there); see split_engine.py.  Inference only.
+    precision = "bf16"
+
     def program(self, batch: int, spatial, x_channels: int, ctx_channels: int = 0,
-                training: bool = False) -> UNet2DProgram:
+                training: bool = False):
+        if self.precision == "split":
+            if training:
+                raise _lib.MriError("precision = 'split' is an inference mode (run under torch.no_grad(), "
+                                    "or set model.precision = 'bf16' for training)")
+            skey = (int(batch), tuple(int(s) for s in spatial), int(x_channels), int(ctx_channels), "split")
+            return self.get_program(skey, lambda: UNet2DSplitProgram(self, skey[0], skey[1], skey[2], skey[3]))
+        if self.precision != "bf16":
+            raise _lib.MriError(f"unknown precision {self.precision!r}: 'bf16' or 'split'")
         key = (int(batch), tuple(int(s) for s in spatial), int(x_channels), int(ctx_channels),
                bool(training))
         return self.get_program(key, lambda: UNet2DProgram(self, key[0], key[1], key[2], key[3],

@@ -271,16 +271,19 @@ def add_bf16(a, b, out) -> None:
 
 # ---- split precision mode (csrc/split_precision.cu) ----------------------------------------------
 def gn_split(x, y, stats, gamma, beta, samples, spatial, C, groups, stats_cpg, eps, silu, rowbias=None,
-             rowbias_ld=0) -> None:
-    """x fp32 [samples, spatial, C] -> y bf16 [samples, spatial, 3C] = [hi | lo | hi] of
-    act(GroupNorm(x)) (+ rowbias); stats None: plain split."""
-    _chk_contig(x, y)
-    _lib.check(_lib.load().mri_gn_split(_p(x), _p(y), _p(stats) if stats is not None else None,
-                                        _p(gamma) if gamma is not None else None,
-                                        _p(beta) if beta is not None else None,
-                                        _p(rowbias) if rowbias is not None else None, rowbias_ld, samples,
-                                        spatial, C, groups, stats.shape[1] if stats is not None else 0,
-                                        stats_cpg, eps, 1 if silu else 0, _s()), "mri_gn_split")
+             rowbias_ld=0, residual=None, y32=None) -> None:
+    """v = act(GroupNorm(x)) (+ rowbias) (+ residual fp32) of x fp32 [samples, spatial, C]; stats None:
+    v = x (+ ...).  y: bf16 [samples, spatial, 3C] = [hi | lo | hi] of v, y32: fp32 v (either may be None)."""
+    _chk_contig(x, y, y32, residual)
+    _lib.check(_lib.load().mri_gn_split(_p(x), _p(y), _p(y32), _p(stats), _p(gamma), _p(beta), _p(rowbias),
+                                        rowbias_ld, _p(residual), samples, spatial, C, groups,
+                                        stats.shape[1] if stats is not None else 0, stats_cpg, eps,
+                                        1 if silu else 0, _s()), "mri_gn_split")
+
+
+def stats_f32(x, stats, samples, spatial, C, groups) -> None:
+    _chk_contig(x, stats)
+    _lib.check(_lib.load().mri_stats_f32(_p(x), _p(stats), samples, spatial, C, groups, _s()), "mri_stats_f32")
 
 
 def split3(src, dst, outer, inner, width, src_outer_ld, src_inner_ld, dst_outer_ld, dst_inner_ld, seg,
@@ -296,9 +299,11 @@ def softmax_rows_split(S, P, rows, cols, ld_s, ld_p, seg, scale) -> None:
                "mri_softmax_rows_split")
 
 
-def bf16_residual_nchw(x, out, samples, per_sample) -> None:
-    _chk_contig(x, out)
-    _lib.check(_lib.load().mri_bf16_residual_nchw(_p(x), _p(out), samples, per_sample, _s()),
+def bf16_residual_nchw(x, out, samples, per_sample, out_sample_stride=0, out_off=0) -> None:
+    """out[b, out_off : out_off + 2 * per_sample] = [x - bf16(x) | x] (flat channel-major samples)."""
+    _chk_contig(x)
+    _lib.check(_lib.load().mri_bf16_residual_nchw(_p(x), out.data_ptr() + 4 * out_off, samples, per_sample,
+                                                  out_sample_stride or 2 * per_sample, _s()),
                "mri_bf16_residual_nchw")
 
 

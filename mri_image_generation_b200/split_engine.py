@@ -1,5 +1,5 @@
-"""Split precision mode of the 3D latent UNet (inference): parity with the reference's fp32 / TF32
-sampling path.
+"""Split precision mode of the UNets (inference): parity with the reference's fp32 / TF32 sampling
+path.
 
 `ddpm_3d_ldm/show_model.py:254` samples WITHOUT autocast, i.e. with fp32 tensors and TF32 cuDNN
 convolutions (1.1e-3 rel-L2 from fp32 on a B200, profiles/r04g_reference_precision_modes.json); the
@@ -88,7 +88,92 @@ class F32Act:
         return n
 
 
-class UNet3DSplitProgram(UNetProgram):
+class _SplitProgram(UNetProgram):
+    """Buffers and op emitters shared by the split precision programs."""
+
+    # ------------------------------------------------------------------ buffers
+    def new_f32(self, sp: Sequence[int], C: int, with_stats: bool = True) -> F32Act:
+        t = torch.zeros(self.B, *sp, C, dtype=torch.float32, device=self.device)
+        if with_stats and C % (8 * self.groups) == 0:
+            return F32Act(t, self.new_stats(self.groups), C // self.groups)
+        return F32Act(t)
+
+    def wide(self, like: torch.Tensor) -> torch.Tensor:
+        return torch.zeros(*like.shape[:-1], 3 * like.shape[-1], dtype=torch.bfloat16, device=self.device)
+
+    # ------------------------------------------------------------------ op emitters
+    def gn_split(self, x: F32Act, gamma, beta, groups: int, eps: float, silu: bool, name: str,
+                 c_off: int = 0, rowbias=None, rowbias_ld: int = 0) -> torch.Tensor:
+        """[hi | lo | hi] of act(GroupNorm(x)) (+ rowbias); gamma / beta channels [c_off, c_off + C) apply."""
+        assert x.stats is not None, f"{name}: input has no statistics"
+        y = self.wide(x.t)
+        B, S, C, xs, st, cpg = self.B, x.spatial, x.C, x.t, x.stats, x.cpg
+        gm, bt = gamma[c_off:c_off + C], beta[c_off:c_off + C]
+        self._add(name, lambda: ops.gn_split(xs, y, st, gm, bt, B, S, C, groups, cpg, eps, silu,
+                                             rowbias=rowbias, rowbias_ld=rowbias_ld), [y])
+        return y
+
+    def gn_f32(self, x: F32Act, gamma, beta, groups: int, eps: float, silu: bool, residual: torch.Tensor,
+               name: str) -> F32Act:
+        """fp32 act(GroupNorm(x)) + residual: the post-norm block output (slice_cond_2d_ddpm/unet.py:52-56)."""
+        assert x.stats is not None, f"{name}: input has no statistics"
+        y = F32Act(torch.zeros_like(x.t))
+        B, S, C, xs, st, cpg, yt = self.B, x.spatial, x.C, x.t, x.stats, x.cpg, y.t
+        self._add(name, lambda: ops.gn_split(xs, None, st, gamma, beta, B, S, C, groups, cpg, eps, silu,
+                                             residual=residual, y32=yt), [yt])
+        return y
+
+    def raw(self, x: F32Act, name: str) -> torch.Tensor:
+        """[hi | lo | hi] of x itself (a convolution operand without a norm in front of it)."""
+        if x.raw3 is None:
+            y = self.wide(x.t)
+            B, S, C, xs = self.B, x.spatial, x.C, x.t
+            self._add(f"{name}.split", lambda: ops.gn_split(xs, y, None, None, None, B, S, C, 1, 1, 0.0, False), [y])
+            x.raw3 = y
+        return x.raw3
+
+    def conv(self, sources, wmat, cout: int, ksize: int, bias, *, rowbias=None, rowbias_ld=0,
+             with_stats=True, name="conv") -> F32Act:
+        sp = sources[0].x.shape[1:-1]
+        y = self.new_f32(sp, cout, with_stats)
+        self.gemm(P.conv_plan(sources, wmat, y.t, ksize, bias=bias, rowbias=rowbias, rowbias_ld=rowbias_ld,
+                              stats=y.stats, stats_cpg=y.cpg, out_f32=True, name=name))
+        return y
+
+    def matrix_in_conv(self, col: torch.Tensor, wmat: torch.Tensor, S: int, kpad: int, cout: int, bias,
+                       name: str, with_stats: bool) -> F32Act:
+        """The first convolution as a GEMM over the patch matrix `col` [B * S, kpad]."""
+        B = self.B
+        h = self.new_f32(self.sp, cout, with_stats)
+        a = P.TView(col, (kpad, S, B, 1, 1), (1, kpad, S * kpad, B * S * kpad, B * S * kpad))
+        bv = P.TView(wmat, (kpad, cout, 1, 1), (1, kpad, kpad * cout, kpad * cout))
+        o = P.TView(h.t, (cout, S, B, 1, 1), (1, cout, S * cout, B * S * cout, B * S * cout))
+        self.gemm(P.matrix_plan(a, (128, 1, 1, 1), bv, o, K=kpad, n_total=cout, block_n=P.pick_block_n(cout),
+                                ext=(S, B, 1, 1), tiles=(-(-S // 128), B, 1, 1), sample_dim=2, bias=bias,
+                                stats=h.stats, stats_cpg=h.cpg, out_f32=True, name=name,
+                                flops=2 * B * S * cout * kpad))
+        return h
+
+    def head(self, a3: torch.Tensor, oc, S: int) -> None:
+        """out_conv with fp32 output, channels-last [.., cout_pad] -> NC[D]HW.  What the samplers read
+        (diffusion_base._reverse_loop_on) is eps in the state's own layout (ldc = 0)."""
+        B, dev = self.B, self.device
+        cout = oc.weight.shape[0]
+        cp = _rup(cout, 16)
+        w_out = self.packed(lambda: P.pack_conv_weight(widen_weight(oc.weight), cout_pad=cp))
+        b_out = self.packed(lambda: _pad_vec(oc.bias.detach(), cp))
+        y = torch.zeros(B, *self.sp, cp, device=dev)
+        self.gemm(P.conv_plan([P.ConvSource(a3)], w_out, y, oc.weight.shape[2], bias=b_out, out_f32=True,
+                              name="out_conv"))
+        self.out = torch.zeros(B, cout, *self.sp, device=dev)
+        src = y.view(B, S, cp)[:, :, :cout].permute(0, 2, 1)
+        dst = self.out.view(B, cout, S)
+        self._add("out.nchw", lambda: ops.copy_cast(src, dst), [self.out])
+        self.eps_nhwc, self.cout, self.cout_pad = self.out, cout, 0
+        self.fused_head = None
+
+
+class UNet3DSplitProgram(_SplitProgram):
     """ddpm_3d_ldm/unet_attention.py:88-200 and ddpm_3d_ldm/unet.py:57-158 in split precision."""
 
     def __init__(self, model, batch: int, spatial: Sequence[int]):
@@ -130,14 +215,7 @@ class UNet3DSplitProgram(UNetProgram):
         self._add("in_conv.im2col", lambda: ops.im2col(x_in, col, B, cin, D, H, W, 3, 3, kpad,
                                                        src2=x6, cin2=2 * cin), [col])
         w_in = self.packed(lambda: _pad_k(P.pack_conv_weight(widen_weight(ic.weight)), kpad))
-        h = self.new_f32(self.sp, chs[0])
-        a = P.TView(col, (kpad, S, B, 1, 1), (1, kpad, S * kpad, B * S * kpad, B * S * kpad))
-        bv = P.TView(w_in, (kpad, chs[0], 1, 1), (1, kpad, kpad * chs[0], kpad * chs[0]))
-        o = P.TView(h.t, (chs[0], S, B, 1, 1), (1, chs[0], S * chs[0], B * S * chs[0], B * S * chs[0]))
-        self.gemm(P.matrix_plan(a, (128, 1, 1, 1), bv, o, K=kpad, n_total=chs[0],
-                                block_n=P.pick_block_n(chs[0]), ext=(S, B, 1, 1),
-                                tiles=(-(-S // 128), B, 1, 1), sample_dim=2, bias=ic.bias, stats=h.stats,
-                                stats_cpg=h.cpg, out_f32=True, name="in_conv", flops=2 * B * S * chs[0] * kpad))
+        h = self.matrix_in_conv(col, w_in, S, kpad, chs[0], ic.bias, "in_conv", True)
 
         # ---- down path ---------------------------------------------------------------------------
         skips: List[F32Act] = []
@@ -177,62 +255,12 @@ class UNet3DSplitProgram(UNetProgram):
             h = self.resblock(h, skip, blk["res1"], eps, f"ups.{j}.res1")
             h = self.resblock(h, None, blk["res2"], eps, f"ups.{j}.res2")
 
-        # ---- head: fp32 eps, channels-last [.., cout_pad] -> NCDHW -----------------------------------
+        # ---- head --------------------------------------------------------------------------------
         on, oc = model.out_norm, model.out_conv
         self.track(on.weight, on.bias, oc.weight, oc.bias)
         a3 = self.gn_split(h, on.weight, on.bias, self.groups, eps, True, name="out_norm")
-        cout = oc.weight.shape[0]
-        cp = _rup(cout, 16)
-        w_out = self.packed(lambda: P.pack_conv_weight(widen_weight(oc.weight), cout_pad=cp))
-        b_out = self.packed(lambda: _pad_vec(oc.bias.detach(), cp))
-        y = torch.zeros(B, D, H, W, cp, device=dev)
-        self.gemm(P.conv_plan([P.ConvSource(a3)], w_out, y, 3, bias=b_out, out_f32=True, name="out_conv"))
-        self.out = torch.zeros(B, cout, D, H, W, device=dev)
-        src = y.view(B, S, cp)[:, :, :cout].permute(0, 2, 1)
-        dst = self.out.view(B, cout, S)
-        self._add("out.nchw", lambda: ops.copy_cast(src, dst), [self.out])
-        # what the samplers read (diffusion_base._reverse_loop_on): eps in the state's own layout
-        self.eps_nhwc, self.cout, self.cout_pad = self.out, cout, 0
-        self.fused_head = None
+        self.head(a3, oc, S)
         self.params_changed()
-
-    # ------------------------------------------------------------------ buffers
-    def new_f32(self, sp: Sequence[int], C: int, with_stats: bool = True) -> F32Act:
-        t = torch.zeros(self.B, *sp, C, dtype=torch.float32, device=self.device)
-        if with_stats and C % (8 * self.groups) == 0:
-            return F32Act(t, self.new_stats(self.groups), C // self.groups)
-        return F32Act(t)
-
-    def wide(self, like: torch.Tensor) -> torch.Tensor:
-        return torch.zeros(*like.shape[:-1], 3 * like.shape[-1], dtype=torch.bfloat16, device=self.device)
-
-    # ------------------------------------------------------------------ op emitters
-    def gn_split(self, x: F32Act, gamma, beta, groups: int, eps: float, silu: bool, name: str,
-                 c_off: int = 0) -> torch.Tensor:
-        """[hi | lo | hi] of act(GroupNorm(x)); gamma / beta channels [c_off, c_off + C) apply."""
-        assert x.stats is not None, f"{name}: input has no statistics"
-        y = self.wide(x.t)
-        B, S, C, xs, st, cpg = self.B, x.spatial, x.C, x.t, x.stats, x.cpg
-        gm, bt = gamma[c_off:c_off + C], beta[c_off:c_off + C]
-        self._add(name, lambda: ops.gn_split(xs, y, st, gm, bt, B, S, C, groups, cpg, eps, silu), [y])
-        return y
-
-    def raw(self, x: F32Act, name: str) -> torch.Tensor:
-        """[hi | lo | hi] of x itself (convolution operand of the skip / down / up paths)."""
-        if x.raw3 is None:
-            y = self.wide(x.t)
-            B, S, C, xs = self.B, x.spatial, x.C, x.t
-            self._add(f"{name}.split", lambda: ops.gn_split(xs, y, None, None, None, B, S, C, 1, 1, 0.0, False), [y])
-            x.raw3 = y
-        return x.raw3
-
-    def conv(self, sources, wmat, cout: int, ksize: int, bias, *, rowbias=None, rowbias_ld=0,
-             with_stats=True, name="conv") -> F32Act:
-        sp = sources[0].x.shape[1:-1]
-        y = self.new_f32(sp, cout, with_stats)
-        self.gemm(P.conv_plan(sources, wmat, y.t, ksize, bias=bias, rowbias=rowbias, rowbias_ld=rowbias_ld,
-                              stats=y.stats, stats_cpg=y.cpg, out_f32=True, name=name))
-        return y
 
     def resblock(self, x: F32Act, skip: Optional[F32Act], blk, eps: float, name: str) -> F32Act:
         """ResidualBlock3D (unet_attention.py:59-85); with `skip` the input is cat([x, skip], 1)."""
@@ -340,5 +368,152 @@ class UNet3DSplitProgram(UNetProgram):
             self.do_refresh()
         self.x_in.copy_(x)
         self.t_in.copy_(t)
+        self.run()
+        return self.out
+
+
+class UNet2DSplitProgram(_SplitProgram):
+    """slice_cond_2d_ddpm/unet.py:108-199 and ddpm_25d_all_modalities/unet.py:109-218 in split
+    precision (their show_model / metrics scripts sample without autocast as well).  Post-norm
+    blocks: every block input / output is an fp32 tensor; conv1 and the 1x1 res_conv read its plain
+    widened copy, the second GroupNorm adds the fp32 residual."""
+
+    def __init__(self, model, batch: int, spatial: Sequence[int], x_channels: int, ctx_channels: int):
+        dev = next(model.parameters()).device
+        super().__init__(dev, batch, spatial, groups=model.out_norm.num_groups, training=False)
+        self.model = model
+        B, (H, W) = batch, self.sp
+        chs = list(model.chs)
+        n_down = len(model.downs)
+        if H % (2 ** n_down) or W % (2 ** n_down):
+            raise _lib.MriError(f"split precision: image size {self.sp} must be divisible by {2 ** n_down}")
+        eps = model.out_norm.eps
+        cin = model.init_conv.weight.shape[1]
+        if x_channels + ctx_channels != cin:
+            raise _lib.MriError(f"init_conv expects {cin} input channels, got {x_channels} + {ctx_channels} context")
+        self.x_in = torch.zeros(B, x_channels, H, W, device=dev)
+        self.ctx_in = torch.zeros(B, ctx_channels, H, W, device=dev) if ctx_channels else None
+        self.t_in = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.z_in = torch.zeros(B, 1, device=dev)
+
+        # ---- conditioning: cond = time_mlp(t) + slice_mlp(z)  (unet.py:173-183), fp32 ---------------
+        tdim = model.time_mlp[1].in_features
+        temb = self.time_embedding(self.t_in, model.time_mlp, tdim)
+        s0, s2 = model.slice_mlp[0], model.slice_mlp[2]
+        self.track(s0.weight, s0.bias, s2.weight, s2.bias)
+        zh = torch.zeros(B, s0.weight.shape[0], device=dev)
+        cond = torch.zeros(B, tdim, device=dev)
+        z_in = self.z_in
+        self._add("slice_mlp.0", lambda: ops.linear(z_in, s0.weight, s0.bias, zh, act=1), [zh])
+        self._add("slice_mlp.2", lambda: ops.linear(zh, s2.weight, s2.bias, cond, addend=temb), [cond])
+        blocks = []
+        for d in model.downs:
+            blocks += [d.res1, d.res2]
+        blocks += [model.mid_block1, model.mid_block2]
+        for u in model.ups:
+            blocks += [u.res1, u.res2]
+        tproj, toffs, tld = self.block_projections(cond, blocks, act=1)   # SiLU on the projection (unet.py:48-50)
+        self._tproj = {id(b): (tproj[:, o:], tld, o) for b, o in zip(blocks, toffs)}
+        self.tape.clear()
+
+        # ---- init_conv over the channels [x | lo(x) | x | ctx | lo(ctx) | ctx] ---------------------
+        S = H * W
+        ic = model.init_conv
+        self.track(ic.weight, ic.bias)
+        n2 = 2 * x_channels + 3 * ctx_channels
+        buf = torch.zeros(B, n2, H, W, device=dev)
+        x_in, ctx_in = self.x_in, self.ctx_in
+        self._add("init_conv.lo", lambda: ops.bf16_residual_nchw(x_in, buf, B, x_channels * S, n2 * S), [buf])
+        if ctx_channels:
+            c0 = 2 * x_channels
+            self._add("init_conv.ctx", lambda: ops.copy_cast(ctx_in.view(B, ctx_channels * S),
+                                                             buf.view(B, n2 * S)[:, c0 * S:(c0 + ctx_channels) * S]), [buf])
+            self._add("init_conv.ctx.lo", lambda: ops.bf16_residual_nchw(
+                ctx_in, buf, B, ctx_channels * S, n2 * S, out_off=(c0 + ctx_channels) * S), [buf])
+        kpad = _rup(9 * 3 * cin, 64)
+        col = torch.zeros(B * S, kpad, dtype=torch.bfloat16, device=dev)
+        self._add("init_conv.im2col", lambda: ops.im2col(x_in, col, B, x_channels, 1, H, W, 3, 2, kpad,
+                                                         src2=buf, cin2=n2), [col])
+        splits = [x_channels] + ([ctx_channels] if ctx_channels else [])
+        w_in = self.packed(lambda: _pad_k(P.pack_conv_weight(widen_weight(ic.weight, splits=splits)), kpad))
+        h = self.matrix_in_conv(col, w_in, S, kpad, chs[0], ic.bias, "init_conv", False)
+
+        skips: List[F32Act] = []
+        for i, d in enumerate(model.downs):
+            h = self.resblock2d(h, None, d.res1, eps, f"downs.{i}.res1")
+            h = self.resblock2d(h, None, d.res2, eps, f"downs.{i}.res2")
+            skips.append(h)
+            dn = d.down
+            self.track(dn.weight, dn.bias)
+            wd = self.packed(lambda dn=dn: P.pack_conv_weight(widen_weight(dn.weight)))
+            y = self.new_f32([s // 2 for s in h.t.shape[1:-1]], dn.weight.shape[0], with_stats=False)
+            self.gemm(P.down_conv_plan(self.raw(h, f"downs.{i}.down.in"), wd, y.t, bias=dn.bias, out_f32=True,
+                                       name=f"downs.{i}.down"))
+            h = y
+        h = self.resblock2d(h, None, model.mid_block1, eps, "mid_block1")
+        h = self.resblock2d(h, None, model.mid_block2, eps, "mid_block2")
+        for j, u in enumerate(model.ups):
+            skip = skips.pop()
+            up = u.up
+            self.track(up.weight, up.bias)
+            wu = self.packed(lambda up=up: P.pack_convT_weight(widen_weight(up.weight, transposed=True)))
+            y = self.new_f32([s * 2 for s in h.t.shape[1:-1]], up.weight.shape[1], with_stats=False)
+            self.gemm(P.up_conv_plan(self.raw(h, f"ups.{j}.up.in"), wu, y.t, bias=up.bias, out_f32=True,
+                                     name=f"ups.{j}.up"))
+            h = self.resblock2d(y, skip, u.res1, eps, f"ups.{j}.res1")
+            h = self.resblock2d(h, None, u.res2, eps, f"ups.{j}.res2")
+
+        on, oc = model.out_norm, model.out_conv
+        self.track(on.weight, on.bias, oc.weight, oc.bias)
+        h.stats = self.new_stats(self.groups)
+        h.cpg = h.C // self.groups
+        ht, hst, C0, G = h.t, h.stats, h.C, self.groups
+        self._add("out_norm.stats", lambda: ops.stats_f32(ht, hst, B, S, C0, G), [hst])
+        a3 = self.gn_split(h, on.weight, on.bias, self.groups, eps, True, name="out_norm")
+        self.head(a3, oc, S)
+        self.params_changed()
+
+    def resblock2d(self, x: F32Act, skip: Optional[F32Act], blk, eps: float, name: str) -> F32Act:
+        """ResidualBlock (slice_cond_2d_ddpm/unet.py:42-56), post-norm:
+        h = silu(gn1(conv1(x))) + silu(lin(cond)); h = silu(gn2(conv2(h))); return h + res_conv(x).
+        With `skip`, x is cat([x, skip], 1) (unet.py:101)."""
+        n1, n2, c1, c2 = blk.norm1, blk.norm2, blk.conv1, blk.conv2
+        self.track(n1.weight, n1.bias, n2.weight, n2.bias, c1.weight, c1.bias, c2.weight, c2.bias)
+        cout = c1.weight.shape[0]
+        rowbias, rb_ld, _ = self._tproj[id(blk)]
+        srcs = [x] if skip is None else [x, skip]
+        cins = [s.C for s in srcs]
+        raws = [self.raw(s, f"{name}.in{k}") for k, s in enumerate(srcs)]
+        w1 = self.packed(lambda: P.pack_conv_weight(widen_weight(c1.weight, splits=cins),
+                                                    splits=[3 * c for c in cins]))
+        h1 = self.conv([P.ConvSource(r) for r in raws], w1, cout, 3, c1.bias, name=f"{name}.conv1")
+        a1 = self.gn_split(h1, n1.weight, n1.bias, self.groups, eps, True, f"{name}.norm1+temb",
+                           rowbias=rowbias, rowbias_ld=rb_ld)
+        w2 = self.packed(lambda: P.pack_conv_weight(widen_weight(c2.weight)))
+        h2 = self.conv([P.ConvSource(a1)], w2, cout, 3, c2.bias, name=f"{name}.conv2")
+        if isinstance(blk.res_conv, torch.nn.Identity):
+            assert skip is None and x.C == cout
+            res = x.t
+        else:
+            rc = blk.res_conv
+            self.track(rc.weight, rc.bias)
+            wr = self.packed(lambda: P.pack_conv_weight(widen_weight(rc.weight, splits=cins),
+                                                        splits=[3 * c for c in cins]))
+            res = self.conv([P.ConvSource(r) for r in raws], wr, cout, 1, rc.bias, with_stats=False,
+                            name=f"{name}.res_conv").t
+        return self.gn_f32(h2, n2.weight, n2.bias, self.groups, eps, True, res, f"{name}.norm2+res")
+
+    # ------------------------------------------------------------------ entry
+    def _load_inputs(self, x, t, z_pos, context):
+        if self.params_changed():
+            self.do_refresh()
+        self.x_in.copy_(x)
+        self.t_in.copy_(t)
+        self.z_in.copy_(z_pos.reshape(-1, 1))
+        if self.ctx_in is not None:
+            self.ctx_in.copy_(context)
+
+    def forward(self, x, t, z_pos, context=None) -> torch.Tensor:
+        self._load_inputs(x, t, z_pos, context)
         self.run()
         return self.out

@@ -136,3 +136,57 @@ def test_sampling_in_split_precision_follows_the_fp32_reference_trajectory():
     with pytest.raises(Exception):
         m.train()
         m(torch.randn(shape, device="cuda"), torch.zeros(2, dtype=torch.long, device="cuda"))
+
+
+@pytest.mark.parametrize("kind", ["2d", "25d"])
+def test_unet2d_split_vs_fp32_oracle(kind):
+    """slice_cond_2d_ddpm / ddpm_25d_all_modalities UNets (post-norm blocks, slice conditioning, context)."""
+    if kind == "2d":
+        from mri_image_generation_b200.model_scripts.slice_cond_2d_ddpm.unet import UNet
+        m = quiet(UNet, img_channels=1, base_channels=64, time_emb_dim=64)
+        cx, cc = 1, 0
+    else:
+        from mri_image_generation_b200.model_scripts.ddpm_25d_all_modalities.unet import UNet
+        m = quiet(UNet, in_channels=20, out_channels=4, base_channels=64, time_emb_dim=64)
+        cx, cc = 4, 16
+    sd = synthetic_state_dict(shapes_of(m), seed=63)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3, cx, 32, 48, generator=g)
+    ctx = torch.randn(3, cc, 32, 48, generator=g) if cc else None
+    t = torch.randint(0, 1000, (3,), generator=g)
+    z = torch.rand(3, generator=g)
+    kw = {} if ctx is None else {"context": ctx}
+    kwc = {} if ctx is None else {"context": ctx.cuda()}
+    with torch.no_grad():
+        want = O.unet2d_forward(sd, x, t, z, **kw)
+        bf16 = m(x.cuda(), t.cuda(), z.cuda(), **kwc).clone()
+        m.precision = "split"
+        got = m(x.cuda(), t.cuda(), z.cuda(), **kwc).clone()
+    e_split, e_bf16 = rel_l2(got, want), rel_l2(bf16, want)
+    print(f"{kind}: split {e_split:.3e}  bf16 {e_bf16:.3e}")
+    assert e_split < TOL and e_bf16 > 10 * e_split
+
+
+def test_2d_sampling_in_split_precision():
+    from mri_image_generation_b200.model_scripts.slice_cond_2d_ddpm.diffusion import GaussianDiffusion
+    from mri_image_generation_b200.model_scripts.slice_cond_2d_ddpm.unet import UNet
+    m = quiet(UNet, img_channels=1, base_channels=64, time_emb_dim=64)
+    sd = synthetic_state_dict(shapes_of(m), seed=64)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    m.precision = "split"
+    T, shape = 10, (2, 1, 32, 32)
+    diff = quiet(GaussianDiffusion, m, 32, channels=1, timesteps=T).cuda()
+    buf = O.schedule_buffers(O.linear_betas(T))
+    z = torch.tensor([0.25, 0.75])
+    torch.manual_seed(12)
+    x_T = torch.randn(shape, device="cuda")
+    noises = [torch.randn(shape, device="cuda").cpu() for _ in range(T)]
+    want = O.sample_loop(buf, lambda x, t: O.unet2d_forward(sd, x, t, z), x_T.cpu(), noises, T)
+    torch.manual_seed(12)
+    got = diff.sample(2, z.cuda())
+    e = rel_l2(got, want)
+    print("2D trajectory error after", T, "steps:", e)
+    assert e < 1e-3
