@@ -13,6 +13,7 @@ import torch.nn as nn
 
 from ... import _lib
 from ...modules import EngineModule, ProgramFunction, on_input_device
+from ...split_engine import VAE3DSplitProgram
 from ...vae_engine import VAE3DProgram
 
 
@@ -78,6 +79,9 @@ class VAE3D(EngineModule):
     """vae.py:90-127."""
 
     MAX_PROGRAMS = 6   # stage 1 alternates encoder / decoder training and inference programs
+    # "bf16" (default) | "split": fp32-class parity with the reference's un-autocast decode
+    # (show_model.py:255) on the bf16 kernels, see split_engine.py.  Inference only.
+    precision = "bf16"
 
     def __init__(self, in_channels=4, base_channels=32, num_down=3, latent_channels=8, groups=8):
         super().__init__()
@@ -90,6 +94,13 @@ class VAE3D(EngineModule):
         self._check_input(x)
         if x.dim() != 5:
             raise _lib.MriError(f"VAE3D expects (B, C, D, H, W), got {tuple(x.shape)}")
+        if self.precision == "split":
+            if training:
+                raise _lib.MriError("precision = 'split' is an inference mode (use 'bf16' for training)")
+            skey = (mode, int(x.shape[0]), tuple(int(s) for s in x.shape[2:]), "split")
+            return self.get_program(skey, lambda: VAE3DSplitProgram(self, mode, skey[1], skey[2]))
+        if self.precision != "bf16":
+            raise _lib.MriError(f"unknown precision {self.precision!r}: 'bf16' or 'split'")
         key = (mode, int(x.shape[0]), tuple(int(s) for s in x.shape[2:]), bool(training))
         return self.get_program(key, lambda: VAE3DProgram(self, mode, key[1], key[2], training=key[3]))
 

@@ -33,7 +33,8 @@ DATA_MODULES: Dict[str, List[str]] = {k: ["dataset"] for k in HOT_MODULES}
 
 
 def install(packages: Optional[Iterable[str]] = None, *, vae: bool = True, datasets: bool = False,
-            overlap_ddp: bool = False, fused_adam: bool = False, root: str = "model_scripts") -> List[str]:
+            overlap_ddp: bool = False, fused_adam: bool = False, precision: Optional[str] = None,
+            root: str = "model_scripts") -> List[str]:
     """Alias the drop-in modules as `<root>.<pkg>.<module>`.  Returns the aliased names.
 
     vae=False keeps the reference's `vae.py` (stage 1 of ddpm_3d_ldm/train.py on the reference
@@ -44,7 +45,9 @@ def install(packages: Optional[Iterable[str]] = None, *, vae: bool = True, datas
     (ddpm_3d_ldm/train.py:16) resolve to the wrapper that overlaps the gradient all-reduce with
     the backward launch list (modules it does not know are handed to torch's wrapper);
     fused_adam=True makes `torch.optim.Adam(...)` (train.py:242-243, model.py:126) the one-launch
-    Adam of this package (same constructor, update rule, state_dict and GradScaler protocol)."""
+    Adam of this package (same constructor, update rule, state_dict and GradScaler protocol);
+    precision="split" makes every UNet / VAE the script builds run in split precision (fp32-class
+    parity with the un-autocast sampling of the show_model scripts; inference only)."""
     done = []
     for pkg in (packages or HOT_MODULES):
         if pkg not in HOT_MODULES:
@@ -67,6 +70,14 @@ def install(packages: Optional[Iterable[str]] = None, *, vae: bool = True, datas
             tud._mri_torch_dataloader = tud.DataLoader
         tud.DataLoader = data.device_dataloader(tud._mri_torch_dataloader)
         done.append("torch.utils.data.DataLoader")
+    if precision is not None:
+        if precision not in ("bf16", "split"):
+            raise ValueError(f"unknown precision {precision!r}")
+        from .model_scripts.ddpm_3d_ldm import unet_attention as _u3, vae as _v
+        from .model_scripts.slice_cond_2d_ddpm import unet as _u2
+        for cls in (_u3._UNet3DBase, _u2._UNet2DBase, _v.VAE3D):
+            cls.precision = precision
+        done.append(f"precision={precision}")
     if fused_adam:
         import torch.optim as topt
 
@@ -112,6 +123,8 @@ def main(argv=None) -> None:
     ap.add_argument("--overlap-ddp", action="store_true",
                     help="DistributedDataParallel -> the wrapper overlapping all-reduce and backward")
     ap.add_argument("--fused-adam", action="store_true", help="torch.optim.Adam -> the one-launch Adam")
+    ap.add_argument("--precision", choices=["bf16", "split"], default=None,
+                    help="split: fp32-class parity for the sampling scripts (inference only)")
     ap.add_argument("--path", action="append", default=[], help="prepend to sys.path (stub modules ...)")
     ap.add_argument("-m", dest="module", required=True, help="the reference script, as for python -m")
     ap.add_argument("args", nargs=argparse.REMAINDER)
@@ -121,7 +134,7 @@ def main(argv=None) -> None:
     if "" not in sys.path and "." not in sys.path:
         sys.path.insert(0, "")      # what `python -m` itself does: the reference checkout is the cwd
     names = install(vae=not ns.keep_vae, datasets=ns.device_datasets, overlap_ddp=ns.overlap_ddp,
-                    fused_adam=ns.fused_adam, root=ns.module.split(".")[0])
+                    fused_adam=ns.fused_adam, precision=ns.precision, root=ns.module.split(".")[0])
     print(f"[mri_b200.overlay] {len(names)} modules bound to the B200 path: {', '.join(names)}", flush=True)
     sys.argv = [ns.module] + list(ns.args)
     runpy.run_module(ns.module, run_name="__main__", alter_sys=True)

@@ -154,18 +154,28 @@ class _SplitProgram(UNetProgram):
                                 flops=2 * B * S * cout * kpad))
         return h
 
-    def head(self, a3: torch.Tensor, oc, S: int) -> None:
+    def head(self, a3: torch.Tensor, oc, S: int, cin_pad: int = 0) -> None:
         """out_conv with fp32 output, channels-last [.., cout_pad] -> NC[D]HW.  What the samplers read
         (diffusion_base._reverse_loop_on) is eps in the state's own layout (ldc = 0)."""
         B, dev = self.B, self.device
         cout = oc.weight.shape[0]
         cp = _rup(cout, 16)
-        w_out = self.packed(lambda: P.pack_conv_weight(widen_weight(oc.weight), cout_pad=cp))
+        sp = tuple(a3.shape[1:-1])
+
+        def make():
+            w = oc.weight.detach()
+            if cin_pad and w.shape[1] != cin_pad:
+                wp = torch.zeros(w.shape[0], cin_pad, *w.shape[2:], dtype=w.dtype, device=w.device)
+                wp[:, :w.shape[1]] = w
+                w = wp
+            return P.pack_conv_weight(widen_weight(w), cout_pad=cp)
+
+        w_out = self.packed(make)
         b_out = self.packed(lambda: _pad_vec(oc.bias.detach(), cp))
-        y = torch.zeros(B, *self.sp, cp, device=dev)
+        y = torch.zeros(B, *sp, cp, device=dev)
         self.gemm(P.conv_plan([P.ConvSource(a3)], w_out, y, oc.weight.shape[2], bias=b_out, out_f32=True,
                               name="out_conv"))
-        self.out = torch.zeros(B, cout, *self.sp, device=dev)
+        self.out = torch.zeros(B, cout, *sp, device=dev)
         src = y.view(B, S, cp)[:, :, :cout].permute(0, 2, 1)
         dst = self.out.view(B, cout, S)
         self._add("out.nchw", lambda: ops.copy_cast(src, dst), [self.out])
@@ -515,5 +525,141 @@ class UNet2DSplitProgram(_SplitProgram):
 
     def forward(self, x, t, z_pos, context=None) -> torch.Tensor:
         self._load_inputs(x, t, z_pos, context)
+        self.run()
+        return self.out
+
+
+class VAE3DSplitProgram(_SplitProgram):
+    """ddpm_3d_ldm/vae.py encode (`mode="encode"`, vae.py:49-55) / decode (`"decode"`, vae.py:82-87) in
+    split precision: the reference's show_model.py decodes the sampled latents without autocast
+    (show_model.py:255).  Same walk and the same channel padding as vae_engine.VAE3DProgram (32-channel
+    levels run zero-padded to 64; GroupNorm(8, 32) over the padded tensor = 16 groups of 4)."""
+
+    def __init__(self, vae, mode: str, batch: int, spatial: Sequence[int]):
+        dev = next(vae.parameters()).device
+        enc, dec = vae.encoder, vae.decoder
+        first_block = enc.downs[0] if mode == "encode" else dec.ups[0]
+        self.gn_groups = first_block.norm1.num_groups
+        super().__init__(dev, batch, spatial, groups=self.gn_groups, training=False)
+        self.mode = mode
+        if len(self.sp) != 3:
+            raise _lib.MriError("VAE3D expects 3 spatial dims")
+        if mode == "encode":
+            for s in self.sp:
+                if s % (2 ** (enc.num_down - 1)) != 0:
+                    raise _lib.MriError(f"volume size {self.sp} must be divisible by {2 ** (enc.num_down - 1)}")
+            first, layers, last, prefix = enc.in_conv, enc.downs, enc.to_mu_logvar, "encoder"
+        elif mode == "decode":
+            first, layers, last, prefix = dec.from_latent, dec.ups, dec.out_conv, "decoder"
+        else:
+            raise ValueError(mode)
+        B, (D, H, W) = batch, self.sp
+        S = D * H * W
+        cin, c0 = first.weight.shape[1], first.weight.shape[0]
+        self.x_in = torch.zeros(B, cin, D, H, W, device=dev)
+        self.track(first.weight, first.bias)
+        x6 = torch.zeros(B, 2 * cin, D, H, W, device=dev)
+        kpad = _rup(27 * 3 * cin, 64)
+        col = torch.zeros(B * S, kpad, dtype=torch.bfloat16, device=dev)
+        x_in, cp0 = self.x_in, self.cpad(c0)
+        self._add(f"{prefix}.in.lo", lambda: ops.bf16_residual_nchw(x_in, x6, B, cin * S), [x6])
+        self._add(f"{prefix}.in.im2col", lambda: ops.im2col(x_in, col, B, cin, D, H, W, 3, 3, kpad,
+                                                            src2=x6, cin2=2 * cin), [col])
+        w_in = self.packed(lambda: _pad_k(P.pack_conv_weight(widen_weight(first.weight), cout_pad=cp0), kpad))
+        b_in = self.packed(lambda: _pad_vec(first.bias.detach(), cp0))
+        h = self.matrix_in_conv(col, w_in, S, kpad, cp0, b_in, f"{prefix}.in", False)
+        c_real = c0
+        for i, layer in enumerate(layers):
+            name = f"{prefix}.{i}"
+            if isinstance(layer, torch.nn.ConvTranspose3d):
+                c_real = layer.weight.shape[1]
+                cip, cop = h.C, self.cpad(c_real)
+                self.track(layer.weight, layer.bias)
+                w = self.packed(lambda l=layer, a=cip, b=cop: P.pack_convT_weight(
+                    widen_weight(self._pad2(l.weight.detach(), a, b), transposed=True), cout_pad=b))
+                bb = self.packed(lambda l=layer, b=cop: _pad_vec(l.bias.detach(), b))
+                y = self.new_f32([s * 2 for s in h.t.shape[1:-1]], cop, with_stats=False)
+                self.gemm(P.up_conv_plan(self.raw(h, f"{name}.in"), w, y.t, bias=bb, out_f32=True, name=name))
+                h = y
+            elif isinstance(layer, torch.nn.Conv3d):
+                c_real = layer.weight.shape[0]
+                cip, cop = h.C, self.cpad(c_real)
+                self.track(layer.weight, layer.bias)
+                w = self.packed(lambda l=layer, a=cip, b=cop: P.pack_conv_weight(
+                    widen_weight(self._pad2(l.weight.detach(), b, a)), cout_pad=b))
+                bb = self.packed(lambda l=layer, b=cop: _pad_vec(l.bias.detach(), b))
+                y = self.new_f32([s // 2 for s in h.t.shape[1:-1]], cop, with_stats=False)
+                self.gemm(P.down_conv_plan(self.raw(h, f"{name}.in"), w, y.t, bias=bb, out_f32=True, name=name))
+                h = y
+            else:
+                h, c_real = self.vae_resblock(h, layer, c_real, name)
+        self.track(last.weight, last.bias)
+        sp_out = tuple(h.t.shape[1:-1])
+        self.head(self.raw(h, f"{prefix}.out.in"), last, sp_out[0] * sp_out[1] * sp_out[2], cin_pad=h.C)
+        self.params_changed()
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def cpad(c: int) -> int:
+        return _rup(c, 64)
+
+    @staticmethod
+    def _pad2(w: torch.Tensor, n0: int, n1: int) -> torch.Tensor:
+        """Zero-pad dims 0 and 1 of a convolution weight to (n0, n1)."""
+        if w.shape[0] == n0 and w.shape[1] == n1:
+            return w
+        out = torch.zeros(n0, n1, *w.shape[2:], dtype=w.dtype, device=w.device)
+        out[:w.shape[0], :w.shape[1]] = w
+        return out
+
+    def norm_split(self, x: F32Act, norm, c_real: int, name: str) -> torch.Tensor:
+        """[hi | lo | hi] of silu(GroupNorm(x)) over the padded tensor: groups of c_real / G channels
+        (the all-zero padding groups give zeros: gamma = beta = 0 there)."""
+        cpg = c_real // self.gn_groups
+        if c_real % self.gn_groups:
+            raise _lib.MriError(f"GroupNorm({self.gn_groups}, {c_real}) does not divide")
+        cp = x.C
+        G = cp // cpg
+        x.stats, x.cpg = self.new_stats(G), cpg
+        B, S, xs, st = self.B, x.spatial, x.t, x.stats
+        self._add(f"{name}.stats", lambda: ops.stats_f32(xs, st, B, S, cp, G), [st])
+        self.track(norm.weight, norm.bias)
+        gm = self.packed(lambda: _pad_vec(norm.weight.detach(), cp))
+        bt = self.packed(lambda: _pad_vec(norm.bias.detach(), cp))
+        return self.gn_split(x, gm, bt, G, norm.eps, True, name)
+
+    def vae_resblock(self, x: F32Act, blk, cin: int, name: str):
+        """ResidualBlock3DNoTime.forward (vae.py:19-22)."""
+        c1, c2 = blk.conv1, blk.conv2
+        cout = c1.weight.shape[0]
+        cip, cop = x.C, self.cpad(cout)
+        self.track(c1.weight, c1.bias, c2.weight, c2.bias)
+        a1 = self.norm_split(x, blk.norm1, cin, f"{name}.norm1")
+        w1 = self.packed(lambda: P.pack_conv_weight(widen_weight(self._pad2(c1.weight.detach(), cop, cip))))
+        b1 = self.packed(lambda: _pad_vec(c1.bias.detach(), cop))
+        h = self.conv([P.ConvSource(a1)], w1, cop, 3, b1, with_stats=False, name=f"{name}.conv1")
+        a2 = self.norm_split(h, blk.norm2, cout, f"{name}.norm2")
+        b2 = self.packed(lambda: _pad_vec(c2.bias.detach(), cop))
+        xr = self.raw(x, f"{name}.in")
+        if isinstance(blk.skip, torch.nn.Identity):
+            w2 = self.packed(lambda: P.pack_conv_weight(widen_weight(self._pad2(c2.weight.detach(), cop, cop)),
+                                                        extra=[identity_weight(cop, self.device)]))
+            out = self.conv([P.ConvSource(a2), P.ConvSource(xr, taps=False)], w2, cop, 3, b2,
+                            with_stats=False, name=f"{name}.conv2+x")
+        else:
+            sk = blk.skip
+            self.track(sk.weight, sk.bias)
+            w2 = self.packed(lambda: P.pack_conv_weight(
+                widen_weight(self._pad2(c2.weight.detach(), cop, cop)),
+                extra=[widen_weight(self._pad2(sk.weight.detach().reshape(cout, cin), cop, cip))]))
+            bs = self.packed(lambda: _pad_vec(sk.bias.detach(), cop))
+            out = self.conv([P.ConvSource(a2), P.ConvSource(xr, taps=False)], w2, cop, 3, b2, rowbias=bs,
+                            rowbias_ld=0, with_stats=False, name=f"{name}.conv2+skip")
+        return out, cout
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.params_changed():
+            self.do_refresh()
+        self.x_in.copy_(x)
         self.run()
         return self.out

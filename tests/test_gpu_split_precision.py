@@ -190,3 +190,33 @@ def test_2d_sampling_in_split_precision():
     e = rel_l2(got, want)
     print("2D trajectory error after", T, "steps:", e)
     assert e < 1e-3
+
+
+@pytest.mark.parametrize("cfg", [dict(base=32, num_down=3, latent=3, shape=(2, 4, 16, 24, 16)),
+                                 dict(base=32, num_down=3, latent=16, shape=(1, 4, 16, 16, 16)),
+                                 dict(base=64, num_down=2, latent=8, shape=(1, 4, 8, 16, 16))])
+def test_vae_split_vs_fp32_oracle(cfg):
+    """VAE3D encode / decode (show_model.py:255 decodes without autocast), padded 32-channel level included."""
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.vae import VAE3D
+    torch.manual_seed(3)
+    m = VAE3D(4, cfg["base"], cfg["num_down"], cfg["latent"])
+    with torch.no_grad():
+        for p_ in m.parameters():
+            if p_.dim() == 1:
+                p_.add_(0.1 * torch.randn_like(p_))
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.cuda().eval()
+    x = torch.randn(*cfg["shape"]).clamp_(-1, 1)
+    with torch.no_grad():
+        want_mu, want_lv = O.vae3d_encode(sd, x)
+        want_rec = O.vae3d_decode(sd, want_mu)
+        mu_b, _ = m.encode(x.cuda())
+        rec_b = m.decode_from_latent(want_mu.cuda())
+        m.precision = "split"
+        mu, lv = m.encode(x.cuda())
+        rec = m.decode_from_latent(want_mu.cuda())
+    errs = dict(mu=rel_l2(mu, want_mu), logvar=rel_l2(lv, want_lv), recon=rel_l2(rec, want_rec),
+                mu_bf16=rel_l2(mu_b, want_mu), recon_bf16=rel_l2(rec_b, want_rec))
+    print({k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["mu"] < TOL and errs["logvar"] < TOL and errs["recon"] < TOL
+    assert errs["recon_bf16"] > 10 * errs["recon"]

@@ -173,6 +173,8 @@ def run_one(name: str, work: Path, out: Path, args) -> dict:
         overlay.append("--device-datasets")
     if args.fused_adam:
         overlay.append("--fused-adam")
+    if args.split_sampling and name.startswith("show"):
+        overlay += ["--precision", "split"]
     overlay += ["-m", module]
     if args.nproc > 1 and name == "train3d":
         cmd = [sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1",
@@ -215,6 +217,8 @@ def main() -> int:
     ap.add_argument("--keep-vae", action="store_true", help="leave vae.py to the reference")
     ap.add_argument("--overlap-ddp", action="store_true")
     ap.add_argument("--fused-adam", action="store_true", help="torch.optim.Adam -> the one-launch Adam")
+    ap.add_argument("--split-sampling", action="store_true",
+                    help="the show_model scripts sample / decode in split precision (fp32-class parity)")
     ap.add_argument("--device-datasets", action="store_true",
                     help="dataset.py -> the device data path (normalise / resize / pad / crop kernels)")
     ap.add_argument("--nproc", type=int, default=1, help="train3d under torchrun with this many ranks")
