@@ -75,6 +75,7 @@ class F32Act:
     def __init__(self, t: torch.Tensor, stats: Optional[torch.Tensor] = None, cpg: int = 0):
         self.t, self.stats, self.cpg = t, stats, cpg
         self.raw3: Optional[torch.Tensor] = None
+        self.keep = False          # a pending skip connection: not released by its first consumer
 
     @property
     def C(self) -> int:
@@ -93,13 +94,30 @@ class _SplitProgram(UNetProgram):
 
     # ------------------------------------------------------------------ buffers
     def new_f32(self, sp: Sequence[int], C: int, with_stats: bool = True) -> F32Act:
-        t = torch.zeros(self.B, *sp, C, dtype=torch.float32, device=self.device)
+        t = self.pool.get((self.B, *sp, C), torch.float32)
         if with_stats and C % (8 * self.groups) == 0:
             return F32Act(t, self.new_stats(self.groups), C // self.groups)
         return F32Act(t)
 
     def wide(self, like: torch.Tensor) -> torch.Tensor:
-        return torch.zeros(*like.shape[:-1], 3 * like.shape[-1], dtype=torch.bfloat16, device=self.device)
+        return self.pool.get((*like.shape[:-1], 3 * like.shape[-1]), torch.bfloat16)
+
+    def free(self, *items) -> None:
+        """Buffers whose last consumer has been emitted go back to the pool (the program is
+        straight-line: a released buffer is only handed to ops emitted later).  An F32Act that is
+        still a pending skip connection (`keep`) stays."""
+        for it in items:
+            if it is None:
+                continue
+            if isinstance(it, F32Act):
+                if it.keep:
+                    continue
+                self.pool.release(it.t)
+                if it.raw3 is not None:
+                    self.pool.release(it.raw3)
+                it.t = it.raw3 = None
+            else:
+                self.pool.release(it)
 
     # ------------------------------------------------------------------ op emitters
     def gn_split(self, x: F32Act, gamma, beta, groups: int, eps: float, silu: bool, name: str,
@@ -117,7 +135,7 @@ class _SplitProgram(UNetProgram):
                name: str) -> F32Act:
         """fp32 act(GroupNorm(x)) + residual: the post-norm block output (slice_cond_2d_ddpm/unet.py:52-56)."""
         assert x.stats is not None, f"{name}: input has no statistics"
-        y = F32Act(torch.zeros_like(x.t))
+        y = F32Act(self.pool.get(tuple(x.t.shape), torch.float32))
         B, S, C, xs, st, cpg, yt = self.B, x.spatial, x.C, x.t, x.stats, x.cpg, y.t
         self._add(name, lambda: ops.gn_split(xs, None, st, gamma, beta, B, S, C, groups, cpg, eps, silu,
                                              residual=residual, y32=yt), [yt])
@@ -232,6 +250,7 @@ class UNet3DSplitProgram(_SplitProgram):
         for i, blk in enumerate(model.downs):
             h = self.resblock(h, None, blk["res1"], eps, f"downs.{i}.res1")
             h = self.resblock(h, None, blk["res2"], eps, f"downs.{i}.res2")
+            h.keep = True
             skips.append(h)
             if i != L - 1:
                 dn = blk["down"]
@@ -258,8 +277,10 @@ class UNet3DSplitProgram(_SplitProgram):
                 u = self.new_f32([s * 2 for s in h.t.shape[1:-1]], chs[i])
                 self.gemm(P.up_conv_plan(self.raw(h, f"ups.{j}.up.in"), wu, u.t, bias=up.bias, stats=u.stats,
                                          stats_cpg=u.cpg, out_f32=True, name=f"ups.{j}.up"))
+                self.free(h)
                 h = u
             skip = skips.pop()
+            skip.keep = False       # its last consumer is the block below
             if tuple(skip.t.shape[1:-1]) != tuple(h.t.shape[1:-1]):
                 raise _lib.MriError("skip/upsample shape mismatch (centre-crop path not supported)")
             h = self.resblock(h, skip, blk["res1"], eps, f"ups.{j}.res1")
@@ -269,6 +290,7 @@ class UNet3DSplitProgram(_SplitProgram):
         on, oc = model.out_norm, model.out_conv
         self.track(on.weight, on.bias, oc.weight, oc.bias)
         a3 = self.gn_split(h, on.weight, on.bias, self.groups, eps, True, name="out_norm")
+        self.free(h)
         self.head(a3, oc, S)
         self.params_changed()
 
@@ -289,7 +311,9 @@ class UNet3DSplitProgram(_SplitProgram):
                                                     splits=[3 * c for c in cins]))
         h = self.conv([P.ConvSource(a) for a in normed], w1, cout, 3, c1.bias, rowbias=rowbias,
                       rowbias_ld=rb_ld, name=f"{name}.conv1")
+        self.free(*normed)
         a2 = self.gn_split(h, n2.weight, n2.bias, self.groups, eps, True, f"{name}.norm2")
+        self.free(h)
         raws = [self.raw(s, f"{name}.in{k}") for k, s in enumerate(srcs)]
         if not isinstance(blk.skip, torch.nn.Identity):
             sk = blk.skip
@@ -298,13 +322,16 @@ class UNet3DSplitProgram(_SplitProgram):
                 widen_weight(c2.weight),
                 extra=[widen_weight(sk.weight.detach().reshape(cout, -1), splits=cins)]))
             sources = [P.ConvSource(a2)] + [P.ConvSource(r, taps=False) for r in raws]
-            return self.conv(sources, w2, cout, 3, c2.bias, rowbias=sk.bias, rowbias_ld=0,
-                             name=f"{name}.conv2+skip")
-        assert skip is None and x.C == cout
-        w2 = self.packed(lambda: P.pack_conv_weight(widen_weight(c2.weight),
-                                                    extra=[identity_weight(cout, self.device)]))
-        return self.conv([P.ConvSource(a2), P.ConvSource(raws[0], taps=False)], w2, cout, 3, c2.bias,
-                         name=f"{name}.conv2+x")
+            out = self.conv(sources, w2, cout, 3, c2.bias, rowbias=sk.bias, rowbias_ld=0,
+                            name=f"{name}.conv2+skip")
+        else:
+            assert skip is None and x.C == cout
+            w2 = self.packed(lambda: P.pack_conv_weight(widen_weight(c2.weight),
+                                                        extra=[identity_weight(cout, self.device)]))
+            out = self.conv([P.ConvSource(a2), P.ConvSource(raws[0], taps=False)], w2, cout, 3, c2.bias,
+                            name=f"{name}.conv2+x")
+        self.free(a2, *srcs)
+        return out
 
     def attention(self, x: F32Act, blk, name: str) -> F32Act:
         """AttentionBlock3D (unet_attention.py:28-56) with every product in split precision."""
@@ -369,8 +396,10 @@ class UNet3DSplitProgram(_SplitProgram):
                                 name=f"{name}.pv", flops=2 * B * heads * n * 3 * npad * d))
         wp = self.packed(lambda: P.pack_conv_weight(widen_weight(blk.proj.weight),
                                                     extra=[identity_weight(C, self.device)]))
-        return self.conv([P.ConvSource(self.raw(O, f"{name}.O")), P.ConvSource(self.raw(x, f"{name}.x"), taps=False)],
-                         wp, C, 1, blk.proj.bias, name=f"{name}.proj+x")
+        out = self.conv([P.ConvSource(self.raw(O, f"{name}.O")), P.ConvSource(self.raw(x, f"{name}.x"), taps=False)],
+                        wp, C, 1, blk.proj.bias, name=f"{name}.proj+x")
+        self.free(hn3, qkv, x)
+        return out
 
     # ------------------------------------------------------------------ entry
     def forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
@@ -452,6 +481,7 @@ class UNet2DSplitProgram(_SplitProgram):
         for i, d in enumerate(model.downs):
             h = self.resblock2d(h, None, d.res1, eps, f"downs.{i}.res1")
             h = self.resblock2d(h, None, d.res2, eps, f"downs.{i}.res2")
+            h.keep = True
             skips.append(h)
             dn = d.down
             self.track(dn.weight, dn.bias)
@@ -464,12 +494,14 @@ class UNet2DSplitProgram(_SplitProgram):
         h = self.resblock2d(h, None, model.mid_block2, eps, "mid_block2")
         for j, u in enumerate(model.ups):
             skip = skips.pop()
+            skip.keep = False
             up = u.up
             self.track(up.weight, up.bias)
             wu = self.packed(lambda up=up: P.pack_convT_weight(widen_weight(up.weight, transposed=True)))
             y = self.new_f32([s * 2 for s in h.t.shape[1:-1]], up.weight.shape[1], with_stats=False)
             self.gemm(P.up_conv_plan(self.raw(h, f"ups.{j}.up.in"), wu, y.t, bias=up.bias, out_f32=True,
                                      name=f"ups.{j}.up"))
+            self.free(h)
             h = self.resblock2d(y, skip, u.res1, eps, f"ups.{j}.res1")
             h = self.resblock2d(h, None, u.res2, eps, f"ups.{j}.res2")
 
@@ -480,6 +512,7 @@ class UNet2DSplitProgram(_SplitProgram):
         ht, hst, C0, G = h.t, h.stats, h.C, self.groups
         self._add("out_norm.stats", lambda: ops.stats_f32(ht, hst, B, S, C0, G), [hst])
         a3 = self.gn_split(h, on.weight, on.bias, self.groups, eps, True, name="out_norm")
+        self.free(h)
         self.head(a3, oc, S)
         self.params_changed()
 
@@ -499,8 +532,11 @@ class UNet2DSplitProgram(_SplitProgram):
         h1 = self.conv([P.ConvSource(r) for r in raws], w1, cout, 3, c1.bias, name=f"{name}.conv1")
         a1 = self.gn_split(h1, n1.weight, n1.bias, self.groups, eps, True, f"{name}.norm1+temb",
                            rowbias=rowbias, rowbias_ld=rb_ld)
+        self.free(h1)
         w2 = self.packed(lambda: P.pack_conv_weight(widen_weight(c2.weight)))
         h2 = self.conv([P.ConvSource(a1)], w2, cout, 3, c2.bias, name=f"{name}.conv2")
+        self.free(a1)
+        res_act = None
         if isinstance(blk.res_conv, torch.nn.Identity):
             assert skip is None and x.C == cout
             res = x.t
@@ -509,9 +545,12 @@ class UNet2DSplitProgram(_SplitProgram):
             self.track(rc.weight, rc.bias)
             wr = self.packed(lambda: P.pack_conv_weight(widen_weight(rc.weight, splits=cins),
                                                         splits=[3 * c for c in cins]))
-            res = self.conv([P.ConvSource(r) for r in raws], wr, cout, 1, rc.bias, with_stats=False,
-                            name=f"{name}.res_conv").t
-        return self.gn_f32(h2, n2.weight, n2.bias, self.groups, eps, True, res, f"{name}.norm2+res")
+            res_act = self.conv([P.ConvSource(r) for r in raws], wr, cout, 1, rc.bias, with_stats=False,
+                                name=f"{name}.res_conv")
+            res = res_act.t
+        out = self.gn_f32(h2, n2.weight, n2.bias, self.groups, eps, True, res, f"{name}.norm2+res")
+        self.free(h2, res_act, *srcs)
+        return out
 
     # ------------------------------------------------------------------ entry
     def _load_inputs(self, x, t, z_pos, context):
@@ -580,6 +619,7 @@ class VAE3DSplitProgram(_SplitProgram):
                 bb = self.packed(lambda l=layer, b=cop: _pad_vec(l.bias.detach(), b))
                 y = self.new_f32([s * 2 for s in h.t.shape[1:-1]], cop, with_stats=False)
                 self.gemm(P.up_conv_plan(self.raw(h, f"{name}.in"), w, y.t, bias=bb, out_f32=True, name=name))
+                self.free(h)
                 h = y
             elif isinstance(layer, torch.nn.Conv3d):
                 c_real = layer.weight.shape[0]
@@ -590,6 +630,7 @@ class VAE3DSplitProgram(_SplitProgram):
                 bb = self.packed(lambda l=layer, b=cop: _pad_vec(l.bias.detach(), b))
                 y = self.new_f32([s // 2 for s in h.t.shape[1:-1]], cop, with_stats=False)
                 self.gemm(P.down_conv_plan(self.raw(h, f"{name}.in"), w, y.t, bias=bb, out_f32=True, name=name))
+                self.free(h)
                 h = y
             else:
                 h, c_real = self.vae_resblock(h, layer, c_real, name)
@@ -638,7 +679,9 @@ class VAE3DSplitProgram(_SplitProgram):
         w1 = self.packed(lambda: P.pack_conv_weight(widen_weight(self._pad2(c1.weight.detach(), cop, cip))))
         b1 = self.packed(lambda: _pad_vec(c1.bias.detach(), cop))
         h = self.conv([P.ConvSource(a1)], w1, cop, 3, b1, with_stats=False, name=f"{name}.conv1")
+        self.free(a1)
         a2 = self.norm_split(h, blk.norm2, cout, f"{name}.norm2")
+        self.free(h)
         b2 = self.packed(lambda: _pad_vec(c2.bias.detach(), cop))
         xr = self.raw(x, f"{name}.in")
         if isinstance(blk.skip, torch.nn.Identity):
@@ -655,6 +698,7 @@ class VAE3DSplitProgram(_SplitProgram):
             bs = self.packed(lambda: _pad_vec(sk.bias.detach(), cop))
             out = self.conv([P.ConvSource(a2), P.ConvSource(xr, taps=False)], w2, cop, 3, b2, rowbias=bs,
                             rowbias_ld=0, with_stats=False, name=f"{name}.conv2+skip")
+        self.free(a2, x)
         return out, cout
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
