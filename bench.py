@@ -324,7 +324,11 @@ def train_record(args, torch, dist, rank, world, dev, B: int, K: int, W: int):
     torch.manual_seed(0)
     model = UNet3DModelWithAttention(**MODEL_KW).to(dev).train()
     overlap = not getattr(args, "torch_ddp", False)
-    net = wrap_ddp(model, dev, overlap=overlap) if world > 1 else model
+    # --no-ddp (attribution only): N independent replicas, no gradient exchange -- what the box
+    # itself costs when all N GPUs train at once (shared power / thermal envelope), to be
+    # subtracted from the DDP step before blaming the all-reduce
+    replicas_only = bool(getattr(args, "no_ddp", False))
+    net = wrap_ddp(model, dev, overlap=overlap) if (world > 1 and not replicas_only) else model
     diff = quiet(GaussianDiffusionLatent3D, net, LATENT[0], timesteps=T_STEPS).to(dev)
     if getattr(args, "torch_adam", False):
         opt = torch.optim.Adam(model.parameters(), lr=2e-4)
@@ -382,7 +386,7 @@ def train_record(args, torch, dist, rank, world, dev, B: int, K: int, W: int):
     comm = None
     ms_noov = 0.0
     prog = model.program(B, LATENT[1:], training=True)
-    if world > 1 and overlap:
+    if world > 1 and overlap and not replicas_only:
         gs = net.grad_sync
         gs.time_buckets = True
         reports = []
@@ -423,7 +427,8 @@ def train_record(args, torch, dist, rank, world, dev, B: int, K: int, W: int):
         "config": {"workload": "ddpm_3d_ldm_train_step", "latent": list(LATENT), "batch_per_gpu": B,
                    "model": "UNet3DModelWithAttention(base 128, mults 1-2-4, 136.4M params)",
                    "step": "q_sample (in-kernel Philox) + fwd + min-SNR loss + bwd + DDP all-reduce + Adam",
-                   "ddp": ("none (1 GPU)" if world == 1 else "torch DDP (reducer after backward)" if not overlap
+                   "ddp": ("none (1 GPU)" if world == 1 else "NONE: independent replicas (--no-ddp, attribution run)"
+                           if replicas_only else "torch DDP (reducer after backward)" if not overlap
                            else "bucketed NCCL all-reduce (545.6 MB fp32) overlapped with the backward launch list"),
                    "optimizer": "torch.optim.Adam" if getattr(args, "torch_adam", False) else "mri_b200 fused Adam",
                    "loss": float(loss.item())},
@@ -830,6 +835,8 @@ def main():
     ap.add_argument("--train-steps", type=int, default=20, help="timed steps of the training record (<= --steps)")
     ap.add_argument("--torch-adam", action="store_true", help="train mode: torch.optim.Adam instead of "
                     "mri_image_generation_b200.optim.Adam")
+    ap.add_argument("--no-ddp", action="store_true", help="train mode, N > 1: independent replicas without "
+                    "gradient exchange (attribution of the multi-GPU step time)")
     ap.add_argument("--torch-ddp", action="store_true", help="train mode, N > 1: torch DDP instead of the "
                     "overlapped bucketed all-reduce (parallel.DistributedDataParallel)")
     ap.add_argument("--per-op", default="", help="write per-GEMM timings (CUDA events) to this file")
