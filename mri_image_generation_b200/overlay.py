@@ -113,6 +113,10 @@ def uninstall(root: str = "model_scripts") -> None:
     if hasattr(topt, "_mri_torch_adam"):
         topt.Adam = topt._mri_torch_adam
         del topt._mri_torch_adam
+    from .model_scripts.ddpm_3d_ldm import unet_attention as _u3, vae as _v
+    from .model_scripts.slice_cond_2d_ddpm import unet as _u2
+    for cls in (_u3._UNet3DBase, _u2._UNet2DBase, _v.VAE3D):
+        cls.precision = "bf16"
 
 
 def main(argv=None) -> None:

@@ -2,7 +2,8 @@
 """Execute the reference's OWN driver scripts, unmodified, over the B200 drop-in.
 
     python tools/run_reference_scripts.py --reference /path/to/mri-image-generation \
-        [--scripts train3d,show3d,model2d,show2d,model25d] [--keep-vae] [--nproc 2]
+        [--scripts train3d,show3d,model2d,show2d,model25d] [--keep-vae] [--nproc 2 --overlap-ddp]
+        [--device-datasets] [--fused-adam] [--split-sampling]
 
 What it does, per script:
   * copies `<reference>/model_scripts` (the .py files) into a scratch work tree -- the scripts
