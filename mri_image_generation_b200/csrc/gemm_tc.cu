@@ -1301,11 +1301,23 @@ extern "C" int mri_gemm_smem_bytes(int block_n, int swap_ab, int stages) {
   return pick_stages(block_n, swap_ab, stages) * stage_bytes(block_n, swap_ab) + kStagingBytes + 1024;
 }
 
+// Tuning probe (profiles/README.md, "Where the multi-GPU training step loses time"): MRI_GEMM_SMS=n
+// makes the persistent GEMM grids n CTAs wide instead of one per SM, which leaves SMs to the
+// all-reduce kernels that run under a DDP backward.  Unset: every SM.
+static int usable_sms(int hw) {
+  static const int env = [] {
+    const char* e = getenv("MRI_GEMM_SMS");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  return (env >= 8 && env < hw) ? env : hw;
+}
+
 extern "C" int mri_gemm_workspace_bytes(int* n_ctas_out) {
   int dev = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return set_cuda_error(e, "mri_gemm_workspace_bytes");
+  sms = usable_sms(sms);
   if (n_ctas_out) *n_ctas_out = sms;
   // [sms][128][256] fp32 partial tiles, then [sms] int32 flags (padded to 1 KB)
   const long long bytes = (long long)sms * kBlockM * kPartialLd * 4 + 1024;
@@ -1359,6 +1371,7 @@ extern "C" int mri_gemm_launch(const MriGemmArgs* a, void* stream) {
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaDeviceGetAttribute(SM count)");
+    n_sms = usable_sms(n_sms);
   }
   MriGemmArgs k = *a;
   // short K loops (2D convolutions: 9 taps): the epilogue, not the main loop, paces the CTA ->
