@@ -68,3 +68,46 @@ def test_identity_and_concat_weights():
     eye = SE.identity_weight(4)
     assert eye.shape == (4, 12) and torch.equal(eye[:, :4], torch.eye(4)) and torch.equal(eye[:, 4:8], torch.eye(4))
     assert not eye[:, 8:].any()
+
+
+def test_widened_attention_products_match_fp32():
+    """q k^T and P v of AttentionBlock3D (unet_attention.py:49-51) with widened operands
+    ([hi | lo | hi] x [hi | hi | lo] along the contraction) through matrix_plan's CPU emulation."""
+    torch.manual_seed(3)
+    B, heads, n, d = 1, 2, 100, 64
+    npad = 128
+    q, k, v = (torch.randn(B, n, heads, d) for _ in range(3))
+    want_S = torch.einsum("bnhd,bmhd->bhnm", q, k)
+
+    def widen(x, pattern):            # along the last axis
+        hi = x.to(torch.bfloat16)
+        lo = (x - hi.float()).to(torch.bfloat16)
+        return torch.cat([hi, lo, hi] if pattern == 0 else [hi, hi, lo], dim=-1).contiguous()
+
+    q3, k3 = widen(q, 0), widen(k, 1)                     # [B, n, heads, 3d]
+    S = torch.zeros(B, heads, n, npad)
+    ld = heads * 3 * d
+    qa = P.TView(q3, (3 * d, n, heads, B, 1), (1, ld, 3 * d, n * ld, B * n * ld))
+    kb = P.TView(k3, (3 * d, n, heads, B), (1, ld, 3 * d, n * ld))
+    so = P.TView(S, (npad, n, heads, B, 1), (1, npad, n * npad, heads * n * npad, B * heads * n * npad))
+    P.matrix_plan(qa, (128, 1, 1, 1), kb, so, K=3 * d, n_total=npad, block_n=128, ext=(n, heads, B, 1),
+                  tiles=(-(-n // 128), heads, B, 1), bz_sel=(3, 4), out_f32=True).simulate()
+    assert rel(S[..., :n], want_S) < 2e-5
+    # P v with widened probabilities [hi | lo | hi] (segments of npad keys) and values [hi | hi | lo]
+    Pm = torch.softmax(want_S * d ** -0.5, -1)
+    want_O = torch.einsum("bhnm,bmhd->bnhd", Pm, v)
+    P3 = torch.zeros(B, heads, n, 3 * npad, dtype=torch.bfloat16)
+    hi = Pm.to(torch.bfloat16)
+    P3[..., :n], P3[..., npad:npad + n], P3[..., 2 * npad:2 * npad + n] = hi, (Pm - hi.float()).to(torch.bfloat16), hi
+    vT = v.permute(0, 2, 3, 1).reshape(B, heads * d, n)   # [B, C, n]: keys contiguous
+    vT3 = torch.zeros(B, heads * d, 3 * npad, dtype=torch.bfloat16)
+    vh = vT.to(torch.bfloat16)
+    vT3[..., :n], vT3[..., npad:npad + n], vT3[..., 2 * npad:2 * npad + n] = vh, vh, (vT - vh.float()).to(torch.bfloat16)
+    C_ = heads * d
+    O = torch.zeros(B, n, C_)
+    pa = P.TView(P3, (3 * npad, n, heads, B, 1), (1, 3 * npad, n * 3 * npad, heads * n * 3 * npad, B * heads * n * 3 * npad))
+    vb = P.TView(vT3, (3 * npad, d, heads, B), (1, 3 * npad, d * 3 * npad, C_ * 3 * npad))
+    oo = P.TView(O, (d, n, heads, B, 1), (1, C_, d, n * C_, B * n * C_))
+    P.matrix_plan(pa, (128, 1, 1, 1), vb, oo, K=3 * npad, n_total=d, block_n=64, ext=(n, heads, B, 1),
+                  tiles=(-(-n // 128), heads, B, 1), bz_sel=(3, 4), out_f32=True).simulate()
+    assert rel(O.view(B, n, heads, d), want_O) < 2e-5
