@@ -93,6 +93,10 @@ class GradSync:
     all-reduce of all UNet gradients, issued in reverse order, overlapped with backward)."""
 
     def __init__(self, process_group=None, bucket_cap_mb: float = 48.0):
+        import os
+        env = os.environ.get("MRI_DDP_BUCKET_MB")     # tuning experiments only
+        if env:
+            bucket_cap_mb = float(env)
         self.group = process_group
         self.bucket_bytes = int(bucket_cap_mb * (1 << 20))
         self.enabled = True                 # False inside DistributedDataParallel.no_sync()

@@ -247,3 +247,48 @@ def test_plan_segments_prefix_property_random_programs():
         assert len(spans) == len(touched)
         for (o1, n1), (o2, _) in zip(spans, spans[1:]):
             assert o1 % 64 == 0 and o1 + n1 <= o2
+
+
+def _ddp_factory_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from torch.nn.parallel import DistributedDataParallel as TorchDDP
+
+    from mri_image_generation_b200 import overlay, parallel
+    # what `overlay --overlap-ddp` binds the scripts' `DDP(...)` to (ddpm_3d_ldm/train.py:232-233):
+    # modules the overlapped wrapper does not know (the reference's own VAE, any plain nn.Module)
+    # go to torch's wrapper with the script's call signature
+    DDP = parallel.ddp_for_scripts(TorchDDP)
+    torch.manual_seed(rank)
+    lin = torch.nn.Linear(4, 3)
+    wrapped = DDP(lin, device_ids=None, output_device=None, find_unused_parameters=False)
+    ok_type = isinstance(wrapped, TorchDDP)
+    x = torch.full((2, 4), float(rank + 1))
+    wrapped(x).sum().backward()
+    g = lin.weight.grad.clone()
+    # install / uninstall round trip of the module-level patch
+    overlay.install(packages=["ddpm_3d_ldm"], overlap_ddp=True, fused_adam=False)
+    import torch.nn.parallel as tnp
+    patched = tnp.DistributedDataParallel is not TorchDDP
+    overlay.uninstall()
+    restored = tnp.DistributedDataParallel is TorchDDP
+    torch.save({"ok_type": ok_type, "grad": g, "patched": patched, "restored": restored},
+               os.path.join(out_dir, f"d{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ddp_factory_for_scripts_hands_plain_modules_to_torch_ddp(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_ddp_factory_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(tmp_path / "d0.pt")
+    r1 = torch.load(tmp_path / "d1.pt")
+    assert r0["ok_type"] and r1["ok_type"] and r0["patched"] and r0["restored"]
+    # torch DDP averaged the two ranks' gradients: d/dW of sum(W x + b) = x summed over the batch
+    want = torch.full((3, 4), 2.0 * (1 + 2) / 2)
+    assert torch.allclose(r0["grad"], want) and torch.allclose(r1["grad"], want)
