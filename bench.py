@@ -143,14 +143,52 @@ def cpu_reference_rate(n_forwards: int, threads: int):
     buf = O.schedule_buffers(O.cosine_betas(T_STEPS))
     x = torch.randn(1, *LATENT)
     times = []
+    first = None
     with torch.no_grad():
         for i in range(n_forwards + 1):
             t = torch.full((1,), T_STEPS - 1 - i, dtype=torch.long)
             t0 = time.perf_counter()
             eps = O.unet3d_forward(sd, x, t)
+            if first is None:     # the checker's answer for one (x, t): parity_record() compares the device paths
+                first = (sd, x.clone(), t.clone(), eps.clone())
             x = O.p_sample_update(buf, x, t, eps, torch.randn_like(x))
             times.append(time.perf_counter() - t0)
-    return sum(times[1:]) / n_forwards  # first call = warm-up
+    return sum(times[1:]) / n_forwards, first  # first call = warm-up
+
+
+def parity_record(torch, dev, first):
+    """Noise prediction of the device paths against the fp32 CPU oracle on the SAME weights and
+    input (B = 1, full latent): the default bf16 path and the split precision mode,
+    plus what one reverse step costs in each at B = 1."""
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.diffusion import GaussianDiffusionLatent3D
+    from mri_image_generation_b200.model_scripts.ddpm_3d_ldm.unet_attention import \
+        UNet3DModelWithAttention
+    sd, x, t, want = first
+    model = UNet3DModelWithAttention(**MODEL_KW)
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    diff = quiet(GaussianDiffusionLatent3D, model, LATENT[0], timesteps=T_STEPS).to(dev)
+    out = {"what": "eps rel-L2 against the fp32 CPU oracle, B = 1, t = %d, same weights and input" % int(t[0]),
+           "tolerance": {"bf16": 2e-2, "split": 3e-4}}
+    xd, td = x.to(dev), t.to(dev)
+    with torch.no_grad():
+        for prec in ("bf16", "split"):
+            model.precision = prec
+            got = model(xd, td)
+            err = ((got.cpu() - want).norm() / want.norm()).item()
+            for _ in range(3):
+                diff.p_sample(xd, td)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(5):
+                diff.p_sample(xd, td)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            out[prec] = {"eps_rel_l2": err, "reverse_step_ms_b1": e0.elapsed_time(e1) / 5}
+    del diff, model
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(args, rank, world):
@@ -638,14 +676,16 @@ def run_ours(args, rank, world, local_rank):
     # forward launch list (its last launch replaced by the fused gather + DDPM update) + step advance
     launches_per_step = len(prog.ops) + (1 if prog.fused_head is not None else 2)
     cpu = None
+    parity = None
     if world == 1 or rank == 0:
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             nfw = 3
-            sec = cpu_reference_rate(nfw, threads)
+            sec, first = cpu_reference_rate(nfw, threads)
             cpu = {"value": 1.0 / (T_STEPS * sec), "unit": "volumes/s", "cores": threads,
                    "kind": "port",
                    "sample": f"{nfw} reverse steps at batch 1 ({sec:.2f} s each) x {T_STEPS} per volume"}
+            parity = parity_record(torch, dev, first)
     traffic = load_traffic(B) or {}
     tr_gemm, tr_gn = traffic.get("gemm_tc", {}), traffic.get("gn_apply", {})
     line = {
@@ -689,6 +729,8 @@ def run_ours(args, rank, world, local_rank):
                          "share_of_step": gn_ms / inst_ms, "launches_per_step": len(prog.gn_ops)},
         "cpu_baseline": cpu,
     }
+    if parity is not None:
+        line["parity"] = parity
     if comparator is not None:
         line["gpu_comparator"] = comparator
     if train is not None:
