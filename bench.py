@@ -685,7 +685,8 @@ def run_ours(args, rank, world, local_rank):
             cpu = {"value": 1.0 / (T_STEPS * sec), "unit": "volumes/s", "cores": threads,
                    "kind": "port",
                    "sample": f"{nfw} reverse steps at batch 1 ({sec:.2f} s each) x {T_STEPS} per volume"}
-            parity = parity_record(torch, dev, first)
+            if world == 1:
+                parity = parity_record(torch, dev, first)
     traffic = load_traffic(B) or {}
     tr_gemm, tr_gn = traffic.get("gemm_tc", {}), traffic.get("gn_apply", {})
     line = {
