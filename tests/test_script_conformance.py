@@ -3,7 +3,8 @@
 perun, nibabel and build datasets at import time -- SURVEY.md 8c), so their source is parsed
 instead: every name they import from the hot-path modules must exist in the overlay package, and
 every constructor / method call they make on those classes must bind to the drop-in's signature
-with the same positional and keyword arguments."""
+with the same positional and keyword arguments.  (Executing the scripts needs a GPU next to the
+reference: tools/run_reference_scripts.py / tests/test_gpu_scripts.py, logs under profiles/r04*.)"""
 import ast
 import contextlib
 import importlib
